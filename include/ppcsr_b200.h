@@ -1,0 +1,182 @@
+/*
+ * ppcsr_b200.h -- C-ABI of the B200-native Parallel Packed CSR edge-update engine.
+ *
+ * This is the drop-in boundary for the hot path named by BASELINE.json:north_star.  The reference
+ * (domargan/parallel-packed-csr) has no FFI layer: its boundary is the C++ class surface
+ *   PCSR            reference src/pcsr/PCSR.h:64-124
+ *   PPPCSR          reference src/pppcsr/PPPCSR.h:11-60
+ *   ThreadPool      reference src/thread_pool/thread_pool.h:17-40
+ *   ThreadPoolPPPCSR reference src/thread_pool_pppcsr/thread_pool_pppcsr.h:17-47
+ * and `parallel-packed-csr_b200/host/` re-implements exactly those classes on top of the entry points
+ * below (see INTEGRATION.md for the binding a maintainer of the reference would add).
+ *
+ * One handle = one shard = one PCSR instance living in the HBM of one GPU.  All functions return 0 on
+ * success and a negative ppcsr_status on failure; ppcsr_last_error() gives the message.  Plain
+ * pointers and sizes only.  A handle is NOT thread-safe: one in-flight batch per shard (the reference's
+ * submit_* calls are single-threaded as well, reference src/main.cpp:68-82).
+ *
+ * Conventions shared by the batch entry points
+ *   - an update is (src, dst, val): val != 0 inserts/overwrites the edge with that value
+ *     (reference PCSR::add_edge, src/pcsr/PCSR.cpp:706,1374-1445); val == 0 removes it
+ *     (reference PCSR::remove_edge, src/pcsr/PCSR.cpp:709-773).  `val == NULL` means "all `default_val`".
+ *   - a batch is applied in array order with last-op-wins per (src,dst), i.e. the result of the
+ *     reference run with -threads=1 on the same stream.
+ *   - inserts with src >= n are ignored (reference PCSR.cpp:1375); dst is not range checked except
+ *     that dst == 0xFFFFFFFF is rejected (it is the sentinel marker, reference PCSR.h:32, PCSR.cpp:64).
+ *   - num_neighbors follows the reference's call-count semantics: +1 per accepted add call, -1 per
+ *     remove call, duplicates and misses included (reference PCSR.cpp:1392,747).
+ */
+#ifndef PPCSR_B200_H
+#define PPCSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ppcsr_shard ppcsr_shard; /* opaque; owns all device memory of one shard */
+
+typedef enum {
+  PPCSR_OK = 0,
+  PPCSR_ERR_CUDA = -1,     /* a CUDA runtime call failed (fatal for the handle) */
+  PPCSR_ERR_ARG = -2,      /* bad argument */
+  PPCSR_ERR_CAPACITY = -3, /* slot count would exceed 2^31 or allocation failed */
+  PPCSR_ERR_NO_DEVICE = -4 /* no CUDA device: there is NO CPU fallback */
+} ppcsr_status;
+
+/* Geometry exactly as reference PCSR::resizeEdgeArray computes it (src/pcsr/PCSR.cpp:68-73). */
+typedef struct {
+  uint64_t N;       /* slots, power of two                       (edge_list_t::N)    */
+  uint32_t logN;    /* leaf size = 1 << bsr(2*bsr(N)+1)          (edge_list_t::logN) */
+  uint32_t H;       /* tree height = bsr(N/logN)                 (edge_list_t::H)    */
+  uint64_t n;       /* vertices                                  (PCSR::get_n)       */
+  uint64_t items;   /* live slots = edges + one sentinel per vertex                  */
+} ppcsr_geometry;
+
+/* What one batch did.  Byte counts are ALGORITHMIC bytes at this build's slot size
+ * of 8 B (SoA: u32 dest + u32 value; the reference's 12-B edge_t also stores src, which is implied by
+ * the sentinel order here). */
+typedef struct {
+  uint64_t batch_size;     /* updates submitted                                              */
+  uint64_t n_ignored;      /* inserts with src >= n or dst == 0xFFFFFFFF, removes with src >= n */
+  uint64_t n_unique;       /* distinct (src,dst) keys after last-op-wins                     */
+  uint64_t n_inserted;     /* new edges                                                      */
+  uint64_t n_overwritten;  /* inserts that hit an existing edge (value replaced)             */
+  uint64_t n_deleted;      /* removes that found their edge                                  */
+  uint64_t n_not_found;    /* removes of absent edges (the reference prints "not found s d") */
+  uint64_t n_windows;      /* disjoint rebalance windows chosen (1 if the whole array was rebuilt) */
+  uint64_t window_slots;   /* sum of window lengths in slots (resize: N_before + N_after)/2 .. see DESIGN.md */
+  uint64_t rebalance_bytes;/* algorithmic bytes of the rebalance: sum 2*len*8 (+8 per moved sentinel) */
+  uint64_t slots_before;   /* N before the batch                                             */
+  uint64_t slots_after;    /* N after the batch (doubling / halving folded into the same pass) */
+  uint32_t resized;        /* 1 grew, 2 shrank, 0 unchanged                                  */
+  uint32_t whole_array;    /* 1 if the batch was applied as one root window                  */
+  float ms_total;          /* device time of the whole pipeline (CUDA events on the shard stream) */
+  float ms_sort;           /* key build + radix sort + last-op-wins                          */
+  float ms_locate;         /* segmented search + per-leaf counts                             */
+  float ms_select;         /* count tree + bottom-up window selection                        */
+  float ms_rebalance;      /* scan + scatter rebalance (+ copy back for multi-CTA windows)   */
+} ppcsr_batch_stats;
+
+typedef struct {
+  uint64_t bad_geometry;     /* I1 */
+  uint64_t bad_sentinel;     /* I2: beg[v] does not hold v's sentinel / ranges not contiguous */
+  uint64_t bad_order;        /* I3: neighbours not strictly ascending                     */
+  uint64_t bad_leaf_layout;  /* leaf not left-packed / count mismatch / tail not null     */
+  uint64_t bad_upper;        /* I4: tree nodes at or above their upper density bound      */
+  uint64_t bad_lower;        /* I5: tree nodes below their lower bound (only meaningful after deletes) */
+  uint64_t bad_tree;         /* count tree inconsistent with the leaves                   */
+  uint64_t live_items;       /* I6: must equal edges + n                                  */
+  uint64_t edges;
+  uint64_t full_leaves;      /* leaves left 100% full (must be 0)                         */
+} ppcsr_invariant_report;
+
+const char *ppcsr_last_error(void);
+int ppcsr_device_count(void);
+
+/* ---- lifetime: reference PCSR::PCSR(init_n, src_n, lock_search, domain), src/pcsr/PCSR.cpp:775-838 ---- */
+/* Creates a shard with src_n vertices on CUDA device `device`; initial N = 2 << bsr(max(init_n+src_n,1024)). */
+int ppcsr_create(uint32_t init_n, uint32_t src_n, int device, ppcsr_shard **out);
+void ppcsr_destroy(ppcsr_shard *h); /* reference PCSR::~PCSR, src/pcsr/PCSR.cpp:840-851 */
+/* Use an external CUDA stream (cudaStream_t) for all work of this shard; NULL = the shard's own stream. */
+int ppcsr_set_stream(ppcsr_shard *h, void *cuda_stream);
+int ppcsr_sync(ppcsr_shard *h);
+/* Pre-allocate buffers so that batches up to `max_batch` updates and arrays up to `max_slots` slots need
+ * no allocation inside a timed region. */
+int ppcsr_reserve(ppcsr_shard *h, uint64_t max_slots, uint64_t max_batch);
+
+/* ---- the hot path: batched add_edge / remove_edge ---- */
+/* Host buffers (pageable or pinned).  Replaces the ThreadPool start()/stop() region
+ * (reference src/thread_pool/thread_pool.cpp:78-113) for the queued tasks. */
+int ppcsr_apply_batch(ppcsr_shard *h, const uint32_t *src, const uint32_t *dst, const uint32_t *val,
+                      uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats);
+/* Same, buffers already resident in this shard's device memory (not modified). */
+int ppcsr_apply_batch_device(ppcsr_shard *h, const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val,
+                             uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats);
+/* Single operations = batches of one (reference PCSR::add_edge / remove_edge). Correctness path, slow. */
+int ppcsr_add_edge(ppcsr_shard *h, uint32_t src, uint32_t dst, uint32_t value);
+int ppcsr_remove_edge(ppcsr_shard *h, uint32_t src, uint32_t dst, int *found);
+/* reference PCSR::add_node (src/pcsr/PCSR.cpp:681-703): appends `count` vertices after the last one. */
+int ppcsr_add_nodes(ppcsr_shard *h, uint32_t count);
+int ppcsr_last_stats(ppcsr_shard *h, ppcsr_batch_stats *stats);
+
+/* ---- multi-GPU routing helper (reference PPPCSR::get_partiton, src/pppcsr/PPPCSR.cpp:58-66) ---- */
+/* Bins `count` device-resident updates by owning shard: shard p owns sources [starts[p], starts[p+1]).
+ * Writes the updates grouped by owner (stable) with src made shard-local (src - starts[owner],
+ * reference PPPCSR.cpp:46-52) and the per-owner counts.  All pointers are device pointers on `device`
+ * except h_counts (host, n_parts entries).  d_val / d_out_val may be NULL. */
+int ppcsr_bin_by_owner(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts,
+                       const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val, uint64_t count,
+                       uint32_t *d_out_src, uint32_t *d_out_dst, uint32_t *d_out_val, uint64_t *h_counts);
+
+/* ---- reads ---- */
+int ppcsr_geometry_of(ppcsr_shard *h, ppcsr_geometry *out);
+/* reference PCSR::edge_exists (src/pcsr/PCSR.cpp:860-869); `out_value` (nullable) gets the stored value. */
+int ppcsr_edge_exists(ppcsr_shard *h, uint32_t src, uint32_t dst, int *exists, uint32_t *out_value);
+/* Batched point queries, host buffers: exists[i] = 1/0. */
+int ppcsr_edges_exist(ppcsr_shard *h, const uint32_t *src, const uint32_t *dst, uint64_t count, uint8_t *exists);
+/* reference PCSR::get_neighbourhood (src/pcsr/PCSR.cpp:901-912): ascending dests of v into out[0..cap);
+ * *count gets the degree even if it exceeds cap. */
+int ppcsr_neighbours(ppcsr_shard *h, uint32_t v, uint32_t *out, uint64_t cap, uint64_t *count);
+/* reference PCSR::read_neighbourhood (src/pcsr/PCSR.cpp:892-899): touch-only scan; returns a checksum. */
+int ppcsr_read_neighbourhood(ppcsr_shard *h, uint32_t v, uint64_t *checksum);
+/* getNode(v).num_neighbors for all v (host buffer of n entries). */
+int ppcsr_num_neighbors(ppcsr_shard *h, uint32_t *out);
+/* getNode(v).{beginning,end} for all v: beg has n entries, end has n entries (last end = N-1). */
+int ppcsr_node_ranges(ppcsr_shard *h, uint32_t *beginning, uint32_t *end);
+/* Compacted adjacency (the logical graph): rowptr[n+1], then col/val with *edges entries.  Call with
+ * col == NULL to size.  Doubles as the snapshot/export of SURVEY.md §5. */
+int ppcsr_export_csr(ppcsr_shard *h, uint64_t *rowptr, uint32_t *col, uint32_t *val, uint64_t *edges);
+/* One PageRank push step, reference src/utility/pagerank.h:16-29: out[dst] += in[v] / num_neighbors[v].
+ * `out_len` entries of out are zeroed then accumulated (dst >= out_len is skipped; the reference would
+ * write out of bounds).  Accumulation is fp64 on device.  Host buffers. */
+int ppcsr_pagerank_step_f64(ppcsr_shard *h, const double *in, double *out, uint64_t out_len);
+int ppcsr_pagerank_step_f32(ppcsr_shard *h, const float *in, float *out, uint64_t out_len);
+/* Device-buffer variant used by the multi-GPU path: accumulates (no zeroing) into d_out[out_len] fp64;
+ * `d_in` is indexed by shard-local vertex. */
+int ppcsr_pagerank_push_device(ppcsr_shard *h, const double *d_in, double *d_out, uint64_t out_len);
+/* reference src/utility/bfs.h:15-36 on one shard holding the whole graph: dist[n], UINT32_MAX = unreached. */
+int ppcsr_bfs(ppcsr_shard *h, uint32_t start, uint32_t *dist);
+
+/* ---- checks and snapshots ---- */
+/* PMA invariants I1-I6.  `check_lower` != 0 also counts lower-bound violations. */
+int ppcsr_check_invariants(ppcsr_shard *h, int check_lower, ppcsr_invariant_report *report);
+/* Device-side copy of the whole shard state (arrays + geometry); restore makes the shard identical
+ * to the snapshot again.  One snapshot per shard. */
+int ppcsr_snapshot(ppcsr_shard *h);
+int ppcsr_restore(ppcsr_shard *h);
+/* Raw physical state for debugging/tests: dest[N], val[N], leaf_cnt[N/logN] (host buffers, nullable). */
+int ppcsr_debug_dump(ppcsr_shard *h, uint32_t *dest, uint32_t *val, uint32_t *leaf_cnt);
+
+/* ---- primitives exposed for unit tests (host buffers, in place) ---- */
+/* Stable LSD radix sort of (key, payload) pairs by key bits [0,lo_bits) and [32,32+hi_bits). */
+int ppcsr_debug_sort_pairs(int device, uint64_t *keys, uint32_t *payload, uint64_t count, int lo_bits, int hi_bits);
+/* out[i] = sum of in[0..i), out[count] = total (out has count+1 entries). */
+int ppcsr_debug_exclusive_scan(int device, const uint32_t *in, uint32_t *out, uint64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPCSR_B200_H */

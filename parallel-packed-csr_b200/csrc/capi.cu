@@ -1,0 +1,1006 @@
+// capi.cu -- C-ABI (include/ppcsr_b200.h) and host orchestration of the batch pipeline.
+// Unity build: all kernels are included here and compiled for sm_100a only.
+#include <algorithm>
+#include <vector>
+
+#include "batch.cuh"
+#include "common.cuh"
+#include "primitives.cuh"
+#include "queries.cuh"
+#include "rebalance.cuh"
+#include "windows.cuh"
+
+thread_local std::string g_ppcsr_error;
+
+namespace {
+
+int bits_of(uint64_t x) { return x == 0 ? 0 : ppcsr_bsr(x) + 1; }
+
+int set_device(ppcsr_shard *s) {
+  CUDA_TRY(cudaSetDevice(s->device));
+  return PPCSR_OK;
+}
+
+// (re)allocate every leaf-granular array for geometry g; contents undefined afterwards except mark (zeroed)
+int reserve_leaf_arrays(ppcsr_shard *s, const Geometry &g) {
+  const size_t L = g.n_leaves;
+  PPCSR_TRY(dev_reserve(s->ins_cnt, L, s->stream));
+  PPCSR_TRY(dev_reserve(s->del_cnt, L, s->stream));
+  PPCSR_TRY(dev_reserve(s->rank_off, L + 1, s->stream));
+  PPCSR_TRY(dev_reserve(s->ins_off, L + 1, s->stream));
+  const size_t old_mark = s->mark.cap;
+  PPCSR_TRY(dev_reserve(s->mark, 2 * L, s->stream));
+  if (s->mark.cap != old_mark) {
+    CUDA_TRY(cudaMemsetAsync(s->mark.p, 0, s->mark.cap * sizeof(uint32_t), s->stream));
+    s->epoch = 0;
+  }
+  return PPCSR_OK;
+}
+
+int reserve_batch_arrays(ppcsr_shard *s, size_t count) {
+  PPCSR_TRY(dev_reserve(s->key_a, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->key_b, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->pay_a, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->pay_b, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->ukey, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->uval, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->uloc, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->ucls, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->ins_dst, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->ins_val, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->ins_pred, count, s->stream));
+  return PPCSR_OK;
+}
+
+int reserve_window_arrays(ppcsr_shard *s, size_t count) {
+  const size_t cap = std::min<size_t>(s->geo.n_leaves, count) + 1;
+  PPCSR_TRY(dev_reserve(s->touched, cap, s->stream));
+  PPCSR_TRY(dev_reserve(s->windows, cap, s->stream));
+  return PPCSR_OK;
+}
+
+int read_scalars(ppcsr_shard *s) {
+  CUDA_TRY(cudaMemcpyAsync(s->h_scalars, s->d_scalars, sizeof(BatchScalars), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return PPCSR_OK;
+}
+
+// Lays out `n` sentinels evenly over geometry s->geo (constructor / empty-graph add_node).
+int init_layout(ppcsr_shard *s) {
+  const Geometry &g = s->geo;
+  CUDA_TRY(cudaMemsetAsync(s->dest.p, 0, g.N * sizeof(uint32_t), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->val.p, 0, g.N * sizeof(uint32_t), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->leaf_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->tree.p, 0, (size_t)2 * g.n_leaves * sizeof(uint32_t), s->stream));
+  if (s->n) {
+    reb::k_init_sentinels<<<div_up(s->n, 256), 256, 0, s->stream>>>(s->dest.p, s->val.p, s->beg.p, 0, s->n, s->n,
+                                                                   g.n_leaves, g.leaf_shift);
+    reb::k_init_leaf_counts<<<div_up(g.n_leaves, 256), 256, 0, s->stream>>>(s->leaf_cnt.p, s->tree.p, s->n,
+                                                                            g.n_leaves);
+    CUDA_TRY(cudaMemsetAsync(s->nn.p, 0, (size_t)s->n * sizeof(uint32_t), s->stream));
+  }
+  reb::k_set_u32<<<1, 1, 0, s->stream>>>(s->beg.p + s->n, (uint32_t)g.N);
+  PPCSR_TRY(win::tree_rebuild(s, s->tree.p, g.H));
+  CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+  CUDA_TRY(cudaGetLastError());
+  s->items = s->n;
+  return PPCSR_OK;
+}
+
+int alloc_geometry(ppcsr_shard *s, const Geometry &g) {
+  PPCSR_TRY(dev_reserve(s->dest, g.N, s->stream));
+  PPCSR_TRY(dev_reserve(s->val, g.N, s->stream));
+  PPCSR_TRY(dev_reserve(s->leaf_cnt, g.n_leaves, s->stream));
+  PPCSR_TRY(dev_reserve(s->tree, (size_t)2 * g.n_leaves, s->stream));
+  PPCSR_TRY(reserve_leaf_arrays(s, g));
+  return PPCSR_OK;
+}
+
+uint64_t grown_slots(uint64_t N, uint64_t items) {
+  uint64_t n2 = N;
+  for (;;) {
+    n2 *= 2;
+    if (n2 > PPCSR_MAX_SLOTS) return 0;
+    Geometry g = make_geometry(n2);
+    if (window_ok_upper(items, n2, g.logN, 0, (int)g.H)) return n2;
+  }
+}
+uint64_t shrunk_slots(uint64_t N, uint64_t items) {
+  uint64_t n2 = N;
+  while (n2 / 2 >= PPCSR_MIN_SLOTS) {
+    Geometry g = make_geometry(n2);
+    if (window_ok_lower(items, n2, 0, (int)g.H)) break;
+    Geometry h = make_geometry(n2 / 2);
+    if (!window_ok_upper(items, n2 / 2, h.logN, 0, (int)h.H)) break;
+    n2 /= 2;
+  }
+  return n2;
+}
+
+// Back half of a batch: s->ins_cnt / del_cnt hold the per-leaf counts, ins_{dst,val,pred} the key-ordered
+// insert list, d_scalars the class counts.  Chooses windows, rebalances, refreshes tree and counts.
+int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
+  const Geometry g = s->geo;
+  const uint32_t L = g.n_leaves;
+  BatchScalars *sc = s->d_scalars;
+  PPCSR_TRY(reserve_window_arrays(s, list_cap));
+  const size_t cap = std::min<size_t>(L, list_cap);
+
+  win::k_leaf_new_counts<<<div_up(L, win::WT), win::WT, 0, s->stream>>>(s->leaf_cnt.p, s->ins_cnt.p, s->del_cnt.p, L,
+                                                                      s->tree.p);
+  PPCSR_TRY(win::tree_rebuild(s, s->tree.p, g.H));
+  PPCSR_TRY(prim::device_scan(s, win::InTouched{s->ins_cnt.p, s->del_cnt.p}, win::OutTouched{s->touched.p}, L, nullptr,
+                              &sc->n_touched));
+  s->epoch++;
+  if (cap) {
+    win::k_select<<<div_up(cap, win::WT), win::WT, 0, s->stream>>>(s->touched.p, &sc->n_touched, s->ins_cnt.p,
+                                                                  s->del_cnt.p, s->tree.p, L, g.logN, (int)g.H,
+                                                                  s->mark.p, s->epoch, sc);
+  }
+  const uint32_t CL = reb::CHUNK_SLOTS >> g.leaf_shift;
+  PPCSR_TRY(prim::device_scan(
+      s, prim::bounded_in(win::InWindowHead{s->touched.p, s->mark.p, s->epoch, L}, &sc->n_touched),
+      win::OutWindow{s->touched.p, s->mark.p, s->tree.p, s->epoch, L, CL, s->windows.p}, cap, nullptr, &sc->n_windows));
+  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinChunks{s->windows.p}, &sc->n_windows),
+                              prim::bounded_out(win::OutWinChunk0{s->windows.p}, &sc->n_windows), cap, nullptr,
+                              &sc->n_chunks));
+  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinSlots{s->windows.p, g.logN, false}, &sc->n_windows),
+                              prim::OutNothing{}, cap, nullptr, &sc->window_slots));
+  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinSlots{s->windows.p, g.logN, true}, &sc->n_windows),
+                              prim::OutNothing{}, cap, nullptr, &sc->multi_slots));
+  // R[] and the per-leaf insert offsets feed the rebalance
+  PPCSR_TRY(prim::device_scan(s, prim::InArray{s->tree.p + L}, prim::OutPrefixWithTotal{s->rank_off.p, L}, L, nullptr,
+                              nullptr));
+  PPCSR_TRY(prim::device_scan(s, prim::InArray{s->ins_cnt.p}, prim::OutPrefixWithTotal{s->ins_off.p, L}, L, nullptr,
+                              nullptr));
+  CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
+  PPCSR_TRY(read_scalars(s));
+  const BatchScalars h = *s->h_scalars;
+
+  const uint64_t items_new = s->items + h.n_inserted - h.n_deleted;
+  st->n_ignored = h.n_ignored;
+  st->n_unique = h.n_unique;
+  st->n_inserted = h.n_inserted;
+  st->n_overwritten = h.n_overwritten;
+  st->n_deleted = h.n_deleted;
+  st->n_not_found = h.n_not_found;
+  st->slots_before = g.N;
+  st->slots_after = g.N;
+
+  uint64_t new_N = g.N;
+  bool whole = false;
+  if (h.root_violation & 1u) {
+    new_N = grown_slots(g.N, items_new);
+    if (new_N == 0) {
+      g_ppcsr_error = "edge array would exceed 2^31 slots";
+      return PPCSR_ERR_CAPACITY;
+    }
+    whole = true;
+    st->resized = 1;
+  } else if (h.root_violation & 2u) {
+    new_N = shrunk_slots(g.N, items_new);
+    whole = true;
+    st->resized = new_N != g.N ? 2 : 0;
+  } else if (h.n_windows > 0) {
+    // a multi-CTA window is written out of place and copied back (4 moves per slot instead of 2):
+    // once the windows cost as much as streaming the whole array, rebuild the whole array instead.
+    const uint64_t cost = 2 * h.window_slots + 2 * h.multi_slots;
+    if (cost >= 2 * g.N) whole = true;
+  }
+
+  if (h.n_windows == 0 && !whole) {
+    st->n_windows = 0;
+  } else if (!whole) {
+    reb::Args A{};
+    A.src_dest = s->dest.p;
+    A.src_val = s->val.p;
+    A.leaf_cnt = s->leaf_cnt.p;
+    A.rank_off = s->rank_off.p;
+    A.ins_off = s->ins_off.p;
+    A.ins_dst = s->ins_dst.p;
+    A.ins_val = s->ins_val.p;
+    A.ins_pred = s->ins_pred.p;
+    A.out_dest_single = s->dest.p;
+    A.out_val_single = s->val.p;
+    if (h.multi_slots) {
+      PPCSR_TRY(dev_reserve(s->dest_alt, g.N, s->stream));
+      PPCSR_TRY(dev_reserve(s->val_alt, g.N, s->stream));
+    }
+    A.out_dest_multi = s->dest_alt.p;
+    A.out_val_multi = s->val_alt.p;
+    A.tree_leaf_out = s->tree.p + L;
+    A.beg = s->beg.p;
+    A.windows = s->windows.p;
+    A.n_windows = (uint32_t)h.n_windows;
+    A.ls_src = A.ls_dst = g.leaf_shift;
+    A.m_dst_override = 0;
+    reb::k_rebalance<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(A);
+    if (h.multi_slots) {
+      reb::k_copy_back<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(s->windows.p, (uint32_t)h.n_windows,
+                                                                        g.leaf_shift, s->dest_alt.p, s->val_alt.p,
+                                                                        s->dest.p, s->val.p);
+    }
+    reb::k_copy_u32<<<div_up(L, 256), 256, 0, s->stream>>>(s->leaf_cnt.p, s->tree.p + L, L);
+    PPCSR_TRY(win::tree_rebuild(s, s->tree.p, g.H));
+    CUDA_TRY(cudaGetLastError());
+    st->n_windows = h.n_windows;
+    st->window_slots = h.window_slots;
+    st->rebalance_bytes = 2ull * h.window_slots * 8ull;
+  } else {
+    // one root window, possibly into a larger / smaller array (double_list / half_list folded in)
+    const Geometry g2 = make_geometry(new_N);
+    PPCSR_TRY(dev_reserve(s->dest_alt, g2.N, s->stream));
+    PPCSR_TRY(dev_reserve(s->val_alt, g2.N, s->stream));
+    PPCSR_TRY(dev_reserve(s->tree, (size_t)2 * g2.n_leaves, s->stream));
+    const uint32_t CL2 = reb::CHUNK_SLOTS >> g2.leaf_shift;
+    WindowDesc *hw = reinterpret_cast<WindowDesc *>(s->h_pinned);
+    hw->node = 1;
+    hw->leaf0 = 0;
+    hw->m = L;
+    hw->items = (uint32_t)items_new;
+    hw->chunk0 = 0;
+    hw->n_chunks = div_up(g2.n_leaves, CL2);
+    PPCSR_TRY(dev_reserve(s->windows, 1, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->windows.p, hw, sizeof(WindowDesc), cudaMemcpyHostToDevice, s->stream));
+    reb::Args A{};
+    A.src_dest = s->dest.p;
+    A.src_val = s->val.p;
+    A.leaf_cnt = s->leaf_cnt.p;
+    A.rank_off = s->rank_off.p;
+    A.ins_off = s->ins_off.p;
+    A.ins_dst = s->ins_dst.p;
+    A.ins_val = s->ins_val.p;
+    A.ins_pred = s->ins_pred.p;
+    A.out_dest_single = A.out_dest_multi = s->dest_alt.p;
+    A.out_val_single = A.out_val_multi = s->val_alt.p;
+    A.tree_leaf_out = s->tree.p + g2.n_leaves;
+    A.beg = s->beg.p;
+    A.windows = s->windows.p;
+    A.n_windows = 1;
+    A.ls_src = g.leaf_shift;
+    A.ls_dst = g2.leaf_shift;
+    A.m_dst_override = g2.n_leaves;
+    reb::k_rebalance<<<hw->n_chunks, reb::RT, 0, s->stream>>>(A);
+    CUDA_TRY(cudaGetLastError());
+    std::swap(s->dest, s->dest_alt);
+    std::swap(s->val, s->val_alt);
+    s->geo = g2;
+    PPCSR_TRY(dev_reserve(s->leaf_cnt, g2.n_leaves, s->stream));
+    PPCSR_TRY(reserve_leaf_arrays(s, g2));
+    reb::k_copy_u32<<<div_up(g2.n_leaves, 256), 256, 0, s->stream>>>(s->leaf_cnt.p, s->tree.p + g2.n_leaves,
+                                                                    g2.n_leaves);
+    PPCSR_TRY(win::tree_rebuild(s, s->tree.p, g2.H));
+    reb::k_set_u32<<<1, 1, 0, s->stream>>>(s->beg.p + s->n, (uint32_t)g2.N);
+    // every leaf was rewritten: for the invariant checker all of them count as touched by this batch
+    qry::k_fill_u32<<<div_up(g2.n_leaves, 256), 256, 0, s->stream>>>(s->ins_cnt.p, h.n_inserted ? 1u : 0u,
+                                                                    g2.n_leaves);
+    qry::k_fill_u32<<<div_up(g2.n_leaves, 256), 256, 0, s->stream>>>(s->del_cnt.p, h.n_deleted ? 1u : 0u,
+                                                                    g2.n_leaves);
+    CUDA_TRY(cudaGetLastError());
+    st->n_windows = 1;
+    st->whole_array = 1;
+    st->window_slots = std::max<uint64_t>(g.N, g2.N);
+    st->rebalance_bytes = (g.N + g2.N) * 8ull;
+    st->slots_after = g2.N;
+  }
+  st->rebalance_bytes += 8ull * 0;  // sentinel back-pointer bytes are reported by the bench from window sizes
+  s->items = items_new;
+  CUDA_TRY(cudaEventRecord(s->ev[4], s->stream));
+  return PPCSR_OK;
+}
+
+int finalize_stats(ppcsr_shard *s, ppcsr_batch_stats *st) {
+  CUDA_TRY(cudaEventSynchronize(s->ev[4]));
+  float t;
+  CUDA_TRY(cudaEventElapsedTime(&t, s->ev[0], s->ev[4]));
+  st->ms_total = t;
+  CUDA_TRY(cudaEventElapsedTime(&t, s->ev[0], s->ev[1]));
+  st->ms_sort = t;
+  CUDA_TRY(cudaEventElapsedTime(&t, s->ev[1], s->ev[2]));
+  st->ms_locate = t;
+  CUDA_TRY(cudaEventElapsedTime(&t, s->ev[2], s->ev[3]));
+  st->ms_select = t;
+  CUDA_TRY(cudaEventElapsedTime(&t, s->ev[3], s->ev[4]));
+  st->ms_rebalance = t;
+  s->last = *st;
+  return PPCSR_OK;
+}
+
+int refresh_rank_off(ppcsr_shard *s) {
+  const uint32_t L = s->geo.n_leaves;
+  return prim::device_scan(s, prim::InArray{s->leaf_cnt.p}, prim::OutPrefixWithTotal{s->rank_off.p, L}, L, nullptr,
+                           nullptr);
+}
+
+__global__ void k_last_live_slot(const uint32_t *__restrict__ leaf_cnt, uint32_t n_leaves, uint32_t ls,
+                                 uint32_t *out) {
+  // single thread: last live slot of the array (trailing empty leaves are rare and short)
+  uint32_t l = n_leaves;
+  while (l > 0 && leaf_cnt[l - 1] == 0) l--;
+  *out = l ? (((l - 1) << ls) + leaf_cnt[l - 1] - 1) : 0xFFFFFFFFu;
+}
+__global__ void k_fill_new_nodes(uint32_t *ins_dst, uint32_t *ins_val, uint32_t *ins_pred, uint32_t first_vertex,
+                                 uint32_t count, const uint32_t *last_slot, uint32_t *ins_cnt, uint32_t ls,
+                                 BatchScalars *sc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    ins_dst[i] = PPCSR_SENT;
+    ins_val[i] = first_vertex + i + 1u;
+    ins_pred[i] = *last_slot;
+  }
+  if (i == 0) {
+    ins_cnt[*last_slot >> ls] = count;
+    sc->n_inserted = count;
+    sc->n_unique = count;
+  }
+}
+
+template <typename W>
+static int pagerank_host(ppcsr_shard *s, const W *in, W *out, uint64_t out_len) {
+  if (!s || !in || !out) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  DevBuf<W> d_in, d_out;
+  PPCSR_TRY(dev_reserve(d_in, (size_t)s->n + 1, s->stream));
+  PPCSR_TRY(dev_reserve(d_out, (size_t)out_len + 1, s->stream));
+  PPCSR_TRY(dev_reserve(s->pr_acc, (size_t)out_len + 1, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_in.p, in, (size_t)s->n * sizeof(W), cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->pr_acc.p, 0, (size_t)out_len * sizeof(double), s->stream));
+  if (s->n) {
+    const unsigned blocks = std::min<unsigned>(div_up((uint64_t)s->n * 32, qry::QT), 148 * 16);
+    qry::k_pagerank_push<W><<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->leaf_cnt.p, s->beg.p, s->nn.p,
+                                                              s->geo.leaf_shift, s->n, d_in.p, s->pr_acc.p, out_len);
+  }
+  if (out_len) qry::k_cast_out<W><<<div_up(out_len, 256), 256, 0, s->stream>>>(s->pr_acc.p, d_out.p, out_len);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, d_out.p, (size_t)out_len * sizeof(W), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  dev_free(d_in);
+  dev_free(d_out);
+  return PPCSR_OK;
+}
+
+template <typename T>
+static int snap_copy(ppcsr_shard *s, DevBuf<T> &dst, const DevBuf<T> &src, size_t elems) {
+  PPCSR_TRY(dev_reserve(dst, elems, s->stream));
+  if (elems) CUDA_TRY(cudaMemcpyAsync(dst.p, src.p, elems * sizeof(T), cudaMemcpyDeviceToDevice, s->stream));
+  return PPCSR_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char *ppcsr_last_error(void) { return g_ppcsr_error.c_str(); }
+
+int ppcsr_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return c;
+}
+
+int ppcsr_create(uint32_t init_n, uint32_t src_n, int device, ppcsr_shard **out) {
+  if (!out) return PPCSR_ERR_ARG;
+  *out = nullptr;
+  if (ppcsr_device_count() <= device || device < 0) {
+    g_ppcsr_error = "no such CUDA device (this engine has no CPU fallback)";
+    return PPCSR_ERR_NO_DEVICE;
+  }
+  const uint64_t N = initial_slots(init_n, src_n);
+  if (N > PPCSR_MAX_SLOTS) {
+    g_ppcsr_error = "initial edge array exceeds 2^31 slots";
+    return PPCSR_ERR_CAPACITY;
+  }
+  ppcsr_shard *s = new ppcsr_shard();
+  s->device = device;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+  s->stream = s->own_stream;
+  for (auto &e : s->ev) CUDA_TRY(cudaEventCreate(&e));
+  CUDA_TRY(cudaMalloc((void **)&s->d_scalars, sizeof(BatchScalars)));
+  CUDA_TRY(cudaMallocHost((void **)&s->h_scalars, sizeof(BatchScalars)));
+  s->h_pinned_bytes = 1 << 16;
+  CUDA_TRY(cudaMallocHost(&s->h_pinned, s->h_pinned_bytes));
+  s->n = src_n;
+  s->geo = make_geometry(N);
+  PPCSR_TRY(alloc_geometry(s, s->geo));
+  PPCSR_TRY(dev_reserve(s->beg, (size_t)src_n + 1, s->stream));
+  PPCSR_TRY(dev_reserve(s->nn, (size_t)src_n + 1, s->stream));
+  PPCSR_TRY(init_layout(s));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  *out = s;
+  return PPCSR_OK;
+}
+
+void ppcsr_destroy(ppcsr_shard *s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  dev_free(s->dest); dev_free(s->val); dev_free(s->dest_alt); dev_free(s->val_alt);
+  dev_free(s->leaf_cnt); dev_free(s->tree); dev_free(s->beg); dev_free(s->nn);
+  dev_free(s->ins_cnt); dev_free(s->del_cnt); dev_free(s->rank_off); dev_free(s->ins_off);
+  dev_free(s->mark); dev_free(s->touched); dev_free(s->touched_win); dev_free(s->windows);
+  dev_free(s->win_chunk_off); dev_free(s->key_a); dev_free(s->key_b); dev_free(s->pay_a); dev_free(s->pay_b);
+  dev_free(s->in_src); dev_free(s->in_dst); dev_free(s->in_val); dev_free(s->ukey); dev_free(s->uval);
+  dev_free(s->uloc); dev_free(s->ucls); dev_free(s->ins_dst); dev_free(s->ins_val); dev_free(s->ins_pred);
+  dev_free(s->block_tmp); dev_free(s->hist); dev_free(s->pr_acc); dev_free(s->misc);
+  dev_free(s->snap.dest); dev_free(s->snap.val); dev_free(s->snap.leaf_cnt); dev_free(s->snap.tree);
+  dev_free(s->snap.beg); dev_free(s->snap.nn);
+  if (s->d_scalars) cudaFree(s->d_scalars);
+  if (s->h_scalars) cudaFreeHost(s->h_scalars);
+  if (s->h_pinned) cudaFreeHost(s->h_pinned);
+  for (auto &e : s->ev) if (e) cudaEventDestroy(e);
+  if (s->own_stream) cudaStreamDestroy(s->own_stream);
+  delete s;
+}
+
+int ppcsr_set_stream(ppcsr_shard *s, void *cuda_stream) {
+  if (!s) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
+  return PPCSR_OK;
+}
+
+int ppcsr_sync(ppcsr_shard *s) {
+  if (!s) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return PPCSR_OK;
+}
+
+int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
+  if (!s) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  if (max_slots > PPCSR_MAX_SLOTS) return PPCSR_ERR_CAPACITY;
+  if (max_slots > s->geo.N) {
+    const Geometry g = make_geometry(max_slots);
+    // keep the live contents: dest/val/leaf_cnt/tree must survive a capacity bump
+    PPCSR_TRY(dev_reserve(s->dest, g.N, s->stream, true));
+    PPCSR_TRY(dev_reserve(s->val, g.N, s->stream, true));
+    PPCSR_TRY(dev_reserve(s->dest_alt, g.N, s->stream));
+    PPCSR_TRY(dev_reserve(s->val_alt, g.N, s->stream));
+    PPCSR_TRY(dev_reserve(s->leaf_cnt, g.n_leaves, s->stream, true));
+    PPCSR_TRY(dev_reserve(s->tree, (size_t)2 * g.n_leaves, s->stream, true));
+    PPCSR_TRY(dev_reserve(s->ins_cnt, g.n_leaves, s->stream, true));
+    PPCSR_TRY(dev_reserve(s->del_cnt, g.n_leaves, s->stream, true));
+    PPCSR_TRY(dev_reserve(s->rank_off, (size_t)g.n_leaves + 1, s->stream));
+    PPCSR_TRY(dev_reserve(s->ins_off, (size_t)g.n_leaves + 1, s->stream));
+    PPCSR_TRY(dev_reserve(s->mark, (size_t)2 * g.n_leaves, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->mark.p, 0, s->mark.cap * sizeof(uint32_t), s->stream));
+    s->epoch = 0;
+    const size_t wcap = std::min<uint64_t>(g.n_leaves, max_batch ? max_batch : g.n_leaves) + 1;
+    PPCSR_TRY(dev_reserve(s->touched, wcap, s->stream));
+    PPCSR_TRY(dev_reserve(s->windows, wcap, s->stream));
+    PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)div_up(g.N, prim::SCAN_TILE) + 2, s->stream));
+  } else {
+    PPCSR_TRY(dev_reserve(s->dest_alt, s->geo.N, s->stream));
+    PPCSR_TRY(dev_reserve(s->val_alt, s->geo.N, s->stream));
+  }
+  if (max_batch) {
+    PPCSR_TRY(reserve_batch_arrays(s, max_batch));
+    PPCSR_TRY(dev_reserve(s->in_src, max_batch, s->stream));
+    PPCSR_TRY(dev_reserve(s->in_dst, max_batch, s->stream));
+    PPCSR_TRY(dev_reserve(s->in_val, max_batch, s->stream));
+    PPCSR_TRY(dev_reserve(s->hist, (size_t)prim::RADIX * div_up(max_batch, prim::SORT_TILE) + 1, s->stream));
+    PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)div_up((size_t)prim::RADIX * div_up(max_batch, prim::SORT_TILE),
+                                                       prim::SCAN_TILE) + 2, s->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return PPCSR_OK;
+}
+
+int ppcsr_apply_batch_device(ppcsr_shard *s, const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val,
+                             uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats) {
+  if (!s || (count && (!d_src || !d_dst))) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  ppcsr_batch_stats st{};
+  st.batch_size = count;
+  st.slots_before = st.slots_after = s->geo.N;
+  if (count == 0) {
+    s->last = st;
+    if (stats) *stats = st;
+    return PPCSR_OK;
+  }
+  if (count >= (1ull << 31)) {
+    g_ppcsr_error = "batch too large (>= 2^31 updates); split it";
+    return PPCSR_ERR_ARG;
+  }
+  const Geometry g = s->geo;
+  PPCSR_TRY(reserve_batch_arrays(s, count));
+  BatchScalars *sc = s->d_scalars;
+  CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(BatchScalars), s->stream));
+  CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+
+  // 1. keys + guards
+  const unsigned kb = std::min<unsigned>(div_up(count, batch::BT * 8), 148 * 16);
+  batch::k_build_keys<<<kb, batch::BT, 0, s->stream>>>(d_src, d_dst, d_val, default_val, count, s->n, s->key_a.p,
+                                                      s->pay_a.p, sc);
+  CUDA_TRY(cudaGetLastError());
+  PPCSR_TRY(read_scalars(s));
+  const int lo_bits = std::max(1, bits_of(s->h_scalars->dst_or));
+  const int hi_bits = std::max(1, bits_of(s->n));
+  // 2. stable radix sort by (src,dst)
+  uint64_t *keys;
+  uint32_t *pay;
+  PPCSR_TRY(prim::radix_sort_pairs(s, s->key_a.p, s->pay_a.p, s->key_b.p, s->pay_b.p, count, lo_bits, hi_bits, &keys,
+                                   &pay));
+  // 3. call counts and last-op-wins
+  const uint64_t invalid_key = (uint64_t)s->n << 32;
+  batch::k_count_calls<<<div_up(count, batch::BT), batch::BT, 0, s->stream>>>(keys, pay, count, invalid_key, s->nn.p);
+  PPCSR_TRY(prim::device_scan(s, batch::InLastOfRun{keys, count, invalid_key},
+                              batch::OutUnique{keys, pay, s->ukey.p, s->uval.p}, count, nullptr, &sc->n_unique));
+  CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
+  // 4. locate + per-leaf counts
+  CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+  batch::k_locate<<<div_up(count, batch::BT), batch::BT, 0, s->stream>>>(
+      s->ukey.p, s->uval.p, &sc->n_unique, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift, s->uloc.p,
+      s->ucls.p, s->ins_cnt.p, s->del_cnt.p, sc);
+  PPCSR_TRY(prim::device_scan(
+      s, prim::bounded_in(batch::InIsInsert{s->ucls.p}, &sc->n_unique),
+      batch::OutInsert{s->ukey.p, s->uval.p, s->uloc.p, s->ins_dst.p, s->ins_val.p, s->ins_pred.p}, count, nullptr,
+      nullptr));
+  CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+  // 5. windows + rebalance
+  PPCSR_TRY(finish_batch(s, count, &st));
+  PPCSR_TRY(finalize_stats(s, &st));
+  if (stats) *stats = st;
+  return PPCSR_OK;
+}
+
+int ppcsr_apply_batch(ppcsr_shard *s, const uint32_t *src, const uint32_t *dst, const uint32_t *val, uint64_t count,
+                      uint32_t default_val, ppcsr_batch_stats *stats) {
+  if (!s || (count && (!src || !dst))) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  if (count == 0) return ppcsr_apply_batch_device(s, nullptr, nullptr, nullptr, 0, default_val, stats);
+  PPCSR_TRY(dev_reserve(s->in_src, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->in_dst, count, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->in_src.p, src, count * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->in_dst.p, dst, count * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+  if (val) {
+    PPCSR_TRY(dev_reserve(s->in_val, count, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->in_val.p, val, count * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+  }
+  return ppcsr_apply_batch_device(s, s->in_src.p, s->in_dst.p, val ? s->in_val.p : nullptr, count, default_val, stats);
+}
+
+int ppcsr_add_edge(ppcsr_shard *s, uint32_t src, uint32_t dst, uint32_t value) {
+  if (value == 0) return PPCSR_OK;  // reference PCSR.cpp:1375: a zero value is silently ignored
+  return ppcsr_apply_batch(s, &src, &dst, &value, 1, 1, nullptr);
+}
+
+int ppcsr_remove_edge(ppcsr_shard *s, uint32_t src, uint32_t dst, int *found) {
+  ppcsr_batch_stats st{};
+  const uint32_t zero = 0;
+  PPCSR_TRY(ppcsr_apply_batch(s, &src, &dst, &zero, 1, 0, &st));
+  if (found) *found = st.n_deleted ? 1 : 0;
+  return PPCSR_OK;
+}
+
+int ppcsr_add_nodes(ppcsr_shard *s, uint32_t count) {
+  if (!s) return PPCSR_ERR_ARG;
+  if (count == 0) return PPCSR_OK;
+  PPCSR_TRY(set_device(s));
+  if ((uint64_t)s->n + count >= 0xFFFFFFFEull) return PPCSR_ERR_CAPACITY;
+  const uint32_t n_old = s->n, n_new = s->n + count;
+  PPCSR_TRY(dev_reserve(s->beg, (size_t)n_new + 1, s->stream, true));
+  PPCSR_TRY(dev_reserve(s->nn, (size_t)n_new + 1, s->stream, true));
+  CUDA_TRY(cudaMemsetAsync(s->nn.p + n_old, 0, (size_t)count * sizeof(uint32_t), s->stream));
+  ppcsr_batch_stats st{};
+  st.batch_size = count;
+  if (s->items == 0) {  // empty structure: lay the new sentinels out directly
+    s->n = n_new;
+    const uint64_t need = initial_slots(n_new, n_new);
+    if (need > s->geo.N) {
+      s->geo = make_geometry(need);
+      PPCSR_TRY(alloc_geometry(s, s->geo));
+    }
+    PPCSR_TRY(init_layout(s));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->last = st;
+    return PPCSR_OK;
+  }
+  const Geometry g = s->geo;
+  PPCSR_TRY(reserve_batch_arrays(s, count));
+  BatchScalars *sc = s->d_scalars;
+  CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(BatchScalars), s->stream));
+  for (int e = 0; e < 3; e++) CUDA_TRY(cudaEventRecord(s->ev[e], s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+  PPCSR_TRY(dev_reserve(s->misc, 16, s->stream));
+  k_last_live_slot<<<1, 1, 0, s->stream>>>(s->leaf_cnt.p, g.n_leaves, g.leaf_shift, s->misc.p);
+  k_fill_new_nodes<<<div_up(count, 256), 256, 0, s->stream>>>(s->ins_dst.p, s->ins_val.p, s->ins_pred.p, n_old, count,
+                                                             s->misc.p, s->ins_cnt.p, g.leaf_shift, sc);
+  CUDA_TRY(cudaGetLastError());
+  s->n = n_new;  // beg[n_new] = N is (re)written below; sentinel fix-up fills beg[n_old .. n_new)
+  PPCSR_TRY(finish_batch(s, count, &st));
+  reb::k_set_u32<<<1, 1, 0, s->stream>>>(s->beg.p + s->n, (uint32_t)s->geo.N);
+  PPCSR_TRY(finalize_stats(s, &st));
+  return PPCSR_OK;
+}
+
+int ppcsr_last_stats(ppcsr_shard *s, ppcsr_batch_stats *stats) {
+  if (!s || !stats) return PPCSR_ERR_ARG;
+  *stats = s->last;
+  return PPCSR_OK;
+}
+
+int ppcsr_bin_by_owner(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts,
+                       const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val, uint64_t count,
+                       uint32_t *d_out_src, uint32_t *d_out_dst, uint32_t *d_out_val, uint64_t *h_counts) {
+  if (n_parts == 0 || n_parts > batch::BIN_MAX_PARTS || !h_counts) return PPCSR_ERR_ARG;
+  for (uint32_t p = 0; p < n_parts; p++) h_counts[p] = 0;
+  if (count == 0) return PPCSR_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  // a throw-away shard struct provides the scan scratch
+  ppcsr_shard tmp;
+  tmp.device = device;
+  tmp.stream = st;
+  const unsigned nblocks = div_up(count, prim::SORT_TILE);
+  const size_t hn = (size_t)n_parts * nblocks;
+  int rc = dev_reserve(tmp.hist, hn + 1, st);
+  if (rc == PPCSR_OK) {
+    batch::k_bin_count<<<nblocks, batch::BT, 0, st>>>(d_src, count, d_starts, n_parts, tmp.hist.p, nblocks);
+    rc = prim::device_scan(&tmp, prim::InArray{tmp.hist.p}, prim::OutPrefixWithTotal{tmp.hist.p, hn}, hn, nullptr,
+                           nullptr);
+  }
+  if (rc == PPCSR_OK) {
+    batch::k_bin_scatter<<<nblocks, batch::BT, 0, st>>>(d_src, d_dst, d_val, count, d_starts, n_parts, tmp.hist.p,
+                                                       nblocks, d_out_src, d_out_dst, d_out_val);
+    std::vector<uint32_t> firsts(n_parts + 1);
+    for (uint32_t p = 0; p < n_parts && rc == PPCSR_OK; p++) {
+      if (cudaMemcpyAsync(&firsts[p], tmp.hist.p + (size_t)p * nblocks, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        rc = PPCSR_ERR_CUDA;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = PPCSR_ERR_CUDA;
+    firsts[n_parts] = (uint32_t)count;
+    for (uint32_t p = 0; p < n_parts; p++) h_counts[p] = firsts[p + 1] - firsts[p];
+  }
+  if (rc == PPCSR_ERR_CUDA) g_ppcsr_error = std::string("bin_by_owner: ") + cudaGetErrorString(cudaGetLastError());
+  dev_free(tmp.hist);
+  dev_free(tmp.block_tmp);
+  return rc;
+}
+
+// ---- reads ------------------------------------------------------------------------------------------
+int ppcsr_geometry_of(ppcsr_shard *s, ppcsr_geometry *out) {
+  if (!s || !out) return PPCSR_ERR_ARG;
+  out->N = s->geo.N;
+  out->logN = s->geo.logN;
+  out->H = s->geo.H;
+  out->n = s->n;
+  out->items = s->items;
+  return PPCSR_OK;
+}
+
+int ppcsr_edges_exist(ppcsr_shard *s, const uint32_t *src, const uint32_t *dst, uint64_t count, uint8_t *exists) {
+  if (!s || (count && (!src || !dst || !exists))) return PPCSR_ERR_ARG;
+  if (count == 0) return PPCSR_OK;
+  PPCSR_TRY(set_device(s));
+  PPCSR_TRY(dev_reserve(s->in_src, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->in_dst, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->ucls, count, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->in_src.p, src, count * 4, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->in_dst.p, dst, count * 4, cudaMemcpyHostToDevice, s->stream));
+  qry::k_edges_exist<<<div_up(count, qry::QT), qry::QT, 0, s->stream>>>(s->in_src.p, s->in_dst.p, count, s->n,
+                                                                       s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p,
+                                                                       s->geo.leaf_shift, s->ucls.p, nullptr);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(exists, s->ucls.p, count, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return PPCSR_OK;
+}
+
+int ppcsr_edge_exists(ppcsr_shard *s, uint32_t src, uint32_t dst, int *exists, uint32_t *out_value) {
+  if (!s || !exists) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  PPCSR_TRY(dev_reserve(s->misc, 16, s->stream));
+  uint32_t *hp = reinterpret_cast<uint32_t *>(s->h_pinned);
+  hp[0] = src;
+  hp[1] = dst;
+  CUDA_TRY(cudaMemcpyAsync(s->misc.p, hp, 8, cudaMemcpyHostToDevice, s->stream));
+  qry::k_edges_exist<<<1, 32, 0, s->stream>>>(s->misc.p, s->misc.p + 1, 1, s->n, s->dest.p, s->val.p, s->leaf_cnt.p,
+                                             s->beg.p, s->geo.leaf_shift, reinterpret_cast<uint8_t *>(s->misc.p + 2),
+                                             s->misc.p + 3);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(hp + 2, s->misc.p + 2, 8, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  *exists = (hp[2] & 0xFF) ? 1 : 0;
+  if (out_value) *out_value = hp[3];
+  return PPCSR_OK;
+}
+
+static int vertex_range(ppcsr_shard *s, uint32_t v, uint32_t *b, uint32_t *e) {
+  uint32_t *hp = reinterpret_cast<uint32_t *>(s->h_pinned);
+  CUDA_TRY(cudaMemcpyAsync(hp, s->beg.p + v, 8, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  *b = hp[0];
+  *e = hp[1];
+  return PPCSR_OK;
+}
+
+int ppcsr_neighbours(ppcsr_shard *s, uint32_t v, uint32_t *out, uint64_t cap, uint64_t *count) {
+  if (!s || !count) return PPCSR_ERR_ARG;
+  *count = 0;
+  if (v >= s->n) return PPCSR_OK;  // reference PCSR.cpp:903: out-of-range vertex -> empty
+  PPCSR_TRY(set_device(s));
+  PPCSR_TRY(refresh_rank_off(s));
+  uint32_t b, e;
+  PPCSR_TRY(vertex_range(s, v, &b, &e));
+  // degree = rank(e) - rank(b) - 1, ranks from rank_off (two small reads)
+  const uint32_t ls = s->geo.leaf_shift, msk = s->geo.logN - 1;
+  uint32_t *hp = reinterpret_cast<uint32_t *>(s->h_pinned);
+  CUDA_TRY(cudaMemcpyAsync(hp, s->rank_off.p + (b >> ls), 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(hp + 1, s->rank_off.p + (e >> ls), 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  const uint64_t deg = (uint64_t)(hp[1] + (e & msk)) - (hp[0] + (b & msk)) - 1;
+  *count = deg;
+  const uint64_t want = std::min<uint64_t>(deg, cap);
+  if (want == 0 || !out) return PPCSR_OK;
+  PPCSR_TRY(dev_reserve(s->misc, want + 16, s->stream));
+  const unsigned blocks = std::min<unsigned>(div_up((uint64_t)e - b, qry::QT), 148 * 8);
+  qry::k_neighbours<<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->leaf_cnt.p, s->rank_off.p, ls, b, e, s->misc.p,
+                                                      want);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, s->misc.p, want * 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return PPCSR_OK;
+}
+
+int ppcsr_read_neighbourhood(ppcsr_shard *s, uint32_t v, uint64_t *checksum) {
+  if (!s) return PPCSR_ERR_ARG;
+  if (checksum) *checksum = 0;
+  if (v >= s->n) return PPCSR_OK;
+  PPCSR_TRY(set_device(s));
+  uint32_t b, e;
+  PPCSR_TRY(vertex_range(s, v, &b, &e));
+  PPCSR_TRY(dev_reserve(s->misc, 16, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->misc.p, 0, 8, s->stream));
+  const unsigned blocks = std::max(1u, std::min<unsigned>(div_up((uint64_t)e - b, qry::QT), 148 * 8));
+  qry::k_touch<<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, b, e, reinterpret_cast<unsigned long long *>(s->misc.p));
+  CUDA_TRY(cudaGetLastError());
+  uint64_t *hp = reinterpret_cast<uint64_t *>(s->h_pinned);
+  CUDA_TRY(cudaMemcpyAsync(hp, s->misc.p, 8, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (checksum) *checksum = hp[0];
+  return PPCSR_OK;
+}
+
+int ppcsr_num_neighbors(ppcsr_shard *s, uint32_t *out) {
+  if (!s || (s->n && !out)) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  if (s->n) CUDA_TRY(cudaMemcpyAsync(out, s->nn.p, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return PPCSR_OK;
+}
+
+int ppcsr_node_ranges(ppcsr_shard *s, uint32_t *beginning, uint32_t *end) {
+  if (!s) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  if (s->n == 0) return PPCSR_OK;
+  std::vector<uint32_t> tmp((size_t)s->n + 1);
+  CUDA_TRY(cudaMemcpyAsync(tmp.data(), s->beg.p, ((size_t)s->n + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  for (uint32_t v = 0; v < s->n; v++) {
+    if (beginning) beginning[v] = tmp[v];
+    // the reference keeps the last vertex's end at N-1 (PCSR.cpp:180-182,811-813)
+    if (end) end[v] = (v + 1 == s->n) ? (uint32_t)(s->geo.N - 1) : tmp[v + 1];
+  }
+  return PPCSR_OK;
+}
+
+int ppcsr_export_csr(ppcsr_shard *s, uint64_t *rowptr, uint32_t *col, uint32_t *val, uint64_t *edges) {
+  if (!s) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  const uint64_t E = s->items - s->n;
+  if (edges) *edges = E;
+  const Geometry g = s->geo;
+  if (rowptr) {
+    PPCSR_TRY(refresh_rank_off(s));
+    DevBuf<uint64_t> d_row;
+    PPCSR_TRY(dev_reserve(d_row, (size_t)s->n + 1, s->stream));
+    qry::k_rowptr<<<div_up((uint64_t)s->n + 1, qry::QT), qry::QT, 0, s->stream>>>(s->beg.p, s->rank_off.p, g.leaf_shift,
+                                                                                s->n, d_row.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(rowptr, d_row.p, ((size_t)s->n + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    dev_free(d_row);
+  }
+  if (col && E) {
+    DevBuf<uint32_t> d_col, d_w;
+    PPCSR_TRY(dev_reserve(d_col, E, s->stream));
+    if (val) PPCSR_TRY(dev_reserve(d_w, E, s->stream));
+    PPCSR_TRY(prim::device_scan(s, qry::InIsEdge{s->dest.p, s->leaf_cnt.p, g.leaf_shift},
+                                qry::OutEdge{s->dest.p, s->val.p, d_col.p, val ? d_w.p : nullptr}, g.N, nullptr,
+                                nullptr));
+    CUDA_TRY(cudaMemcpyAsync(col, d_col.p, E * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (val) CUDA_TRY(cudaMemcpyAsync(val, d_w.p, E * 4, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    dev_free(d_col);
+    dev_free(d_w);
+  }
+  return PPCSR_OK;
+}
+
+int ppcsr_pagerank_push_device(ppcsr_shard *s, const double *d_in, double *d_out, uint64_t out_len) {
+  if (!s || !d_in || !d_out) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  if (s->n == 0) return PPCSR_OK;
+  const unsigned blocks = std::min<unsigned>(div_up((uint64_t)s->n * 32, qry::QT), 148 * 16);
+  qry::k_pagerank_push<double><<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->leaf_cnt.p, s->beg.p, s->nn.p,
+                                                                 s->geo.leaf_shift, s->n, d_in, d_out, out_len);
+  CUDA_TRY(cudaGetLastError());
+  return PPCSR_OK;
+}
+
+int ppcsr_pagerank_step_f64(ppcsr_shard *s, const double *in, double *out, uint64_t out_len) {
+  return pagerank_host<double>(s, in, out, out_len);
+}
+int ppcsr_pagerank_step_f32(ppcsr_shard *s, const float *in, float *out, uint64_t out_len) {
+  return pagerank_host<float>(s, in, out, out_len);
+}
+
+int ppcsr_bfs(ppcsr_shard *s, uint32_t start, uint32_t *dist) {
+  if (!s || (s->n && !dist)) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  if (s->n == 0) return PPCSR_OK;
+  DevBuf<uint32_t> d_dist;
+  PPCSR_TRY(dev_reserve(d_dist, (size_t)s->n + 1, s->stream));
+  PPCSR_TRY(dev_reserve(s->misc, 16, s->stream));
+  qry::k_fill_u32<<<div_up(s->n, 256), 256, 0, s->stream>>>(d_dist.p, 0xFFFFFFFFu, s->n);
+  if (start < s->n) {
+    reb::k_set_u32<<<1, 1, 0, s->stream>>>(d_dist.p + start, 0u);
+    uint32_t *hp = reinterpret_cast<uint32_t *>(s->h_pinned);
+    const unsigned blocks = std::min<unsigned>(div_up((uint64_t)s->n * 32, qry::QT), 148 * 16);
+    for (uint32_t level = 0; level < s->n; level++) {
+      CUDA_TRY(cudaMemsetAsync(s->misc.p, 0, 4, s->stream));
+      qry::k_bfs_level<<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->leaf_cnt.p, s->beg.p, s->geo.leaf_shift, s->n,
+                                                         d_dist.p, level, s->misc.p);
+      CUDA_TRY(cudaMemcpyAsync(hp, s->misc.p, 4, cudaMemcpyDeviceToHost, s->stream));
+      CUDA_TRY(cudaStreamSynchronize(s->stream));
+      if (hp[0] == 0) break;
+    }
+  }
+  CUDA_TRY(cudaMemcpyAsync(dist, d_dist.p, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  dev_free(d_dist);
+  return PPCSR_OK;
+}
+
+// ---- checks and snapshots ---------------------------------------------------------------------------
+int ppcsr_check_invariants(ppcsr_shard *s, int check_lower, ppcsr_invariant_report *r) {
+  if (!s || !r) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  memset(r, 0, sizeof(*r));
+  const Geometry g = s->geo;
+  const Geometry want = make_geometry(g.N);
+  if ((g.N & (g.N - 1)) != 0 || want.logN != g.logN || want.H != g.H || g.n_leaves != (1u << g.H)) r->bad_geometry = 1;
+  DevBuf<qry::InvCounters> d_c;
+  PPCSR_TRY(dev_reserve(d_c, 1, s->stream));
+  CUDA_TRY(cudaMemsetAsync(d_c.p, 0, sizeof(qry::InvCounters), s->stream));
+  const uint32_t L = g.n_leaves;
+  qry::k_check_leaves<<<div_up(L, qry::QT), qry::QT, 0, s->stream>>>(s->dest.p, s->val.p, s->leaf_cnt.p, s->tree.p, L,
+                                                                    g.leaf_shift, d_c.p);
+  qry::k_check_vertices<<<div_up((uint64_t)s->n + 1, qry::QT), qry::QT, 0, s->stream>>>(
+      s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, s->n, g.N, g.leaf_shift, d_c.p);
+  if (L > 1) qry::k_check_tree<<<div_up(L, qry::QT), qry::QT, 0, s->stream>>>(s->tree.p, L, d_c.p);
+  qry::k_check_bounds<<<div_up(L, qry::QT), qry::QT, 0, s->stream>>>(s->tree.p, s->ins_cnt.p, s->del_cnt.p, L, g.logN,
+                                                                    (int)g.H, check_lower, d_c.p);
+  CUDA_TRY(cudaGetLastError());
+  qry::InvCounters *hc = reinterpret_cast<qry::InvCounters *>(s->h_pinned);
+  CUDA_TRY(cudaMemcpyAsync(hc, d_c.p, sizeof(qry::InvCounters), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  r->bad_sentinel = hc->bad_sentinel + (hc->sentinels != s->n ? 1 : 0);
+  r->bad_order = hc->bad_order;
+  r->bad_leaf_layout = hc->bad_leaf_layout;
+  r->bad_upper = hc->bad_upper;
+  r->bad_lower = hc->bad_lower;
+  r->bad_tree = hc->bad_tree + (hc->live_items != s->items ? 1 : 0);
+  r->live_items = hc->live_items;
+  r->edges = hc->live_items - hc->sentinels;
+  r->full_leaves = hc->full_leaves;
+  dev_free(d_c);
+  return PPCSR_OK;
+}
+
+int ppcsr_snapshot(ppcsr_shard *s) {
+  if (!s) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  Snapshot &k = s->snap;
+  k.geo = s->geo;
+  k.n = s->n;
+  k.items = s->items;
+  PPCSR_TRY(snap_copy(s, k.dest, s->dest, s->geo.N));
+  PPCSR_TRY(snap_copy(s, k.val, s->val, s->geo.N));
+  PPCSR_TRY(snap_copy(s, k.leaf_cnt, s->leaf_cnt, s->geo.n_leaves));
+  PPCSR_TRY(snap_copy(s, k.tree, s->tree, (size_t)2 * s->geo.n_leaves));
+  PPCSR_TRY(snap_copy(s, k.beg, s->beg, (size_t)s->n + 1));
+  PPCSR_TRY(snap_copy(s, k.nn, s->nn, s->n));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  k.valid = true;
+  return PPCSR_OK;
+}
+
+int ppcsr_restore(ppcsr_shard *s) {
+  if (!s || !s->snap.valid) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  Snapshot &k = s->snap;
+  s->geo = k.geo;
+  s->n = k.n;
+  s->items = k.items;
+  PPCSR_TRY(alloc_geometry(s, k.geo));
+  PPCSR_TRY(dev_reserve(s->beg, (size_t)k.n + 1, s->stream));
+  PPCSR_TRY(dev_reserve(s->nn, (size_t)k.n + 1, s->stream));
+  PPCSR_TRY(snap_copy(s, s->dest, k.dest, k.geo.N));
+  PPCSR_TRY(snap_copy(s, s->val, k.val, k.geo.N));
+  PPCSR_TRY(snap_copy(s, s->leaf_cnt, k.leaf_cnt, k.geo.n_leaves));
+  PPCSR_TRY(snap_copy(s, s->tree, k.tree, (size_t)2 * k.geo.n_leaves));
+  PPCSR_TRY(snap_copy(s, s->beg, k.beg, (size_t)k.n + 1));
+  PPCSR_TRY(snap_copy(s, s->nn, k.nn, k.n));
+  CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)k.geo.n_leaves * 4, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)k.geo.n_leaves * 4, s->stream));
+  return PPCSR_OK;
+}
+
+int ppcsr_debug_dump(ppcsr_shard *s, uint32_t *dest, uint32_t *val, uint32_t *leaf_cnt) {
+  if (!s) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  if (dest) CUDA_TRY(cudaMemcpyAsync(dest, s->dest.p, s->geo.N * 4, cudaMemcpyDeviceToHost, s->stream));
+  if (val) CUDA_TRY(cudaMemcpyAsync(val, s->val.p, s->geo.N * 4, cudaMemcpyDeviceToHost, s->stream));
+  if (leaf_cnt)
+    CUDA_TRY(cudaMemcpyAsync(leaf_cnt, s->leaf_cnt.p, (size_t)s->geo.n_leaves * 4, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return PPCSR_OK;
+}
+
+int ppcsr_debug_sort_pairs(int device, uint64_t *keys, uint32_t *payload, uint64_t count, int lo_bits, int hi_bits) {
+  if (ppcsr_device_count() <= device) return PPCSR_ERR_NO_DEVICE;
+  if (count == 0) return PPCSR_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  ppcsr_shard tmp;
+  tmp.device = device;
+  tmp.stream = nullptr;
+  int rc = reserve_batch_arrays(&tmp, count);
+  if (rc != PPCSR_OK) return rc;
+  CUDA_TRY(cudaMemcpy(tmp.key_a.p, keys, count * 8, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(tmp.pay_a.p, payload, count * 4, cudaMemcpyHostToDevice));
+  uint64_t *rk;
+  uint32_t *rp;
+  rc = prim::radix_sort_pairs(&tmp, tmp.key_a.p, tmp.pay_a.p, tmp.key_b.p, tmp.pay_b.p, count, lo_bits, hi_bits, &rk,
+                              &rp);
+  if (rc == PPCSR_OK) {
+    CUDA_TRY(cudaMemcpy(keys, rk, count * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(payload, rp, count * 4, cudaMemcpyDeviceToHost));
+  }
+  dev_free(tmp.key_a); dev_free(tmp.key_b); dev_free(tmp.pay_a); dev_free(tmp.pay_b);
+  dev_free(tmp.ukey); dev_free(tmp.uval); dev_free(tmp.uloc); dev_free(tmp.ucls);
+  dev_free(tmp.ins_dst); dev_free(tmp.ins_val); dev_free(tmp.ins_pred);
+  dev_free(tmp.hist); dev_free(tmp.block_tmp);
+  return rc;
+}
+
+int ppcsr_debug_exclusive_scan(int device, const uint32_t *in, uint32_t *out, uint64_t count) {
+  if (ppcsr_device_count() <= device) return PPCSR_ERR_NO_DEVICE;
+  CUDA_TRY(cudaSetDevice(device));
+  ppcsr_shard tmp;
+  tmp.device = device;
+  tmp.stream = nullptr;
+  DevBuf<uint32_t> a, b;
+  PPCSR_TRY(dev_reserve(a, count + 1, nullptr));
+  PPCSR_TRY(dev_reserve(b, count + 1, nullptr));
+  CUDA_TRY(cudaMemset(b.p, 0, (count + 1) * 4));
+  if (count) CUDA_TRY(cudaMemcpy(a.p, in, count * 4, cudaMemcpyHostToDevice));
+  int rc = prim::device_scan(&tmp, prim::InArray{a.p}, prim::OutPrefixWithTotal{b.p, (size_t)count}, count, nullptr,
+                             nullptr);
+  if (rc == PPCSR_OK) CUDA_TRY(cudaMemcpy(out, b.p, (count + 1) * 4, cudaMemcpyDeviceToHost));
+  dev_free(a); dev_free(b); dev_free(tmp.block_tmp);
+  return rc;
+}
+
+}  // extern "C"

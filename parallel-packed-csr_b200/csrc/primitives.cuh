@@ -1,0 +1,284 @@
+// primitives.cuh -- device-wide exclusive scan / stream compaction and the LSD radix sort.
+// Hand-written (no CUB/Thrust): three-phase scan (tile reduce -> spine -> tile scan) with functor
+// input/output so the same code serves prefix sums, order-preserving selects and histogram offsets.
+#pragma once
+#include "common.cuh"
+
+namespace prim {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+    if ((int)lane_id() >= d) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one value per thread over the block; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total, uint32_t *s_warp /*[32]*/) {
+  const unsigned w = threadIdx.x >> 5, l = lane_id();
+  uint32_t inc = warp_incl_scan(v);
+  if (l == 31) s_warp[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t x = (l < (blockDim.x >> 5)) ? s_warp[l] : 0;
+    uint32_t xi = warp_incl_scan(x);
+    s_warp[l] = xi - x;  // exclusive warp offsets
+    if (l == 31) s_warp[32] = xi;
+  }
+  __syncthreads();
+  uint32_t r = s_warp[w] + inc - v;
+  *total = s_warp[32];
+  __syncthreads();
+  return r;
+}
+
+template <class In>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, size_t n, uint32_t *block_sums) {
+  __shared__ uint32_t s_warp[33];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    size_t i = base + k;
+    if (i < n) sum += in(i);
+  }
+  uint32_t total;
+  block_excl_scan(sum, &total, s_warp);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of block_sums[0..nb) in place; total to *total32 / *total64 (nullable)
+__global__ void __launch_bounds__(1024) k_scan_spine(uint32_t *block_sums, uint32_t nb, uint32_t *total32,
+                                                     unsigned long long *total64) {
+  __shared__ uint32_t s_warp[33];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nb; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = (i < nb) ? block_sums[i] : 0;
+    uint32_t total;
+    uint32_t ex = block_excl_scan(v, &total, s_warp);
+    uint32_t carry = s_carry;
+    if (i < nb) block_sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (total32) *total32 = s_carry;
+    if (total64) *total64 = s_carry;
+  }
+}
+
+template <class In, class Out>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(In in, Out out, size_t n, const uint32_t *block_sums) {
+  __shared__ uint32_t s_warp[33];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    size_t i = base + k;
+    v[k] = (i < n) ? in(i) : 0;
+    sum += v[k];
+  }
+  uint32_t total;
+  uint32_t ex = block_excl_scan(sum, &total, s_warp) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    size_t i = base + k;
+    if (i < n) out(i, ex, v[k]);
+    ex += v[k];
+  }
+}
+
+__global__ void k_zero_totals(uint32_t *total32, unsigned long long *total64) {
+  if (total32) *total32 = 0;
+  if (total64) *total64 = 0;
+}
+
+// Exclusive scan of in(i), i in [0,n): out(i, exclusive_prefix, in(i)) is called once per element.
+// The grand total goes to *d_total32 and/or *d_total64 (device pointers, nullable).
+template <class In, class Out>
+int device_scan(ppcsr_shard *s, In in, Out out, size_t n, uint32_t *d_total32, unsigned long long *d_total64) {
+  if (n == 0) {
+    if (d_total32 || d_total64) k_zero_totals<<<1, 1, 0, s->stream>>>(d_total32, d_total64);
+    CUDA_TRY(cudaGetLastError());
+    return PPCSR_OK;
+  }
+  const unsigned nb = div_up(n, SCAN_TILE);
+  PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)nb + 1, s->stream));
+  k_scan_reduce<<<nb, SCAN_THREADS, 0, s->stream>>>(in, n, s->block_tmp.p);
+  k_scan_spine<<<1, 1024, 0, s->stream>>>(s->block_tmp.p, nb, d_total32, d_total64);
+  k_scan_apply<<<nb, SCAN_THREADS, 0, s->stream>>>(in, out, n, s->block_tmp.p);
+  CUDA_TRY(cudaGetLastError());
+  return PPCSR_OK;
+}
+
+// ---- common functors ----
+struct InArray {
+  const uint32_t *a;
+  __device__ uint32_t operator()(size_t i) const { return a[i]; }
+};
+// writes the exclusive prefix to out[i] and the grand total to out[n]
+struct OutPrefixWithTotal {
+  uint32_t *out;
+  size_t n;
+  __device__ void operator()(size_t i, uint32_t ex, uint32_t own) const {
+    out[i] = ex;
+    if (i + 1 == n) out[n] = ex + own;
+  }
+};
+struct OutNothing {
+  __device__ void operator()(size_t, uint32_t, uint32_t) const {}
+};
+// list lengths that only the device knows: wrap a functor so elements at or beyond *n count as 0 / are skipped
+template <class In>
+struct BoundedIn {
+  In f;
+  const unsigned long long *n;
+  __device__ uint32_t operator()(size_t i) const { return i < (size_t)*n ? f(i) : 0u; }
+};
+template <class Out>
+struct BoundedOut {
+  Out o;
+  const unsigned long long *n;
+  __device__ void operator()(size_t i, uint32_t ex, uint32_t own) const {
+    if (i < (size_t)*n) o(i, ex, own);
+  }
+};
+template <class In>
+BoundedIn<In> bounded_in(In f, const unsigned long long *n) { return BoundedIn<In>{f, n}; }
+template <class Out>
+BoundedOut<Out> bounded_out(Out o, const unsigned long long *n) { return BoundedOut<Out>{o, n}; }
+
+// ---------------------------------------------------------------------------------------------
+// LSD radix sort of (u64 key, u32 payload), 8-bit digits, stable.
+// Per pass: per-tile digit histogram -> exclusive scan in digit-major order -> stable scatter with
+// warp-synchronous ranking (__match_any_sync), so equal keys keep their submission order: the LAST
+// element of a run of equal keys is the last op submitted for that (src,dst).
+// ---------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ROUNDS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;  // 4096 keys per CTA
+constexpr int RADIX = 256;
+
+__global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint64_t *__restrict__ keys, size_t n, int shift,
+                                                             uint32_t mask, uint32_t *__restrict__ hist,
+                                                             uint32_t nblocks) {
+  __shared__ uint32_t s_hist[RADIX];
+  for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) s_hist[d] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * SORT_TILE;
+#pragma unroll 4
+  for (int r = 0; r < SORT_ROUNDS; r++) {
+    size_t i = base + (size_t)r * SORT_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&s_hist[(uint32_t)(keys[i] >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = s_hist[d];
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint64_t *__restrict__ keys,
+                                                                const uint32_t *__restrict__ pay, size_t n,
+                                                                int shift, uint32_t mask,
+                                                                const uint32_t *__restrict__ offs, uint32_t nblocks,
+                                                                uint64_t *__restrict__ out_keys,
+                                                                uint32_t *__restrict__ out_pay) {
+  __shared__ uint32_t s_cnt[SORT_WARPS][RADIX];
+  for (int d = threadIdx.x; d < SORT_WARPS * RADIX; d += SORT_THREADS) (&s_cnt[0][0])[d] = 0;
+  __syncthreads();
+  const unsigned w = threadIdx.x >> 5, l = lane_id();
+  const unsigned lt = lanemask_lt();
+  // warp w owns the contiguous sub-tile [w*512, (w+1)*512): round r covers 32 consecutive keys
+  const size_t wbase = (size_t)blockIdx.x * SORT_TILE + (size_t)w * (32 * SORT_ROUNDS);
+  uint64_t k[SORT_ROUNDS];
+  uint32_t rank[SORT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < SORT_ROUNDS; r++) {
+    size_t i = wbase + (size_t)r * 32 + l;
+    k[r] = (i < n) ? keys[i] : 0;
+  }
+#pragma unroll
+  for (int r = 0; r < SORT_ROUNDS; r++) {
+    size_t i = wbase + (size_t)r * 32 + l;
+    const bool valid = i < n;
+    const uint32_t d = valid ? ((uint32_t)(k[r] >> shift) & mask) : 0x1FFu;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+    uint32_t base = 0;
+    if (valid) base = s_cnt[w][d];
+    __syncwarp();
+    if (valid && (peers & lt) == 0) s_cnt[w][d] = base + __popc(peers);
+    __syncwarp();
+    rank[r] = base + __popc(peers & lt);
+  }
+  __syncthreads();
+  // exclusive prefix over warps per digit, seeded with this tile's global offset for the digit
+  for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) {
+    uint32_t run = offs[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < SORT_WARPS; ww++) {
+      uint32_t t = s_cnt[ww][d];
+      s_cnt[ww][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < SORT_ROUNDS; r++) {
+    size_t i = wbase + (size_t)r * 32 + l;
+    if (i < n) {
+      const uint32_t d = (uint32_t)(k[r] >> shift) & mask;
+      const uint32_t pos = s_cnt[w][d] + rank[r];
+      out_keys[pos] = k[r];
+      out_pay[pos] = pay[i];
+    }
+  }
+}
+
+// Sorts n (key,payload) pairs by the key bits [0,lo_bits) and [32, 32+hi_bits).  Input in (ka,pa); the
+// sorted result ends up in *rk / *rp which point at either buffer pair.
+inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t *kb, uint32_t *pb, size_t n,
+                            int lo_bits, int hi_bits, uint64_t **rk, uint32_t **rp) {
+  *rk = ka;
+  *rp = pa;
+  if (n <= 1) return PPCSR_OK;
+  const unsigned nblocks = div_up(n, SORT_TILE);
+  PPCSR_TRY(dev_reserve(s->hist, (size_t)RADIX * nblocks + 1, s->stream));
+  uint64_t *src_k = ka, *dst_k = kb;
+  uint32_t *src_p = pa, *dst_p = pb;
+  for (int field = 0; field < 2; field++) {
+    const int bits = field == 0 ? lo_bits : hi_bits;
+    const int base = field == 0 ? 0 : 32;
+    for (int done = 0; done < bits; done += 8) {
+      const int width = (bits - done) < 8 ? (bits - done) : 8;
+      const uint32_t mask = (1u << width) - 1u;
+      const int shift = base + done;
+      k_radix_hist<<<nblocks, SORT_THREADS, 0, s->stream>>>(src_k, n, shift, mask, s->hist.p, nblocks);
+      PPCSR_TRY(device_scan(s, InArray{s->hist.p}, OutPrefixWithTotal{s->hist.p, (size_t)RADIX * nblocks},
+                            (size_t)RADIX * nblocks, nullptr, nullptr));
+      k_radix_scatter<<<nblocks, SORT_THREADS, 0, s->stream>>>(src_k, src_p, n, shift, mask, s->hist.p, nblocks,
+                                                               dst_k, dst_p);
+      CUDA_TRY(cudaGetLastError());
+      uint64_t *tk = src_k;
+      src_k = dst_k;
+      dst_k = tk;
+      uint32_t *tp = src_p;
+      src_p = dst_p;
+      dst_p = tp;
+    }
+  }
+  *rk = src_k;
+  *rp = src_p;
+  return PPCSR_OK;
+}
+
+}  // namespace prim

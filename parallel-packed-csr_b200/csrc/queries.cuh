@@ -1,0 +1,259 @@
+// queries.cuh -- read side: point queries, neighbour scans, CSR export, the PageRank push step,
+// level-synchronous BFS and the PMA invariant checker.
+// Replaces reference PCSR::edge_exists / get_neighbourhood / read_neighbourhood (src/pcsr/PCSR.cpp:860-912),
+// pagerank.h:16-29 and bfs.h:15-36.
+#pragma once
+#include "batch.cuh"
+#include "common.cuh"
+#include "primitives.cuh"
+
+namespace qry {
+
+constexpr int QT = 256;
+
+__global__ void __launch_bounds__(QT) k_edges_exist(const uint32_t *__restrict__ src, const uint32_t *__restrict__ dst,
+                                                    size_t count, uint32_t n, const uint32_t *__restrict__ dest,
+                                                    const uint32_t *__restrict__ val,
+                                                    const uint32_t *__restrict__ leaf_cnt,
+                                                    const uint32_t *__restrict__ beg, uint32_t ls,
+                                                    uint8_t *__restrict__ exists, uint32_t *__restrict__ out_val) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t s = src[i], d = dst[i];
+  uint8_t hit = 0;
+  uint32_t v = 0;
+  if (s < n && d != PPCSR_SENT) {
+    uint32_t slot;
+    if (batch::find_edge(dest, leaf_cnt, beg[s], beg[s + 1], ls, d, &slot)) {
+      hit = 1;
+      v = val[slot];
+    }
+  }
+  exists[i] = hit;
+  if (out_val) out_val[i] = v;
+}
+
+// global live rank of a slot: rank_off[leaf] + offset (valid for live slots and for slot == N)
+__device__ __forceinline__ uint32_t slot_rank(const uint32_t *__restrict__ rank_off, uint32_t ls, uint32_t slot) {
+  return rank_off[slot >> ls] + (slot & ((1u << ls) - 1u));
+}
+
+// rowptr[v] = live non-sentinel items before v's sentinel = rank(beg[v]) - v
+__global__ void __launch_bounds__(QT) k_rowptr(const uint32_t *__restrict__ beg, const uint32_t *__restrict__ rank_off,
+                                               uint32_t ls, uint32_t n, uint64_t *__restrict__ rowptr) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > n) return;
+  rowptr[v] = (uint64_t)slot_rank(rank_off, ls, beg[v]) - v;
+}
+
+// all live non-sentinel slots in array order = the concatenated adjacency lists
+struct InIsEdge {
+  const uint32_t *dest, *leaf_cnt;
+  uint32_t ls;
+  __device__ uint32_t operator()(size_t slot) const {
+    const uint32_t f = (uint32_t)slot & ((1u << ls) - 1u);
+    return (f < leaf_cnt[slot >> ls] && dest[slot] != PPCSR_SENT) ? 1u : 0u;
+  }
+};
+struct OutEdge {
+  const uint32_t *dest, *val;
+  uint32_t *col, *w;
+  __device__ void operator()(size_t slot, uint32_t ex, uint32_t own) const {
+    if (own) {
+      col[ex] = dest[slot];
+      if (w) w[ex] = val[slot];
+    }
+  }
+};
+
+// neighbours of one vertex, ascending (get_neighbourhood): live slots of (beg[v], beg[v+1])
+__global__ void __launch_bounds__(QT) k_neighbours(const uint32_t *__restrict__ dest,
+                                                   const uint32_t *__restrict__ leaf_cnt,
+                                                   const uint32_t *__restrict__ rank_off, uint32_t ls, uint32_t b,
+                                                   uint32_t e, uint32_t *__restrict__ out, uint64_t cap) {
+  const uint32_t r0 = slot_rank(rank_off, ls, b) + 1;
+  for (uint32_t slot = b + 1 + blockIdx.x * blockDim.x + threadIdx.x; slot < e; slot += gridDim.x * blockDim.x) {
+    const uint32_t f = slot & ((1u << ls) - 1u);
+    if (f < leaf_cnt[slot >> ls]) {
+      const uint32_t k = rank_off[slot >> ls] + f - r0;
+      if (k < cap) out[k] = dest[slot];
+    }
+  }
+}
+
+// read_neighbourhood: touch every slot of the range (PCSR.cpp:892-899), return a checksum so the loads stay
+__global__ void __launch_bounds__(QT) k_touch(const uint32_t *__restrict__ dest, uint32_t b, uint32_t e,
+                                              unsigned long long *sum) {
+  unsigned long long acc = 0;
+  for (uint32_t slot = b + 1 + blockIdx.x * blockDim.x + threadIdx.x; slot < e; slot += gridDim.x * blockDim.x)
+    acc += dest[slot];
+  for (int d = 16; d; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d);
+  if (lane_id() == 0 && acc) atomicAdd(sum, acc);
+}
+
+// ---- PageRank push step: warp per vertex, fp64 accumulation -----------------------------------------
+// out[dst] += in[v] / num_neighbors[v] for every edge (v,dst)  (reference pagerank.h:19-26; the divisor
+// is the call-count num_neighbors, not the degree).  A vertex without live edges contributes nothing,
+// whatever its divisor.
+template <typename W>
+__global__ void __launch_bounds__(QT) k_pagerank_push(const uint32_t *__restrict__ dest,
+                                                      const uint32_t *__restrict__ leaf_cnt,
+                                                      const uint32_t *__restrict__ beg, const uint32_t *__restrict__ nn,
+                                                      uint32_t ls, uint32_t n, const W *__restrict__ in,
+                                                      double *__restrict__ acc, uint64_t out_len) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = lane_id();
+  for (uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n; v += warps) {
+    const uint32_t b = beg[v], e = beg[v + 1];
+    if (e - b <= 1) continue;
+    const W contrib = in[v] / (W)nn[v];
+    for (uint32_t slot = b + 1 + lane; slot < e; slot += 32) {
+      const uint32_t f = slot & ((1u << ls) - 1u);
+      if (f < leaf_cnt[slot >> ls]) {
+        const uint32_t d = dest[slot];
+        if (d < out_len) atomicAdd(&acc[d], (double)contrib);
+      }
+    }
+  }
+}
+template <typename W>
+__global__ void k_cast_out(const double *__restrict__ acc, W *__restrict__ out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (W)acc[i];
+}
+template <typename W>
+__global__ void k_cast_in(const W *__restrict__ in, double *__restrict__ out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+
+// ---- BFS (level synchronous, warp per frontier vertex) ------------------------------------------------
+__global__ void __launch_bounds__(QT) k_bfs_level(const uint32_t *__restrict__ dest,
+                                                  const uint32_t *__restrict__ leaf_cnt,
+                                                  const uint32_t *__restrict__ beg, uint32_t ls, uint32_t n,
+                                                  uint32_t *__restrict__ dist, uint32_t level, uint32_t *changed) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = lane_id();
+  for (uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n; v += warps) {
+    if (dist[v] != level) continue;
+    const uint32_t b = beg[v], e = beg[v + 1];
+    for (uint32_t slot = b + 1 + lane; slot < e; slot += 32) {
+      const uint32_t f = slot & ((1u << ls) - 1u);
+      if (f < leaf_cnt[slot >> ls]) {
+        const uint32_t d = dest[slot];
+        if (d < n && dist[d] == 0xFFFFFFFFu) {
+          dist[d] = level + 1;  // benign race: every writer stores the same value
+          *changed = 1;
+        }
+      }
+    }
+  }
+}
+__global__ void k_fill_u32(uint32_t *p, uint32_t v, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---- invariants -------------------------------------------------------------------
+struct InvCounters {
+  unsigned long long bad_sentinel, bad_order, bad_leaf_layout, bad_upper, bad_lower, bad_tree, live_items, sentinels,
+      full_leaves;
+};
+
+// one thread per leaf: left-packed layout, null tail, ascending order inside the leaf and across to the
+// next non-empty leaf (a sentinel restarts the order: the next vertex begins)
+__global__ void __launch_bounds__(QT) k_check_leaves(const uint32_t *__restrict__ dest,
+                                                     const uint32_t *__restrict__ val,
+                                                     const uint32_t *__restrict__ leaf_cnt,
+                                                     const uint32_t *__restrict__ tree, uint32_t n_leaves, uint32_t ls,
+                                                     InvCounters *c) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_leaves) return;
+  const uint32_t logN = 1u << ls, cnt = leaf_cnt[l];
+  const size_t base = (size_t)l << ls;
+  unsigned bad_layout = 0, bad_order = 0, sent = 0;
+  if (cnt > logN) bad_layout++;
+  if (tree[n_leaves + l] != cnt) atomicAdd(&c->bad_tree, 1ull);
+  if (cnt == logN) atomicAdd(&c->full_leaves, 1ull);
+  uint32_t prev = 0;
+  bool have_prev = false;
+  for (uint32_t f = 0; f < logN; f++) {
+    const uint32_t d = dest[base + f], v = val[base + f];
+    if (f < cnt) {
+      if (v == 0) bad_layout++;
+      if (d == PPCSR_SENT) {
+        sent++;
+        have_prev = false;
+      } else {
+        if (have_prev && d <= prev) bad_order++;
+        prev = d;
+        have_prev = true;
+      }
+    } else if (v != 0 || d != 0) {
+      bad_layout++;
+    }
+  }
+  if (cnt > 0 && have_prev) {  // compare with the first item of the next non-empty leaf
+    uint32_t l2 = l + 1;
+    while (l2 < n_leaves && leaf_cnt[l2] == 0) l2++;
+    if (l2 < n_leaves) {
+      const uint32_t d2 = dest[(size_t)l2 << ls];
+      if (d2 != PPCSR_SENT && d2 <= prev) bad_order++;
+    }
+  }
+  if (bad_layout) atomicAdd(&c->bad_leaf_layout, (unsigned long long)bad_layout);
+  if (bad_order) atomicAdd(&c->bad_order, (unsigned long long)bad_order);
+  if (sent) atomicAdd(&c->sentinels, (unsigned long long)sent);
+  if (cnt) atomicAdd(&c->live_items, (unsigned long long)cnt);
+}
+
+__global__ void __launch_bounds__(QT) k_check_vertices(const uint32_t *__restrict__ dest,
+                                                       const uint32_t *__restrict__ val,
+                                                       const uint32_t *__restrict__ leaf_cnt,
+                                                       const uint32_t *__restrict__ beg, uint32_t n, uint64_t N,
+                                                       uint32_t ls, InvCounters *c) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > n) return;
+  if (v == n) {
+    if (beg[n] != (uint32_t)N) atomicAdd(&c->bad_sentinel, 1ull);
+    return;
+  }
+  const uint32_t b = beg[v];
+  bool bad = b >= N || b >= beg[v + 1];
+  if (!bad) {
+    bad = dest[b] != PPCSR_SENT || val[b] != v + 1u || (b & ((1u << ls) - 1u)) >= leaf_cnt[b >> ls];
+  }
+  if (bad) atomicAdd(&c->bad_sentinel, 1ull);
+}
+
+__global__ void __launch_bounds__(QT) k_check_tree(const uint32_t *__restrict__ tree, uint32_t n_leaves,
+                                                   InvCounters *c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (i >= n_leaves) return;  // internal nodes 1 .. n_leaves-1
+  if (tree[i] != tree[2 * i] + tree[2 * i + 1]) atomicAdd(&c->bad_tree, 1ull);
+}
+
+// density bounds on every path touched by the last batch (ins_cnt/del_cnt still hold its per-leaf counts)
+__global__ void __launch_bounds__(QT) k_check_bounds(const uint32_t *__restrict__ tree,
+                                                     const uint32_t *__restrict__ ins_cnt,
+                                                     const uint32_t *__restrict__ del_cnt, uint32_t n_leaves,
+                                                     uint32_t logN, int H, int check_lower, InvCounters *c) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_leaves) return;
+  const bool ins = ins_cnt[l] != 0, del = del_cnt[l] != 0;
+  if (!ins && !del) return;
+  uint32_t node = n_leaves + l;
+  uint64_t len = logN;
+  unsigned up = 0, lo = 0;
+  for (int depth = H; depth >= 0; depth--) {
+    const uint32_t cnt = tree[node];
+    if (ins && !window_ok_upper(cnt, len, logN, depth, H)) up++;
+    if (del && check_lower && !window_ok_lower(cnt, len, depth, H)) lo++;
+    node >>= 1;
+    len <<= 1;
+  }
+  if (up) atomicAdd(&c->bad_upper, (unsigned long long)up);
+  if (lo) atomicAdd(&c->bad_lower, (unsigned long long)lo);
+}
+
+}  // namespace qry

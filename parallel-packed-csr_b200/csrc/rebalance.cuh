@@ -1,0 +1,262 @@
+// rebalance.cuh -- the rebalance kernel: merge the kept items of a window with the batch's inserts,
+// drop the tombstones, and spread the result evenly over the window's leaves, fixing the vertex
+// sentinels' back pointers in the same pass.
+// Replaces reference PCSR::redistribute + fix_sentinel + slide_right/slide_left + double_list/half_list
+// (src/pcsr/PCSR.cpp:222-249, 168-183, 326-390, 251-320).
+//
+// Formulation (gather, output-driven).  For a window of m source leaves the merged sequence is the
+// concatenation over source leaves i of merge(kept(i), inserts(i)); its ranks are
+//     rank(kept item at offset f of leaf i) = R[i] + #kept before f + #inserts of i whose predecessor < f
+//     rank(q-th insert of leaf i)           = R[i] + q + #kept items of i at offsets <= offset(pred)
+// with R = exclusive scan of the post-batch leaf counts.  Output leaf o of m_out receives the ranks
+// [floor(o*j/m_out), floor((o+1)*j/m_out)) left-packed, the rest of the leaf is nulled.  Each CTA owns
+// a chunk of CHUNK_SLOTS consecutive output slots: it finds the source leaves that feed its rank range
+// by binary search in R, stages the items in shared memory at (rank - first rank) and writes the chunk
+// with 16-byte stores.  Algorithmic traffic: every window slot is read once and written once.
+#pragma once
+#include "common.cuh"
+
+namespace reb {
+
+constexpr int RT = 256;
+constexpr int RWARPS = RT / 32;
+constexpr int CHUNK_SLOTS = 2048;  // output slots per CTA (16 KB of staging)
+constexpr int TILE_LEAVES = 64;    // source leaves examined per inner iteration
+
+struct Args {
+  const uint32_t *src_dest, *src_val;  // source slots
+  const uint32_t *leaf_cnt;            // source physical leaf counts (tombstones included)
+  const uint32_t *rank_off;            // R[], n_leaves_src + 1
+  const uint32_t *ins_off;             // first insert of each source leaf, n_leaves_src + 1
+  const uint32_t *ins_dst, *ins_val, *ins_pred;
+  uint32_t *out_dest_single, *out_val_single;  // target of single-CTA windows (in place)
+  uint32_t *out_dest_multi, *out_val_multi;    // target of multi-CTA windows (out of place)
+  uint32_t *tree_leaf_out;                     // post-rebalance leaf counts (leaf level of the tree)
+  uint32_t *beg;
+  const WindowDesc *windows;
+  uint32_t n_windows;
+  uint32_t ls_src, ls_dst;
+  uint32_t m_dst_override;  // != 0: resize, the single window maps onto this many output leaves from leaf 0
+};
+
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t *a, uint32_t n, uint32_t key) {
+  uint32_t lo = 0, hi = n;  // first index with a[idx] > key
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] <= key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint32_t key) {
+  uint32_t lo = 0, hi = n;  // first index with a[idx] >= key
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(RT) k_rebalance(Args A) {
+  __shared__ __align__(16) uint32_t s_dest[CHUNK_SLOTS];
+  __shared__ __align__(16) uint32_t s_val[CHUNK_SLOTS];
+  __shared__ uint32_t t_mask[TILE_LEAVES], t_rank[TILE_LEAVES], t_ioff[TILE_LEAVES + 1];
+  __shared__ WindowDesc s_w;
+  __shared__ uint32_t s_ilo, s_ihi, s_qb, s_qe;
+
+  const uint32_t chunk = blockIdx.x;
+  if (threadIdx.x == 0) {
+    uint32_t lo = 0, hi = A.n_windows;  // last window with chunk0 <= chunk
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (A.windows[mid].chunk0 <= chunk) lo = mid;
+      else hi = mid;
+    }
+    s_w = A.windows[lo];
+  }
+  __syncthreads();
+  const WindowDesc w = s_w;
+  const uint32_t logN_src = 1u << A.ls_src, logN_dst = 1u << A.ls_dst;
+  const uint32_t m_dst = A.m_dst_override ? A.m_dst_override : w.m;
+  const uint32_t dst_leaf0 = A.m_dst_override ? 0u : w.leaf0;
+  const uint32_t CL = CHUNK_SLOTS >> A.ls_dst;  // output leaves per chunk
+  const uint32_t o_lo = (chunk - w.chunk0) * CL;
+  const uint32_t o_hi = min(o_lo + CL, m_dst);
+  const uint64_t j = w.items;
+  const uint32_t a = (uint32_t)rank_begin(o_lo, j, m_dst);
+  const uint32_t b = (uint32_t)rank_begin(o_hi, j, m_dst);
+  const uint32_t R0 = A.rank_off[w.leaf0];
+  const bool multi = w.n_chunks > 1;
+  uint32_t *out_dest = multi ? A.out_dest_multi : A.out_dest_single;
+  uint32_t *out_val = multi ? A.out_val_multi : A.out_val_single;
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
+
+  if (b > a) {
+    if (threadIdx.x == 0) {
+      const uint32_t *R = A.rank_off + w.leaf0;
+      s_ilo = upper_bound_u32(R, w.m, R0 + a) - 1;      // source leaf holding rank a
+      s_ihi = upper_bound_u32(R, w.m, R0 + b - 1) - 1;  // source leaf holding rank b-1
+    }
+    __syncthreads();
+    const uint32_t i_lo = s_ilo, i_hi = s_ihi;
+    for (uint32_t tile = i_lo; tile <= i_hi; tile += TILE_LEAVES) {
+      const uint32_t tl_n = min((uint32_t)TILE_LEAVES, i_hi - tile + 1);
+      // phase A: kept items of the tile's leaves, one warp per leaf (a leaf is <= 32 slots)
+      for (uint32_t li = warp; li < tl_n; li += RWARPS) {
+        const uint32_t i = w.leaf0 + tile + li;
+        const uint32_t c_old = A.leaf_cnt[i];
+        const uint32_t Ri = A.rank_off[i] - R0;
+        const uint32_t io = A.ins_off[i], ic = A.ins_off[i + 1] - io;
+        const uint32_t slot = (i << A.ls_src) + lane;
+        const bool live = lane < c_old && lane < logN_src;
+        const uint32_t d = live ? A.src_dest[slot] : 0u;
+        const uint32_t v = live ? A.src_val[slot] : 0u;
+        const bool kept = live && v != 0u;
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, kept);
+        if (kept) {
+          const uint32_t ib = ic ? lower_bound_u32(A.ins_pred + io, ic, slot) : 0u;  // inserts with pred < slot
+          const uint32_t r = Ri + (uint32_t)__popc(mask & lt) + ib;
+          if (r >= a && r < b) {
+            s_dest[r - a] = d;
+            s_val[r - a] = v;
+          }
+        }
+        if (lane == 0) {
+          t_mask[li] = mask;
+          t_rank[li] = Ri;
+          t_ioff[li] = io;
+          if (li == tl_n - 1) t_ioff[tl_n] = io + ic;
+        }
+      }
+      __syncthreads();
+      // phase B: the tile's inserts.  Only the first and last source leaf of the chunk can straddle the
+      // chunk's rank range; clamp there by binary search on the (strictly increasing) insert ranks.
+      if (threadIdx.x == 0) {
+        uint32_t qb = t_ioff[0], qe = t_ioff[tl_n];
+        if (tile == i_lo) {
+          const uint32_t io = t_ioff[0], ie = t_ioff[1];
+          const uint32_t mask = t_mask[0], Ri = t_rank[0];
+          uint32_t lo = io, hi = ie;  // first q with rank(q) >= a
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t f = A.ins_pred[mid] & (logN_src - 1u);
+            const uint32_t r = Ri + (mid - io) + (uint32_t)__popc(mask & ((2u << f) - 1u));
+            if (r < a) lo = mid + 1;
+            else hi = mid;
+          }
+          qb = lo;
+        }
+        if (tile + tl_n - 1 == i_hi) {
+          const uint32_t io = t_ioff[tl_n - 1], ie = t_ioff[tl_n];
+          const uint32_t mask = t_mask[tl_n - 1], Ri = t_rank[tl_n - 1];
+          uint32_t lo = io, hi = ie;  // first q with rank(q) >= b
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t f = A.ins_pred[mid] & (logN_src - 1u);
+            const uint32_t r = Ri + (mid - io) + (uint32_t)__popc(mask & ((2u << f) - 1u));
+            if (r < b) lo = mid + 1;
+            else hi = mid;
+          }
+          qe = lo;
+        }
+        s_qb = qb;
+        s_qe = max(qb, qe);
+      }
+      __syncthreads();
+      const uint32_t tile_leaf0 = w.leaf0 + tile;
+      for (uint32_t q = s_qb + threadIdx.x; q < s_qe; q += RT) {
+        const uint32_t pred = A.ins_pred[q];
+        const uint32_t li = (pred >> A.ls_src) - tile_leaf0;
+        const uint32_t f = pred & (logN_src - 1u);
+        const uint32_t r = t_rank[li] + (q - t_ioff[li]) + (uint32_t)__popc(t_mask[li] & ((2u << f) - 1u));
+        if (r >= a && r < b) {
+          s_dest[r - a] = A.ins_dst[q];
+          s_val[r - a] = A.ins_val[q];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // write-out: 4 consecutive slots per thread, 16-byte stores to dest[] and val[]
+  const uint32_t out_slots = (o_hi - o_lo) << A.ls_dst;
+  for (uint32_t x = threadIdx.x * 4; x < out_slots; x += RT * 4) {
+    const uint32_t o = o_lo + (x >> A.ls_dst);
+    const uint32_t f0 = x & (logN_dst - 1u);
+    const uint32_t a_o = (uint32_t)rank_begin(o, j, m_dst);
+    const uint32_t b_o = (uint32_t)rank_begin((uint64_t)o + 1, j, m_dst);
+    const size_t gslot = ((size_t)(dst_leaf0 + o) << A.ls_dst) + f0;
+    uint32_t dd[4], vv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t r = a_o + f0 + k;
+      const bool live = r < b_o;
+      dd[k] = live ? s_dest[r - a] : 0u;
+      vv[k] = live ? s_val[r - a] : 0u;
+      if (live && dd[k] == PPCSR_SENT) A.beg[vv[k] - 1u] = (uint32_t)(gslot + k);  // fix_sentinel, PCSR.cpp:168-183
+    }
+    *reinterpret_cast<uint4 *>(out_dest + gslot) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+    *reinterpret_cast<uint4 *>(out_val + gslot) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+    if (f0 == 0) A.tree_leaf_out[dst_leaf0 + o] = b_o - a_o;
+  }
+}
+
+// copy the chunks of multi-CTA windows back from the out-of-place target into the live array
+__global__ void __launch_bounds__(RT) k_copy_back(const WindowDesc *__restrict__ windows, uint32_t n_windows,
+                                                  uint32_t ls, const uint32_t *__restrict__ alt_dest,
+                                                  const uint32_t *__restrict__ alt_val, uint32_t *__restrict__ dest,
+                                                  uint32_t *__restrict__ val) {
+  __shared__ WindowDesc s_w;
+  const uint32_t chunk = blockIdx.x;
+  if (threadIdx.x == 0) {
+    uint32_t lo = 0, hi = n_windows;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (windows[mid].chunk0 <= chunk) lo = mid;
+      else hi = mid;
+    }
+    s_w = windows[lo];
+  }
+  __syncthreads();
+  const WindowDesc w = s_w;
+  if (w.n_chunks <= 1) return;
+  const uint32_t CL = CHUNK_SLOTS >> ls;
+  const uint32_t o_lo = (chunk - w.chunk0) * CL;
+  const uint32_t o_hi = min(o_lo + CL, w.m);
+  const size_t base = (size_t)(w.leaf0 + o_lo) << ls;
+  const uint32_t slots = (o_hi - o_lo) << ls;
+  for (uint32_t x = threadIdx.x * 4; x < slots; x += RT * 4) {
+    *reinterpret_cast<uint4 *>(dest + base + x) = *reinterpret_cast<const uint4 *>(alt_dest + base + x);
+    *reinterpret_cast<uint4 *>(val + base + x) = *reinterpret_cast<const uint4 *>(alt_val + base + x);
+  }
+}
+
+// initial layout: src_n sentinels spread evenly (reference PCSR::PCSR, PCSR.cpp:796-837, in leaf-packed form)
+__global__ void k_init_sentinels(uint32_t *__restrict__ dest, uint32_t *__restrict__ val, uint32_t *__restrict__ beg,
+                                 uint32_t first_vertex, uint32_t count, uint32_t n_total, uint32_t m, uint32_t ls) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  // rank k of n_total items spread over m leaves: leaf = last o with floor(o*n/m) <= k
+  const uint64_t o = (((uint64_t)k + 1) * m - 1) / n_total;
+  const uint32_t f = k - (uint32_t)rank_begin(o, n_total, m);
+  const size_t slot = ((size_t)o << ls) + f;
+  dest[slot] = PPCSR_SENT;
+  val[slot] = first_vertex + k + 1u;
+  beg[first_vertex + k] = (uint32_t)slot;
+}
+__global__ void k_init_leaf_counts(uint32_t *__restrict__ leaf_cnt, uint32_t *__restrict__ tree, uint32_t n_total,
+                                   uint32_t m) {
+  const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= m) return;
+  const uint32_t c = (uint32_t)(rank_begin((uint64_t)o + 1, n_total, m) - rank_begin(o, n_total, m));
+  leaf_cnt[o] = c;
+  tree[m + o] = c;
+}
+__global__ void k_set_u32(uint32_t *p, uint32_t v) { *p = v; }
+__global__ void k_copy_u32(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+}  // namespace reb

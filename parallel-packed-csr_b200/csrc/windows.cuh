@@ -1,0 +1,159 @@
+// windows.cuh -- the implicit PMA tree: live-count tree maintenance and the bottom-up choice of
+// rebalance windows under the reference's density bounds.
+// Replaces reference get_density / density_bound / the walks in PCSR::insert and PCSR::remove
+// (src/pcsr/PCSR.cpp:126-133, 156-165, 578-591, 616-628) and the window pre-computation of
+// acquire_insert_locks / acquire_remove_locks (PCSR.cpp:1012-1084, 1191-1231).
+#pragma once
+#include "common.cuh"
+#include "primitives.cuh"
+
+namespace win {
+
+constexpr int WT = 256;
+
+// post-batch live count of every leaf = old + inserted - deleted  -> leaf level of the tree
+__global__ void __launch_bounds__(WT) k_leaf_new_counts(const uint32_t *__restrict__ leaf_cnt,
+                                                        const uint32_t *__restrict__ ins_cnt,
+                                                        const uint32_t *__restrict__ del_cnt, uint32_t n_leaves,
+                                                        uint32_t *__restrict__ tree) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < n_leaves) tree[n_leaves + l] = leaf_cnt[l] + ins_cnt[l] - del_cnt[l];
+}
+
+// Sums five tree levels per launch with warp shuffles: a warp loads 32 consecutive nodes of depth D
+// (one coalesced 128-B line) and writes their ancestors at depths D-1 .. D-5.
+__global__ void __launch_bounds__(WT) k_tree_up5(uint32_t *__restrict__ tree, uint32_t D) {
+  const uint32_t level_nodes = 1u << D;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // position inside the level
+  uint32_t v = (i < level_nodes) ? tree[level_nodes + i] : 0u;
+  const unsigned l = lane_id();
+#pragma unroll
+  for (uint32_t k = 1; k <= 5; k++) {
+    v += __shfl_down_sync(0xFFFFFFFFu, v, 1u << (k - 1));
+    if (k <= D && (l & ((1u << k) - 1u)) == 0 && i < level_nodes) tree[(level_nodes + i) >> k] = v;
+  }
+}
+
+inline int tree_rebuild(ppcsr_shard *s, uint32_t *tree, uint32_t H) {
+  for (int D = (int)H; D > 0; D -= 5) {
+    const uint32_t nodes = 1u << D;
+    k_tree_up5<<<div_up(nodes, WT), WT, 0, s->stream>>>(tree, (uint32_t)D);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PPCSR_OK;
+}
+
+// touched leaves = leaves that gained or lost an item in this batch (key order == leaf order)
+struct InTouched {
+  const uint32_t *ins_cnt, *del_cnt;
+  __device__ uint32_t operator()(size_t l) const { return (ins_cnt[l] | del_cnt[l]) ? 1u : 0u; }
+};
+struct OutTouched {
+  uint32_t *touched;
+  __device__ void operator()(size_t l, uint32_t ex, uint32_t own) const {
+    if (own) touched[ex] = (uint32_t)l;
+  }
+};
+
+// For one touched leaf: walk the whole path to the root with the post-batch counts.  Every ancestor
+// is tested against the reference's bounds (upper if the leaf received inserts, lower if it lost
+// items).  The window to rebalance is the parent of the HIGHEST violating node (the first node above
+// which the path is within bounds); with no violation it is the leaf itself (the reference rewrites
+// the leaf on every insert/remove, PCSR.cpp:552-560,609).  Checking all ancestors rather than stopping
+// at the first in-bounds one is strictly tighter than the reference and gives invariant I4/I5 of
+// SURVEY §8a on every touched path.  A violated root means double_list / half_list.
+__global__ void __launch_bounds__(WT) k_select(const uint32_t *__restrict__ touched,
+                                               const unsigned long long *__restrict__ n_touched,
+                                               const uint32_t *__restrict__ ins_cnt,
+                                               const uint32_t *__restrict__ del_cnt,
+                                               const uint32_t *__restrict__ tree, uint32_t n_leaves, uint32_t logN,
+                                               int H, uint32_t *__restrict__ mark, uint32_t epoch, BatchScalars *sc) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)*n_touched) return;
+  const uint32_t l = touched[t];
+  const bool ins = ins_cnt[l] != 0, del = del_cnt[l] != 0;
+  uint32_t node = n_leaves + l;
+  uint64_t len = logN;
+  uint32_t top = 0;        // heap index of the highest violating node (0 = none)
+  unsigned viol_bits = 0;  // what the highest violator violated
+  for (int depth = H; depth >= 0; depth--) {
+    const uint32_t cnt = tree[node];
+    const bool bad_up = ins && !window_ok_upper(cnt, len, logN, depth, H);
+    const bool bad_lo = del && !window_ok_lower(cnt, len, depth, H);
+    if (bad_up || bad_lo) {
+      top = node;
+      viol_bits = bad_up ? 1u : 2u;
+    }
+    node >>= 1;
+    len <<= 1;
+  }
+  uint32_t w;
+  if (top == 0) {
+    w = n_leaves + l;
+  } else if (top == 1) {
+    w = 1;
+    atomicOr(&sc->root_violation, viol_bits);
+  } else {
+    w = top >> 1;
+  }
+  mark[w] = epoch;
+}
+
+__device__ __forceinline__ uint32_t highest_marked(const uint32_t *__restrict__ mark, uint32_t epoch, uint32_t node) {
+  uint32_t best = 0;
+  while (node >= 1) {
+    if (mark[node] == epoch) best = node;
+    node >>= 1;
+  }
+  return best;
+}
+
+// One window per maximal marked node; touched leaves are sorted, so leaves of the same window are adjacent.
+struct InWindowHead {
+  const uint32_t *touched, *mark;
+  uint32_t epoch, n_leaves;
+  __device__ uint32_t operator()(size_t t) const {
+    const uint32_t w = highest_marked(mark, epoch, n_leaves + touched[t]);
+    if (t == 0) return 1u;
+    return highest_marked(mark, epoch, n_leaves + touched[t - 1]) != w ? 1u : 0u;
+  }
+};
+struct OutWindow {
+  const uint32_t *touched, *mark, *tree;
+  uint32_t epoch, n_leaves, chunk_leaves;
+  WindowDesc *windows;
+  __device__ void operator()(size_t t, uint32_t ex, uint32_t own) const {
+    if (!own) return;
+    const uint32_t w = highest_marked(mark, epoch, n_leaves + touched[t]);
+    const uint32_t depth = 31u - (uint32_t)__clz(w);
+    const uint32_t m = n_leaves >> depth;
+    WindowDesc d;
+    d.node = w;
+    d.m = m;
+    d.leaf0 = (w - (1u << depth)) * m;
+    d.items = tree[w];
+    d.n_chunks = (m + chunk_leaves - 1) / chunk_leaves;
+    d.chunk0 = 0;
+    windows[ex] = d;
+  }
+};
+
+struct InWinChunks {
+  const WindowDesc *w;
+  __device__ uint32_t operator()(size_t i) const { return w[i].n_chunks; }
+};
+struct OutWinChunk0 {
+  WindowDesc *w;
+  __device__ void operator()(size_t i, uint32_t ex, uint32_t) const { w[i].chunk0 = ex; }
+};
+struct InWinSlots {
+  const WindowDesc *w;
+  uint32_t logN;
+  bool only_multi;
+  __device__ uint32_t operator()(size_t i) const {
+    if (only_multi && w[i].n_chunks <= 1) return 0;
+    return w[i].m * logN;
+  }
+};
+
+}  // namespace win
