@@ -65,30 +65,42 @@ struct InLastOfRun {
 struct OutUnique {
   const uint64_t *keys;
   const uint32_t *pay;
+  uint64_t invalid_key;
   uint64_t *ukey;
   uint32_t *uval;
+  uint8_t *ufirst_del;  // 1 if the FIRST op of the key's run in this batch is a remove
   __device__ void operator()(size_t i, uint32_t ex, uint32_t own) const {
+    const uint64_t k = keys[i];
     if (own) {
-      ukey[ex] = keys[i];
+      ukey[ex] = k;
       uval[ex] = pay[i];
     }
+    // `ex` = number of complete runs before i = index of i's run in the unique list
+    if (k < invalid_key && (i == 0 || keys[i - 1] != k)) ufirst_del[ex] = pay[i] == 0 ? 1 : 0;
   }
 };
 
 // num_neighbors += (#add calls) - (#remove calls) per source over the WHOLE sorted batch, duplicates
 // included (reference PCSR.cpp:1392 and :747).  Sorted by src => warp-aggregated atomics.
+// Also counts the removes that the sequential reference would report as `not found` because the previous
+// op on the same key in this batch was already a remove (reference PCSR.cpp:750-754).
 __global__ void __launch_bounds__(BT) k_count_calls(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay,
-                                                    size_t count, uint64_t invalid_key, uint32_t *__restrict__ nn) {
+                                                    size_t count, uint64_t invalid_key, uint32_t *__restrict__ nn,
+                                                    BatchScalars *sc) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t s = 0xFFFFFFFFu;
   int delta = 0;
+  bool dup_miss = false;
   if (i < count) {
     const uint64_t k = keys[i];
     if (k < invalid_key) {
       s = (uint32_t)(k >> 32);
       delta = pay[i] != 0 ? 1 : -1;
+      dup_miss = delta < 0 && i > 0 && keys[i - 1] == k && pay[i - 1] == 0;
     }
   }
+  const unsigned dm = __ballot_sync(0xFFFFFFFFu, dup_miss);
+  if (dm && lane_id() == 0) atomicAdd(&sc->n_not_found, (unsigned long long)__popc(dm));
   const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
   const unsigned adds = __ballot_sync(0xFFFFFFFFu, delta > 0);
   const unsigned dels = __ballot_sync(0xFFFFFFFFu, delta < 0);
@@ -141,6 +153,7 @@ __device__ __forceinline__ bool find_edge(const uint32_t *__restrict__ dest, con
 }
 
 __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ ukey, const uint32_t *__restrict__ uval,
+                                               const uint8_t *__restrict__ ufirst_del,
                                                const unsigned long long *__restrict__ n_unique,
                                                const uint32_t *__restrict__ dest, uint32_t *__restrict__ val,
                                                const uint32_t *__restrict__ leaf_cnt, const uint32_t *__restrict__ beg,
@@ -153,6 +166,7 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ ukey
   const size_t U = (size_t)*n_unique;
   const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t cls = 0xFFu, leaf = 0xFFFFFFFFu;
+  bool first_miss = false;  // the key's first op is a remove and the key is absent: a sequential `not found`
   if (u < U) {
     const uint64_t k = ukey[u];
     const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k, v = uval[u];
@@ -165,6 +179,7 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ ukey
       cls = hit ? CLS_DELETE : CLS_MISS;
       if (hit) val[slot] = 0;  // tombstone; compacted away by the rebalance of this leaf (PCSR.cpp:605-606)
     }
+    first_miss = ufirst_del[u] != 0 && !hit;
     uloc[u] = slot;
     ucls[u] = (uint8_t)cls;
     leaf = slot >> ls;
@@ -183,7 +198,9 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ ukey
   }
 #pragma unroll
   for (uint32_t c = 0; c < 4; c++) {
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == c);
+    // CLS_MISS only says "nothing to remove physically"; the reported not-found count follows the
+    // sequential rule: first op of the key is a remove of an absent edge (+ the repeats counted earlier)
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, c == CLS_MISS ? first_miss : cls == c);
     if (lane_id() == 0 && m) atomicAdd(&s_stat[c], (uint32_t)__popc(m));
   }
   __syncthreads();

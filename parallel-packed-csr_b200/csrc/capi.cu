@@ -46,6 +46,7 @@ int reserve_batch_arrays(ppcsr_shard *s, size_t count) {
   PPCSR_TRY(dev_reserve(s->uval, count, s->stream));
   PPCSR_TRY(dev_reserve(s->uloc, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ucls, count, s->stream));
+  PPCSR_TRY(dev_reserve(s->ufirst, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_dst, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_val, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_pred, count, s->stream));
@@ -426,7 +427,7 @@ void ppcsr_destroy(ppcsr_shard *s) {
   dev_free(s->mark); dev_free(s->touched); dev_free(s->touched_win); dev_free(s->windows);
   dev_free(s->win_chunk_off); dev_free(s->key_a); dev_free(s->key_b); dev_free(s->pay_a); dev_free(s->pay_b);
   dev_free(s->in_src); dev_free(s->in_dst); dev_free(s->in_val); dev_free(s->ukey); dev_free(s->uval);
-  dev_free(s->uloc); dev_free(s->ucls); dev_free(s->ins_dst); dev_free(s->ins_val); dev_free(s->ins_pred);
+  dev_free(s->uloc); dev_free(s->ucls); dev_free(s->ufirst); dev_free(s->ins_dst); dev_free(s->ins_val); dev_free(s->ins_pred);
   dev_free(s->block_tmp); dev_free(s->hist); dev_free(s->pr_acc); dev_free(s->misc);
   dev_free(s->snap.dest); dev_free(s->snap.val); dev_free(s->snap.leaf_cnt); dev_free(s->snap.tree);
   dev_free(s->snap.beg); dev_free(s->snap.nn);
@@ -531,15 +532,16 @@ int ppcsr_apply_batch_device(ppcsr_shard *s, const uint32_t *d_src, const uint32
                                    &pay));
   // 3. call counts and last-op-wins
   const uint64_t invalid_key = (uint64_t)s->n << 32;
-  batch::k_count_calls<<<div_up(count, batch::BT), batch::BT, 0, s->stream>>>(keys, pay, count, invalid_key, s->nn.p);
+  batch::k_count_calls<<<div_up(count, batch::BT), batch::BT, 0, s->stream>>>(keys, pay, count, invalid_key, s->nn.p,
+                                                                              sc);
   PPCSR_TRY(prim::device_scan(s, batch::InLastOfRun{keys, count, invalid_key},
-                              batch::OutUnique{keys, pay, s->ukey.p, s->uval.p}, count, nullptr, &sc->n_unique));
+                              batch::OutUnique{keys, pay, invalid_key, s->ukey.p, s->uval.p, s->ufirst.p}, count, nullptr, &sc->n_unique));
   CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
   // 4. locate + per-leaf counts
   CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
   CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
   batch::k_locate<<<div_up(count, batch::BT), batch::BT, 0, s->stream>>>(
-      s->ukey.p, s->uval.p, &sc->n_unique, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift, s->uloc.p,
+      s->ukey.p, s->uval.p, s->ufirst.p, &sc->n_unique, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift, s->uloc.p,
       s->ucls.p, s->ins_cnt.p, s->del_cnt.p, sc);
   PPCSR_TRY(prim::device_scan(
       s, prim::bounded_in(batch::InIsInsert{s->ucls.p}, &sc->n_unique),
@@ -979,7 +981,7 @@ int ppcsr_debug_sort_pairs(int device, uint64_t *keys, uint32_t *payload, uint64
     CUDA_TRY(cudaMemcpy(payload, rp, count * 4, cudaMemcpyDeviceToHost));
   }
   dev_free(tmp.key_a); dev_free(tmp.key_b); dev_free(tmp.pay_a); dev_free(tmp.pay_b);
-  dev_free(tmp.ukey); dev_free(tmp.uval); dev_free(tmp.uloc); dev_free(tmp.ucls);
+  dev_free(tmp.ukey); dev_free(tmp.uval); dev_free(tmp.uloc); dev_free(tmp.ucls); dev_free(tmp.ufirst);
   dev_free(tmp.ins_dst); dev_free(tmp.ins_val); dev_free(tmp.ins_pred);
   dev_free(tmp.hist); dev_free(tmp.block_tmp);
   return rc;

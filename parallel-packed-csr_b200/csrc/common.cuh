@@ -184,6 +184,7 @@ struct ppcsr_shard {
   DevBuf<uint32_t> uval;               // [batch]
   DevBuf<uint32_t> uloc;               // [batch] slot: predecessor (new insert) or hit (exists)
   DevBuf<uint8_t> ucls;                // [batch] class
+  DevBuf<uint8_t> ufirst;              // [batch] first op of the key in this batch is a remove
   DevBuf<uint32_t> ins_dst, ins_val, ins_pred;  // [batch] compacted pure inserts, key order
   DevBuf<uint32_t> block_tmp;          // scan/sort block scratch
   DevBuf<uint32_t> hist;               // radix histograms
