@@ -78,6 +78,9 @@ typedef struct {
   float ms_locate;         /* segmented search + per-leaf counts                             */
   float ms_select;         /* count tree + bottom-up window selection                        */
   float ms_rebalance;      /* scan + scatter rebalance (+ copy back for multi-CTA windows)   */
+  float ms_rebalance_kernel; /* the k_rebalance launch alone (roofline numerator: rebalance_bytes / this) */
+  uint32_t kernel_launches;  /* kernels launched for this batch                                */
+  uint32_t reserved0;
 } ppcsr_batch_stats;
 
 typedef struct {

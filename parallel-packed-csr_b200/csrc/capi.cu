@@ -128,6 +128,7 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
   PPCSR_TRY(reserve_window_arrays(s, list_cap));
   const size_t cap = std::min<size_t>(L, list_cap);
 
+  s->launches += 2;  // leaf counts + select
   win::k_leaf_new_counts<<<div_up(L, win::WT), win::WT, 0, s->stream>>>(s->leaf_cnt.p, s->ins_cnt.p, s->del_cnt.p, L,
                                                                       s->tree.p);
   PPCSR_TRY(win::tree_rebuild(s, s->tree.p, g.H));
@@ -192,6 +193,8 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
 
   if (h.n_windows == 0 && !whole) {
     st->n_windows = 0;
+    CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
   } else if (!whole) {
     reb::Args A{};
     A.src_dest = s->dest.p;
@@ -216,7 +219,10 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     A.n_windows = (uint32_t)h.n_windows;
     A.ls_src = A.ls_dst = g.leaf_shift;
     A.m_dst_override = 0;
+    s->launches += 2 + (h.multi_slots ? 1 : 0);
+    CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
     reb::k_rebalance<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(A);
+    CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     if (h.multi_slots) {
       reb::k_copy_back<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(s->windows.p, (uint32_t)h.n_windows,
                                                                         g.leaf_shift, s->dest_alt.p, s->val_alt.p,
@@ -262,7 +268,10 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     A.ls_src = g.leaf_shift;
     A.ls_dst = g2.leaf_shift;
     A.m_dst_override = g2.n_leaves;
+    s->launches += 5;
+    CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
     reb::k_rebalance<<<hw->n_chunks, reb::RT, 0, s->stream>>>(A);
+    CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     CUDA_TRY(cudaGetLastError());
     std::swap(s->dest, s->dest_alt);
     std::swap(s->val, s->val_alt);
@@ -304,6 +313,9 @@ int finalize_stats(ppcsr_shard *s, ppcsr_batch_stats *st) {
   st->ms_select = t;
   CUDA_TRY(cudaEventElapsedTime(&t, s->ev[3], s->ev[4]));
   st->ms_rebalance = t;
+  CUDA_TRY(cudaEventElapsedTime(&t, s->ev[5], s->ev[6]));
+  st->ms_rebalance_kernel = t;
+  st->kernel_launches = s->launches;
   s->last = *st;
   return PPCSR_OK;
 }
@@ -516,6 +528,7 @@ int ppcsr_apply_batch_device(ppcsr_shard *s, const uint32_t *d_src, const uint32
   BatchScalars *sc = s->d_scalars;
   CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(BatchScalars), s->stream));
   CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
+  s->launches = 3;  // build_keys, count_calls, locate
 
   // 1. keys + guards
   const unsigned kb = std::min<unsigned>(div_up(count, batch::BT * 8), 148 * 16);
@@ -612,6 +625,7 @@ int ppcsr_add_nodes(ppcsr_shard *s, uint32_t count) {
   BatchScalars *sc = s->d_scalars;
   CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(BatchScalars), s->stream));
   for (int e = 0; e < 3; e++) CUDA_TRY(cudaEventRecord(s->ev[e], s->stream));
+  s->launches = 2;
   CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
   CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
   PPCSR_TRY(dev_reserve(s->misc, 16, s->stream));

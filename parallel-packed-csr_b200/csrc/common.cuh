@@ -158,6 +158,7 @@ struct ppcsr_shard {
   uint32_t n = 0;        // vertices
   uint64_t items = 0;    // live slots (edges + sentinels), host mirror of tree[1]
   uint32_t epoch = 0;    // batch counter, stamps `mark`
+  uint32_t launches = 0; // kernels launched since the current batch started
 
   DevBuf<uint32_t> dest, val;          // [N]
   DevBuf<uint32_t> dest_alt, val_alt;  // out-of-place target (resize / multi-CTA windows)
@@ -196,7 +197,7 @@ struct ppcsr_shard {
   void *h_pinned = nullptr;            // pinned staging for small D2H/H2D
   size_t h_pinned_bytes = 0;
 
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[8] = {};  // 0 start, 1 sorted, 2 located, 3 selected, 4 done, 5/6 around k_rebalance
   ppcsr_batch_stats last{};
   Snapshot snap;
 };

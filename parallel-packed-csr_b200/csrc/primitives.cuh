@@ -115,6 +115,7 @@ int device_scan(ppcsr_shard *s, In in, Out out, size_t n, uint32_t *d_total32, u
   }
   const unsigned nb = div_up(n, SCAN_TILE);
   PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)nb + 1, s->stream));
+  s->launches += 3;
   k_scan_reduce<<<nb, SCAN_THREADS, 0, s->stream>>>(in, n, s->block_tmp.p);
   k_scan_spine<<<1, 1024, 0, s->stream>>>(s->block_tmp.p, nb, d_total32, d_total64);
   k_scan_apply<<<nb, SCAN_THREADS, 0, s->stream>>>(in, out, n, s->block_tmp.p);
@@ -262,6 +263,7 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
       const int width = (bits - done) < 8 ? (bits - done) : 8;
       const uint32_t mask = (1u << width) - 1u;
       const int shift = base + done;
+      s->launches += 2;
       k_radix_hist<<<nblocks, SORT_THREADS, 0, s->stream>>>(src_k, n, shift, mask, s->hist.p, nblocks);
       PPCSR_TRY(device_scan(s, InArray{s->hist.p}, OutPrefixWithTotal{s->hist.p, (size_t)RADIX * nblocks},
                             (size_t)RADIX * nblocks, nullptr, nullptr));

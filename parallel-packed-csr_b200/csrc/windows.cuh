@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(WT) k_tree_up5(uint32_t *__restrict__ tree, ui
 inline int tree_rebuild(ppcsr_shard *s, uint32_t *tree, uint32_t H) {
   for (int D = (int)H; D > 0; D -= 5) {
     const uint32_t nodes = 1u << D;
+    s->launches++;
     k_tree_up5<<<div_up(nodes, WT), WT, 0, s->stream>>>(tree, (uint32_t)D);
   }
   CUDA_TRY(cudaGetLastError());

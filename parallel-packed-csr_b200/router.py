@@ -1,0 +1,182 @@
+"""Vertex-range shards, one per GPU, with NCCL all-to-all routing of update batches.
+
+The reference's PPPCSR (src/pppcsr/PPPCSR.cpp:13-66) splits [0,n) into contiguous vertex ranges, one PCSR
+per NUMA domain, and ThreadPoolPPPCSR::submit_* (src/thread_pool_pppcsr/thread_pool_pppcsr.cpp:96-118)
+hands every op to a thread of the domain that owns `src`.  Here a range is a shard on one GPU (one process
+per GPU, torch.distributed over NCCL for the plumbing) and that hand-over is: bin the batch by owner on the
+device (C-ABI ppcsr_bin_by_owner), exchange the counts, ONE all-to-all of packed (src,dst) records, then
+the owning shard applies what it received.  Shards never exchange edges afterwards (the reference's
+migration hooks are empty stubs, src/pcsr/PCSR.cpp:1447-1468).
+
+`binner` / `shard_factory` are injectable so the host-side logic (shard table, split sizes, exchange) is
+testable on CPU with the gloo backend; the defaults are the CUDA kernels and fail loudly without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+
+def equal_vertex_starts(n: int, parts: int) -> np.ndarray:
+    """The reference's split: parts equal vertex counts, remainder to the last (PPPCSR.cpp:20,27-29)."""
+    size = n // parts
+    starts = [p * size for p in range(parts)] + [n]
+    return np.asarray(starts, dtype=np.uint64)
+
+
+def owner_of(starts: np.ndarray, v: int) -> int:
+    """reference PPPCSR::get_partiton (PPPCSR.cpp:58-66): first boundary > v, else the last partition."""
+    parts = len(starts) - 1
+    for i in range(1, parts):
+        if starts[i] > v:
+            return i - 1
+    return parts - 1
+
+
+def edge_balanced_starts(core_src, n: int, parts: int, dist=None) -> np.ndarray:
+    """Contiguous vertex ranges holding ~equal numbers of core edges (R-MAT puts ~44 % of the sources in the
+    first eighth of the id space).  `core_src`: this rank's slice of the core sources (torch)."""
+    import torch
+
+    hist = torch.bincount(core_src.long(), minlength=n)
+    if dist is not None:
+        dist.all_reduce(hist)
+    csum = torch.cumsum(hist, 0)
+    total = int(csum[-1].item())
+    targets = torch.tensor([total * p // parts for p in range(1, parts)], device=csum.device, dtype=csum.dtype)
+    cuts = torch.searchsorted(csum, targets, right=False).cpu().numpy().astype(np.int64) + 1
+    starts = np.zeros(parts + 1, dtype=np.int64)
+    starts[parts] = n
+    for p in range(1, parts):
+        starts[p] = min(max(int(cuts[p - 1]), starts[p - 1] + 1), n - (parts - p))
+    return starts.astype(np.uint64)
+
+
+def split_counts_by_owner(src: np.ndarray, starts: np.ndarray) -> np.ndarray:
+    """Host statement of the all-to-all send counts (used by tests): updates per owning shard."""
+    owners = np.searchsorted(np.asarray(starts[1:-1], dtype=np.uint64), np.asarray(src, dtype=np.uint64), side="right")
+    return np.bincount(owners, minlength=len(starts) - 1).astype(np.int64)
+
+
+class CudaBinner:
+    """Device binning through the C-ABI (k_bin_count / k_bin_scatter): stable, src made shard-local."""
+
+    def __init__(self, device_index: int):
+        from . import load_library
+
+        self.L = load_library()
+        self.device_index = device_index
+
+    def __call__(self, starts_dev, parts, src, dst, val):
+        import torch
+
+        count = src.numel()
+        out_src = torch.empty_like(src)
+        out_dst = torch.empty_like(dst)
+        out_val = torch.empty_like(src) if val is not None else None
+        counts = (C.c_uint64 * parts)()
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = self.L.ppcsr_bin_by_owner(self.device_index, stream, starts_dev.data_ptr(), parts, src.data_ptr(),
+                                       dst.data_ptr(), val.data_ptr() if val is not None else None, count,
+                                       out_src.data_ptr(), out_dst.data_ptr(),
+                                       out_val.data_ptr() if out_val is not None else None, counts)
+        if rc != 0:
+            raise RuntimeError(f"ppcsr_bin_by_owner failed: {self.L.ppcsr_last_error().decode()}")
+        return out_src, out_dst, out_val, [int(c) for c in counts]
+
+
+class TorchBinner:
+    """Pure-torch statement of the same binning (stable sort by owner).  TEST DOUBLE for the CPU/gloo tests;
+    the product path uses CudaBinner."""
+
+    def __call__(self, starts_dev, parts, src, dst, val):
+        import torch
+
+        owners = torch.searchsorted(starts_dev[1:parts].contiguous(), src.long(), right=True)
+        order = torch.argsort(owners, stable=True)
+        counts = torch.bincount(owners, minlength=parts).tolist()
+        local = (src.long() - starts_dev[owners]).to(src.dtype)
+        return local[order], dst[order], (val[order] if val is not None else None), counts
+
+
+class ShardedGraph:
+    """PPPCSR recast: rank r owns sources [starts[r], starts[r+1]) in a Shard on its GPU."""
+
+    def __init__(self, n, starts, rank, world, device_index, dist=None, shard_factory=None, binner=None):
+        import torch
+
+        self.n, self.rank, self.world, self.dist = int(n), rank, world, dist
+        self.starts = np.asarray(starts, dtype=np.uint64)
+        assert len(self.starts) == world + 1 and self.starts[0] == 0 and self.starts[-1] == n
+        self.n_local = int(self.starts[rank + 1] - self.starts[rank])
+        if shard_factory is None:
+            from . import Shard
+
+            shard_factory = lambda n_local: Shard(n_local, device=device_index)  # noqa: E731
+        self.shard = shard_factory(self.n_local)
+        self.torch = torch
+        on_gpu = torch.cuda.is_available() and not isinstance(binner, TorchBinner)
+        self.dev = torch.device("cuda", device_index) if on_gpu else torch.device("cpu")
+        self.binner = binner if binner is not None else (CudaBinner(device_index) if world > 1 else None)
+        self.starts_dev = torch.from_numpy(self.starts.astype(np.int64)).to(self.dev)
+        self.last_route = None
+
+    def get_partition(self, v: int) -> int:
+        return owner_of(self.starts, v)
+
+    # ---- routing ----
+    def route(self, src, dst, val=None):
+        """Returns this rank's share of the global batch: (local_src, dst, val) tensors, after one all-to-all."""
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return src, dst, val
+        b_src, b_dst, b_val, send = self.binner(self.starts_dev, self.world, src, dst, val)
+        send_t = torch.tensor(send, dtype=torch.int64, device=src.device)
+        recv_t = torch.empty_like(send_t)
+        dist.all_to_all_single(recv_t, send_t)
+        recv = recv_t.tolist()
+        packed = (b_src.long() << 32) | (b_dst.long() & 0xFFFFFFFF)
+        got = torch.empty(sum(recv), dtype=torch.int64, device=src.device)
+        dist.all_to_all_single(got, packed, output_split_sizes=recv, input_split_sizes=send)
+        r_src = (got >> 32).to(src.dtype)
+        r_dst = (got & 0xFFFFFFFF).to(dst.dtype)
+        r_val = None
+        if val is not None:
+            r_val = torch.empty(sum(recv), dtype=val.dtype, device=src.device)
+            dist.all_to_all_single(r_val, b_val, output_split_sizes=recv, input_split_sizes=send)
+        self.last_route = {"send": send, "recv": recv}
+        return r_src, r_dst, r_val
+
+    def apply(self, src, dst, val=None, default_val=1):
+        """Device tensors (int32 bit patterns of u32 ids) holding this rank's slice of the global batch."""
+        r_src, r_dst, r_val = self.route(src, dst, val)
+        r_src, r_dst = r_src.contiguous(), r_dst.contiguous()
+        return self.shard.apply_device(r_src.data_ptr(), r_dst.data_ptr(),
+                                       r_val.contiguous().data_ptr() if r_val is not None else None,
+                                       r_src.numel(), default_val)
+
+    def apply_host(self, src, dst, val=None, default_val=1):
+        """Host (pinned) numpy arrays: the public end-to-end call. H2D happens inside."""
+        if self.world == 1:
+            return self.shard.apply(src, dst, val, default_val)
+        torch = self.torch
+        d_src = torch.from_numpy(src).to(self.dev, non_blocking=True)
+        d_dst = torch.from_numpy(dst).to(self.dev, non_blocking=True)
+        d_val = torch.from_numpy(val).to(self.dev, non_blocking=True) if val is not None else None
+        return self.apply(d_src, d_dst, d_val, default_val)
+
+    # ---- PageRank across shards: every shard pushes into a full-length vector, then one all-reduce ----
+    def pagerank_step(self, values_global):
+        """values_global: float64 device tensor of length n (replicated). Returns the summed push result."""
+        torch = self.torch
+        lo, hi = int(self.starts[self.rank]), int(self.starts[self.rank + 1])
+        local_in = values_global[lo:hi].contiguous()
+        out = torch.zeros(self.n, dtype=torch.float64, device=values_global.device)
+        from . import _check
+
+        _check(self.shard.L.ppcsr_pagerank_push_device(self.shard.h, local_in.data_ptr(), out.data_ptr(), self.n))
+        self.shard.sync()
+        if self.world > 1:
+            self.dist.all_reduce(out)
+        return out

@@ -49,8 +49,13 @@ def _base_hash(idx, seed):
 
 def rmat(scale: int, lo: int, hi: int, seed: int, device=None):
     """Edges [lo, hi) of the R-MAT stream `seed`. Returns (src, dst) int64 arrays/tensors."""
+    return rmat_at(scale, _arange(lo, hi, device), seed)
+
+
+def rmat_at(scale: int, idx, seed: int):
+    """Edges of the R-MAT stream `seed` at the given int64 element indices (numpy array or torch tensor)."""
+    device = None if isinstance(idx, np.ndarray) else idx.device
     with np.errstate(over="ignore"):
-        idx = _arange(lo, hi, device)
         h0 = _base_hash(idx, seed)
         src = idx * 0
         dst = idx * 0

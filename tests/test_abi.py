@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import ctypes as C
 
-    assert C.sizeof(pp.BatchStats) == 12 * 8 + 2 * 4 + 5 * 4 + 4  # trailing pad to 8
+    assert C.sizeof(pp.BatchStats) == 12 * 8 + 2 * 4 + 6 * 4 + 2 * 4
     assert C.sizeof(pp.Geometry) == 32
     assert C.sizeof(pp.InvariantReport) == 80
 
