@@ -219,13 +219,16 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     A.n_windows = (uint32_t)h.n_windows;
     A.ls_src = A.ls_dst = g.leaf_shift;
     A.m_dst_override = 0;
-    s->launches += 2 + (h.multi_slots ? 1 : 0);
+    PPCSR_TRY(dev_reserve(s->plan, (size_t)h.n_chunks, s->stream));
+    A.plan = s->plan.p;
+    reb::k_plan_chunks<<<div_up(h.n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
+        s->windows.p, (uint32_t)h.n_windows, s->rank_off.p, g.leaf_shift, 0, (uint32_t)h.n_chunks, s->plan.p);
+    s->launches += 3 + (h.multi_slots ? 1 : 0);
     CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
     reb::k_rebalance<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(A);
     CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     if (h.multi_slots) {
-      reb::k_copy_back<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(s->windows.p, (uint32_t)h.n_windows,
-                                                                        g.leaf_shift, s->dest_alt.p, s->val_alt.p,
+      reb::k_copy_back<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(s->windows.p, s->plan.p, g.leaf_shift, s->dest_alt.p, s->val_alt.p,
                                                                         s->dest.p, s->val.p);
     }
     reb::k_copy_u32<<<div_up(L, 256), 256, 0, s->stream>>>(s->leaf_cnt.p, s->tree.p + L, L);
@@ -268,7 +271,11 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     A.ls_src = g.leaf_shift;
     A.ls_dst = g2.leaf_shift;
     A.m_dst_override = g2.n_leaves;
-    s->launches += 5;
+    PPCSR_TRY(dev_reserve(s->plan, (size_t)hw->n_chunks, s->stream));
+    A.plan = s->plan.p;
+    reb::k_plan_chunks<<<div_up(hw->n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
+        s->windows.p, 1u, s->rank_off.p, g2.leaf_shift, g2.n_leaves, hw->n_chunks, s->plan.p);
+    s->launches += 6;
     CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
     reb::k_rebalance<<<hw->n_chunks, reb::RT, 0, s->stream>>>(A);
     CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
@@ -437,7 +444,7 @@ void ppcsr_destroy(ppcsr_shard *s) {
   dev_free(s->leaf_cnt); dev_free(s->tree); dev_free(s->beg); dev_free(s->nn);
   dev_free(s->ins_cnt); dev_free(s->del_cnt); dev_free(s->rank_off); dev_free(s->ins_off);
   dev_free(s->mark); dev_free(s->touched); dev_free(s->touched_win); dev_free(s->windows);
-  dev_free(s->win_chunk_off); dev_free(s->key_a); dev_free(s->key_b); dev_free(s->pay_a); dev_free(s->pay_b);
+  dev_free(s->win_chunk_off); dev_free(s->plan); dev_free(s->key_a); dev_free(s->key_b); dev_free(s->pay_a); dev_free(s->pay_b);
   dev_free(s->in_src); dev_free(s->in_dst); dev_free(s->in_val); dev_free(s->ukey); dev_free(s->uval);
   dev_free(s->uloc); dev_free(s->ucls); dev_free(s->ufirst); dev_free(s->ins_dst); dev_free(s->ins_val); dev_free(s->ins_pred);
   dev_free(s->block_tmp); dev_free(s->hist); dev_free(s->pr_acc); dev_free(s->misc);

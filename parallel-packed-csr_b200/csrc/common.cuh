@@ -150,6 +150,15 @@ struct WindowDesc {
   uint32_t n_chunks;
 };
 
+// Where one rebalance CTA (one chunk of CHUNK_SLOTS output slots) finds its work: precomputed by
+// k_plan_chunks so that no CTA runs a serial binary search while 255 threads wait at a barrier.
+struct ChunkPlan {
+  uint32_t win;   // index into the window list
+  uint32_t i_lo;  // first source leaf (relative to the window) feeding the chunk's rank range
+  uint32_t i_hi;  // last source leaf; i_lo > i_hi means the chunk receives no items
+  uint32_t pad;
+};
+
 struct ppcsr_shard {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -176,6 +185,7 @@ struct ppcsr_shard {
   DevBuf<uint32_t> touched_win;        // [n_leaves] window node of each touched leaf
   DevBuf<WindowDesc> windows;          // [n_leaves]
   DevBuf<uint32_t> win_chunk_off;      // [n_leaves+1]
+  DevBuf<ChunkPlan> plan;              // [n_chunks]
 
   // per-batch update-granular scratch
   DevBuf<uint64_t> key_a, key_b;       // [batch]

@@ -41,11 +41,11 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total,
 template <class In>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, size_t n, uint32_t *block_sums) {
   __shared__ uint32_t s_warp[33];
-  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + threadIdx.x;  // coalesced: item k*256 + tid
   uint32_t sum = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
-    size_t i = base + k;
+    size_t i = base + (size_t)k * SCAN_THREADS;
     if (i < n) sum += in(i);
   }
   uint32_t total;
@@ -77,25 +77,44 @@ __global__ void __launch_bounds__(1024) k_scan_spine(uint32_t *block_sums, uint3
   }
 }
 
+// padded index: thread t later reads the 8 consecutive items t*8..t*8+7 without bank conflicts
+__device__ __forceinline__ uint32_t scan_pad(uint32_t j) { return j + (j >> 5); }
+
+// Loads and stores are evaluated in coalesced order (item k*256 + tid); the tile is transposed through
+// shared memory so that each thread scans 8 consecutive items.
 template <class In, class Out>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(In in, Out out, size_t n, const uint32_t *block_sums) {
   __shared__ uint32_t s_warp[33];
-  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  __shared__ uint32_t s_v[SCAN_TILE + SCAN_TILE / 32];
+  __shared__ uint32_t s_ex[SCAN_TILE + SCAN_TILE / 32];
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const uint32_t j = k * SCAN_THREADS + threadIdx.x;
+    const size_t i = base + j;
+    s_v[scan_pad(j)] = (i < n) ? in(i) : 0u;
+  }
+  __syncthreads();
   uint32_t v[SCAN_ITEMS];
   uint32_t sum = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
-    size_t i = base + k;
-    v[k] = (i < n) ? in(i) : 0;
+    v[k] = s_v[scan_pad(threadIdx.x * SCAN_ITEMS + k)];
     sum += v[k];
   }
   uint32_t total;
   uint32_t ex = block_excl_scan(sum, &total, s_warp) + block_sums[blockIdx.x];
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
-    size_t i = base + k;
-    if (i < n) out(i, ex, v[k]);
+    s_ex[scan_pad(threadIdx.x * SCAN_ITEMS + k)] = ex;
     ex += v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const uint32_t j = k * SCAN_THREADS + threadIdx.x;
+    const size_t i = base + j;
+    if (i < n) out(i, s_ex[scan_pad(j)], s_v[scan_pad(j)]);
   }
 }
 
@@ -188,21 +207,32 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint64_t *__r
   for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = s_hist[d];
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint64_t *__restrict__ keys,
-                                                                const uint32_t *__restrict__ pay, size_t n,
-                                                                int shift, uint32_t mask,
-                                                                const uint32_t *__restrict__ offs, uint32_t nblocks,
-                                                                uint64_t *__restrict__ out_keys,
-                                                                uint32_t *__restrict__ out_pay) {
+// dynamic shared memory of k_radix_scatter: the tile in block-sorted order (keys, payloads) so that the
+// global stores are coalesced runs per digit
+constexpr size_t SCATTER_SMEM = (size_t)SORT_TILE * (sizeof(uint64_t) + sizeof(uint32_t));
+
+__global__ void __launch_bounds__(SORT_THREADS, 3) k_radix_scatter(const uint64_t *__restrict__ keys,
+                                                                   const uint32_t *__restrict__ pay, size_t n,
+                                                                   int shift, uint32_t mask,
+                                                                   const uint32_t *__restrict__ offs, uint32_t nblocks,
+                                                                   uint64_t *__restrict__ out_keys,
+                                                                   uint32_t *__restrict__ out_pay) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_dyn);
+  uint32_t *s_pay = reinterpret_cast<uint32_t *>(s_dyn + (size_t)SORT_TILE * sizeof(uint64_t));
   __shared__ uint32_t s_cnt[SORT_WARPS][RADIX];
+  __shared__ uint32_t s_dbase[RADIX];  // first position of the digit inside the block-sorted tile
+  __shared__ uint32_t s_goff[RADIX];   // global offset of the digit's run minus s_dbase
+  __shared__ uint32_t s_warp[33];
   for (int d = threadIdx.x; d < SORT_WARPS * RADIX; d += SORT_THREADS) (&s_cnt[0][0])[d] = 0;
   __syncthreads();
   const unsigned w = threadIdx.x >> 5, l = lane_id();
   const unsigned lt = lanemask_lt();
   // warp w owns the contiguous sub-tile [w*512, (w+1)*512): round r covers 32 consecutive keys
-  const size_t wbase = (size_t)blockIdx.x * SORT_TILE + (size_t)w * (32 * SORT_ROUNDS);
+  const size_t tile0 = (size_t)blockIdx.x * SORT_TILE;
+  const size_t wbase = tile0 + (size_t)w * (32 * SORT_ROUNDS);
   uint64_t k[SORT_ROUNDS];
-  uint32_t rank[SORT_ROUNDS];
+  uint16_t rank[SORT_ROUNDS];
 #pragma unroll
   for (int r = 0; r < SORT_ROUNDS; r++) {
     size_t i = wbase + (size_t)r * 32 + l;
@@ -219,18 +249,23 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint64_t *
     __syncwarp();
     if (valid && (peers & lt) == 0) s_cnt[w][d] = base + __popc(peers);
     __syncwarp();
-    rank[r] = base + __popc(peers & lt);
+    rank[r] = (uint16_t)(base + __popc(peers & lt));
   }
   __syncthreads();
-  // exclusive prefix over warps per digit, seeded with this tile's global offset for the digit
-  for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) {
-    uint32_t run = offs[(size_t)d * nblocks + blockIdx.x];
+  // per digit: exclusive prefix over warps, block-wide exclusive prefix over digits
+  {
+    const int d = threadIdx.x;  // SORT_THREADS == RADIX
+    uint32_t run = 0;
 #pragma unroll
     for (int ww = 0; ww < SORT_WARPS; ww++) {
       uint32_t t = s_cnt[ww][d];
       s_cnt[ww][d] = run;
       run += t;
     }
+    uint32_t total;
+    const uint32_t dbase = block_excl_scan(run, &total, s_warp);
+    s_dbase[d] = dbase;
+    s_goff[d] = offs[(size_t)d * nblocks + blockIdx.x] - dbase;
   }
   __syncthreads();
 #pragma unroll
@@ -238,10 +273,19 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint64_t *
     size_t i = wbase + (size_t)r * 32 + l;
     if (i < n) {
       const uint32_t d = (uint32_t)(k[r] >> shift) & mask;
-      const uint32_t pos = s_cnt[w][d] + rank[r];
-      out_keys[pos] = k[r];
-      out_pay[pos] = pay[i];
+      const uint32_t pos = s_dbase[d] + s_cnt[w][d] + rank[r];
+      s_keys[pos] = k[r];
+      s_pay[pos] = pay[i];
     }
+  }
+  __syncthreads();
+  const uint32_t tile_n = (uint32_t)min((size_t)SORT_TILE, n - tile0);
+  for (uint32_t j = threadIdx.x; j < tile_n; j += SORT_THREADS) {
+    const uint64_t key = s_keys[j];
+    const uint32_t d = (uint32_t)(key >> shift) & mask;
+    const uint32_t pos = s_goff[d] + j;
+    out_keys[pos] = key;
+    out_pay[pos] = s_pay[j];
   }
 }
 
@@ -254,6 +298,8 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
   if (n <= 1) return PPCSR_OK;
   const unsigned nblocks = div_up(n, SORT_TILE);
   PPCSR_TRY(dev_reserve(s->hist, (size_t)RADIX * nblocks + 1, s->stream));
+  // > 48 KB of dynamic shared memory needs an explicit opt-in (per device, cheap)
+  CUDA_TRY(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
   uint64_t *src_k = ka, *dst_k = kb;
   uint32_t *src_p = pa, *dst_p = pb;
   for (int field = 0; field < 2; field++) {
@@ -267,7 +313,7 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
       k_radix_hist<<<nblocks, SORT_THREADS, 0, s->stream>>>(src_k, n, shift, mask, s->hist.p, nblocks);
       PPCSR_TRY(device_scan(s, InArray{s->hist.p}, OutPrefixWithTotal{s->hist.p, (size_t)RADIX * nblocks},
                             (size_t)RADIX * nblocks, nullptr, nullptr));
-      k_radix_scatter<<<nblocks, SORT_THREADS, 0, s->stream>>>(src_k, src_p, n, shift, mask, s->hist.p, nblocks,
+      k_radix_scatter<<<nblocks, SORT_THREADS, SCATTER_SMEM, s->stream>>>(src_k, src_p, n, shift, mask, s->hist.p, nblocks,
                                                                dst_k, dst_p);
       CUDA_TRY(cudaGetLastError());
       uint64_t *tk = src_k;

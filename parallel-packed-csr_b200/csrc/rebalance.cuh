@@ -37,7 +37,10 @@ struct Args {
   uint32_t n_windows;
   uint32_t ls_src, ls_dst;
   uint32_t m_dst_override;  // != 0: resize, the single window maps onto this many output leaves from leaf 0
+  const ChunkPlan *plan;    // one entry per CTA
 };
+
+constexpr uint32_t CLAMP_THRESHOLD = 256;  // leaves with more inserts than this get their insert range clamped
 
 __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t *a, uint32_t n, uint32_t key) {
   uint32_t lo = 0, hi = n;  // first index with a[idx] > key
@@ -58,25 +61,51 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t 
   return lo;
 }
 
+// One thread per chunk: which window the chunk belongs to and which source leaves feed its rank range.
+__global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict__ windows, uint32_t n_windows,
+                                                    const uint32_t *__restrict__ rank_off, uint32_t ls_dst,
+                                                    uint32_t m_dst_override, uint32_t n_chunks,
+                                                    ChunkPlan *__restrict__ plan) {
+  const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk >= n_chunks) return;
+  uint32_t lo = 0, hi = n_windows;  // last window with chunk0 <= chunk
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (windows[mid].chunk0 <= chunk) lo = mid;
+    else hi = mid;
+  }
+  const WindowDesc w = windows[lo];
+  const uint32_t m_dst = m_dst_override ? m_dst_override : w.m;
+  const uint32_t CL = CHUNK_SLOTS >> ls_dst;
+  const uint32_t o_lo = (chunk - w.chunk0) * CL;
+  const uint32_t o_hi = min(o_lo + CL, m_dst);
+  const uint64_t j = w.items;
+  const uint32_t a = (uint32_t)rank_begin(o_lo, j, m_dst);
+  const uint32_t b = (uint32_t)rank_begin(o_hi, j, m_dst);
+  ChunkPlan p;
+  p.win = lo;
+  p.pad = 0;
+  if (b > a) {
+    const uint32_t *R = rank_off + w.leaf0;
+    const uint32_t R0 = R[0];
+    p.i_lo = upper_bound_u32(R, w.m, R0 + a) - 1;      // source leaf holding rank a
+    p.i_hi = upper_bound_u32(R, w.m, R0 + b - 1) - 1;  // source leaf holding rank b-1
+  } else {
+    p.i_lo = 1;
+    p.i_hi = 0;
+  }
+  plan[chunk] = p;
+}
+
 __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
   __shared__ __align__(16) uint32_t s_dest[CHUNK_SLOTS];
   __shared__ __align__(16) uint32_t s_val[CHUNK_SLOTS];
   __shared__ uint32_t t_mask[TILE_LEAVES], t_rank[TILE_LEAVES], t_ioff[TILE_LEAVES + 1];
-  __shared__ WindowDesc s_w;
-  __shared__ uint32_t s_ilo, s_ihi, s_qb, s_qe;
+  __shared__ uint32_t s_qb, s_qe;
 
   const uint32_t chunk = blockIdx.x;
-  if (threadIdx.x == 0) {
-    uint32_t lo = 0, hi = A.n_windows;  // last window with chunk0 <= chunk
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (A.windows[mid].chunk0 <= chunk) lo = mid;
-      else hi = mid;
-    }
-    s_w = A.windows[lo];
-  }
-  __syncthreads();
-  const WindowDesc w = s_w;
+  const ChunkPlan plan = A.plan[chunk];
+  const WindowDesc w = A.windows[plan.win];
   const uint32_t logN_src = 1u << A.ls_src, logN_dst = 1u << A.ls_dst;
   const uint32_t m_dst = A.m_dst_override ? A.m_dst_override : w.m;
   const uint32_t dst_leaf0 = A.m_dst_override ? 0u : w.leaf0;
@@ -93,13 +122,7 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
   const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
 
   if (b > a) {
-    if (threadIdx.x == 0) {
-      const uint32_t *R = A.rank_off + w.leaf0;
-      s_ilo = upper_bound_u32(R, w.m, R0 + a) - 1;      // source leaf holding rank a
-      s_ihi = upper_bound_u32(R, w.m, R0 + b - 1) - 1;  // source leaf holding rank b-1
-    }
-    __syncthreads();
-    const uint32_t i_lo = s_ilo, i_hi = s_ihi;
+    const uint32_t i_lo = plan.i_lo, i_hi = plan.i_hi;
     for (uint32_t tile = i_lo; tile <= i_hi; tile += TILE_LEAVES) {
       const uint32_t tl_n = min((uint32_t)TILE_LEAVES, i_hi - tile + 1);
       // phase A: kept items of the tile's leaves, one warp per leaf (a leaf is <= 32 slots)
@@ -132,40 +155,49 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
       __syncthreads();
       // phase B: the tile's inserts.  Only the first and last source leaf of the chunk can straddle the
       // chunk's rank range; clamp there by binary search on the (strictly increasing) insert ranks.
-      if (threadIdx.x == 0) {
-        uint32_t qb = t_ioff[0], qe = t_ioff[tl_n];
-        if (tile == i_lo) {
-          const uint32_t io = t_ioff[0], ie = t_ioff[1];
-          const uint32_t mask = t_mask[0], Ri = t_rank[0];
-          uint32_t lo = io, hi = ie;  // first q with rank(q) >= a
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            const uint32_t f = A.ins_pred[mid] & (logN_src - 1u);
-            const uint32_t r = Ri + (mid - io) + (uint32_t)__popc(mask & ((2u << f) - 1u));
-            if (r < a) lo = mid + 1;
-            else hi = mid;
+      // Inserts whose rank falls outside [a,b) are skipped by the range test below, so clamping is only an
+      // optimisation for hub leaves whose insert run spans many chunks (CTA-uniform condition).
+      const bool clamp_lo = tile == i_lo && (t_ioff[1] - t_ioff[0]) > CLAMP_THRESHOLD;
+      const bool clamp_hi = tile + tl_n - 1 == i_hi && (t_ioff[tl_n] - t_ioff[tl_n - 1]) > CLAMP_THRESHOLD;
+      uint32_t q_begin = t_ioff[0], q_end = t_ioff[tl_n];
+      if (clamp_lo || clamp_hi) {
+        if (threadIdx.x == 0) {
+          uint32_t qb = t_ioff[0], qe = t_ioff[tl_n];
+          if (clamp_lo) {
+            const uint32_t io = t_ioff[0], ie = t_ioff[1];
+            const uint32_t mask = t_mask[0], Ri = t_rank[0];
+            uint32_t lo = io, hi = ie;  // first q with rank(q) >= a
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi) >> 1;
+              const uint32_t f = A.ins_pred[mid] & (logN_src - 1u);
+              const uint32_t r = Ri + (mid - io) + (uint32_t)__popc(mask & ((2u << f) - 1u));
+              if (r < a) lo = mid + 1;
+              else hi = mid;
+            }
+            qb = lo;
           }
-          qb = lo;
-        }
-        if (tile + tl_n - 1 == i_hi) {
-          const uint32_t io = t_ioff[tl_n - 1], ie = t_ioff[tl_n];
-          const uint32_t mask = t_mask[tl_n - 1], Ri = t_rank[tl_n - 1];
-          uint32_t lo = io, hi = ie;  // first q with rank(q) >= b
-          while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            const uint32_t f = A.ins_pred[mid] & (logN_src - 1u);
-            const uint32_t r = Ri + (mid - io) + (uint32_t)__popc(mask & ((2u << f) - 1u));
-            if (r < b) lo = mid + 1;
-            else hi = mid;
+          if (clamp_hi) {
+            const uint32_t io = t_ioff[tl_n - 1], ie = t_ioff[tl_n];
+            const uint32_t mask = t_mask[tl_n - 1], Ri = t_rank[tl_n - 1];
+            uint32_t lo = io, hi = ie;  // first q with rank(q) >= b
+            while (lo < hi) {
+              const uint32_t mid = (lo + hi) >> 1;
+              const uint32_t f = A.ins_pred[mid] & (logN_src - 1u);
+              const uint32_t r = Ri + (mid - io) + (uint32_t)__popc(mask & ((2u << f) - 1u));
+              if (r < b) lo = mid + 1;
+              else hi = mid;
+            }
+            qe = lo;
           }
-          qe = lo;
+          s_qb = qb;
+          s_qe = max(qb, qe);
         }
-        s_qb = qb;
-        s_qe = max(qb, qe);
+        __syncthreads();
+        q_begin = s_qb;
+        q_end = s_qe;
       }
-      __syncthreads();
       const uint32_t tile_leaf0 = w.leaf0 + tile;
-      for (uint32_t q = s_qb + threadIdx.x; q < s_qe; q += RT) {
+      for (uint32_t q = q_begin + threadIdx.x; q < q_end; q += RT) {
         const uint32_t pred = A.ins_pred[q];
         const uint32_t li = (pred >> A.ls_src) - tile_leaf0;
         const uint32_t f = pred & (logN_src - 1u);
@@ -203,23 +235,12 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
 }
 
 // copy the chunks of multi-CTA windows back from the out-of-place target into the live array
-__global__ void __launch_bounds__(RT) k_copy_back(const WindowDesc *__restrict__ windows, uint32_t n_windows,
-                                                  uint32_t ls, const uint32_t *__restrict__ alt_dest,
+__global__ void __launch_bounds__(RT) k_copy_back(const WindowDesc *__restrict__ windows,
+                                                  const ChunkPlan *__restrict__ plan, uint32_t ls, const uint32_t *__restrict__ alt_dest,
                                                   const uint32_t *__restrict__ alt_val, uint32_t *__restrict__ dest,
                                                   uint32_t *__restrict__ val) {
-  __shared__ WindowDesc s_w;
   const uint32_t chunk = blockIdx.x;
-  if (threadIdx.x == 0) {
-    uint32_t lo = 0, hi = n_windows;
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (windows[mid].chunk0 <= chunk) lo = mid;
-      else hi = mid;
-    }
-    s_w = windows[lo];
-  }
-  __syncthreads();
-  const WindowDesc w = s_w;
+  const WindowDesc w = windows[plan[chunk].win];
   if (w.n_chunks <= 1) return;
   const uint32_t CL = CHUNK_SLOTS >> ls;
   const uint32_t o_lo = (chunk - w.chunk0) * CL;
