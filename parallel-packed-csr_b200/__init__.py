@@ -127,7 +127,11 @@ def _np_ptr(a):
 def _u32_array(a, n=None):
     if a is None:
         return None
-    a = np.ascontiguousarray(a, dtype=np.uint32)
+    a = np.asarray(a)
+    if a.dtype == np.int32 and a.flags.c_contiguous:
+        a = a.view(np.uint32)  # same bits, no copy (pinned buffers stay pinned)
+    else:
+        a = np.ascontiguousarray(a, dtype=np.uint32)
     if n is not None and a.shape != (n,):
         a = np.ascontiguousarray(np.broadcast_to(a, (n,)))
     return a

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(BT) k_build_keys(const uint32_t *__restrict__ 
     const uint32_t v = val ? val[i] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
     keys[i] = ok ? (((uint64_t)s << 32) | d) : ((uint64_t)n << 32);
-    pay[i] = ok ? v : 0u;
+    if (pay) pay[i] = ok ? v : 0u;
     if (ok) my_or |= d;
     else my_bad++;
   }
@@ -48,65 +48,6 @@ __global__ void __launch_bounds__(BT) k_build_keys(const uint32_t *__restrict__ 
   if (threadIdx.x == 0) {
     if (s_or) atomicOr(&sc->dst_or, s_or);
     if (s_bad) atomicAdd(&sc->n_ignored, (unsigned long long)s_bad);
-  }
-}
-
-// ---- last op wins + call counts ----------------------------------------------------------------
-struct InLastOfRun {
-  const uint64_t *keys;
-  size_t count;
-  uint64_t invalid_key;
-  __device__ uint32_t operator()(size_t i) const {
-    const uint64_t k = keys[i];
-    if (k >= invalid_key) return 0;
-    return (i + 1 == count || keys[i + 1] != k) ? 1u : 0u;
-  }
-};
-struct OutUnique {
-  const uint64_t *keys;
-  const uint32_t *pay;
-  uint64_t invalid_key;
-  uint64_t *ukey;
-  uint32_t *uval;
-  uint8_t *ufirst_del;  // 1 if the FIRST op of the key's run in this batch is a remove
-  __device__ void operator()(size_t i, uint32_t ex, uint32_t own) const {
-    const uint64_t k = keys[i];
-    if (own) {
-      ukey[ex] = k;
-      uval[ex] = pay[i];
-    }
-    // `ex` = number of complete runs before i = index of i's run in the unique list
-    if (k < invalid_key && (i == 0 || keys[i - 1] != k)) ufirst_del[ex] = pay[i] == 0 ? 1 : 0;
-  }
-};
-
-// num_neighbors += (#add calls) - (#remove calls) per source over the WHOLE sorted batch, duplicates
-// included (reference PCSR.cpp:1392 and :747).  Sorted by src => warp-aggregated atomics.
-// Also counts the removes that the sequential reference would report as `not found` because the previous
-// op on the same key in this batch was already a remove (reference PCSR.cpp:750-754).
-__global__ void __launch_bounds__(BT) k_count_calls(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay,
-                                                    size_t count, uint64_t invalid_key, uint32_t *__restrict__ nn,
-                                                    BatchScalars *sc) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t s = 0xFFFFFFFFu;
-  int delta = 0;
-  bool dup_miss = false;
-  if (i < count) {
-    const uint64_t k = keys[i];
-    if (k < invalid_key) {
-      s = (uint32_t)(k >> 32);
-      delta = pay[i] != 0 ? 1 : -1;
-      dup_miss = delta < 0 && i > 0 && keys[i - 1] == k && pay[i - 1] == 0;
-    }
-  }
-  const unsigned dm = __ballot_sync(0xFFFFFFFFu, dup_miss);
-  if (dm && lane_id() == 0) atomicAdd(&sc->n_not_found, (unsigned long long)__popc(dm));
-  const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
-  const unsigned adds = __ballot_sync(0xFFFFFFFFu, delta > 0);
-  const unsigned dels = __ballot_sync(0xFFFFFFFFu, delta < 0);
-  if (s != 0xFFFFFFFFu && (peers & lanemask_lt()) == 0) {
-    const int sum = __popc(peers & adds) - __popc(peers & dels);
-    if (sum) atomicAdd(&nn[s], (uint32_t)sum);
   }
 }
 
@@ -152,40 +93,75 @@ __device__ __forceinline__ bool find_edge(const uint32_t *__restrict__ dest, con
   return false;
 }
 
-__global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ ukey, const uint32_t *__restrict__ uval,
-                                               const uint8_t *__restrict__ ufirst_del,
-                                               const unsigned long long *__restrict__ n_unique,
+// One thread per SORTED batch element.  Fuses what used to be three passes:
+//   * num_neighbors += (#add calls) - (#remove calls) per source over the whole batch, duplicates included
+//     (reference PCSR.cpp:1392 and :747); sorted by src => one warp-aggregated atomic per run;
+//   * last-op-wins: only the last element of a run of equal keys acts on the structure (the batch result
+//     equals the sequential reference on the same stream);
+//   * the segmented search of the winner and the per-leaf insert/delete counts.
+// `not found` follows the sequential rule (reference PCSR.cpp:750-754): a remove misses iff the previous op
+// on the same key in this batch was a remove, or it is the key's first op and the edge is absent.
+// pay == nullptr: every payload equals default_val (keys-only sort).
+__global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay,
+                                               uint32_t default_val, size_t count, uint64_t invalid_key,
                                                const uint32_t *__restrict__ dest, uint32_t *__restrict__ val,
                                                const uint32_t *__restrict__ leaf_cnt, const uint32_t *__restrict__ beg,
-                                               uint32_t ls, uint32_t *__restrict__ uloc, uint8_t *__restrict__ ucls,
-                                               uint32_t *__restrict__ ins_cnt, uint32_t *__restrict__ del_cnt,
-                                               BatchScalars *sc) {
-  __shared__ uint32_t s_stat[4];
-  if (threadIdx.x < 4) s_stat[threadIdx.x] = 0;
+                                               uint32_t ls, uint32_t *__restrict__ nn, uint32_t *__restrict__ uloc,
+                                               uint8_t *__restrict__ ucls, uint32_t *__restrict__ ins_cnt,
+                                               uint32_t *__restrict__ del_cnt, BatchScalars *sc) {
+  __shared__ uint32_t s_stat[5];
+  if (threadIdx.x < 5) s_stat[threadIdx.x] = 0;
   __syncthreads();
-  const size_t U = (size_t)*n_unique;
-  const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t cls = 0xFFu, leaf = 0xFFFFFFFFu;
-  bool first_miss = false;  // the key's first op is a remove and the key is absent: a sequential `not found`
-  if (u < U) {
-    const uint64_t k = ukey[u];
-    const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k, v = uval[u];
-    uint32_t slot;
-    const bool hit = find_edge(dest, leaf_cnt, beg[s], beg[s + 1], ls, d, &slot);
-    if (v != 0) {
-      cls = hit ? CLS_OVERWRITE : CLS_INSERT;
-      if (hit) val[slot] = v;  // duplicate insert overwrites the value (reference PCSR.cpp:529-532)
-    } else {
-      cls = hit ? CLS_DELETE : CLS_MISS;
-      if (hit) val[slot] = 0;  // tombstone; compacted away by the rebalance of this leaf (PCSR.cpp:605-606)
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned lt = lanemask_lt();
+  uint32_t cls = 0xFFu, leaf = 0xFFFFFFFFu, s = 0xFFFFFFFFu;
+  int delta = 0;
+  bool miss_dup = false, miss_first = false, winner = false;
+  if (i < count) {
+    const uint64_t k = keys[i];
+    if (k < invalid_key) {
+      s = (uint32_t)(k >> 32);
+      const uint32_t v = pay ? pay[i] : default_val;
+      delta = v != 0 ? 1 : -1;
+      const bool same_prev = i > 0 && keys[i - 1] == k;
+      winner = i + 1 == count || keys[i + 1] != k;
+      // a remove right after a remove of the same key: the sequential reference reports `not found`
+      if (v == 0 && same_prev && (pay ? pay[i - 1] : default_val) == 0) miss_dup = true;
+      if (winner) {
+        bool first_del = v == 0;  // is the FIRST op of this key's run a remove?
+        if (same_prev) {
+          size_t h = i - 1;
+          while (h > 0 && keys[h - 1] == k) h--;
+          first_del = (pay ? pay[h] : default_val) == 0;
+        }
+        const uint32_t d = (uint32_t)k;
+        uint32_t slot;
+        const bool hit = find_edge(dest, leaf_cnt, beg[s], beg[s + 1], ls, d, &slot);
+        if (v != 0) {
+          cls = hit ? CLS_OVERWRITE : CLS_INSERT;
+          if (hit) val[slot] = v;  // duplicate insert overwrites the value (reference PCSR.cpp:529-532)
+        } else {
+          cls = hit ? CLS_DELETE : CLS_MISS;
+          if (hit) val[slot] = 0;  // tombstone; compacted away by the rebalance of this leaf (PCSR.cpp:605-606)
+        }
+        if (first_del && !hit) miss_first = true;  // counted on the winner: the run's head op found nothing
+        uloc[i] = slot;
+        leaf = slot >> ls;
+      }
     }
-    first_miss = ufirst_del[u] != 0 && !hit;
-    uloc[u] = slot;
-    ucls[u] = (uint8_t)cls;
-    leaf = slot >> ls;
+    ucls[i] = (uint8_t)cls;
+  }
+  // call counts: one atomic per run of equal sources inside the warp
+  {
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
+    const unsigned adds = __ballot_sync(0xFFFFFFFFu, delta > 0);
+    const unsigned dels = __ballot_sync(0xFFFFFFFFu, delta < 0);
+    if (s != 0xFFFFFFFFu && (peers & lt) == 0) {
+      const int sum = __popc(peers & adds) - __popc(peers & dels);
+      if (sum) atomicAdd(&nn[s], (uint32_t)sum);
+    }
   }
   // per-leaf counts: the batch is key-sorted, so equal leaves are adjacent -> one atomic per warp run
-  const unsigned lt = lanemask_lt();
   {
     const uint32_t key = (cls == CLS_INSERT) ? leaf : 0xFFFFFFFFu;
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
@@ -196,19 +172,28 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ ukey
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
     if (key != 0xFFFFFFFFu && (peers & lt) == 0) atomicAdd(&del_cnt[leaf], (uint32_t)__popc(peers));
   }
-#pragma unroll
-  for (uint32_t c = 0; c < 4; c++) {
-    // CLS_MISS only says "nothing to remove physically"; the reported not-found count follows the
-    // sequential rule: first op of the key is a remove of an absent edge (+ the repeats counted earlier)
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, c == CLS_MISS ? first_miss : cls == c);
-    if (lane_id() == 0 && m) atomicAdd(&s_stat[c], (uint32_t)__popc(m));
+  {
+    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, cls == CLS_INSERT);
+    const unsigned m1 = __ballot_sync(0xFFFFFFFFu, cls == CLS_OVERWRITE);
+    const unsigned m2 = __ballot_sync(0xFFFFFFFFu, cls == CLS_DELETE);
+    const unsigned m3 = __ballot_sync(0xFFFFFFFFu, miss_dup);
+    const unsigned m5 = __ballot_sync(0xFFFFFFFFu, miss_first);
+    const unsigned m4 = __ballot_sync(0xFFFFFFFFu, winner);
+    if (lane_id() == 0) {
+      if (m0) atomicAdd(&s_stat[0], (uint32_t)__popc(m0));
+      if (m1) atomicAdd(&s_stat[1], (uint32_t)__popc(m1));
+      if (m2) atomicAdd(&s_stat[2], (uint32_t)__popc(m2));
+      if (m3 | m5) atomicAdd(&s_stat[3], (uint32_t)(__popc(m3) + __popc(m5)));
+      if (m4) atomicAdd(&s_stat[4], (uint32_t)__popc(m4));
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (s_stat[CLS_INSERT]) atomicAdd(&sc->n_inserted, (unsigned long long)s_stat[CLS_INSERT]);
-    if (s_stat[CLS_OVERWRITE]) atomicAdd(&sc->n_overwritten, (unsigned long long)s_stat[CLS_OVERWRITE]);
-    if (s_stat[CLS_DELETE]) atomicAdd(&sc->n_deleted, (unsigned long long)s_stat[CLS_DELETE]);
-    if (s_stat[CLS_MISS]) atomicAdd(&sc->n_not_found, (unsigned long long)s_stat[CLS_MISS]);
+    if (s_stat[0]) atomicAdd(&sc->n_inserted, (unsigned long long)s_stat[0]);
+    if (s_stat[1]) atomicAdd(&sc->n_overwritten, (unsigned long long)s_stat[1]);
+    if (s_stat[2]) atomicAdd(&sc->n_deleted, (unsigned long long)s_stat[2]);
+    if (s_stat[3]) atomicAdd(&sc->n_not_found, (unsigned long long)s_stat[3]);
+    if (s_stat[4]) atomicAdd(&sc->n_unique, (unsigned long long)s_stat[4]);
   }
 }
 
@@ -218,14 +203,15 @@ struct InIsInsert {
   __device__ uint32_t operator()(size_t i) const { return ucls[i] == CLS_INSERT ? 1u : 0u; }
 };
 struct OutInsert {
-  const uint64_t *ukey;
-  const uint32_t *uval;
+  const uint64_t *keys;  // sorted batch
+  const uint32_t *pay;   // nullable: all default_val
+  uint32_t default_val;
   const uint32_t *uloc;
   uint32_t *ins_dst, *ins_val, *ins_pred;
   __device__ void operator()(size_t i, uint32_t ex, uint32_t own) const {
     if (own) {
-      ins_dst[ex] = (uint32_t)ukey[i];
-      ins_val[ex] = uval[i];
+      ins_dst[ex] = (uint32_t)keys[i];
+      ins_val[ex] = pay ? pay[i] : default_val;
       ins_pred[ex] = uloc[i];
     }
   }

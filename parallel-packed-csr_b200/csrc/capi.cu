@@ -42,11 +42,8 @@ int reserve_batch_arrays(ppcsr_shard *s, size_t count) {
   PPCSR_TRY(dev_reserve(s->key_b, count, s->stream));
   PPCSR_TRY(dev_reserve(s->pay_a, count, s->stream));
   PPCSR_TRY(dev_reserve(s->pay_b, count, s->stream));
-  PPCSR_TRY(dev_reserve(s->ukey, count, s->stream));
-  PPCSR_TRY(dev_reserve(s->uval, count, s->stream));
   PPCSR_TRY(dev_reserve(s->uloc, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ucls, count, s->stream));
-  PPCSR_TRY(dev_reserve(s->ufirst, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_dst, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_val, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_pred, count, s->stream));
@@ -56,6 +53,7 @@ int reserve_batch_arrays(ppcsr_shard *s, size_t count) {
 int reserve_window_arrays(ppcsr_shard *s, size_t count) {
   const size_t cap = std::min<size_t>(s->geo.n_leaves, count) + 1;
   PPCSR_TRY(dev_reserve(s->touched, cap, s->stream));
+  PPCSR_TRY(dev_reserve(s->touched_win, cap, s->stream));
   PPCSR_TRY(dev_reserve(s->windows, cap, s->stream));
   return PPCSR_OK;
 }
@@ -141,15 +139,22 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
                                                                   s->mark.p, s->epoch, sc);
   }
   const uint32_t CL = reb::CHUNK_SLOTS >> g.leaf_shift;
-  PPCSR_TRY(prim::device_scan(
-      s, prim::bounded_in(win::InWindowHead{s->touched.p, s->mark.p, s->epoch, L}, &sc->n_touched),
-      win::OutWindow{s->touched.p, s->mark.p, s->tree.p, s->epoch, L, CL, s->windows.p}, cap, nullptr, &sc->n_windows));
-  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinChunks{s->windows.p}, &sc->n_windows),
-                              prim::bounded_out(win::OutWinChunk0{s->windows.p}, &sc->n_windows), cap, nullptr,
+  const unsigned int *skip = &sc->root_violation;  // a violated root needs no window list (whole-array rebuild)
+  if (cap) {
+    s->launches++;
+    win::k_touched_windows<<<div_up(cap, win::WT), win::WT, 0, s->stream>>>(s->touched.p, &sc->n_touched, s->mark.p,
+                                                                           s->epoch, L, sc, s->touched_win.p);
+  }
+  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWindowHead{s->touched_win.p}, &sc->n_touched, skip),
+                              prim::bounded_out(win::OutWindow{s->touched_win.p, s->tree.p, L, CL, s->windows.p},
+                                                &sc->n_touched, skip),
+                              cap, nullptr, &sc->n_windows));
+  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinChunks{s->windows.p}, &sc->n_windows, skip),
+                              prim::bounded_out(win::OutWinChunk0{s->windows.p}, &sc->n_windows, skip), cap, nullptr,
                               &sc->n_chunks));
-  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinSlots{s->windows.p, g.logN, false}, &sc->n_windows),
+  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinSlots{s->windows.p, g.logN, false}, &sc->n_windows, skip),
                               prim::OutNothing{}, cap, nullptr, &sc->window_slots));
-  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinSlots{s->windows.p, g.logN, true}, &sc->n_windows),
+  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinSlots{s->windows.p, g.logN, true}, &sc->n_windows, skip),
                               prim::OutNothing{}, cap, nullptr, &sc->multi_slots));
   // R[] and the per-leaf insert offsets feed the rebalance
   PPCSR_TRY(prim::device_scan(s, prim::InArray{s->tree.p + L}, prim::OutPrefixWithTotal{s->rank_off.p, L}, L, nullptr,
@@ -495,6 +500,7 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
     s->epoch = 0;
     const size_t wcap = std::min<uint64_t>(g.n_leaves, max_batch ? max_batch : g.n_leaves) + 1;
     PPCSR_TRY(dev_reserve(s->touched, wcap, s->stream));
+    PPCSR_TRY(dev_reserve(s->touched_win, wcap, s->stream));
     PPCSR_TRY(dev_reserve(s->windows, wcap, s->stream));
     PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)div_up(g.N, prim::SCAN_TILE) + 2, s->stream));
   } else {
@@ -506,8 +512,8 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
     PPCSR_TRY(dev_reserve(s->in_src, max_batch, s->stream));
     PPCSR_TRY(dev_reserve(s->in_dst, max_batch, s->stream));
     PPCSR_TRY(dev_reserve(s->in_val, max_batch, s->stream));
-    PPCSR_TRY(dev_reserve(s->hist, (size_t)prim::RADIX * div_up(max_batch, prim::SORT_TILE) + 1, s->stream));
-    PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)div_up((size_t)prim::RADIX * div_up(max_batch, prim::SORT_TILE),
+    PPCSR_TRY(dev_reserve(s->hist, (size_t)prim::RADIX_MAX * div_up(max_batch, prim::SORT_TILE) + 1, s->stream));
+    PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)div_up((size_t)prim::RADIX_MAX * div_up(max_batch, prim::SORT_TILE),
                                                        prim::SCAN_TILE) + 2, s->stream));
   }
   CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -535,37 +541,34 @@ int ppcsr_apply_batch_device(ppcsr_shard *s, const uint32_t *d_src, const uint32
   BatchScalars *sc = s->d_scalars;
   CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(BatchScalars), s->stream));
   CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
-  s->launches = 3;  // build_keys, count_calls, locate
+  s->launches = 2;  // build_keys, locate
 
-  // 1. keys + guards
+  // 1. keys + guards.  With no per-update values every payload is default_val: sort keys only.
+  const bool has_pay = d_val != nullptr;
   const unsigned kb = std::min<unsigned>(div_up(count, batch::BT * 8), 148 * 16);
   batch::k_build_keys<<<kb, batch::BT, 0, s->stream>>>(d_src, d_dst, d_val, default_val, count, s->n, s->key_a.p,
-                                                      s->pay_a.p, sc);
+                                                      has_pay ? s->pay_a.p : nullptr, sc);
   CUDA_TRY(cudaGetLastError());
   PPCSR_TRY(read_scalars(s));
   const int lo_bits = std::max(1, bits_of(s->h_scalars->dst_or));
-  const int hi_bits = std::max(1, bits_of(s->n));
+  // rejected updates carry the key (n << 32): they need bits_of(n) source bits, valid ones bits_of(n-1)
+  const int hi_bits = std::max(1, s->h_scalars->n_ignored ? bits_of(s->n) : bits_of(s->n ? s->n - 1 : 0));
   // 2. stable radix sort by (src,dst)
   uint64_t *keys;
   uint32_t *pay;
-  PPCSR_TRY(prim::radix_sort_pairs(s, s->key_a.p, s->pay_a.p, s->key_b.p, s->pay_b.p, count, lo_bits, hi_bits, &keys,
-                                   &pay));
-  // 3. call counts and last-op-wins
-  const uint64_t invalid_key = (uint64_t)s->n << 32;
-  batch::k_count_calls<<<div_up(count, batch::BT), batch::BT, 0, s->stream>>>(keys, pay, count, invalid_key, s->nn.p,
-                                                                              sc);
-  PPCSR_TRY(prim::device_scan(s, batch::InLastOfRun{keys, count, invalid_key},
-                              batch::OutUnique{keys, pay, invalid_key, s->ukey.p, s->uval.p, s->ufirst.p}, count, nullptr, &sc->n_unique));
+  PPCSR_TRY(prim::radix_sort_pairs(s, s->key_a.p, has_pay ? s->pay_a.p : nullptr, s->key_b.p, s->pay_b.p, count,
+                                   lo_bits, hi_bits, &keys, &pay));
   CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
-  // 4. locate + per-leaf counts
+  // 3+4. call counts, last-op-wins, locate, per-leaf counts -- one kernel over the sorted batch
+  const uint64_t invalid_key = (uint64_t)s->n << 32;
   CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
   CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
   batch::k_locate<<<div_up(count, batch::BT), batch::BT, 0, s->stream>>>(
-      s->ukey.p, s->uval.p, s->ufirst.p, &sc->n_unique, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift, s->uloc.p,
-      s->ucls.p, s->ins_cnt.p, s->del_cnt.p, sc);
+      keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
+      s->nn.p, s->uloc.p, s->ucls.p, s->ins_cnt.p, s->del_cnt.p, sc);
   PPCSR_TRY(prim::device_scan(
-      s, prim::bounded_in(batch::InIsInsert{s->ucls.p}, &sc->n_unique),
-      batch::OutInsert{s->ukey.p, s->uval.p, s->uloc.p, s->ins_dst.p, s->ins_val.p, s->ins_pred.p}, count, nullptr,
+      s, batch::InIsInsert{s->ucls.p},
+      batch::OutInsert{keys, pay, default_val, s->uloc.p, s->ins_dst.p, s->ins_val.p, s->ins_pred.p}, count, nullptr,
       nullptr));
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
   // 5. windows + rebalance

@@ -15,6 +15,7 @@
 // with 16-byte stores.  Algorithmic traffic: every window slot is read once and written once.
 #pragma once
 #include "common.cuh"
+#include "primitives.cuh"
 
 namespace reb {
 
@@ -97,10 +98,15 @@ __global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict
   plan[chunk] = p;
 }
 
+constexpr int LEAVES_PER_WARP = TILE_LEAVES / RWARPS;
+constexpr int MAX_CHUNK_LEAVES = CHUNK_SLOTS / 8;  // smallest leaf is 8 slots (N >= 32)
+
 __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
   __shared__ __align__(16) uint32_t s_dest[CHUNK_SLOTS];
   __shared__ __align__(16) uint32_t s_val[CHUNK_SLOTS];
-  __shared__ uint32_t t_mask[TILE_LEAVES], t_rank[TILE_LEAVES], t_ioff[TILE_LEAVES + 1];
+  __shared__ uint32_t s_a[MAX_CHUNK_LEAVES + 1];  // first rank of every output leaf of the chunk
+  __shared__ uint32_t t_cnt[TILE_LEAVES], t_mask[TILE_LEAVES], t_rank[TILE_LEAVES], t_ioff[TILE_LEAVES + 1];
+  __shared__ uint32_t s_pred[TILE_LEAVES][32];    // inserts whose predecessor is offset f of tile leaf li
   __shared__ uint32_t s_qb, s_qe;
 
   const uint32_t chunk = blockIdx.x;
@@ -112,51 +118,56 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
   const uint32_t CL = CHUNK_SLOTS >> A.ls_dst;  // output leaves per chunk
   const uint32_t o_lo = (chunk - w.chunk0) * CL;
   const uint32_t o_hi = min(o_lo + CL, m_dst);
+  const uint32_t n_out = o_hi - o_lo;
   const uint64_t j = w.items;
-  const uint32_t a = (uint32_t)rank_begin(o_lo, j, m_dst);
-  const uint32_t b = (uint32_t)rank_begin(o_hi, j, m_dst);
   const uint32_t R0 = A.rank_off[w.leaf0];
   const bool multi = w.n_chunks > 1;
   uint32_t *out_dest = multi ? A.out_dest_multi : A.out_dest_single;
   uint32_t *out_val = multi ? A.out_val_multi : A.out_val_single;
   const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
 
+  for (uint32_t x = threadIdx.x; x <= n_out; x += RT) s_a[x] = (uint32_t)rank_begin((uint64_t)o_lo + x, j, m_dst);
+  __syncthreads();
+  const uint32_t a = s_a[0], b = s_a[n_out];
+
   if (b > a) {
     const uint32_t i_lo = plan.i_lo, i_hi = plan.i_hi;
     for (uint32_t tile = i_lo; tile <= i_hi; tile += TILE_LEAVES) {
       const uint32_t tl_n = min((uint32_t)TILE_LEAVES, i_hi - tile + 1);
-      // phase A: kept items of the tile's leaves, one warp per leaf (a leaf is <= 32 slots)
-      for (uint32_t li = warp; li < tl_n; li += RWARPS) {
-        const uint32_t i = w.leaf0 + tile + li;
-        const uint32_t c_old = A.leaf_cnt[i];
-        const uint32_t Ri = A.rank_off[i] - R0;
-        const uint32_t io = A.ins_off[i], ic = A.ins_off[i + 1] - io;
-        const uint32_t slot = (i << A.ls_src) + lane;
-        const bool live = lane < c_old && lane < logN_src;
-        const uint32_t d = live ? A.src_dest[slot] : 0u;
-        const uint32_t v = live ? A.src_val[slot] : 0u;
-        const bool kept = live && v != 0u;
-        const unsigned mask = __ballot_sync(0xFFFFFFFFu, kept);
-        if (kept) {
-          const uint32_t ib = ic ? lower_bound_u32(A.ins_pred + io, ic, slot) : 0u;  // inserts with pred < slot
-          const uint32_t r = Ri + (uint32_t)__popc(mask & lt) + ib;
-          if (r >= a && r < b) {
-            s_dest[r - a] = d;
-            s_val[r - a] = v;
-          }
-        }
-        if (lane == 0) {
-          t_mask[li] = mask;
-          t_rank[li] = Ri;
-          t_ioff[li] = io;
-          if (li == tl_n - 1) t_ioff[tl_n] = io + ic;
+      const uint32_t tile_leaf0 = w.leaf0 + tile;
+      // A0: per-leaf metadata of the tile in one coalesced sweep
+      for (uint32_t li = threadIdx.x; li < tl_n; li += RT) {
+        const uint32_t i = tile_leaf0 + li;
+        t_cnt[li] = A.leaf_cnt[i];
+        t_rank[li] = A.rank_off[i] - R0;
+        t_ioff[li] = A.ins_off[i];
+        if (li == tl_n - 1) t_ioff[tl_n] = A.ins_off[i + 1];
+      }
+      for (uint32_t x = threadIdx.x; x < tl_n * 32; x += RT) (&s_pred[0][0])[x] = 0;
+      __syncthreads();
+      // A1: one warp per leaf (a leaf is <= 32 slots): load the live prefix, publish the kept mask
+      uint32_t d[LEAVES_PER_WARP], v[LEAVES_PER_WARP];
+#pragma unroll
+      for (int k = 0; k < LEAVES_PER_WARP; k++) {
+        const uint32_t li = warp + k * RWARPS;
+        d[k] = 0;
+        v[k] = 0;
+        if (li < tl_n && lane < t_cnt[li]) {
+          const size_t slot = ((size_t)(tile_leaf0 + li) << A.ls_src) + lane;
+          d[k] = A.src_dest[slot];
+          v[k] = A.src_val[slot];
         }
       }
+#pragma unroll
+      for (int k = 0; k < LEAVES_PER_WARP; k++) {
+        const uint32_t li = warp + k * RWARPS;
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, v[k] != 0u);  // tombstones (val 0) drop out here
+        if (li < tl_n && lane == 0) t_mask[li] = mask;
+      }
       __syncthreads();
-      // phase B: the tile's inserts.  Only the first and last source leaf of the chunk can straddle the
-      // chunk's rank range; clamp there by binary search on the (strictly increasing) insert ranks.
-      // Inserts whose rank falls outside [a,b) are skipped by the range test below, so clamping is only an
-      // optimisation for hub leaves whose insert run spans many chunks (CTA-uniform condition).
+      // Only the first and last source leaf of the chunk can straddle its rank range [a,b).  Inserts outside
+      // the range are skipped by the test below, so clamping is only done for hub leaves whose insert run
+      // spans many chunks (CTA-uniform condition).
       const bool clamp_lo = tile == i_lo && (t_ioff[1] - t_ioff[0]) > CLAMP_THRESHOLD;
       const bool clamp_hi = tile + tl_n - 1 == i_hi && (t_ioff[tl_n] - t_ioff[tl_n - 1]) > CLAMP_THRESHOLD;
       uint32_t q_begin = t_ioff[0], q_end = t_ioff[tl_n];
@@ -196,29 +207,51 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
         q_begin = s_qb;
         q_end = s_qe;
       }
-      const uint32_t tile_leaf0 = w.leaf0 + tile;
+      // B: the tile's inserts: rank = R[i] + index in the leaf's insert run + kept items up to the predecessor
       for (uint32_t q = q_begin + threadIdx.x; q < q_end; q += RT) {
         const uint32_t pred = A.ins_pred[q];
         const uint32_t li = (pred >> A.ls_src) - tile_leaf0;
         const uint32_t f = pred & (logN_src - 1u);
         const uint32_t r = t_rank[li] + (q - t_ioff[li]) + (uint32_t)__popc(t_mask[li] & ((2u << f) - 1u));
+        atomicAdd(&s_pred[li][f], 1u);
         if (r >= a && r < b) {
           s_dest[r - a] = A.ins_dst[q];
           s_val[r - a] = A.ins_val[q];
         }
       }
       __syncthreads();
+      // A2: kept items: rank = R[i] + kept before + inserts hanging on earlier offsets (warp prefix of s_pred)
+#pragma unroll
+      for (int k = 0; k < LEAVES_PER_WARP; k++) {
+        const uint32_t li = warp + k * RWARPS;
+        if (li < tl_n) {  // warp-uniform
+          const unsigned mask = t_mask[li];
+          const uint32_t hang = s_pred[li][lane];
+          uint32_t ib = prim::warp_incl_scan(hang) - hang;
+          if ((mask >> lane) & 1u) {
+            if ((li == 0 && clamp_lo) || (li == tl_n - 1 && clamp_hi)) {
+              // clamped leaf: s_pred only saw part of its inserts -> count them in the sorted list instead
+              const uint32_t io = t_ioff[li], ic = t_ioff[li + 1] - io;
+              ib = lower_bound_u32(A.ins_pred + io, ic, ((tile_leaf0 + li) << A.ls_src) + lane);
+            }
+            const uint32_t r = t_rank[li] + (uint32_t)__popc(mask & lt) + ib;
+            if (r >= a && r < b) {
+              s_dest[r - a] = d[k];
+              s_val[r - a] = v[k];
+            }
+          }
+        }
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
   // write-out: 4 consecutive slots per thread, 16-byte stores to dest[] and val[]
-  const uint32_t out_slots = (o_hi - o_lo) << A.ls_dst;
+  const uint32_t out_slots = n_out << A.ls_dst;
   for (uint32_t x = threadIdx.x * 4; x < out_slots; x += RT * 4) {
-    const uint32_t o = o_lo + (x >> A.ls_dst);
+    const uint32_t ol = x >> A.ls_dst;
     const uint32_t f0 = x & (logN_dst - 1u);
-    const uint32_t a_o = (uint32_t)rank_begin(o, j, m_dst);
-    const uint32_t b_o = (uint32_t)rank_begin((uint64_t)o + 1, j, m_dst);
-    const size_t gslot = ((size_t)(dst_leaf0 + o) << A.ls_dst) + f0;
+    const uint32_t a_o = s_a[ol], b_o = s_a[ol + 1];
+    const size_t gslot = ((size_t)(dst_leaf0 + o_lo + ol) << A.ls_dst) + f0;
     uint32_t dd[4], vv[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -230,7 +263,7 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
     }
     *reinterpret_cast<uint4 *>(out_dest + gslot) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
     *reinterpret_cast<uint4 *>(out_val + gslot) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-    if (f0 == 0) A.tree_leaf_out[dst_leaf0 + o] = b_o - a_o;
+    if (f0 == 0) A.tree_leaf_out[dst_leaf0 + o_lo + ol] = b_o - a_o;
   }
 }
 

@@ -109,23 +109,33 @@ __device__ __forceinline__ uint32_t highest_marked(const uint32_t *__restrict__ 
   return best;
 }
 
+// window (heap index of the highest marked ancestor) of every touched leaf; skipped when the root is violated
+__global__ void __launch_bounds__(WT) k_touched_windows(const uint32_t *__restrict__ touched,
+                                                        const unsigned long long *__restrict__ n_touched,
+                                                        const uint32_t *__restrict__ mark, uint32_t epoch,
+                                                        uint32_t n_leaves, const BatchScalars *__restrict__ sc,
+                                                        uint32_t *__restrict__ touched_win) {
+  if (sc->root_violation) return;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)*n_touched) return;
+  touched_win[t] = highest_marked(mark, epoch, n_leaves + touched[t]);
+}
+
 // One window per maximal marked node; touched leaves are sorted, so leaves of the same window are adjacent.
 struct InWindowHead {
-  const uint32_t *touched, *mark;
-  uint32_t epoch, n_leaves;
+  const uint32_t *touched_win;
   __device__ uint32_t operator()(size_t t) const {
-    const uint32_t w = highest_marked(mark, epoch, n_leaves + touched[t]);
     if (t == 0) return 1u;
-    return highest_marked(mark, epoch, n_leaves + touched[t - 1]) != w ? 1u : 0u;
+    return touched_win[t - 1] != touched_win[t] ? 1u : 0u;
   }
 };
 struct OutWindow {
-  const uint32_t *touched, *mark, *tree;
-  uint32_t epoch, n_leaves, chunk_leaves;
+  const uint32_t *touched_win, *tree;
+  uint32_t n_leaves, chunk_leaves;
   WindowDesc *windows;
   __device__ void operator()(size_t t, uint32_t ex, uint32_t own) const {
     if (!own) return;
-    const uint32_t w = highest_marked(mark, epoch, n_leaves + touched[t]);
+    const uint32_t w = touched_win[t];
     const uint32_t depth = 31u - (uint32_t)__clz(w);
     const uint32_t m = n_leaves >> depth;
     WindowDesc d;
