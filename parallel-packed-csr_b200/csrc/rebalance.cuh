@@ -101,12 +101,13 @@ __global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict
 constexpr int LEAVES_PER_WARP = TILE_LEAVES / RWARPS;
 constexpr int MAX_CHUNK_LEAVES = CHUNK_SLOTS / 8;  // smallest leaf is 8 slots (N >= 32)
 
-__global__ void __launch_bounds__(RT) k_rebalance(Args A) {
-  __shared__ __align__(16) uint32_t s_dest[CHUNK_SLOTS];
+__global__ void __launch_bounds__(RT, 8) k_rebalance(Args A) {
+  __shared__ __align__(16) uint32_t s_dest[CHUNK_SLOTS];  // staged items at (rank - first rank of the chunk)
   __shared__ __align__(16) uint32_t s_val[CHUNK_SLOTS];
   __shared__ uint32_t s_a[MAX_CHUNK_LEAVES + 1];  // first rank of every output leaf of the chunk
   __shared__ uint32_t t_cnt[TILE_LEAVES], t_mask[TILE_LEAVES], t_rank[TILE_LEAVES], t_ioff[TILE_LEAVES + 1];
-  __shared__ uint32_t s_pred[TILE_LEAVES][32];    // inserts whose predecessor is offset f of tile leaf li
+  // s_last[li][f]: 1 + index (inside leaf li's insert run) of the LAST insert whose predecessor is offset f
+  __shared__ uint32_t s_last[TILE_LEAVES][32];
   __shared__ uint32_t s_qb, s_qe;
 
   const uint32_t chunk = blockIdx.x;
@@ -126,7 +127,20 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
   uint32_t *out_val = multi ? A.out_val_multi : A.out_val_single;
   const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
 
-  for (uint32_t x = threadIdx.x; x <= n_out; x += RT) s_a[x] = (uint32_t)rank_begin((uint64_t)o_lo + x, j, m_dst);
+  // s_a[x] = floor((o_lo + x) * j / m_dst).  One exact 64-bit division per CTA (x = 0); the others add
+  // floor((x*j + rem) / m_dst) whose numerator is < 2^40, so a double reciprocal is exact up to a +-1 fix-up.
+  {
+    const uint64_t base_num = (uint64_t)o_lo * j;
+    const uint64_t base_q = base_num / m_dst, base_r = base_num - base_q * m_dst;
+    const double inv_m = 1.0 / (double)m_dst;
+    for (uint32_t x = threadIdx.x; x <= n_out; x += RT) {
+      const uint64_t num = (uint64_t)x * j + base_r;
+      uint64_t q = (uint64_t)((double)num * inv_m);
+      if (q * m_dst > num) q--;
+      else if ((q + 1) * m_dst <= num) q++;
+      s_a[x] = (uint32_t)(base_q + q);
+    }
+  }
   __syncthreads();
   const uint32_t a = s_a[0], b = s_a[n_out];
 
@@ -143,7 +157,7 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
         t_ioff[li] = A.ins_off[i];
         if (li == tl_n - 1) t_ioff[tl_n] = A.ins_off[i + 1];
       }
-      for (uint32_t x = threadIdx.x; x < tl_n * 32; x += RT) (&s_pred[0][0])[x] = 0;
+      for (uint32_t x = threadIdx.x; x < tl_n * 32; x += RT) (&s_last[0][0])[x] = 0;
       __syncthreads();
       // A1: one warp per leaf (a leaf is <= 32 slots): load the live prefix, publish the kept mask
       uint32_t d[LEAVES_PER_WARP], v[LEAVES_PER_WARP];
@@ -161,8 +175,10 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
 #pragma unroll
       for (int k = 0; k < LEAVES_PER_WARP; k++) {
         const uint32_t li = warp + k * RWARPS;
-        const unsigned mask = __ballot_sync(0xFFFFFFFFu, v[k] != 0u);  // tombstones (val 0) drop out here
-        if (li < tl_n && lane == 0) t_mask[li] = mask;
+        if (li < tl_n) {  // warp-uniform
+          const unsigned mask = __ballot_sync(0xFFFFFFFFu, v[k] != 0u);  // tombstones (val 0) drop out here
+          if (lane == 0) t_mask[li] = mask;
+        }
       }
       __syncthreads();
       // Only the first and last source leaf of the chunk can straddle its rank range [a,b).  Inserts outside
@@ -212,25 +228,29 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
         const uint32_t pred = A.ins_pred[q];
         const uint32_t li = (pred >> A.ls_src) - tile_leaf0;
         const uint32_t f = pred & (logN_src - 1u);
-        const uint32_t r = t_rank[li] + (q - t_ioff[li]) + (uint32_t)__popc(t_mask[li] & ((2u << f) - 1u));
-        atomicAdd(&s_pred[li][f], 1u);
+        const uint32_t t = q - t_ioff[li];
+        const uint32_t r = t_rank[li] + t + (uint32_t)__popc(t_mask[li] & ((2u << f) - 1u));
+        atomicMax(&s_last[li][f], t + 1u);
         if (r >= a && r < b) {
           s_dest[r - a] = A.ins_dst[q];
           s_val[r - a] = A.ins_val[q];
         }
       }
       __syncthreads();
-      // A2: kept items: rank = R[i] + kept before + inserts hanging on earlier offsets (warp prefix of s_pred)
+      // A2: kept items: rank = R[i] + kept before + inserts hanging on earlier offsets.  The inserts of a leaf
+      // are ordered by predecessor, so that count is s_last of the nearest earlier offset that has any.
 #pragma unroll
       for (int k = 0; k < LEAVES_PER_WARP; k++) {
         const uint32_t li = warp + k * RWARPS;
         if (li < tl_n) {  // warp-uniform
           const unsigned mask = t_mask[li];
-          const uint32_t hang = s_pred[li][lane];
-          uint32_t ib = prim::warp_incl_scan(hang) - hang;
+          const uint32_t last = s_last[li][lane];
+          const unsigned hang = __ballot_sync(0xFFFFFFFFu, last != 0u) & lt;
+          uint32_t ib = __shfl_sync(0xFFFFFFFFu, last, hang ? 31 - __clz(hang) : 0);
+          if (!hang) ib = 0;
           if ((mask >> lane) & 1u) {
             if ((li == 0 && clamp_lo) || (li == tl_n - 1 && clamp_hi)) {
-              // clamped leaf: s_pred only saw part of its inserts -> count them in the sorted list instead
+              // clamped leaf: s_last only saw part of its inserts -> count them in the sorted list instead
               const uint32_t io = t_ioff[li], ic = t_ioff[li + 1] - io;
               ib = lower_bound_u32(A.ins_pred + io, ic, ((tile_leaf0 + li) << A.ls_src) + lane);
             }
@@ -247,24 +267,27 @@ __global__ void __launch_bounds__(RT) k_rebalance(Args A) {
   }
   // write-out: 4 consecutive slots per thread, 16-byte stores to dest[] and val[]
   const uint32_t out_slots = n_out << A.ls_dst;
+  const size_t chunk_slot0 = (size_t)(dst_leaf0 + o_lo) << A.ls_dst;
   for (uint32_t x = threadIdx.x * 4; x < out_slots; x += RT * 4) {
     const uint32_t ol = x >> A.ls_dst;
     const uint32_t f0 = x & (logN_dst - 1u);
     const uint32_t a_o = s_a[ol], b_o = s_a[ol + 1];
-    const size_t gslot = ((size_t)(dst_leaf0 + o_lo + ol) << A.ls_dst) + f0;
-    uint32_t dd[4], vv[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t r = a_o + f0 + k;
-      const bool live = r < b_o;
-      dd[k] = live ? s_dest[r - a] : 0u;
-      vv[k] = live ? s_val[r - a] : 0u;
-      if (live && dd[k] == PPCSR_SENT) A.beg[vv[k] - 1u] = (uint32_t)(gslot + k);  // fix_sentinel, PCSR.cpp:168-183
-    }
-    *reinterpret_cast<uint4 *>(out_dest + gslot) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
-    *reinterpret_cast<uint4 *>(out_val + gslot) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-    if (f0 == 0) A.tree_leaf_out[dst_leaf0 + o_lo + ol] = b_o - a_o;
+    const uint32_t base = a_o - a + f0;        // staging index of slot f0
+    const uint32_t live_n = b_o - a_o > f0 ? min(4u, b_o - a_o - f0) : 0u;  // live slots among the 4
+    uint4 dd = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
+    if (live_n > 0) { dd.x = s_dest[base]; vv.x = s_val[base]; }
+    if (live_n > 1) { dd.y = s_dest[base + 1]; vv.y = s_val[base + 1]; }
+    if (live_n > 2) { dd.z = s_dest[base + 2]; vv.z = s_val[base + 2]; }
+    if (live_n > 3) { dd.w = s_dest[base + 3]; vv.w = s_val[base + 3]; }
+    // fix_sentinel (reference PCSR.cpp:168-183): a sentinel that lands here refreshes its vertex's back pointer
+    if (dd.x == PPCSR_SENT) A.beg[vv.x - 1u] = (uint32_t)(chunk_slot0 + x);
+    if (dd.y == PPCSR_SENT) A.beg[vv.y - 1u] = (uint32_t)(chunk_slot0 + x + 1);
+    if (dd.z == PPCSR_SENT) A.beg[vv.z - 1u] = (uint32_t)(chunk_slot0 + x + 2);
+    if (dd.w == PPCSR_SENT) A.beg[vv.w - 1u] = (uint32_t)(chunk_slot0 + x + 3);
+    *reinterpret_cast<uint4 *>(out_dest + chunk_slot0 + x) = dd;
+    *reinterpret_cast<uint4 *>(out_val + chunk_slot0 + x) = vv;
   }
+  for (uint32_t x = threadIdx.x; x < n_out; x += RT) A.tree_leaf_out[dst_leaf0 + o_lo + x] = s_a[x + 1] - s_a[x];
 }
 
 // copy the chunks of multi-CTA windows back from the out-of-place target into the live array
