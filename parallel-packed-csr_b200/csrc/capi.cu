@@ -55,6 +55,7 @@ int reserve_window_arrays(ppcsr_shard *s, size_t count) {
   PPCSR_TRY(dev_reserve(s->touched, cap, s->stream));
   PPCSR_TRY(dev_reserve(s->touched_win, cap, s->stream));
   PPCSR_TRY(dev_reserve(s->windows, cap, s->stream));
+  PPCSR_TRY(dev_reserve(s->small_list, cap, s->stream));
   return PPCSR_OK;
 }
 
@@ -146,12 +147,16 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
                                                                            s->epoch, L, sc, s->touched_win.p);
   }
   PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWindowHead{s->touched_win.p}, &sc->n_touched, skip),
-                              prim::bounded_out(win::OutWindow{s->touched_win.p, s->tree.p, L, CL, s->windows.p},
+                              prim::bounded_out(win::OutWindow{s->touched_win.p, s->tree.p, L, CL, (uint32_t)reb::SMALL_MAX_LEAVES,
+                                                                s->windows.p},
                                                 &sc->n_touched, skip),
                               cap, nullptr, &sc->n_windows));
   PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinChunks{s->windows.p}, &sc->n_windows, skip),
                               prim::bounded_out(win::OutWinChunk0{s->windows.p}, &sc->n_windows, skip), cap, nullptr,
                               &sc->n_chunks));
+  PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinSmall{s->windows.p}, &sc->n_windows, skip),
+                              prim::bounded_out(win::OutWinSmall{s->small_list.p}, &sc->n_windows, skip), cap, nullptr,
+                              &sc->n_small));
   PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinSlots{s->windows.p, g.logN, false}, &sc->n_windows, skip),
                               prim::OutNothing{}, cap, nullptr, &sc->window_slots));
   PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinSlots{s->windows.p, g.logN, true}, &sc->n_windows, skip),
@@ -224,18 +229,40 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     A.n_windows = (uint32_t)h.n_windows;
     A.ls_src = A.ls_dst = g.leaf_shift;
     A.m_dst_override = 0;
-    PPCSR_TRY(dev_reserve(s->plan, (size_t)h.n_chunks, s->stream));
-    A.plan = s->plan.p;
-    reb::k_plan_chunks<<<div_up(h.n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
-        s->windows.p, (uint32_t)h.n_windows, s->rank_off.p, g.leaf_shift, 0, (uint32_t)h.n_chunks, s->plan.p);
-    s->launches += 3 + (h.multi_slots ? 1 : 0);
     CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
-    reb::k_rebalance<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(A);
+    if (h.n_small) {
+      reb::SmallArgs S{};
+      S.dest = s->dest.p;
+      S.val = s->val.p;
+      S.leaf_cnt = s->leaf_cnt.p;
+      S.rank_off = s->rank_off.p;
+      S.ins_off = s->ins_off.p;
+      S.ins_dst = s->ins_dst.p;
+      S.ins_val = s->ins_val.p;
+      S.ins_pred = s->ins_pred.p;
+      S.tree_leaf_out = s->tree.p + L;
+      S.beg = s->beg.p;
+      S.windows = s->windows.p;
+      S.small_list = s->small_list.p;
+      S.n_small = (uint32_t)h.n_small;
+      S.ls = g.leaf_shift;
+      s->launches++;
+      reb::k_rebalance_small<<<div_up(h.n_small, reb::RWARPS), reb::RT, 0, s->stream>>>(S);
+    }
+    if (h.n_chunks) {
+      PPCSR_TRY(dev_reserve(s->plan, (size_t)h.n_chunks, s->stream));
+      A.plan = s->plan.p;
+      reb::k_plan_chunks<<<div_up(h.n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
+          s->windows.p, (uint32_t)h.n_windows, s->rank_off.p, g.leaf_shift, 0, (uint32_t)h.n_chunks, s->plan.p);
+      s->launches += 2 + (h.multi_slots ? 1 : 0);
+      reb::k_rebalance<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(A);
+    }
     CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     if (h.multi_slots) {
-      reb::k_copy_back<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(s->windows.p, s->plan.p, g.leaf_shift, s->dest_alt.p, s->val_alt.p,
-                                                                        s->dest.p, s->val.p);
+      reb::k_copy_back<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(s->windows.p, s->plan.p, g.leaf_shift,
+                                                                        s->dest_alt.p, s->val_alt.p, s->dest.p, s->val.p);
     }
+    s->launches += 1;
     reb::k_copy_u32<<<div_up(L, 256), 256, 0, s->stream>>>(s->leaf_cnt.p, s->tree.p + L, L);
     PPCSR_TRY(win::tree_rebuild(s, s->tree.p, g.H));
     CUDA_TRY(cudaGetLastError());
@@ -449,7 +476,7 @@ void ppcsr_destroy(ppcsr_shard *s) {
   dev_free(s->leaf_cnt); dev_free(s->tree); dev_free(s->beg); dev_free(s->nn);
   dev_free(s->ins_cnt); dev_free(s->del_cnt); dev_free(s->rank_off); dev_free(s->ins_off);
   dev_free(s->mark); dev_free(s->touched); dev_free(s->touched_win); dev_free(s->windows);
-  dev_free(s->win_chunk_off); dev_free(s->plan); dev_free(s->key_a); dev_free(s->key_b); dev_free(s->pay_a); dev_free(s->pay_b);
+  dev_free(s->win_chunk_off); dev_free(s->plan); dev_free(s->small_list); dev_free(s->key_a); dev_free(s->key_b); dev_free(s->pay_a); dev_free(s->pay_b);
   dev_free(s->in_src); dev_free(s->in_dst); dev_free(s->in_val); dev_free(s->ukey); dev_free(s->uval);
   dev_free(s->uloc); dev_free(s->ucls); dev_free(s->ufirst); dev_free(s->ins_dst); dev_free(s->ins_val); dev_free(s->ins_pred);
   dev_free(s->block_tmp); dev_free(s->hist); dev_free(s->pr_acc); dev_free(s->misc);
@@ -502,6 +529,7 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
     PPCSR_TRY(dev_reserve(s->touched, wcap, s->stream));
     PPCSR_TRY(dev_reserve(s->touched_win, wcap, s->stream));
     PPCSR_TRY(dev_reserve(s->windows, wcap, s->stream));
+    PPCSR_TRY(dev_reserve(s->small_list, wcap, s->stream));
     PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)div_up(g.N, prim::SCAN_TILE) + 2, s->stream));
   } else {
     PPCSR_TRY(dev_reserve(s->dest_alt, s->geo.N, s->stream));

@@ -136,10 +136,12 @@ struct BatchScalars {
   unsigned long long window_slots;
   unsigned long long window_sentinels;
   unsigned long long multi_slots;   // slots in windows that need more than one CTA (copy-back path)
+  unsigned long long n_small;       // windows handled one per warp
   unsigned int dst_or;              // OR of all dst (sort width)
   unsigned int root_violation;      // bit0: root above upper bound, bit1: root below lower bound
   unsigned int pad0, pad1;
 };
+static_assert(sizeof(BatchScalars) % 8 == 0, "BatchScalars must stay 8-byte sized");
 
 struct WindowDesc {
   uint32_t node;        // heap index of the tree node
@@ -186,6 +188,7 @@ struct ppcsr_shard {
   DevBuf<WindowDesc> windows;          // [n_leaves]
   DevBuf<uint32_t> win_chunk_off;      // [n_leaves+1]
   DevBuf<ChunkPlan> plan;              // [n_chunks]
+  DevBuf<uint32_t> small_list;         // [n_windows] indices of the warp-sized windows
 
   // per-batch update-granular scratch
   DevBuf<uint64_t> key_a, key_b;       // [batch]

@@ -290,6 +290,121 @@ __global__ void __launch_bounds__(RT, 8) k_rebalance(Args A) {
   for (uint32_t x = threadIdx.x; x < n_out; x += RT) A.tree_leaf_out[dst_leaf0 + o_lo + x] = s_a[x + 1] - s_a[x];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Small windows (<= SMALL_MAX_LEAVES leaves, the overwhelmingly common case of a steady-state batch: a touched
+// leaf that stays within its bounds is its own window): ONE WARP per window, no block barriers, in place.
+// Same rank arithmetic as k_rebalance; the window's items are staged in the warp's 2 KB slice of shared memory.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SMALL_MAX_LEAVES = 8;
+constexpr int SMALL_MAX_SLOTS = SMALL_MAX_LEAVES * 32;
+
+struct SmallArgs {
+  uint32_t *dest, *val;          // rebalanced in place
+  const uint32_t *leaf_cnt, *rank_off, *ins_off;
+  const uint32_t *ins_dst, *ins_val, *ins_pred;
+  uint32_t *tree_leaf_out, *beg;
+  const WindowDesc *windows;
+  const uint32_t *small_list;    // indices of the small windows
+  uint32_t n_small;
+  uint32_t ls;
+};
+
+__global__ void __launch_bounds__(RT) k_rebalance_small(SmallArgs A) {
+  __shared__ uint32_t s_dest[RWARPS][SMALL_MAX_SLOTS];
+  __shared__ uint32_t s_val[RWARPS][SMALL_MAX_SLOTS];
+  __shared__ uint32_t s_last[RWARPS][SMALL_MAX_LEAVES][32];
+  __shared__ uint32_t s_mask[RWARPS][SMALL_MAX_LEAVES], s_rank[RWARPS][SMALL_MAX_LEAVES],
+      s_ioff[RWARPS][SMALL_MAX_LEAVES + 1];
+  const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
+  const uint32_t wid = blockIdx.x * RWARPS + warp;
+  if (wid >= A.n_small) return;  // whole warp exits together
+  const WindowDesc w = A.windows[A.small_list[wid]];
+  const uint32_t m = w.m, j = w.items, logN = 1u << A.ls;
+  const uint32_t R0 = A.rank_off[w.leaf0];
+  uint32_t *sd = s_dest[warp], *sv = s_val[warp];
+
+  // per-leaf metadata: lane k < m owns leaf k
+  uint32_t my_cnt = 0;
+  if (lane <= m) {
+    const uint32_t i = w.leaf0 + lane;
+    s_ioff[warp][lane] = A.ins_off[i];
+    if (lane < m) {
+      my_cnt = A.leaf_cnt[i];
+      s_rank[warp][lane] = A.rank_off[i] - R0;
+    }
+  }
+  for (uint32_t x = lane; x < m * 32; x += 32) (&s_last[warp][0][0])[x] = 0;
+  uint32_t d[SMALL_MAX_LEAVES], v[SMALL_MAX_LEAVES];
+#pragma unroll
+  for (int k = 0; k < SMALL_MAX_LEAVES; k++) {
+    d[k] = 0;
+    v[k] = 0;
+    const uint32_t cnt_k = __shfl_sync(0xFFFFFFFFu, my_cnt, k);
+    if ((uint32_t)k < m && lane < cnt_k) {
+      const size_t slot = ((size_t)(w.leaf0 + k) << A.ls) + lane;
+      d[k] = A.dest[slot];
+      v[k] = A.val[slot];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < SMALL_MAX_LEAVES; k++) {
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, v[k] != 0u);
+    if ((uint32_t)k < m && lane == 0) s_mask[warp][k] = mask;
+  }
+  __syncwarp();
+  // inserts of the window
+  const uint32_t q_end = s_ioff[warp][m];
+  for (uint32_t q = s_ioff[warp][0] + lane; q < q_end; q += 32) {
+    const uint32_t pred = A.ins_pred[q];
+    const uint32_t k = (pred >> A.ls) - w.leaf0;
+    const uint32_t f = pred & (logN - 1u);
+    const uint32_t t = q - s_ioff[warp][k];
+    const uint32_t r = s_rank[warp][k] + t + (uint32_t)__popc(s_mask[warp][k] & ((2u << f) - 1u));
+    atomicMax(&s_last[warp][k][f], t + 1u);
+    sd[r] = A.ins_dst[q];
+    sv[r] = A.ins_val[q];
+  }
+  __syncwarp();
+  // kept items
+#pragma unroll
+  for (int k = 0; k < SMALL_MAX_LEAVES; k++) {
+    if ((uint32_t)k < m) {  // warp-uniform
+      const unsigned mask = s_mask[warp][k];
+      const uint32_t last = s_last[warp][k][lane];
+      const unsigned hang = __ballot_sync(0xFFFFFFFFu, last != 0u) & lt;
+      uint32_t ib = __shfl_sync(0xFFFFFFFFu, last, hang ? 31 - __clz(hang) : 0);
+      if (!hang) ib = 0;
+      if ((mask >> lane) & 1u) {
+        const uint32_t r = s_rank[warp][k] + (uint32_t)__popc(mask & lt) + ib;
+        sd[r] = d[k];
+        sv[r] = v[k];
+      }
+    }
+  }
+  __syncwarp();
+  // write-out (in place: every source slot of the window has been read above)
+  const uint32_t out_slots = m << A.ls;
+  const size_t slot0 = (size_t)w.leaf0 << A.ls;
+  for (uint32_t x = lane * 4; x < out_slots; x += 32 * 4) {
+    const uint32_t ol = x >> A.ls, f0 = x & (logN - 1u);
+    const uint32_t a_o = (ol * j) / m, b_o = ((ol + 1) * j) / m;  // j <= m*(logN-1): 32-bit is plenty
+    const uint32_t live_n = b_o - a_o > f0 ? min(4u, b_o - a_o - f0) : 0u;
+    const uint32_t base = a_o + f0;
+    uint4 dd = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
+    if (live_n > 0) { dd.x = sd[base]; vv.x = sv[base]; }
+    if (live_n > 1) { dd.y = sd[base + 1]; vv.y = sv[base + 1]; }
+    if (live_n > 2) { dd.z = sd[base + 2]; vv.z = sv[base + 2]; }
+    if (live_n > 3) { dd.w = sd[base + 3]; vv.w = sv[base + 3]; }
+    if (dd.x == PPCSR_SENT) A.beg[vv.x - 1u] = (uint32_t)(slot0 + x);
+    if (dd.y == PPCSR_SENT) A.beg[vv.y - 1u] = (uint32_t)(slot0 + x + 1);
+    if (dd.z == PPCSR_SENT) A.beg[vv.z - 1u] = (uint32_t)(slot0 + x + 2);
+    if (dd.w == PPCSR_SENT) A.beg[vv.w - 1u] = (uint32_t)(slot0 + x + 3);
+    *reinterpret_cast<uint4 *>(A.dest + slot0 + x) = dd;
+    *reinterpret_cast<uint4 *>(A.val + slot0 + x) = vv;
+    if (f0 == 0) A.tree_leaf_out[w.leaf0 + ol] = b_o - a_o;
+  }
+}
+
 // copy the chunks of multi-CTA windows back from the out-of-place target into the live array
 __global__ void __launch_bounds__(RT) k_copy_back(const WindowDesc *__restrict__ windows,
                                                   const ChunkPlan *__restrict__ plan, uint32_t ls, const uint32_t *__restrict__ alt_dest,

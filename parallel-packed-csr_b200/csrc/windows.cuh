@@ -131,7 +131,7 @@ struct InWindowHead {
 };
 struct OutWindow {
   const uint32_t *touched_win, *tree;
-  uint32_t n_leaves, chunk_leaves;
+  uint32_t n_leaves, chunk_leaves, small_max_leaves;
   WindowDesc *windows;
   __device__ void operator()(size_t t, uint32_t ex, uint32_t own) const {
     if (!own) return;
@@ -143,7 +143,8 @@ struct OutWindow {
     d.m = m;
     d.leaf0 = (w - (1u << depth)) * m;
     d.items = tree[w];
-    d.n_chunks = (m + chunk_leaves - 1) / chunk_leaves;
+    // small windows are rebalanced one per warp (k_rebalance_small) and take no CTA of the chunked kernel
+    d.n_chunks = m <= small_max_leaves ? 0u : (m + chunk_leaves - 1) / chunk_leaves;
     d.chunk0 = 0;
     windows[ex] = d;
   }
@@ -156,6 +157,16 @@ struct InWinChunks {
 struct OutWinChunk0 {
   WindowDesc *w;
   __device__ void operator()(size_t i, uint32_t ex, uint32_t) const { w[i].chunk0 = ex; }
+};
+struct InWinSmall {
+  const WindowDesc *w;
+  __device__ uint32_t operator()(size_t i) const { return w[i].n_chunks == 0 ? 1u : 0u; }
+};
+struct OutWinSmall {
+  uint32_t *small_list;
+  __device__ void operator()(size_t i, uint32_t ex, uint32_t own) const {
+    if (own) small_list[ex] = (uint32_t)i;
+  }
 };
 struct InWinSlots {
   const WindowDesc *w;
