@@ -252,7 +252,8 @@ def main_b200(args):
     cs, cd = synth.rmat(scale, lo, hi, 42, device=dev)
     cs, cd = cs.to(torch.int32), cd.to(torch.int32)
     if world > 1:
-        starts = router.edge_balanced_starts(cs, n, world, dist)
+        # balance stored edges against the uniform update stream (a shard's share of it ~ its vertex count)
+        starts = router.edge_balanced_starts(cs, n, world, dist, vertex_weight=None if args.workload == "insert" else 0.0)
     else:
         starts = np.array([0, n], dtype=np.uint64)
     graph = router.ShardedGraph(n, starts, rank, world, local_rank, dist=dist)
@@ -310,6 +311,13 @@ def main_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = B * world * args.steps / (total_ms / 1e3)
+    if world > 1:  # per-rank view (stderr): how many updates each shard received and where its time went
+        s0 = stats_acc[-1]
+        print(f"[rank {rank}] local ms/step {sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)) / args.steps:.3f} "
+              f"received {s0['batch_size']} apply {s0['ms_total']:.3f} ms (sort {s0['ms_sort']:.3f} locate "
+              f"{s0['ms_locate']:.3f} select {s0['ms_select']:.3f} rebalance {s0['ms_rebalance']:.3f}) "
+              f"windows {s0['n_windows']} N {s0['slots_before']}->{s0['slots_after']} "
+              f"vertices {graph.n_local}", file=sys.stderr)
 
     # ---- end to end through the public host-buffer call: pinned host inputs, H2D inside the timed region
     hs = torch.empty(B, dtype=torch.int32).pin_memory()

@@ -134,6 +134,15 @@ int ppcsr_bin_by_owner(int device, void *cuda_stream, const uint64_t *d_starts, 
                        const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val, uint64_t count,
                        uint32_t *d_out_src, uint32_t *d_out_dst, uint32_t *d_out_val, uint64_t *h_counts);
 
+/* Same binning, but emits the packed 64-bit records (local_src << 32 | dst) that travel through the all-to-all
+ * and that ppcsr_apply_batch_packed_device consumes directly. */
+int ppcsr_bin_by_owner_packed(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts,
+                              const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val, uint64_t count,
+                              uint64_t *d_out_packed, uint32_t *d_out_val, uint64_t *h_counts);
+/* Applies a device-resident batch of packed records (src << 32 | dst), e.g. what the all-to-all delivered. */
+int ppcsr_apply_batch_packed_device(ppcsr_shard *h, const uint64_t *d_packed, const uint32_t *d_val, uint64_t count,
+                                    uint32_t default_val, ppcsr_batch_stats *stats);
+
 /* ---- reads ---- */
 int ppcsr_geometry_of(ppcsr_shard *h, ppcsr_geometry *out);
 /* reference PCSR::edge_exists (src/pcsr/PCSR.cpp:860-869); `out_value` (nullable) gets the stored value. */

@@ -73,6 +73,8 @@ SYMBOLS = {
     "ppcsr_add_nodes": (_i, [_vp, _u32]),
     "ppcsr_last_stats": (_i, [_vp, C.POINTER(BatchStats)]),
     "ppcsr_bin_by_owner": (_i, [_i, _vp, _vp, _u32, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "ppcsr_bin_by_owner_packed": (_i, [_i, _vp, _vp, _u32, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "ppcsr_apply_batch_packed_device": (_i, [_vp, _vp, _vp, _u64, _u32, C.POINTER(BatchStats)]),
     "ppcsr_geometry_of": (_i, [_vp, C.POINTER(Geometry)]),
     "ppcsr_edge_exists": (_i, [_vp, _u32, _u32, C.POINTER(_i), C.POINTER(_u32)]),
     "ppcsr_edges_exist": (_i, [_vp, _vp, _vp, _u64, _vp]),
@@ -175,6 +177,12 @@ class Shard:
         """Raw device pointers (e.g. torch tensor .data_ptr()) of uint32/int32 arrays."""
         st = BatchStats()
         _check(self.L.ppcsr_apply_batch_device(self.h, d_src, d_dst, d_val, count, default_val, C.byref(st)))
+        return st.as_dict()
+
+    def apply_packed_device(self, d_packed: int, d_val: int | None, count: int, default_val: int = 1) -> dict:
+        """Device pointer to packed u64 records (src << 32 | dst), e.g. the all-to-all result."""
+        st = BatchStats()
+        _check(self.L.ppcsr_apply_batch_packed_device(self.h, d_packed, d_val, count, default_val, C.byref(st)))
         return st.as_dict()
 
     def add_edge(self, s, d, v=1):

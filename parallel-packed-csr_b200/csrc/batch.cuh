@@ -51,6 +51,41 @@ __global__ void __launch_bounds__(BT) k_build_keys(const uint32_t *__restrict__ 
   }
 }
 
+// same guards for records that arrive already packed as (src << 32 | dst) (the all-to-all payload)
+__global__ void __launch_bounds__(BT) k_build_keys_packed(const uint64_t *__restrict__ packed,
+                                                          const uint32_t *__restrict__ val, uint32_t default_val,
+                                                          size_t count, uint32_t n, uint64_t *__restrict__ keys,
+                                                          uint32_t *__restrict__ pay, BatchScalars *sc) {
+  __shared__ uint32_t s_or, s_bad;
+  if (threadIdx.x == 0) {
+    s_or = 0;
+    s_bad = 0;
+  }
+  __syncthreads();
+  uint32_t my_or = 0, my_bad = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    const uint64_t k = packed[i];
+    const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k;
+    const uint32_t v = val ? val[i] : default_val;
+    const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
+    keys[i] = ok ? k : ((uint64_t)n << 32);
+    if (pay) pay[i] = ok ? v : 0u;
+    if (ok) my_or |= d;
+    else my_bad++;
+  }
+  my_or = __reduce_or_sync(0xFFFFFFFFu, my_or);
+  my_bad = __reduce_add_sync(0xFFFFFFFFu, my_bad);
+  if (lane_id() == 0) {
+    if (my_or) atomicOr(&s_or, my_or);
+    if (my_bad) atomicAdd(&s_bad, my_bad);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_or) atomicOr(&sc->dst_or, s_or);
+    if (s_bad) atomicAdd(&sc->n_ignored, (unsigned long long)s_bad);
+  }
+}
+
 // ---- segmented search ----------------------------------------------------------------------------
 // Finds (src,dst) inside vertex src's slot range (beg[src], beg[src+1]).  Two levels: a binary search
 // over the LEAVES of the range on their first item (empty leaves are skipped to the right), then a
@@ -255,7 +290,7 @@ __global__ void __launch_bounds__(BT) k_bin_scatter(const uint32_t *__restrict__
                                                     const uint64_t *__restrict__ starts, uint32_t parts,
                                                     const uint32_t *__restrict__ offs, uint32_t nblocks,
                                                     uint32_t *__restrict__ out_src, uint32_t *__restrict__ out_dst,
-                                                    uint32_t *__restrict__ out_val) {
+                                                    uint32_t *__restrict__ out_val, uint64_t *__restrict__ out_packed) {
   __shared__ uint32_t s_cnt[prim::SORT_WARPS][BIN_MAX_PARTS];
   __shared__ uint64_t s_st[BIN_MAX_PARTS];
   for (int d = threadIdx.x; d < prim::SORT_WARPS * BIN_MAX_PARTS; d += BT) (&s_cnt[0][0])[d] = 0;
@@ -294,8 +329,13 @@ __global__ void __launch_bounds__(BT) k_bin_scatter(const uint32_t *__restrict__
     if (i < count) {
       const uint32_t d = own[r];
       const uint32_t pos = s_cnt[w][d] + rank[r];
-      out_src[pos] = src[i] - (uint32_t)s_st[d];  // shard-local id (reference PPPCSR.cpp:46-52)
-      out_dst[pos] = dst[i];
+      const uint32_t local = src[i] - (uint32_t)s_st[d];  // shard-local id (reference PPPCSR.cpp:46-52)
+      if (out_packed) {
+        out_packed[pos] = ((uint64_t)local << 32) | dst[i];
+      } else {
+        out_src[pos] = local;
+        out_dst[pos] = dst[i];
+      }
       if (out_val) out_val[pos] = val ? val[i] : 1u;
     }
   }

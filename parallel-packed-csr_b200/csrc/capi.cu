@@ -548,9 +548,9 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
   return PPCSR_OK;
 }
 
-int ppcsr_apply_batch_device(ppcsr_shard *s, const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val,
-                             uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats) {
-  if (!s || (count && (!d_src || !d_dst))) return PPCSR_ERR_ARG;
+// shared by the (src,dst) and the packed entry points: `packed` != nullptr selects the packed key builder
+static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint32_t *d_dst, const uint64_t *d_packed,
+                               const uint32_t *d_val, uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats) {
   PPCSR_TRY(set_device(s));
   ppcsr_batch_stats st{};
   st.batch_size = count;
@@ -574,8 +574,13 @@ int ppcsr_apply_batch_device(ppcsr_shard *s, const uint32_t *d_src, const uint32
   // 1. keys + guards.  With no per-update values every payload is default_val: sort keys only.
   const bool has_pay = d_val != nullptr;
   const unsigned kb = std::min<unsigned>(div_up(count, batch::BT * 8), 148 * 16);
-  batch::k_build_keys<<<kb, batch::BT, 0, s->stream>>>(d_src, d_dst, d_val, default_val, count, s->n, s->key_a.p,
-                                                      has_pay ? s->pay_a.p : nullptr, sc);
+  if (d_packed) {
+    batch::k_build_keys_packed<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, count, s->n, s->key_a.p,
+                                                               has_pay ? s->pay_a.p : nullptr, sc);
+  } else {
+    batch::k_build_keys<<<kb, batch::BT, 0, s->stream>>>(d_src, d_dst, d_val, default_val, count, s->n, s->key_a.p,
+                                                        has_pay ? s->pay_a.p : nullptr, sc);
+  }
   CUDA_TRY(cudaGetLastError());
   PPCSR_TRY(read_scalars(s));
   const int lo_bits = std::max(1, bits_of(s->h_scalars->dst_or));
@@ -604,6 +609,18 @@ int ppcsr_apply_batch_device(ppcsr_shard *s, const uint32_t *d_src, const uint32
   PPCSR_TRY(finalize_stats(s, &st));
   if (stats) *stats = st;
   return PPCSR_OK;
+}
+
+int ppcsr_apply_batch_device(ppcsr_shard *s, const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val,
+                             uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats) {
+  if (!s || (count && (!d_src || !d_dst))) return PPCSR_ERR_ARG;
+  return apply_device_common(s, d_src, d_dst, nullptr, d_val, count, default_val, stats);
+}
+
+int ppcsr_apply_batch_packed_device(ppcsr_shard *s, const uint64_t *d_packed, const uint32_t *d_val, uint64_t count,
+                                    uint32_t default_val, ppcsr_batch_stats *stats) {
+  if (!s || (count && !d_packed)) return PPCSR_ERR_ARG;
+  return apply_device_common(s, nullptr, nullptr, d_packed, d_val, count, default_val, stats);
 }
 
 int ppcsr_apply_batch(ppcsr_shard *s, const uint32_t *src, const uint32_t *dst, const uint32_t *val, uint64_t count,
@@ -684,9 +701,9 @@ int ppcsr_last_stats(ppcsr_shard *s, ppcsr_batch_stats *stats) {
   return PPCSR_OK;
 }
 
-int ppcsr_bin_by_owner(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts,
-                       const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val, uint64_t count,
-                       uint32_t *d_out_src, uint32_t *d_out_dst, uint32_t *d_out_val, uint64_t *h_counts) {
+static int bin_common(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts, const uint32_t *d_src,
+                      const uint32_t *d_dst, const uint32_t *d_val, uint64_t count, uint32_t *d_out_src,
+                      uint32_t *d_out_dst, uint32_t *d_out_val, uint64_t *d_out_packed, uint64_t *h_counts) {
   if (n_parts == 0 || n_parts > batch::BIN_MAX_PARTS || !h_counts) return PPCSR_ERR_ARG;
   for (uint32_t p = 0; p < n_parts; p++) h_counts[p] = 0;
   if (count == 0) return PPCSR_OK;
@@ -706,7 +723,7 @@ int ppcsr_bin_by_owner(int device, void *cuda_stream, const uint64_t *d_starts, 
   }
   if (rc == PPCSR_OK) {
     batch::k_bin_scatter<<<nblocks, batch::BT, 0, st>>>(d_src, d_dst, d_val, count, d_starts, n_parts, tmp.hist.p,
-                                                       nblocks, d_out_src, d_out_dst, d_out_val);
+                                                       nblocks, d_out_src, d_out_dst, d_out_val, d_out_packed);
     std::vector<uint32_t> firsts(n_parts + 1);
     for (uint32_t p = 0; p < n_parts && rc == PPCSR_OK; p++) {
       if (cudaMemcpyAsync(&firsts[p], tmp.hist.p + (size_t)p * nblocks, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
@@ -720,6 +737,22 @@ int ppcsr_bin_by_owner(int device, void *cuda_stream, const uint64_t *d_starts, 
   dev_free(tmp.hist);
   dev_free(tmp.block_tmp);
   return rc;
+}
+
+int ppcsr_bin_by_owner(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts,
+                       const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val, uint64_t count,
+                       uint32_t *d_out_src, uint32_t *d_out_dst, uint32_t *d_out_val, uint64_t *h_counts) {
+  if (count && (!d_out_src || !d_out_dst)) return PPCSR_ERR_ARG;
+  return bin_common(device, cuda_stream, d_starts, n_parts, d_src, d_dst, d_val, count, d_out_src, d_out_dst, d_out_val,
+                    nullptr, h_counts);
+}
+
+int ppcsr_bin_by_owner_packed(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts,
+                              const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val, uint64_t count,
+                              uint64_t *d_out_packed, uint32_t *d_out_val, uint64_t *h_counts) {
+  if (count && !d_out_packed) return PPCSR_ERR_ARG;
+  return bin_common(device, cuda_stream, d_starts, n_parts, d_src, d_dst, d_val, count, nullptr, nullptr, d_out_val,
+                    d_out_packed, h_counts);
 }
 
 // ---- reads ------------------------------------------------------------------------------------------

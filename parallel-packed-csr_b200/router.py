@@ -34,14 +34,21 @@ def owner_of(starts: np.ndarray, v: int) -> int:
     return parts - 1
 
 
-def edge_balanced_starts(core_src, n: int, parts: int, dist=None) -> np.ndarray:
-    """Contiguous vertex ranges holding ~equal numbers of core edges (R-MAT puts ~44 % of the sources in the
-    first eighth of the id space).  `core_src`: this rank's slice of the core sources (torch)."""
+def edge_balanced_starts(core_src, n: int, parts: int, dist=None, vertex_weight: float | None = 0.0) -> np.ndarray:
+    """Contiguous vertex ranges with ~equal weight sum(deg(v) + vertex_weight) (R-MAT puts ~44 % of the sources in
+    the first eighth of the id space, SURVEY §7).  vertex_weight = 0 balances the stored edges only;
+    vertex_weight = None uses the average degree, which balances storage against a uniform update stream
+    (a shard's share of uniform updates is proportional to its vertex count).
+    `core_src`: this rank's slice of the core sources (torch)."""
     import torch
 
     hist = torch.bincount(core_src.long(), minlength=n)
     if dist is not None:
         dist.all_reduce(hist)
+    if vertex_weight is None:
+        vertex_weight = float(hist.sum().item()) / n
+    if vertex_weight:
+        hist = hist * 16 + int(round(vertex_weight * 16))
     csum = torch.cumsum(hist, 0)
     total = int(csum[-1].item())
     targets = torch.tensor([total * p // parts for p in range(1, parts)], device=csum.device, dtype=csum.dtype)
@@ -84,6 +91,22 @@ class CudaBinner:
         if rc != 0:
             raise RuntimeError(f"ppcsr_bin_by_owner failed: {self.L.ppcsr_last_error().decode()}")
         return out_src, out_dst, out_val, [int(c) for c in counts]
+
+    def packed(self, starts_dev, parts, src, dst, val):
+        """Same binning, emitting the packed (local_src << 32 | dst) records of the all-to-all."""
+        import torch
+
+        count = src.numel()
+        out = torch.empty(count, dtype=torch.int64, device=src.device)
+        out_val = torch.empty_like(src) if val is not None else None
+        counts = (C.c_uint64 * parts)()
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = self.L.ppcsr_bin_by_owner_packed(self.device_index, stream, starts_dev.data_ptr(), parts, src.data_ptr(),
+                                              dst.data_ptr(), val.data_ptr() if val is not None else None, count,
+                                              out.data_ptr(), out_val.data_ptr() if out_val is not None else None, counts)
+        if rc != 0:
+            raise RuntimeError(f"ppcsr_bin_by_owner_packed failed: {self.L.ppcsr_last_error().decode()}")
+        return out, out_val, [int(c) for c in counts]
 
 
 class TorchBinner:
@@ -148,8 +171,30 @@ class ShardedGraph:
         self.last_route = {"send": send, "recv": recv}
         return r_src, r_dst, r_val
 
+    def route_packed(self, src, dst, val=None):
+        """Product path: bin straight into packed records, one all-to-all, no unpacking (the shard consumes
+        packed records).  Returns (packed int64 tensor, val tensor or None)."""
+        torch, dist = self.torch, self.dist
+        packed, b_val, send = self.binner.packed(self.starts_dev, self.world, src, dst, val)
+        send_t = torch.tensor(send, dtype=torch.int64, device=src.device)
+        recv_t = torch.empty_like(send_t)
+        dist.all_to_all_single(recv_t, send_t)
+        recv = recv_t.tolist()
+        got = torch.empty(sum(recv), dtype=torch.int64, device=src.device)
+        dist.all_to_all_single(got, packed, output_split_sizes=recv, input_split_sizes=send)
+        r_val = None
+        if val is not None:
+            r_val = torch.empty(sum(recv), dtype=val.dtype, device=src.device)
+            dist.all_to_all_single(r_val, b_val, output_split_sizes=recv, input_split_sizes=send)
+        self.last_route = {"send": send, "recv": recv}
+        return got, r_val
+
     def apply(self, src, dst, val=None, default_val=1):
         """Device tensors (int32 bit patterns of u32 ids) holding this rank's slice of the global batch."""
+        if self.world > 1 and hasattr(self.binner, "packed"):
+            got, r_val = self.route_packed(src, dst, val)
+            return self.shard.apply_packed_device(got.data_ptr(), r_val.data_ptr() if r_val is not None else None,
+                                                  got.numel(), default_val)
         r_src, r_dst, r_val = self.route(src, dst, val)
         r_src, r_dst = r_src.contiguous(), r_dst.contiguous()
         return self.shard.apply_device(r_src.data_ptr(), r_dst.data_ptr(),
