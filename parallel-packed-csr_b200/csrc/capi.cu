@@ -701,6 +701,35 @@ int ppcsr_last_stats(ppcsr_shard *s, ppcsr_batch_stats *stats) {
   return PPCSR_OK;
 }
 
+// scratch of the binning entry points: one per device, kept for the life of the process so that routing a batch
+// never allocates (a cudaMalloc/cudaFree pair costs more than the binning kernels themselves)
+struct BinScratch {
+  ppcsr_shard shard;  // provides hist / block_tmp for the scan
+  uint32_t *d_firsts = nullptr;
+  uint32_t *h_firsts = nullptr;  // pinned
+};
+static BinScratch *bin_scratch(int device) {
+  static std::vector<BinScratch *> per_device(64, nullptr);
+  if (device < 0 || device >= 64) return nullptr;
+  if (!per_device[device]) {
+    BinScratch *b = new BinScratch();
+    b->shard.device = device;
+    if (cudaMalloc((void **)&b->d_firsts, (batch::BIN_MAX_PARTS + 1) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMallocHost((void **)&b->h_firsts, (batch::BIN_MAX_PARTS + 1) * sizeof(uint32_t)) != cudaSuccess) {
+      cudaGetLastError();
+      delete b;
+      return nullptr;
+    }
+    per_device[device] = b;
+  }
+  return per_device[device];
+}
+__global__ void k_gather_firsts(const uint32_t *__restrict__ offs, uint32_t nblocks, uint32_t parts,
+                                uint32_t *__restrict__ firsts) {
+  const uint32_t p = threadIdx.x;
+  if (p < parts) firsts[p] = offs[(size_t)p * nblocks];
+}
+
 static int bin_common(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts, const uint32_t *d_src,
                       const uint32_t *d_dst, const uint32_t *d_val, uint64_t count, uint32_t *d_out_src,
                       uint32_t *d_out_dst, uint32_t *d_out_val, uint64_t *d_out_packed, uint64_t *h_counts) {
@@ -709,34 +738,30 @@ static int bin_common(int device, void *cuda_stream, const uint64_t *d_starts, u
   if (count == 0) return PPCSR_OK;
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  // a throw-away shard struct provides the scan scratch
-  ppcsr_shard tmp;
-  tmp.device = device;
+  BinScratch *bs = bin_scratch(device);
+  if (!bs) {
+    g_ppcsr_error = "bin_by_owner: cannot allocate scratch";
+    return PPCSR_ERR_CAPACITY;
+  }
+  ppcsr_shard &tmp = bs->shard;
   tmp.stream = st;
   const unsigned nblocks = div_up(count, prim::SORT_TILE);
   const size_t hn = (size_t)n_parts * nblocks;
-  int rc = dev_reserve(tmp.hist, hn + 1, st);
-  if (rc == PPCSR_OK) {
-    batch::k_bin_count<<<nblocks, batch::BT, 0, st>>>(d_src, count, d_starts, n_parts, tmp.hist.p, nblocks);
-    rc = prim::device_scan(&tmp, prim::InArray{tmp.hist.p}, prim::OutPrefixWithTotal{tmp.hist.p, hn}, hn, nullptr,
-                           nullptr);
+  PPCSR_TRY(dev_reserve(tmp.hist, hn + 1, st));
+  batch::k_bin_count<<<nblocks, batch::BT, 0, st>>>(d_src, count, d_starts, n_parts, tmp.hist.p, nblocks);
+  PPCSR_TRY(prim::device_scan(&tmp, prim::InArray{tmp.hist.p}, prim::OutPrefixWithTotal{tmp.hist.p, hn}, hn, nullptr,
+                              nullptr));
+  batch::k_bin_scatter<<<nblocks, batch::BT, 0, st>>>(d_src, d_dst, d_val, count, d_starts, n_parts, tmp.hist.p, nblocks,
+                                                     d_out_src, d_out_dst, d_out_val, d_out_packed);
+  k_gather_firsts<<<1, batch::BIN_MAX_PARTS, 0, st>>>(tmp.hist.p, nblocks, n_parts, bs->d_firsts);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(bs->h_firsts, bs->d_firsts, n_parts * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (uint32_t p = 0; p < n_parts; p++) {
+    const uint64_t next = p + 1 < n_parts ? bs->h_firsts[p + 1] : count;
+    h_counts[p] = next - bs->h_firsts[p];
   }
-  if (rc == PPCSR_OK) {
-    batch::k_bin_scatter<<<nblocks, batch::BT, 0, st>>>(d_src, d_dst, d_val, count, d_starts, n_parts, tmp.hist.p,
-                                                       nblocks, d_out_src, d_out_dst, d_out_val, d_out_packed);
-    std::vector<uint32_t> firsts(n_parts + 1);
-    for (uint32_t p = 0; p < n_parts && rc == PPCSR_OK; p++) {
-      if (cudaMemcpyAsync(&firsts[p], tmp.hist.p + (size_t)p * nblocks, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
-        rc = PPCSR_ERR_CUDA;
-    }
-    if (cudaStreamSynchronize(st) != cudaSuccess) rc = PPCSR_ERR_CUDA;
-    firsts[n_parts] = (uint32_t)count;
-    for (uint32_t p = 0; p < n_parts; p++) h_counts[p] = firsts[p + 1] - firsts[p];
-  }
-  if (rc == PPCSR_ERR_CUDA) g_ppcsr_error = std::string("bin_by_owner: ") + cudaGetErrorString(cudaGetLastError());
-  dev_free(tmp.hist);
-  dev_free(tmp.block_tmp);
-  return rc;
+  return PPCSR_OK;
 }
 
 int ppcsr_bin_by_owner(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts,

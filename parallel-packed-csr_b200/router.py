@@ -176,10 +176,7 @@ class ShardedGraph:
         packed records).  Returns (packed int64 tensor, val tensor or None)."""
         torch, dist = self.torch, self.dist
         packed, b_val, send = self.binner.packed(self.starts_dev, self.world, src, dst, val)
-        send_t = torch.tensor(send, dtype=torch.int64, device=src.device)
-        recv_t = torch.empty_like(send_t)
-        dist.all_to_all_single(recv_t, send_t)
-        recv = recv_t.tolist()
+        recv = self._exchange_counts(send, src.device)
         got = torch.empty(sum(recv), dtype=torch.int64, device=src.device)
         dist.all_to_all_single(got, packed, output_split_sizes=recv, input_split_sizes=send)
         r_val = None
@@ -188,6 +185,23 @@ class ShardedGraph:
             dist.all_to_all_single(r_val, b_val, output_split_sizes=recv, input_split_sizes=send)
         self.last_route = {"send": send, "recv": recv}
         return got, r_val
+
+    def _exchange_counts(self, send, device):
+        """Every rank learns how many records each peer sends it: a tiny all-to-all through pinned staging."""
+        torch, dist = self.torch, self.dist
+        if getattr(self, "_cnt_send", None) is None:
+            pin = device.type == "cuda"
+            self._cnt_host = torch.empty(self.world, dtype=torch.int64, pin_memory=pin)
+            self._cnt_back = torch.empty(self.world, dtype=torch.int64, pin_memory=pin)
+            self._cnt_send = torch.empty(self.world, dtype=torch.int64, device=device)
+            self._cnt_recv = torch.empty(self.world, dtype=torch.int64, device=device)
+        self._cnt_host.copy_(torch.tensor(send, dtype=torch.int64))
+        self._cnt_send.copy_(self._cnt_host, non_blocking=True)
+        dist.all_to_all_single(self._cnt_recv, self._cnt_send)
+        self._cnt_back.copy_(self._cnt_recv, non_blocking=True)
+        if device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        return self._cnt_back.tolist()
 
     def apply(self, src, dst, val=None, default_val=1):
         """Device tensors (int32 bit patterns of u32 ids) holding this rank's slice of the global batch."""
