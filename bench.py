@@ -237,8 +237,8 @@ def main_b200(args):
     if world > 1:
         import torch.distributed as dist_mod
 
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/WARN; rank 0 must print ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
@@ -255,10 +255,10 @@ def main_b200(args):
     cs, cd = synth.rmat(scale, lo, hi, 42, device=dev)
     cs, cd = cs.to(torch.int32), cd.to(torch.int32)
     if world > 1:
-        # Shard cost model measured at N=1: ~0.115 us per routed update (sort + locate) and ~0.022 us per stored
+        # Shard cost model measured at N=1/2: ~0.13 us per routed update (sort + locate) and ~0.016 us per stored
         # item (window selection + rebalance).  A uniform stream sends B*world/n updates to every vertex, so a
-        # vertex weighs (0.115/0.022) * B*world/n "edges"; deletes follow the edge distribution instead.
-        vw = 5.2 * B * world / n if args.workload == "insert" else 0.0
+        # vertex weighs ~8 * B*world/n "edges"; deletes follow the edge distribution instead.
+        vw = 8.0 * B * world / n if args.workload == "insert" else 0.0
         starts = router.edge_balanced_starts(cs, n, world, dist, vertex_weight=vw)
     else:
         starts = np.array([0, n], dtype=np.uint64)
