@@ -253,9 +253,12 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
       PPCSR_TRY(dev_reserve(s->plan, (size_t)h.n_chunks, s->stream));
       A.plan = s->plan.p;
       reb::k_plan_chunks<<<div_up(h.n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
-          s->windows.p, (uint32_t)h.n_windows, s->rank_off.p, g.leaf_shift, 0, (uint32_t)h.n_chunks, s->plan.p);
+          s->windows.p, (uint32_t)h.n_windows, s->rank_off.p, s->ins_off.p, g.leaf_shift, 0, (uint32_t)h.n_chunks,
+          s->plan.p);
       s->launches += 2 + (h.multi_slots ? 1 : 0);
-      reb::k_rebalance<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(A);
+      CUDA_TRY(cudaFuncSetAttribute(reb::k_rebalance, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)reb::REBALANCE_SMEM));
+      reb::k_rebalance<<<(unsigned)h.n_chunks, reb::RT, reb::REBALANCE_SMEM, s->stream>>>(A);
     }
     CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     if (h.multi_slots) {
@@ -306,10 +309,12 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     PPCSR_TRY(dev_reserve(s->plan, (size_t)hw->n_chunks, s->stream));
     A.plan = s->plan.p;
     reb::k_plan_chunks<<<div_up(hw->n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
-        s->windows.p, 1u, s->rank_off.p, g2.leaf_shift, g2.n_leaves, hw->n_chunks, s->plan.p);
+        s->windows.p, 1u, s->rank_off.p, s->ins_off.p, g2.leaf_shift, g2.n_leaves, hw->n_chunks, s->plan.p);
     s->launches += 6;
     CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
-    reb::k_rebalance<<<hw->n_chunks, reb::RT, 0, s->stream>>>(A);
+    CUDA_TRY(cudaFuncSetAttribute(reb::k_rebalance, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)reb::REBALANCE_SMEM));
+    reb::k_rebalance<<<hw->n_chunks, reb::RT, reb::REBALANCE_SMEM, s->stream>>>(A);
     CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     CUDA_TRY(cudaGetLastError());
     std::swap(s->dest, s->dest_alt);

@@ -158,7 +158,9 @@ struct ChunkPlan {
   uint32_t win;   // index into the window list
   uint32_t i_lo;  // first source leaf (relative to the window) feeding the chunk's rank range
   uint32_t i_hi;  // last source leaf; i_lo > i_hi means the chunk receives no items
-  uint32_t pad;
+  uint32_t q_lo;  // insert run of the source leaves i_lo..i_hi: [q_lo, q_hi) in the insert list
+  uint32_t q_hi;
+  uint32_t pad[3];
 };
 
 struct ppcsr_shard {

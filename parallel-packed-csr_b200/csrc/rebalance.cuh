@@ -64,7 +64,8 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t 
 
 // One thread per chunk: which window the chunk belongs to and which source leaves feed its rank range.
 __global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict__ windows, uint32_t n_windows,
-                                                    const uint32_t *__restrict__ rank_off, uint32_t ls_dst,
+                                                    const uint32_t *__restrict__ rank_off,
+                                                    const uint32_t *__restrict__ ins_off, uint32_t ls_dst,
                                                     uint32_t m_dst_override, uint32_t n_chunks,
                                                     ChunkPlan *__restrict__ plan) {
   const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,15 +86,18 @@ __global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict
   const uint32_t b = (uint32_t)rank_begin(o_hi, j, m_dst);
   ChunkPlan p;
   p.win = lo;
-  p.pad = 0;
+  p.pad[0] = p.pad[1] = p.pad[2] = 0;
   if (b > a) {
     const uint32_t *R = rank_off + w.leaf0;
     const uint32_t R0 = R[0];
     p.i_lo = upper_bound_u32(R, w.m, R0 + a) - 1;      // source leaf holding rank a
     p.i_hi = upper_bound_u32(R, w.m, R0 + b - 1) - 1;  // source leaf holding rank b-1
+    p.q_lo = ins_off[w.leaf0 + p.i_lo];
+    p.q_hi = ins_off[w.leaf0 + p.i_hi + 1];
   } else {
     p.i_lo = 1;
     p.i_hi = 0;
+    p.q_lo = p.q_hi = 0;
   }
   plan[chunk] = p;
 }
@@ -101,13 +105,62 @@ __global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict
 constexpr int LEAVES_PER_WARP = TILE_LEAVES / RWARPS;
 constexpr int MAX_CHUNK_LEAVES = CHUNK_SLOTS / 8;  // smallest leaf is 8 slots (N >= 32)
 
-__global__ void __launch_bounds__(RT, 8) k_rebalance(Args A) {
-  __shared__ __align__(16) uint32_t s_dest[CHUNK_SLOTS];  // staged items at (rank - first rank of the chunk)
-  __shared__ __align__(16) uint32_t s_val[CHUNK_SLOTS];
-  __shared__ uint32_t s_a[MAX_CHUNK_LEAVES + 1];  // first rank of every output leaf of the chunk
-  __shared__ uint32_t t_cnt[TILE_LEAVES], t_mask[TILE_LEAVES], t_rank[TILE_LEAVES], t_ioff[TILE_LEAVES + 1];
-  // s_last[li][f]: 1 + index (inside leaf li's insert run) of the LAST insert whose predecessor is offset f
-  __shared__ uint32_t s_last[TILE_LEAVES][32];
+// ---- TMA (bulk async copy) + mbarrier helpers: sm_90+/sm_100a PTX ----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (SASS: UBLKCP); dst/src 16-byte aligned, bytes a non-zero multiple of 16
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr uint32_t INS_CAP = 1024;                      // inserts staged per round
+constexpr uint32_t META_CAP = TILE_LEAVES + 8;          // leaf metadata entries staged (alignment slack included)
+constexpr size_t REBALANCE_SMEM = (size_t)CHUNK_SLOTS * 8 /* staged output */ + (size_t)TILE_LEAVES * 32 * 8 /* source */ +
+                                  (size_t)INS_CAP * 12 + (size_t)META_CAP * 12 + (size_t)TILE_LEAVES * 32 * 4 /* s_last */ +
+                                  (size_t)(MAX_CHUNK_LEAVES + 4) * 4 + (size_t)TILE_LEAVES * 4 + 64;
+
+// One CTA per chunk of CHUNK_SLOTS output slots.  One elected thread prefetches everything the chunk needs --
+// the contiguous run of source leaves (dest[], val[]), their leaf_cnt / rank_off / ins_off entries and the insert
+// run -- with bulk async copies (TMA) that signal one mbarrier, so the chunk pays ONE global-memory latency instead
+// of a chain of dependent loads; all rank arithmetic then runs out of shared memory.
+__global__ void __launch_bounds__(RT, 4) k_rebalance(Args A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t *s_dest = reinterpret_cast<uint32_t *>(smem_raw);              // staged items at (rank - a)
+  uint32_t *s_val = s_dest + CHUNK_SLOTS;
+  uint32_t *s_src_dest = s_val + CHUNK_SLOTS;                             // source leaves of the tile
+  uint32_t *s_src_val = s_src_dest + TILE_LEAVES * 32;
+  uint32_t *s_ins_pred = s_src_val + TILE_LEAVES * 32;                    // one round of inserts
+  uint32_t *s_ins_dst = s_ins_pred + INS_CAP;
+  uint32_t *s_ins_val = s_ins_dst + INS_CAP;
+  uint32_t *s_cnt = s_ins_val + INS_CAP;                                  // metadata, 16-byte aligned windows
+  uint32_t *s_rank = s_cnt + META_CAP;
+  uint32_t *s_ioff = s_rank + META_CAP;
+  uint32_t *s_last = s_ioff + META_CAP;                                   // [TILE_LEAVES][32]
+  uint32_t *s_a = s_last + TILE_LEAVES * 32;                              // [MAX_CHUNK_LEAVES + 1]
+  uint32_t *t_mask = s_a + MAX_CHUNK_LEAVES + 4;                          // [TILE_LEAVES]
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_qb, s_qe;
 
   const uint32_t chunk = blockIdx.x;
@@ -121,14 +174,64 @@ __global__ void __launch_bounds__(RT, 8) k_rebalance(Args A) {
   const uint32_t o_hi = min(o_lo + CL, m_dst);
   const uint32_t n_out = o_hi - o_lo;
   const uint64_t j = w.items;
-  const uint32_t R0 = A.rank_off[w.leaf0];
   const bool multi = w.n_chunks > 1;
   uint32_t *out_dest = multi ? A.out_dest_multi : A.out_dest_single;
   uint32_t *out_val = multi ? A.out_val_multi : A.out_val_single;
   const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
+  const uint32_t i_lo = plan.i_lo, i_hi = plan.i_hi;
+  const bool has_items = i_lo <= i_hi;
+  uint32_t phase = 0;
 
-  // s_a[x] = floor((o_lo + x) * j / m_dst).  One exact 64-bit division per CTA (x = 0); the others add
-  // floor((x*j + rem) / m_dst) whose numerator is < 2^40, so a double reciprocal is exact up to a +-1 fix-up.
+  // geometry of one tile's prefetch (all threads compute it; thread 0 issues)
+  auto tile_leaves = [&](uint32_t tile) { return min((uint32_t)TILE_LEAVES, i_hi - tile + 1); };
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // stage 1 of a tile: source leaves + metadata (+ the insert run when it is known and fits: the common case)
+  auto issue_tile = [&](uint32_t tile, bool with_inserts, uint32_t q0, uint32_t q1) {
+    const uint32_t tl_n = tile_leaves(tile);
+    const uint32_t leaf = w.leaf0 + tile;
+    const uint32_t src_bytes = (tl_n << A.ls_src) * 4u;
+    const uint32_t al = leaf & ~3u;                              // metadata windows start 16-byte aligned
+    const uint32_t meta_n = ((leaf - al) + tl_n + 1 + 3) & ~3u;  // +1: ins_off of the leaf after the tile
+    uint32_t bytes = 2 * src_bytes + 3 * meta_n * 4u;
+    uint32_t qa = 0, qn = 0;
+    if (with_inserts && q1 > q0) {
+      qa = q0 & ~3u;
+      qn = ((q1 - qa) + 3) & ~3u;
+      bytes += 3 * qn * 4u;
+    }
+    mbar_expect_tx(&s_bar, bytes);
+    bulk_g2s(s_src_dest, A.src_dest + ((size_t)leaf << A.ls_src), src_bytes, &s_bar);
+    bulk_g2s(s_src_val, A.src_val + ((size_t)leaf << A.ls_src), src_bytes, &s_bar);
+    bulk_g2s(s_cnt, A.leaf_cnt + al, meta_n * 4u, &s_bar);
+    bulk_g2s(s_rank, A.rank_off + al, meta_n * 4u, &s_bar);
+    bulk_g2s(s_ioff, A.ins_off + al, meta_n * 4u, &s_bar);
+    if (qn) {
+      bulk_g2s(s_ins_pred, A.ins_pred + qa, qn * 4u, &s_bar);
+      bulk_g2s(s_ins_dst, A.ins_dst + qa, qn * 4u, &s_bar);
+      bulk_g2s(s_ins_val, A.ins_val + qa, qn * 4u, &s_bar);
+    }
+  };
+  auto issue_inserts = [&](uint32_t q0, uint32_t q1) {  // q1 - (q0 & ~3) <= INS_CAP
+    const uint32_t qa = q0 & ~3u;
+    const uint32_t qn = ((q1 - qa) + 3) & ~3u;
+    mbar_expect_tx(&s_bar, 3 * qn * 4u);
+    bulk_g2s(s_ins_pred, A.ins_pred + qa, qn * 4u, &s_bar);
+    bulk_g2s(s_ins_dst, A.ins_dst + qa, qn * 4u, &s_bar);
+    bulk_g2s(s_ins_val, A.ins_val + qa, qn * 4u, &s_bar);
+  };
+
+  // fast path: the chunk is fed by one tile of source leaves and its whole insert run fits one round
+  const bool one_shot = has_items && (i_hi - i_lo) < TILE_LEAVES && (plan.q_hi - (plan.q_lo & ~3u)) <= INS_CAP;
+  if (has_items && threadIdx.x == 0) issue_tile(i_lo, one_shot, plan.q_lo, plan.q_hi);
+
+  // overlapped with the copies in flight: first rank of every output leaf.  One exact 64-bit division per CTA;
+  // the others add floor((x*j + rem)/m_dst) whose numerator is < 2^40: double reciprocal + a +-1 fix-up is exact.
   {
     const uint64_t base_num = (uint64_t)o_lo * j;
     const uint64_t base_q = base_num / m_dst, base_r = base_num - base_q * m_dst;
@@ -141,49 +244,44 @@ __global__ void __launch_bounds__(RT, 8) k_rebalance(Args A) {
       s_a[x] = (uint32_t)(base_q + q);
     }
   }
+  const uint32_t R0 = A.rank_off[w.leaf0];
   __syncthreads();
   const uint32_t a = s_a[0], b = s_a[n_out];
 
-  if (b > a) {
-    const uint32_t i_lo = plan.i_lo, i_hi = plan.i_hi;
+  if (has_items) {
     for (uint32_t tile = i_lo; tile <= i_hi; tile += TILE_LEAVES) {
-      const uint32_t tl_n = min((uint32_t)TILE_LEAVES, i_hi - tile + 1);
+      const uint32_t tl_n = tile_leaves(tile);
       const uint32_t tile_leaf0 = w.leaf0 + tile;
-      // A0: per-leaf metadata of the tile in one coalesced sweep
-      for (uint32_t li = threadIdx.x; li < tl_n; li += RT) {
-        const uint32_t i = tile_leaf0 + li;
-        t_cnt[li] = A.leaf_cnt[i];
-        t_rank[li] = A.rank_off[i] - R0;
-        t_ioff[li] = A.ins_off[i];
-        if (li == tl_n - 1) t_ioff[tl_n] = A.ins_off[i + 1];
+      const uint32_t mo = tile_leaf0 & 3u;  // offset of the tile's first leaf inside the aligned metadata window
+      if (tile != i_lo) {
+        __syncthreads();  // everyone is done with the previous tile's buffers
+        if (threadIdx.x == 0) issue_tile(tile, false, 0, 0);
       }
-      for (uint32_t x = threadIdx.x; x < tl_n * 32; x += RT) (&s_last[0][0])[x] = 0;
-      __syncthreads();
-      // A1: one warp per leaf (a leaf is <= 32 slots): load the live prefix, publish the kept mask
+      for (uint32_t x = threadIdx.x * 4; x < tl_n * 32; x += RT * 4)
+        *reinterpret_cast<uint4 *>(s_last + x) = make_uint4(0u, 0u, 0u, 0u);
+      mbar_wait(&s_bar, phase);
+      phase ^= 1;
+      // A1: one warp per leaf: the live prefix comes from shared memory now; publish the kept mask
       uint32_t d[LEAVES_PER_WARP], v[LEAVES_PER_WARP];
 #pragma unroll
       for (int k = 0; k < LEAVES_PER_WARP; k++) {
         const uint32_t li = warp + k * RWARPS;
+        if (li >= tl_n) break;  // warp-uniform early exit: a 2x expansion feeds a chunk from ~32 leaves, not 64
         d[k] = 0;
         v[k] = 0;
-        if (li < tl_n && lane < t_cnt[li]) {
-          const size_t slot = ((size_t)(tile_leaf0 + li) << A.ls_src) + lane;
-          d[k] = A.src_dest[slot];
-          v[k] = A.src_val[slot];
+        if (lane < s_cnt[mo + li]) {
+          d[k] = s_src_dest[(li << A.ls_src) + lane];
+          v[k] = s_src_val[(li << A.ls_src) + lane];
         }
-      }
-#pragma unroll
-      for (int k = 0; k < LEAVES_PER_WARP; k++) {
-        const uint32_t li = warp + k * RWARPS;
-        if (li < tl_n) {  // warp-uniform
-          const unsigned mask = __ballot_sync(0xFFFFFFFFu, v[k] != 0u);  // tombstones (val 0) drop out here
-          if (lane == 0) t_mask[li] = mask;
-        }
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, v[k] != 0u);  // tombstones (val 0) drop out here
+        if (lane == 0) t_mask[li] = mask;
       }
       __syncthreads();
-      // Only the first and last source leaf of the chunk can straddle its rank range [a,b).  Inserts outside
-      // the range are skipped by the test below, so clamping is only done for hub leaves whose insert run
-      // spans many chunks (CTA-uniform condition).
+      const uint32_t *t_ioff = s_ioff + mo;
+      const uint32_t *t_rank = s_rank + mo;
+      // Only the first and last source leaf of the chunk can straddle its rank range [a,b).  Inserts outside the
+      // range are skipped by the test below, so clamping is only done for hub leaves whose insert run spans many
+      // chunks (CTA-uniform condition).
       const bool clamp_lo = tile == i_lo && (t_ioff[1] - t_ioff[0]) > CLAMP_THRESHOLD;
       const bool clamp_hi = tile + tl_n - 1 == i_hi && (t_ioff[tl_n] - t_ioff[tl_n - 1]) > CLAMP_THRESHOLD;
       uint32_t q_begin = t_ioff[0], q_end = t_ioff[tl_n];
@@ -192,7 +290,7 @@ __global__ void __launch_bounds__(RT, 8) k_rebalance(Args A) {
           uint32_t qb = t_ioff[0], qe = t_ioff[tl_n];
           if (clamp_lo) {
             const uint32_t io = t_ioff[0], ie = t_ioff[1];
-            const uint32_t mask = t_mask[0], Ri = t_rank[0];
+            const uint32_t mask = t_mask[0], Ri = t_rank[0] - R0;
             uint32_t lo = io, hi = ie;  // first q with rank(q) >= a
             while (lo < hi) {
               const uint32_t mid = (lo + hi) >> 1;
@@ -205,7 +303,7 @@ __global__ void __launch_bounds__(RT, 8) k_rebalance(Args A) {
           }
           if (clamp_hi) {
             const uint32_t io = t_ioff[tl_n - 1], ie = t_ioff[tl_n];
-            const uint32_t mask = t_mask[tl_n - 1], Ri = t_rank[tl_n - 1];
+            const uint32_t mask = t_mask[tl_n - 1], Ri = t_rank[tl_n - 1] - R0;
             uint32_t lo = io, hi = ie;  // first q with rank(q) >= b
             while (lo < hi) {
               const uint32_t mid = (lo + hi) >> 1;
@@ -223,48 +321,64 @@ __global__ void __launch_bounds__(RT, 8) k_rebalance(Args A) {
         q_begin = s_qb;
         q_end = s_qe;
       }
-      // B: the tile's inserts: rank = R[i] + index in the leaf's insert run + kept items up to the predecessor
-      for (uint32_t q = q_begin + threadIdx.x; q < q_end; q += RT) {
-        const uint32_t pred = A.ins_pred[q];
-        const uint32_t li = (pred >> A.ls_src) - tile_leaf0;
-        const uint32_t f = pred & (logN_src - 1u);
-        const uint32_t t = q - t_ioff[li];
-        const uint32_t r = t_rank[li] + t + (uint32_t)__popc(t_mask[li] & ((2u << f) - 1u));
-        atomicMax(&s_last[li][f], t + 1u);
-        if (r >= a && r < b) {
-          s_dest[r - a] = A.ins_dst[q];
-          s_val[r - a] = A.ins_val[q];
+      // B: the tile's inserts, one round of <= INS_CAP staged entries at a time (one round in the common case,
+      // already in flight with the tile): rank = R[i] + index in the leaf's run + kept items up to the predecessor
+      for (uint32_t q0 = q_begin; q0 < q_end;) {
+        const uint32_t qa = q0 & ~3u;
+        const uint32_t q1 = min(q_end, qa + INS_CAP);
+        if (!(one_shot && q0 == q_begin)) {
+          __syncthreads();  // previous round consumed
+          if (threadIdx.x == 0) issue_inserts(q0, q1);
+          mbar_wait(&s_bar, phase);
+          phase ^= 1;
         }
+        const uint32_t sa = one_shot ? (plan.q_lo & ~3u) : qa;  // global index of staged entry 0
+        for (uint32_t q = q0 + threadIdx.x; q < q1; q += RT) {
+          const uint32_t pred = s_ins_pred[q - sa];
+          const uint32_t li = (pred >> A.ls_src) - tile_leaf0;
+          const uint32_t f = pred & (logN_src - 1u);
+          const uint32_t t = q - t_ioff[li];
+          const uint32_t r = t_rank[li] - R0 + t + (uint32_t)__popc(t_mask[li] & ((2u << f) - 1u));
+          atomicMax(&s_last[li * 32 + f], t + 1u);
+          if (r >= a && r < b) {
+            s_dest[r - a] = s_ins_dst[q - sa];
+            s_val[r - a] = s_ins_val[q - sa];
+          }
+        }
+        q0 = q1;
       }
       __syncthreads();
-      // A2: kept items: rank = R[i] + kept before + inserts hanging on earlier offsets.  The inserts of a leaf
-      // are ordered by predecessor, so that count is s_last of the nearest earlier offset that has any.
+      // A2: kept items: rank = R[i] + kept before + inserts hanging on earlier offsets.  The inserts of a leaf are
+      // ordered by predecessor, so that count is s_last of the nearest earlier offset that has any.
 #pragma unroll
       for (int k = 0; k < LEAVES_PER_WARP; k++) {
         const uint32_t li = warp + k * RWARPS;
-        if (li < tl_n) {  // warp-uniform
-          const unsigned mask = t_mask[li];
-          const uint32_t last = s_last[li][lane];
-          const unsigned hang = __ballot_sync(0xFFFFFFFFu, last != 0u) & lt;
-          uint32_t ib = __shfl_sync(0xFFFFFFFFu, last, hang ? 31 - __clz(hang) : 0);
+        if (li >= tl_n) break;  // warp-uniform
+        const unsigned mask = t_mask[li];
+        const uint32_t last = s_last[li * 32 + lane];
+        const unsigned hang_all = __ballot_sync(0xFFFFFFFFu, last != 0u);
+        uint32_t ib = 0;
+        if (hang_all) {  // warp-uniform: most leaves of a sparse batch have no inserts at all
+          const unsigned hang = hang_all & lt;
+          ib = __shfl_sync(0xFFFFFFFFu, last, hang ? 31 - __clz(hang) : 0);
           if (!hang) ib = 0;
-          if ((mask >> lane) & 1u) {
-            if ((li == 0 && clamp_lo) || (li == tl_n - 1 && clamp_hi)) {
-              // clamped leaf: s_last only saw part of its inserts -> count them in the sorted list instead
-              const uint32_t io = t_ioff[li], ic = t_ioff[li + 1] - io;
-              ib = lower_bound_u32(A.ins_pred + io, ic, ((tile_leaf0 + li) << A.ls_src) + lane);
-            }
-            const uint32_t r = t_rank[li] + (uint32_t)__popc(mask & lt) + ib;
-            if (r >= a && r < b) {
-              s_dest[r - a] = d[k];
-              s_val[r - a] = v[k];
-            }
+        }
+        if ((mask >> lane) & 1u) {
+          if ((li == 0 && clamp_lo) || (li == tl_n - 1 && clamp_hi)) {
+            // clamped leaf: s_last only saw part of its inserts -> count them in the sorted list instead
+            const uint32_t io = t_ioff[li], ic = t_ioff[li + 1] - io;
+            ib = lower_bound_u32(A.ins_pred + io, ic, ((tile_leaf0 + li) << A.ls_src) + lane);
+          }
+          const uint32_t r = t_rank[li] - R0 + (uint32_t)__popc(mask & lt) + ib;
+          if (r >= a && r < b) {
+            s_dest[r - a] = d[k];
+            s_val[r - a] = v[k];
           }
         }
       }
-      __syncthreads();
     }
   }
+  __syncthreads();
   // write-out: 4 consecutive slots per thread, 16-byte stores to dest[] and val[]
   const uint32_t out_slots = n_out << A.ls_dst;
   const size_t chunk_slot0 = (size_t)(dst_leaf0 + o_lo) << A.ls_dst;
@@ -272,7 +386,7 @@ __global__ void __launch_bounds__(RT, 8) k_rebalance(Args A) {
     const uint32_t ol = x >> A.ls_dst;
     const uint32_t f0 = x & (logN_dst - 1u);
     const uint32_t a_o = s_a[ol], b_o = s_a[ol + 1];
-    const uint32_t base = a_o - a + f0;        // staging index of slot f0
+    const uint32_t base = a_o - a + f0;  // staging index of slot f0
     const uint32_t live_n = b_o - a_o > f0 ? min(4u, b_o - a_o - f0) : 0u;  // live slots among the 4
     uint4 dd = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
     if (live_n > 0) { dd.x = s_dest[base]; vv.x = s_val[base]; }
@@ -280,10 +394,12 @@ __global__ void __launch_bounds__(RT, 8) k_rebalance(Args A) {
     if (live_n > 2) { dd.z = s_dest[base + 2]; vv.z = s_val[base + 2]; }
     if (live_n > 3) { dd.w = s_dest[base + 3]; vv.w = s_val[base + 3]; }
     // fix_sentinel (reference PCSR.cpp:168-183): a sentinel that lands here refreshes its vertex's back pointer
-    if (dd.x == PPCSR_SENT) A.beg[vv.x - 1u] = (uint32_t)(chunk_slot0 + x);
-    if (dd.y == PPCSR_SENT) A.beg[vv.y - 1u] = (uint32_t)(chunk_slot0 + x + 1);
-    if (dd.z == PPCSR_SENT) A.beg[vv.z - 1u] = (uint32_t)(chunk_slot0 + x + 2);
-    if (dd.w == PPCSR_SENT) A.beg[vv.w - 1u] = (uint32_t)(chunk_slot0 + x + 3);
+    if (max(max(dd.x, dd.y), max(dd.z, dd.w)) == PPCSR_SENT) {  // rare: ~1 slot in 16+ holds a sentinel
+      if (dd.x == PPCSR_SENT) A.beg[vv.x - 1u] = (uint32_t)(chunk_slot0 + x);
+      if (dd.y == PPCSR_SENT) A.beg[vv.y - 1u] = (uint32_t)(chunk_slot0 + x + 1);
+      if (dd.z == PPCSR_SENT) A.beg[vv.z - 1u] = (uint32_t)(chunk_slot0 + x + 2);
+      if (dd.w == PPCSR_SENT) A.beg[vv.w - 1u] = (uint32_t)(chunk_slot0 + x + 3);
+    }
     *reinterpret_cast<uint4 *>(out_dest + chunk_slot0 + x) = dd;
     *reinterpret_cast<uint4 *>(out_val + chunk_slot0 + x) = vv;
   }
