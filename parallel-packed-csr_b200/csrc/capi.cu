@@ -8,6 +8,7 @@
 #include "primitives.cuh"
 #include "queries.cuh"
 #include "rebalance.cuh"
+#include "sort.cuh"
 #include "windows.cuh"
 
 thread_local std::string g_ppcsr_error;
@@ -545,9 +546,8 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
     PPCSR_TRY(dev_reserve(s->in_src, max_batch, s->stream));
     PPCSR_TRY(dev_reserve(s->in_dst, max_batch, s->stream));
     PPCSR_TRY(dev_reserve(s->in_val, max_batch, s->stream));
-    PPCSR_TRY(dev_reserve(s->hist, (size_t)prim::RADIX_MAX * div_up(max_batch, prim::SORT_TILE) + 1, s->stream));
-    PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)div_up((size_t)prim::RADIX_MAX * div_up(max_batch, prim::SORT_TILE),
-                                                       prim::SCAN_TILE) + 2, s->stream));
+    PPCSR_TRY(dev_reserve(s->hist, prim::radix_sort_scratch_words(max_batch), s->stream));
+    PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)div_up(max_batch, prim::SCAN_TILE) + 2, s->stream));
   }
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   return PPCSR_OK;

@@ -1,4 +1,4 @@
-// primitives.cuh -- device-wide exclusive scan / stream compaction and the LSD radix sort.
+// primitives.cuh -- device-wide exclusive scan / stream compaction (the radix sort lives in sort.cuh).
 // Hand-written (no CUB/Thrust): three-phase scan (tile reduce -> spine -> tile scan) with functor
 // input/output so the same code serves prefix sums, order-preserving selects and histogram offsets.
 #pragma once
@@ -191,198 +191,10 @@ BoundedOut<Out> bounded_out(Out o, const unsigned long long *n, const unsigned i
   return BoundedOut<Out>{o, n, skip};
 }
 
-// ---------------------------------------------------------------------------------------------
-// LSD radix sort of (u64 key, u32 payload), stable, digits of up to 11 bits.
-// The key (src << 32 | dst) is compacted on the fly to (src << lo_bits | dst) so that the passes cover
-// one contiguous field of lo_bits + hi_bits bits: 40 bits (R-MAT scale 20) sort in 4 passes of 10 bits.
-// Per pass: per-tile digit histogram -> exclusive scan in digit-major order -> stable scatter with
-// warp-synchronous ranking (__match_any_sync); the tile is reordered in shared memory first so that the
-// global stores are coalesced runs per digit.  Equal keys keep their submission order: the LAST element
-// of a run of equal keys is the last op submitted for that (src,dst).  HAS_PAY = false sorts keys only
-// (all payloads equal: the thread pools' value-1 inserts or pure delete batches).
-// ---------------------------------------------------------------------------------------------
+// tile geometry of the owner-binning kernels (batch.cuh): 256 threads x 16 rounds, warp-contiguous sub-tiles
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ROUNDS = 16;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;  // 4096 keys per CTA
-constexpr int RADIX_BITS_MAX = 11;
-constexpr int RADIX_MAX = 1 << RADIX_BITS_MAX;
-
-__device__ __forceinline__ uint32_t sort_digit(uint64_t key, int lo_bits, int shift, uint32_t mask) {
-  const uint64_t ck = lo_bits >= 32 ? key : (((key >> 32) << lo_bits) | (uint32_t)key);
-  return (uint32_t)(ck >> shift) & mask;
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) k_radix_hist(const uint64_t *__restrict__ keys, size_t n, int lo_bits,
-                                                             int shift, uint32_t mask, uint32_t *__restrict__ hist,
-                                                             uint32_t nblocks) {
-  __shared__ uint32_t s_hist[RADIX_MAX];
-  const uint32_t radix = mask + 1;
-  for (uint32_t d = threadIdx.x; d < radix; d += SORT_THREADS) s_hist[d] = 0;
-  __syncthreads();
-  const size_t base = (size_t)blockIdx.x * SORT_TILE;
-#pragma unroll 4
-  for (int r = 0; r < SORT_ROUNDS; r++) {
-    size_t i = base + (size_t)r * SORT_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&s_hist[sort_digit(keys[i], lo_bits, shift, mask)], 1u);
-  }
-  __syncthreads();
-  for (uint32_t d = threadIdx.x; d < radix; d += SORT_THREADS) hist[(size_t)d * nblocks + blockIdx.x] = s_hist[d];
-}
-
-// dynamic shared memory layout of k_radix_scatter (bytes):
-//   keys[SORT_TILE] u64 | pay[SORT_TILE] u32 (HAS_PAY) | dbase[radix] u32 | goff[radix] u32 | cnt[8][radix] u16
-inline size_t scatter_smem_bytes(uint32_t radix, bool has_pay) {
-  return (size_t)SORT_TILE * 8 + (has_pay ? (size_t)SORT_TILE * 4 : 0) + (size_t)radix * 8 +
-         (size_t)SORT_WARPS * radix * 2;
-}
-
-template <bool HAS_PAY>
-__global__ void __launch_bounds__(SORT_THREADS, 2) k_radix_scatter(const uint64_t *__restrict__ keys,
-                                                                   const uint32_t *__restrict__ pay, size_t n,
-                                                                   int lo_bits, int shift, uint32_t mask,
-                                                                   const uint32_t *__restrict__ offs, uint32_t nblocks,
-                                                                   uint64_t *__restrict__ out_keys,
-                                                                   uint32_t *__restrict__ out_pay) {
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  const uint32_t radix = mask + 1;
-  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_dyn);
-  uint32_t *s_pay = reinterpret_cast<uint32_t *>(s_dyn + (size_t)SORT_TILE * 8);
-  uint32_t *s_dbase = reinterpret_cast<uint32_t *>(s_dyn + (size_t)SORT_TILE * 8 + (HAS_PAY ? (size_t)SORT_TILE * 4 : 0));
-  uint32_t *s_goff = s_dbase + radix;
-  uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_goff + radix);  // [SORT_WARPS][radix]
-  __shared__ uint32_t s_warp[33];
-  for (uint32_t d = threadIdx.x; d < SORT_WARPS * radix / 2; d += SORT_THREADS) reinterpret_cast<uint32_t *>(s_cnt)[d] = 0;
-  __syncthreads();
-  const unsigned w = threadIdx.x >> 5, l = lane_id();
-  const unsigned lt = lanemask_lt();
-  uint16_t *my_cnt = s_cnt + (size_t)w * radix;
-  // warp w owns the contiguous sub-tile [w*512, (w+1)*512): round r covers 32 consecutive keys
-  const size_t tile0 = (size_t)blockIdx.x * SORT_TILE;
-  const size_t wbase = tile0 + (size_t)w * (32 * SORT_ROUNDS);
-  uint64_t k[SORT_ROUNDS];
-  uint16_t rank[SORT_ROUNDS];
-#pragma unroll
-  for (int r = 0; r < SORT_ROUNDS; r++) {
-    size_t i = wbase + (size_t)r * 32 + l;
-    k[r] = (i < n) ? keys[i] : 0;
-  }
-#pragma unroll
-  for (int r = 0; r < SORT_ROUNDS; r++) {
-    size_t i = wbase + (size_t)r * 32 + l;
-    const bool valid = i < n;
-    const uint32_t d = valid ? sort_digit(k[r], lo_bits, shift, mask) : 0xFFFFu;
-    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
-    uint32_t base = 0;
-    if (valid) base = my_cnt[d];
-    __syncwarp();
-    if (valid && (peers & lt) == 0) my_cnt[d] = (uint16_t)(base + __popc(peers));
-    __syncwarp();
-    rank[r] = (uint16_t)(base + __popc(peers & lt));
-  }
-  __syncthreads();
-  // per digit: exclusive prefix over warps; block-wide exclusive prefix over digits (radix/256 digits per thread)
-  {
-    const uint32_t per = radix / SORT_THREADS ? radix / SORT_THREADS : 1;
-    const uint32_t d0 = threadIdx.x * per;
-    uint32_t tot[RADIX_MAX / SORT_THREADS];
-    uint32_t sum = 0;
-#pragma unroll
-    for (uint32_t x = 0; x < RADIX_MAX / SORT_THREADS; x++) {
-      tot[x] = 0;
-      const uint32_t d = d0 + x;
-      if (x < per && d < radix) {
-        uint32_t run = 0;
-#pragma unroll
-        for (int ww = 0; ww < SORT_WARPS; ww++) {
-          const uint32_t t = s_cnt[(size_t)ww * radix + d];
-          s_cnt[(size_t)ww * radix + d] = (uint16_t)run;
-          run += t;
-        }
-        tot[x] = run;
-        sum += run;
-      }
-    }
-    uint32_t total;
-    uint32_t dbase = block_excl_scan(sum, &total, s_warp);
-#pragma unroll
-    for (uint32_t x = 0; x < RADIX_MAX / SORT_THREADS; x++) {
-      const uint32_t d = d0 + x;
-      if (x < per && d < radix) {
-        s_dbase[d] = dbase;
-        s_goff[d] = offs[(size_t)d * nblocks + blockIdx.x] - dbase;
-        dbase += tot[x];
-      }
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < SORT_ROUNDS; r++) {
-    size_t i = wbase + (size_t)r * 32 + l;
-    if (i < n) {
-      const uint32_t d = sort_digit(k[r], lo_bits, shift, mask);
-      const uint32_t pos = s_dbase[d] + my_cnt[d] + rank[r];
-      s_keys[pos] = k[r];
-      if (HAS_PAY) s_pay[pos] = pay[i];
-    }
-  }
-  __syncthreads();
-  const uint32_t tile_n = (uint32_t)min((size_t)SORT_TILE, n - tile0);
-  for (uint32_t j = threadIdx.x; j < tile_n; j += SORT_THREADS) {
-    const uint64_t key = s_keys[j];
-    const uint32_t d = sort_digit(key, lo_bits, shift, mask);
-    const uint32_t pos = s_goff[d] + j;
-    out_keys[pos] = key;
-    if (HAS_PAY) out_pay[pos] = s_pay[j];
-  }
-}
-
-// Sorts n (key,payload) pairs by the key bits [0,lo_bits) and [32, 32+hi_bits).  Input in (ka,pa); the
-// sorted result ends up in *rk / *rp which point at either buffer pair.  pa == nullptr sorts keys only.
-inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t *kb, uint32_t *pb, size_t n,
-                            int lo_bits, int hi_bits, uint64_t **rk, uint32_t **rp) {
-  *rk = ka;
-  *rp = pa;
-  if (n <= 1) return PPCSR_OK;
-  const bool has_pay = pa != nullptr;
-  const unsigned nblocks = div_up(n, SORT_TILE);
-  const int total = lo_bits + hi_bits;
-  const int passes = (total + RADIX_BITS_MAX - 1) / RADIX_BITS_MAX;
-  const int width = (total + passes - 1) / passes;
-  PPCSR_TRY(dev_reserve(s->hist, ((size_t)1 << width) * nblocks + 1, s->stream));
-  // > 48 KB of dynamic shared memory needs an explicit opt-in (per device, cheap)
-  CUDA_TRY(cudaFuncSetAttribute(k_radix_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)scatter_smem_bytes(RADIX_MAX, true)));
-  CUDA_TRY(cudaFuncSetAttribute(k_radix_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)scatter_smem_bytes(RADIX_MAX, false)));
-  uint64_t *src_k = ka, *dst_k = kb;
-  uint32_t *src_p = pa, *dst_p = pb;
-  for (int done = 0; done < total; done += width) {
-    const int w = (total - done) < width ? (total - done) : width;
-    const uint32_t mask = (1u << w) - 1u;
-    const uint32_t radix = mask + 1;
-    const size_t hn = (size_t)radix * nblocks;
-    s->launches += 2;
-    k_radix_hist<<<nblocks, SORT_THREADS, 0, s->stream>>>(src_k, n, lo_bits, done, mask, s->hist.p, nblocks);
-    PPCSR_TRY(device_scan(s, InArray{s->hist.p}, OutPrefixWithTotal{s->hist.p, hn}, hn, nullptr, nullptr));
-    if (has_pay) {
-      k_radix_scatter<true><<<nblocks, SORT_THREADS, scatter_smem_bytes(radix, true), s->stream>>>(
-          src_k, src_p, n, lo_bits, done, mask, s->hist.p, nblocks, dst_k, dst_p);
-    } else {
-      k_radix_scatter<false><<<nblocks, SORT_THREADS, scatter_smem_bytes(radix, false), s->stream>>>(
-          src_k, nullptr, n, lo_bits, done, mask, s->hist.p, nblocks, dst_k, nullptr);
-    }
-    CUDA_TRY(cudaGetLastError());
-    uint64_t *tk = src_k;
-    src_k = dst_k;
-    dst_k = tk;
-    uint32_t *tp = src_p;
-    src_p = dst_p;
-    dst_p = tp;
-  }
-  *rk = src_k;
-  *rp = has_pay ? src_p : nullptr;
-  return PPCSR_OK;
-}
+constexpr int SORT_TILE = SORT_THREADS * SORT_ROUNDS;  // 4096 records per CTA
 
 }  // namespace prim

@@ -1,0 +1,368 @@
+// sort.cuh -- stable LSD radix sort of the update batch by (src,dst): single-pass-per-digit ("onesweep")
+// with decoupled look-back, hand-written for sm_100a (no CUB/Thrust).
+//
+// Orders the batch the way the reference's per-op lock acquisition would serialise it
+// (src/pcsr/PCSR.cpp:1374-1445): by source vertex, then by destination, submission order kept among
+// equal keys, so that the LAST element of a run of equal keys is the last op submitted for that edge.
+//
+// The key (src << 32 | dst) is compacted on the fly to (src << lo_bits | dst): only lo_bits + hi_bits
+// bits are live (40 at R-MAT scale 20, 48 at scale 24) and the passes cover exactly that field in
+// digits of <= 8 bits (5 passes at scale 20).
+//
+//   k_os_hist   one read of the keys: the global digit histograms of ALL passes (shared-memory atomics)
+//   k_os_scan   exclusive scan of each pass's 256 bins  -> first output position of every digit
+//   k_os_pass   per pass, ONE read and ONE write of the batch: a CTA takes the next tile of 8192 keys
+//               (ticket counter, so that every earlier tile is already running), ranks its keys
+//               warp-synchronously, publishes the tile's digit counts, resolves the counts of all
+//               earlier tiles by decoupled look-back (aggregate / inclusive-prefix flags in one word),
+//               reorders the tile in shared memory and writes digit runs (32 keys = 256 B on average).
+// HBM traffic per pass: 16 B per update (+8 with per-update values) -- the floor for an LSD pass.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+#include "primitives.cuh"
+
+namespace prim {
+
+constexpr int OS_THREADS = 512;
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_ITEMS = 16;
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;  // 8192 keys per CTA
+constexpr int OS_RADIX_BITS = 8;
+constexpr int OS_RADIX = 1 << OS_RADIX_BITS;
+constexpr int OS_MAX_PASSES = 8;
+constexpr uint32_t OS_FLAG_AGG = 1u << 30;  // tile-local count published
+constexpr uint32_t OS_FLAG_INC = 2u << 30;  // inclusive prefix over all tiles up to this one published
+constexpr uint32_t OS_VAL_MASK = (1u << 30) - 1u;
+constexpr uint64_t OS_MAX_COUNT = OS_VAL_MASK;  // look-back words carry 30-bit counts
+
+struct SortPasses {
+  int n_pass;
+  int lo_bits;
+  int shift[OS_MAX_PASSES];
+  uint32_t mask[OS_MAX_PASSES];
+};
+
+inline SortPasses make_sort_passes(int lo_bits, int hi_bits) {
+  SortPasses P{};
+  P.lo_bits = lo_bits;
+  const int total = lo_bits + hi_bits;
+  P.n_pass = (total + OS_RADIX_BITS - 1) / OS_RADIX_BITS;
+  const int width = (total + P.n_pass - 1) / P.n_pass;
+  int done = 0;
+  for (int p = 0; p < P.n_pass; p++) {
+    const int w = (total - done) < width ? (total - done) : width;
+    P.shift[p] = done;
+    P.mask[p] = (1u << w) - 1u;
+    done += w;
+  }
+  return P;
+}
+
+__device__ __forceinline__ uint64_t sort_compact(uint64_t key, int lo_bits) {
+  return lo_bits >= 32 ? key : (((key >> 32) << lo_bits) | (uint32_t)key);
+}
+__device__ __forceinline__ uint32_t sort_digit(uint64_t key, int lo_bits, int shift, uint32_t mask) {
+  return (uint32_t)(sort_compact(key, lo_bits) >> shift) & mask;
+}
+
+// ---- global histograms of every pass, one read of the keys --------------------------------------------
+constexpr int OSH_THREADS = 512;
+constexpr int OSH_ITEMS = 8;
+
+__global__ void __launch_bounds__(OSH_THREADS) k_os_hist(const uint64_t *__restrict__ keys, size_t n, SortPasses P,
+                                                         uint32_t *__restrict__ ghist) {
+  __shared__ uint32_t s_h[OS_MAX_PASSES * OS_RADIX];
+  for (int i = threadIdx.x; i < P.n_pass * OS_RADIX; i += OSH_THREADS) s_h[i] = 0;
+  __syncthreads();
+  const size_t chunk = (size_t)OSH_THREADS * OSH_ITEMS;
+  for (size_t base = (size_t)blockIdx.x * chunk; base < n; base += (size_t)gridDim.x * chunk) {
+    uint64_t k[OSH_ITEMS];
+#pragma unroll
+    for (int r = 0; r < OSH_ITEMS; r++) {
+      const size_t i = base + (size_t)r * OSH_THREADS + threadIdx.x;
+      k[r] = i < n ? keys[i] : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < OSH_ITEMS; r++) {
+      const size_t i = base + (size_t)r * OSH_THREADS + threadIdx.x;
+      if (i < n) {
+        const uint64_t ck = sort_compact(k[r], P.lo_bits);
+#pragma unroll
+        for (int p = 0; p < OS_MAX_PASSES; p++)
+          if (p < P.n_pass) atomicAdd(&s_h[p * OS_RADIX + ((uint32_t)(ck >> P.shift[p]) & P.mask[p])], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P.n_pass * OS_RADIX; i += OSH_THREADS)
+    if (s_h[i]) atomicAdd(&ghist[i], s_h[i]);
+}
+
+// one block per pass: ghist[p][d] -> exclusive prefix (first output position of digit d in pass p)
+__global__ void __launch_bounds__(OS_RADIX) k_os_scan(uint32_t *__restrict__ ghist) {
+  __shared__ uint32_t s_warp[33];
+  uint32_t *h = ghist + (size_t)blockIdx.x * OS_RADIX;
+  const uint32_t v = h[threadIdx.x];
+  uint32_t total;
+  const uint32_t ex = block_excl_scan(v, &total, s_warp);
+  h[threadIdx.x] = ex;
+}
+
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t *p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Where the digit of one pass sits in the (hi = src, lo = dst) halves of a key: digit = ((lo >> a) | (hi << c)
+// | (hi >> e)) & mask with PTX shift semantics (a shift count >= 32 yields 0), so that no 64-bit compaction is
+// needed per key: a pass inside the dst field uses only `a`, one inside the src field only `e`, the straddling
+// pass `a` and `c`.
+struct DigitSel {
+  uint32_t a, c, e, mask;
+};
+inline DigitSel make_digit_sel(int lo_bits, int shift, uint32_t mask) {
+  DigitSel g;
+  g.mask = mask;
+  if (lo_bits >= 32) {  // no compaction: plain 64-bit key
+    g.a = shift < 32 ? (uint32_t)shift : 32u;
+    g.c = shift < 32 ? (uint32_t)(32 - shift) : 32u;
+    g.e = shift >= 32 ? (uint32_t)(shift - 32) : 32u;
+    if (shift == 0) g.c = 32u;
+    return g;
+  }
+  if (shift >= lo_bits) {
+    g.a = 32u;
+    g.c = 32u;
+    g.e = (uint32_t)(shift - lo_bits);
+  } else {
+    g.a = (uint32_t)shift;
+    g.c = (uint32_t)(lo_bits - shift);  // bits of hi enter above the remaining lo bits (harmless beyond the mask)
+    g.e = 32u;
+  }
+  return g;
+}
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t x, uint32_t n) {
+  uint32_t r;
+  asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+  return r;
+}
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) {
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+  return r;
+}
+__device__ __forceinline__ uint32_t sel_digit(uint64_t key, const DigitSel &g) {
+  const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+  return (shr_clamp(lo, g.a) | shl_clamp(hi, g.c) | shr_clamp(hi, g.e)) & g.mask;
+}
+
+// Lanes holding the same digit.  MATCH.ANY costs one step per DISTINCT value in the warp (~30 for random 8-bit
+// digits; measured: it alone made a pass issue-bound), so the peers are intersected from one ballot per digit
+// bit: test-bit, VOTE, conditional NOT, AND -- four instructions per bit.
+template <int B>
+__device__ __forceinline__ void match_bit(unsigned &peers, uint32_t d) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " .reg .b32 m, t;\n"
+      " and.b32 t, %1, %2;\n"
+      " setp.ne.u32 p, t, 0;\n"
+      " vote.sync.ballot.b32 m, p, 0xffffffff;\n"
+      " @!p not.b32 m, m;\n"
+      " and.b32 %0, %0, m;\n"
+      "}\n"
+      : "+r"(peers)
+      : "r"(d), "n"(1 << B));
+}
+__device__ __forceinline__ unsigned match_digit(uint32_t d) {
+  static_assert(OS_RADIX_BITS == 8, "match_digit is unrolled for 8-bit digits");
+  unsigned peers = 0xFFFFFFFFu;
+  match_bit<0>(peers, d);
+  match_bit<1>(peers, d);
+  match_bit<2>(peers, d);
+  match_bit<3>(peers, d);
+  match_bit<4>(peers, d);
+  match_bit<5>(peers, d);
+  match_bit<6>(peers, d);
+  match_bit<7>(peers, d);
+  return peers;
+}
+
+// dynamic shared memory of k_os_pass (bytes): keys[OS_TILE] u64 | pay[OS_TILE] u32 (HAS_PAY) |
+// cnt[OS_WARPS][OS_RADIX] u16 | dbase[OS_RADIX] u32 | goff[OS_RADIX] u32
+inline size_t os_pass_smem(bool has_pay) {
+  return (size_t)OS_TILE * 8 + (has_pay ? (size_t)OS_TILE * 4 : 0) + (size_t)OS_WARPS * OS_RADIX * 2 +
+         (size_t)OS_RADIX * 8;
+}
+
+template <bool HAS_PAY>
+__global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__restrict__ keys,
+                                                           const uint32_t *__restrict__ pay, size_t n, DigitSel sel,
+                                                           const uint32_t *__restrict__ gbase,
+                                                           uint32_t *__restrict__ lookback, uint32_t *tile_counter,
+                                                           uint64_t *__restrict__ out_keys,
+                                                           uint32_t *__restrict__ out_pay) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_dyn);
+  uint32_t *s_pay = reinterpret_cast<uint32_t *>(s_dyn + (size_t)OS_TILE * 8);
+  uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_dyn + (size_t)OS_TILE * 8 + (HAS_PAY ? (size_t)OS_TILE * 4 : 0));
+  uint32_t *s_dbase = reinterpret_cast<uint32_t *>(s_cnt + OS_WARPS * OS_RADIX);
+  uint32_t *s_goff = s_dbase + OS_RADIX;
+  __shared__ uint32_t s_warp[33];
+  __shared__ uint32_t s_tile;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+  for (uint32_t d = threadIdx.x; d < OS_WARPS * OS_RADIX / 2; d += OS_THREADS) reinterpret_cast<uint32_t *>(s_cnt)[d] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const unsigned w = threadIdx.x >> 5, l = lane_id(), lt = lanemask_lt();
+  uint16_t *my_cnt = s_cnt + (size_t)w * OS_RADIX;
+  // warp w owns the contiguous sub-tile [w*512, (w+1)*512): round r covers 32 consecutive keys (stability).
+  // Keys past the end of the batch are all-ones: they carry the largest digit of every pass and, being the last
+  // elements of the last tile, rank behind every real key, so they need no special case until the write-out.
+  const size_t tile0 = (size_t)tile * OS_TILE;
+  const size_t wbase = tile0 + (size_t)w * (32 * OS_ITEMS);
+  uint64_t k[OS_ITEMS];
+  uint32_t rank[OS_ITEMS / 2];  // two 16-bit ranks per register
+#pragma unroll
+  for (int r = 0; r < OS_ITEMS; r++) {
+    const size_t i = wbase + (size_t)r * 32 + l;
+    k[r] = (i < n) ? keys[i] : ~0ull;
+  }
+#pragma unroll
+  for (int r = 0; r < OS_ITEMS; r++) {
+    const uint32_t d = sel_digit(k[r], sel);
+    const unsigned peers = match_digit(d);
+    const uint32_t base = my_cnt[d];
+    __syncwarp();
+    if ((peers & lt) == 0) my_cnt[d] = (uint16_t)(base + __popc(peers));
+    __syncwarp();
+    const uint32_t rk = base + __popc(peers & lt);
+    if (r & 1) rank[r >> 1] |= rk << 16;
+    else rank[r >> 1] = rk;
+  }
+  __syncthreads();
+  // thread d < 256: exclusive prefix of digit d over the warps, tile count; publish the count at once so that
+  // later tiles can look back through this one while it is still busy
+  uint32_t cnt = 0;
+  if (threadIdx.x < OS_RADIX) {
+    const uint32_t d = threadIdx.x;
+#pragma unroll
+    for (int ww = 0; ww < OS_WARPS; ww++) {
+      const uint32_t t = s_cnt[ww * OS_RADIX + d];
+      s_cnt[ww * OS_RADIX + d] = (uint16_t)cnt;
+      cnt += t;
+    }
+    // the padding keys of a partial last tile are counted in digit `mask`; nobody looks back through the last tile
+    st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + d, cnt | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG));
+  }
+  uint32_t total;
+  const uint32_t dbase = block_excl_scan(cnt, &total, s_warp);  // threads >= 256 contribute 0
+  if (threadIdx.x < OS_RADIX) s_dbase[threadIdx.x] = dbase;
+  __syncthreads();
+  // reorder the tile in shared memory: position = digit base + warp offset + rank inside the warp
+#pragma unroll
+  for (int r = 0; r < OS_ITEMS; r++) {
+    const uint32_t d = sel_digit(k[r], sel);
+    const uint32_t rk = (r & 1) ? (rank[r >> 1] >> 16) : (rank[r >> 1] & 0xFFFFu);
+    const uint32_t pos = s_dbase[d] + my_cnt[d] + rk;
+    s_keys[pos] = k[r];
+    if (HAS_PAY) {
+      const size_t i = wbase + (size_t)r * 32 + l;
+      s_pay[pos] = i < n ? pay[i] : 0u;
+    }
+  }
+  // decoupled look-back: sum the counts of the earlier tiles until one with an inclusive prefix is met
+  if (threadIdx.x < OS_RADIX) {
+    const uint32_t d = threadIdx.x;
+    uint32_t excl = 0;
+    if (tile > 0) {
+      int64_t t = (int64_t)tile - 1;
+      for (;;) {
+        uint32_t v;
+        do {
+          v = ld_relaxed_gpu(lookback + (size_t)t * OS_RADIX + d);
+        } while ((v >> 30) == 0u);
+        excl += v & OS_VAL_MASK;
+        if (v & OS_FLAG_INC) break;
+        t--;
+      }
+      st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + d, (excl + cnt) | OS_FLAG_INC);
+    }
+    s_goff[d] = gbase[d] + excl - dbase;
+  }
+  __syncthreads();
+  const uint32_t tile_n = (uint32_t)min((size_t)OS_TILE, n - tile0);
+#pragma unroll 4
+  for (uint32_t j = threadIdx.x; j < tile_n; j += OS_THREADS) {
+    const uint64_t key = s_keys[j];
+    const uint32_t pos = s_goff[sel_digit(key, sel)] + j;
+    out_keys[pos] = key;
+    if (HAS_PAY) out_pay[pos] = s_pay[j];
+  }
+}
+
+// scratch (u32 words) the sort needs in s->hist for `n` keys
+inline size_t radix_sort_scratch_words(size_t n) {
+  const size_t ntiles = (n + OS_TILE - 1) / OS_TILE;
+  return (size_t)OS_MAX_PASSES * OS_RADIX + 64 + (size_t)OS_MAX_PASSES * ntiles * OS_RADIX;
+}
+
+// Sorts n (key,payload) pairs by the key bits [0,lo_bits) and [32, 32+hi_bits).  Input in (ka,pa); the
+// sorted result ends up in *rk / *rp which point at either buffer pair.  pa == nullptr sorts keys only.
+inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t *kb, uint32_t *pb, size_t n,
+                            int lo_bits, int hi_bits, uint64_t **rk, uint32_t **rp) {
+  *rk = ka;
+  *rp = pa;
+  if (n <= 1) return PPCSR_OK;
+  if (n > OS_MAX_COUNT) {
+    g_ppcsr_error = "batch too large for one sort (>= 2^30 updates); split it";
+    return PPCSR_ERR_ARG;
+  }
+  const bool has_pay = pa != nullptr;
+  const SortPasses P = make_sort_passes(lo_bits, hi_bits);
+  const size_t ntiles = (n + OS_TILE - 1) / OS_TILE;
+  // scratch layout in s->hist: ghist[8][256] | tile counters[64] | lookback[n_pass][ntiles][256]
+  const size_t words = (size_t)OS_MAX_PASSES * OS_RADIX + 64 + (size_t)P.n_pass * ntiles * OS_RADIX;
+  PPCSR_TRY(dev_reserve(s->hist, words, s->stream));
+  uint32_t *ghist = s->hist.p;
+  uint32_t *counters = ghist + OS_MAX_PASSES * OS_RADIX;
+  uint32_t *lookback = counters + 64;
+  CUDA_TRY(cudaMemsetAsync(s->hist.p, 0, words * sizeof(uint32_t), s->stream));
+  static bool attr_done[64] = {};
+  if (s->device >= 64 || !attr_done[s->device]) {  // > 48 KB of dynamic shared memory needs an explicit opt-in
+    CUDA_TRY(cudaFuncSetAttribute(k_os_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(true)));
+    CUDA_TRY(cudaFuncSetAttribute(k_os_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(false)));
+    if (s->device < 64) attr_done[s->device] = true;
+  }
+  const unsigned hblocks = (unsigned)std::min<size_t>((n + (size_t)OSH_THREADS * OSH_ITEMS - 1) / ((size_t)OSH_THREADS * OSH_ITEMS), 148 * 4);
+  s->launches += 2 + P.n_pass;
+  k_os_hist<<<hblocks, OSH_THREADS, 0, s->stream>>>(ka, n, P, ghist);
+  k_os_scan<<<P.n_pass, OS_RADIX, 0, s->stream>>>(ghist);
+  uint64_t *src_k = ka, *dst_k = kb;
+  uint32_t *src_p = pa, *dst_p = pb;
+  for (int p = 0; p < P.n_pass; p++) {
+    if (has_pay) {
+      k_os_pass<true><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(true), s->stream>>>(
+          src_k, src_p, n, make_digit_sel(lo_bits, P.shift[p], P.mask[p]), ghist + p * OS_RADIX,
+          lookback + (size_t)p * ntiles * OS_RADIX, counters + p, dst_k, dst_p);
+    } else {
+      k_os_pass<false><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(false), s->stream>>>(
+          src_k, nullptr, n, make_digit_sel(lo_bits, P.shift[p], P.mask[p]), ghist + p * OS_RADIX,
+          lookback + (size_t)p * ntiles * OS_RADIX, counters + p, dst_k, nullptr);
+    }
+    std::swap(src_k, dst_k);
+    std::swap(src_p, dst_p);
+  }
+  CUDA_TRY(cudaGetLastError());
+  *rk = src_k;
+  *rp = has_pay ? src_p : nullptr;
+  return PPCSR_OK;
+}
+
+}  // namespace prim
