@@ -11,11 +11,11 @@
 //
 //   k_os_hist   one read of the keys: the global digit histograms of ALL passes (shared-memory atomics)
 //   k_os_scan   exclusive scan of each pass's 256 bins  -> first output position of every digit
-//   k_os_pass   per pass, ONE read and ONE write of the batch: a CTA takes the next tile of 8192 keys
+//   k_os_pass   per pass, ONE read and ONE write of the batch: a CTA takes the next tile of 4096 keys
 //               (ticket counter, so that every earlier tile is already running), ranks its keys
 //               warp-synchronously, publishes the tile's digit counts, resolves the counts of all
 //               earlier tiles by decoupled look-back (aggregate / inclusive-prefix flags in one word),
-//               reorders the tile in shared memory and writes digit runs (32 keys = 256 B on average).
+//               reorders the tile in shared memory and writes digit runs (16 keys = 128 B on average).
 // HBM traffic per pass: 16 B per update (+8 with per-update values) -- the floor for an LSD pass.
 #pragma once
 #include <algorithm>
@@ -25,16 +25,17 @@
 
 namespace prim {
 
-constexpr int OS_THREADS = 512;
+constexpr int OS_THREADS = 256;
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr int OS_ITEMS = 16;
-constexpr int OS_TILE = OS_THREADS * OS_ITEMS;  // 8192 keys per CTA
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;  // 4096 keys per CTA
 constexpr int OS_RADIX_BITS = 8;
 constexpr int OS_RADIX = 1 << OS_RADIX_BITS;
 constexpr int OS_MAX_PASSES = 8;
 constexpr uint32_t OS_FLAG_AGG = 1u << 30;  // tile-local count published
 constexpr uint32_t OS_FLAG_INC = 2u << 30;  // inclusive prefix over all tiles up to this one published
 constexpr uint32_t OS_VAL_MASK = (1u << 30) - 1u;
+constexpr int OS_LB_DEPTH = 8;               // predecessors examined per look-back step
 constexpr uint64_t OS_MAX_COUNT = OS_VAL_MASK;  // look-back words carry 30-bit counts
 
 struct SortPasses {
@@ -100,14 +101,18 @@ __global__ void __launch_bounds__(OSH_THREADS) k_os_hist(const uint64_t *__restr
     if (s_h[i]) atomicAdd(&ghist[i], s_h[i]);
 }
 
-// one block per pass: ghist[p][d] -> exclusive prefix (first output position of digit d in pass p)
-__global__ void __launch_bounds__(OS_RADIX) k_os_scan(uint32_t *__restrict__ ghist) {
+// one block per pass: ghist[p][d] -> exclusive prefix (first output position of digit d in pass p); also
+// stamps the (INC, 0) rows in front of the pass's look-back table
+__global__ void __launch_bounds__(OS_RADIX) k_os_scan(uint32_t *__restrict__ ghist, uint32_t *__restrict__ lookback,
+                                                      size_t rows_per_pass) {
   __shared__ uint32_t s_warp[33];
   uint32_t *h = ghist + (size_t)blockIdx.x * OS_RADIX;
   const uint32_t v = h[threadIdx.x];
   uint32_t total;
   const uint32_t ex = block_excl_scan(v, &total, s_warp);
   h[threadIdx.x] = ex;
+  uint32_t *pad = lookback + (size_t)blockIdx.x * rows_per_pass * OS_RADIX;
+  for (int x = 0; x < OS_LB_DEPTH; x++) pad[x * OS_RADIX + threadIdx.x] = OS_FLAG_INC;
 }
 
 __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
@@ -166,43 +171,38 @@ __device__ __forceinline__ uint32_t sel_digit(uint64_t key, const DigitSel &g) {
 // digits; measured: it alone made a pass issue-bound), so the peers are intersected from one ballot per digit
 // bit: test-bit, VOTE, conditional NOT, AND -- four instructions per bit.
 template <int B>
-__device__ __forceinline__ void match_bit(unsigned &peers, uint32_t d) {
+__device__ __forceinline__ unsigned match_bit(uint32_t d) {
+  unsigned m;
   asm volatile(
       "{\n"
       " .reg .pred p;\n"
-      " .reg .b32 m, t;\n"
+      " .reg .b32 t;\n"
       " and.b32 t, %1, %2;\n"
       " setp.ne.u32 p, t, 0;\n"
-      " vote.sync.ballot.b32 m, p, 0xffffffff;\n"
-      " @!p not.b32 m, m;\n"
-      " and.b32 %0, %0, m;\n"
+      " vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+      " @!p not.b32 %0, %0;\n"
       "}\n"
-      : "+r"(peers)
+      : "=r"(m)
       : "r"(d), "n"(1 << B));
+  return m;
 }
 __device__ __forceinline__ unsigned match_digit(uint32_t d) {
   static_assert(OS_RADIX_BITS == 8, "match_digit is unrolled for 8-bit digits");
-  unsigned peers = 0xFFFFFFFFu;
-  match_bit<0>(peers, d);
-  match_bit<1>(peers, d);
-  match_bit<2>(peers, d);
-  match_bit<3>(peers, d);
-  match_bit<4>(peers, d);
-  match_bit<5>(peers, d);
-  match_bit<6>(peers, d);
-  match_bit<7>(peers, d);
-  return peers;
+  // the eight per-bit masks are combined with three-input logic ops (4 instead of 7)
+  const unsigned m0 = match_bit<0>(d), m1 = match_bit<1>(d), m2 = match_bit<2>(d), m3 = match_bit<3>(d);
+  const unsigned m4 = match_bit<4>(d), m5 = match_bit<5>(d), m6 = match_bit<6>(d), m7 = match_bit<7>(d);
+  return (m0 & m1 & m2) & (m3 & m4 & m5) & (m6 & m7);
 }
 
 // dynamic shared memory of k_os_pass (bytes): keys[OS_TILE] u64 | pay[OS_TILE] u32 (HAS_PAY) |
-// cnt[OS_WARPS][OS_RADIX] u16 | dbase[OS_RADIX] u32 | goff[OS_RADIX] u32
+// cnt[OS_WARPS][OS_RADIX] u16 | goff[OS_RADIX] u32
 inline size_t os_pass_smem(bool has_pay) {
   return (size_t)OS_TILE * 8 + (has_pay ? (size_t)OS_TILE * 4 : 0) + (size_t)OS_WARPS * OS_RADIX * 2 +
-         (size_t)OS_RADIX * 8;
+         (size_t)OS_RADIX * 4;
 }
 
 template <bool HAS_PAY>
-__global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__restrict__ keys,
+__global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(const uint64_t *__restrict__ keys,
                                                            const uint32_t *__restrict__ pay, size_t n, DigitSel sel,
                                                            const uint32_t *__restrict__ gbase,
                                                            uint32_t *__restrict__ lookback, uint32_t *tile_counter,
@@ -212,12 +212,12 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
   uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_dyn);
   uint32_t *s_pay = reinterpret_cast<uint32_t *>(s_dyn + (size_t)OS_TILE * 8);
   uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_dyn + (size_t)OS_TILE * 8 + (HAS_PAY ? (size_t)OS_TILE * 4 : 0));
-  uint32_t *s_dbase = reinterpret_cast<uint32_t *>(s_cnt + OS_WARPS * OS_RADIX);
-  uint32_t *s_goff = s_dbase + OS_RADIX;
+  uint32_t *s_goff = reinterpret_cast<uint32_t *>(s_cnt + OS_WARPS * OS_RADIX);
   __shared__ uint32_t s_warp[33];
   __shared__ uint32_t s_tile;
   if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
   for (uint32_t d = threadIdx.x; d < OS_WARPS * OS_RADIX / 2; d += OS_THREADS) reinterpret_cast<uint32_t *>(s_cnt)[d] = 0;
+  s_goff[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const unsigned w = threadIdx.x >> 5, l = lane_id(), lt = lanemask_lt();
@@ -234,6 +234,16 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
     const size_t i = wbase + (size_t)r * 32 + l;
     k[r] = (i < n) ? keys[i] : ~0ull;
   }
+  // early counts: the tile's digit histogram by shared-memory atomics, published BEFORE the (long) ranking phase,
+  // so that by the time this tile looks back most of its predecessors have already resolved their prefix
+  static_assert(OS_THREADS == OS_RADIX, "one thread per digit");
+  const uint32_t dg = threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < OS_ITEMS; r++) atomicAdd(&s_goff[sel_digit(k[r], sel)], 1u);
+  __syncthreads();
+  // the padding keys of a partial last tile are counted in digit `mask`; nobody looks back through the last tile
+  const uint32_t cnt = s_goff[dg];
+  st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + dg, cnt | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG));
 #pragma unroll
   for (int r = 0; r < OS_ITEMS; r++) {
     const uint32_t d = sel_digit(k[r], sel);
@@ -247,54 +257,56 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
     else rank[r >> 1] = rk;
   }
   __syncthreads();
-  // thread d < 256: exclusive prefix of digit d over the warps, tile count; publish the count at once so that
-  // later tiles can look back through this one while it is still busy
-  uint32_t cnt = 0;
-  if (threadIdx.x < OS_RADIX) {
-    const uint32_t d = threadIdx.x;
+  uint32_t total;
+  const uint32_t dbase = block_excl_scan(cnt, &total, s_warp);
+  {  // s_cnt[w][d] := first tile-local position of warp w's keys of digit d
+    uint32_t run = dbase;
 #pragma unroll
     for (int ww = 0; ww < OS_WARPS; ww++) {
-      const uint32_t t = s_cnt[ww * OS_RADIX + d];
-      s_cnt[ww * OS_RADIX + d] = (uint16_t)cnt;
-      cnt += t;
+      const uint32_t t = s_cnt[ww * OS_RADIX + dg];
+      s_cnt[ww * OS_RADIX + dg] = (uint16_t)run;
+      run += t;
     }
-    // the padding keys of a partial last tile are counted in digit `mask`; nobody looks back through the last tile
-    st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + d, cnt | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG));
   }
-  uint32_t total;
-  const uint32_t dbase = block_excl_scan(cnt, &total, s_warp);  // threads >= 256 contribute 0
-  if (threadIdx.x < OS_RADIX) s_dbase[threadIdx.x] = dbase;
   __syncthreads();
-  // reorder the tile in shared memory: position = digit base + warp offset + rank inside the warp
+  // reorder the tile in shared memory: position = (digit base + warp offset) + rank inside the warp
 #pragma unroll
   for (int r = 0; r < OS_ITEMS; r++) {
     const uint32_t d = sel_digit(k[r], sel);
     const uint32_t rk = (r & 1) ? (rank[r >> 1] >> 16) : (rank[r >> 1] & 0xFFFFu);
-    const uint32_t pos = s_dbase[d] + my_cnt[d] + rk;
+    const uint32_t pos = my_cnt[d] + rk;
     s_keys[pos] = k[r];
     if (HAS_PAY) {
       const size_t i = wbase + (size_t)r * 32 + l;
       s_pay[pos] = i < n ? pay[i] : 0u;
     }
   }
-  // decoupled look-back: sum the counts of the earlier tiles until one with an inclusive prefix is met
-  if (threadIdx.x < OS_RADIX) {
-    const uint32_t d = threadIdx.x;
+  // decoupled look-back: sum the counts of the earlier tiles until one with an inclusive prefix is met.
+  // OS_LB_DEPTH predecessors are read at once (independent loads, not one dependent L2 round trip each); the
+  // OS_LB_DEPTH rows in front of tile 0 hold (INC, 0), so the walk needs no bounds checks.
+  {
     uint32_t excl = 0;
     if (tile > 0) {
-      int64_t t = (int64_t)tile - 1;
+      const uint32_t *p = lookback + (size_t)(tile - 1) * OS_RADIX + dg;
       for (;;) {
-        uint32_t v;
-        do {
-          v = ld_relaxed_gpu(lookback + (size_t)t * OS_RADIX + d);
-        } while ((v >> 30) == 0u);
-        excl += v & OS_VAL_MASK;
-        if (v & OS_FLAG_INC) break;
-        t--;
+        uint32_t v[OS_LB_DEPTH];
+#pragma unroll
+        for (int x = 0; x < OS_LB_DEPTH; x++) v[x] = ld_relaxed_gpu(p - x * OS_RADIX);
+        bool done = false;
+#pragma unroll
+        for (int x = 0; x < OS_LB_DEPTH; x++) {
+          while (v[x] < OS_FLAG_AGG) v[x] = ld_relaxed_gpu(p - x * OS_RADIX);
+          if (!done) {
+            excl += v[x] & OS_VAL_MASK;
+            done = v[x] >= OS_FLAG_INC;
+          }
+        }
+        if (done) break;
+        p -= OS_LB_DEPTH * OS_RADIX;
       }
-      st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + d, (excl + cnt) | OS_FLAG_INC);
+      st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + dg, (excl + cnt) | OS_FLAG_INC);
     }
-    s_goff[d] = gbase[d] + excl - dbase;
+    s_goff[dg] = gbase[dg] + excl - dbase;
   }
   __syncthreads();
   const uint32_t tile_n = (uint32_t)min((size_t)OS_TILE, n - tile0);
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t *__res
 // scratch (u32 words) the sort needs in s->hist for `n` keys
 inline size_t radix_sort_scratch_words(size_t n) {
   const size_t ntiles = (n + OS_TILE - 1) / OS_TILE;
-  return (size_t)OS_MAX_PASSES * OS_RADIX + 64 + (size_t)OS_MAX_PASSES * ntiles * OS_RADIX;
+  return (size_t)OS_MAX_PASSES * OS_RADIX + 64 + (size_t)OS_MAX_PASSES * (ntiles + OS_LB_DEPTH) * OS_RADIX;
 }
 
 // Sorts n (key,payload) pairs by the key bits [0,lo_bits) and [32, 32+hi_bits).  Input in (ka,pa); the
@@ -327,8 +339,9 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
   const bool has_pay = pa != nullptr;
   const SortPasses P = make_sort_passes(lo_bits, hi_bits);
   const size_t ntiles = (n + OS_TILE - 1) / OS_TILE;
-  // scratch layout in s->hist: ghist[8][256] | tile counters[64] | lookback[n_pass][ntiles][256]
-  const size_t words = (size_t)OS_MAX_PASSES * OS_RADIX + 64 + (size_t)P.n_pass * ntiles * OS_RADIX;
+  // scratch layout in s->hist: ghist[8][256] | tile counters[64] | lookback[n_pass][OS_LB_DEPTH + ntiles][256]
+  const size_t rows = ntiles + OS_LB_DEPTH;
+  const size_t words = (size_t)OS_MAX_PASSES * OS_RADIX + 64 + (size_t)P.n_pass * rows * OS_RADIX;
   PPCSR_TRY(dev_reserve(s->hist, words, s->stream));
   uint32_t *ghist = s->hist.p;
   uint32_t *counters = ghist + OS_MAX_PASSES * OS_RADIX;
@@ -343,18 +356,18 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
   const unsigned hblocks = (unsigned)std::min<size_t>((n + (size_t)OSH_THREADS * OSH_ITEMS - 1) / ((size_t)OSH_THREADS * OSH_ITEMS), 148 * 4);
   s->launches += 2 + P.n_pass;
   k_os_hist<<<hblocks, OSH_THREADS, 0, s->stream>>>(ka, n, P, ghist);
-  k_os_scan<<<P.n_pass, OS_RADIX, 0, s->stream>>>(ghist);
+  k_os_scan<<<P.n_pass, OS_RADIX, 0, s->stream>>>(ghist, lookback, rows);
   uint64_t *src_k = ka, *dst_k = kb;
   uint32_t *src_p = pa, *dst_p = pb;
   for (int p = 0; p < P.n_pass; p++) {
     if (has_pay) {
       k_os_pass<true><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(true), s->stream>>>(
           src_k, src_p, n, make_digit_sel(lo_bits, P.shift[p], P.mask[p]), ghist + p * OS_RADIX,
-          lookback + (size_t)p * ntiles * OS_RADIX, counters + p, dst_k, dst_p);
+          lookback + ((size_t)p * rows + OS_LB_DEPTH) * OS_RADIX, counters + p, dst_k, dst_p);
     } else {
       k_os_pass<false><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(false), s->stream>>>(
           src_k, nullptr, n, make_digit_sel(lo_bits, P.shift[p], P.mask[p]), ghist + p * OS_RADIX,
-          lookback + (size_t)p * ntiles * OS_RADIX, counters + p, dst_k, nullptr);
+          lookback + ((size_t)p * rows + OS_LB_DEPTH) * OS_RADIX, counters + p, dst_k, nullptr);
     }
     std::swap(src_k, dst_k);
     std::swap(src_p, dst_p);
