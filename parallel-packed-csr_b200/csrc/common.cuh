@@ -190,7 +190,6 @@ struct ppcsr_shard {
   DevBuf<WindowDesc> windows;          // [n_leaves]
   DevBuf<uint32_t> win_chunk_off;      // [n_leaves+1]
   DevBuf<ChunkPlan> plan;              // [n_chunks]
-  DevBuf<uint32_t> small_list;         // [n_windows] indices of the warp-sized windows
 
   // per-batch update-granular scratch
   DevBuf<uint64_t> key_a, key_b;       // [batch]

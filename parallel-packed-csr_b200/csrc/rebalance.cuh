@@ -420,8 +420,7 @@ struct SmallArgs {
   const uint32_t *ins_dst, *ins_val, *ins_pred;
   uint32_t *tree_leaf_out, *beg;
   const WindowDesc *windows;
-  const uint32_t *small_list;    // indices of the small windows
-  uint32_t n_small;
+  uint32_t n_windows;            // one warp per window of the list; chunked (large) windows are skipped
   uint32_t ls;
 };
 
@@ -433,8 +432,9 @@ __global__ void __launch_bounds__(RT) k_rebalance_small(SmallArgs A) {
       s_ioff[RWARPS][SMALL_MAX_LEAVES + 1];
   const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
   const uint32_t wid = blockIdx.x * RWARPS + warp;
-  if (wid >= A.n_small) return;  // whole warp exits together
-  const WindowDesc w = A.windows[A.small_list[wid]];
+  if (wid >= A.n_windows) return;  // whole warp exits together
+  const WindowDesc w = A.windows[wid];
+  if (w.n_chunks != 0) return;     // a large window: k_rebalance owns it
   const uint32_t m = w.m, j = w.items, logN = 1u << A.ls;
   const uint32_t R0 = A.rank_off[w.leaf0];
   uint32_t *sd = s_dest[warp], *sv = s_val[warp];

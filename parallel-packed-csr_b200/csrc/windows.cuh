@@ -131,8 +131,9 @@ struct InWindowHead {
 };
 struct OutWindow {
   const uint32_t *touched_win, *tree;
-  uint32_t n_leaves, chunk_leaves, small_max_leaves;
+  uint32_t n_leaves, chunk_leaves, small_max_leaves, logN;
   WindowDesc *windows;
+  BatchScalars *sc;
   __device__ void operator()(size_t t, uint32_t ex, uint32_t own) const {
     if (!own) return;
     const uint32_t w = touched_win[t];
@@ -147,6 +148,11 @@ struct OutWindow {
     d.n_chunks = m <= small_max_leaves ? 0u : (m + chunk_leaves - 1) / chunk_leaves;
     d.chunk0 = 0;
     windows[ex] = d;
+    // totals for the host's policy decision: windows are far fewer than updates, plain atomics do
+    const unsigned long long slots = (unsigned long long)m * logN;
+    atomicAdd(&sc->window_slots, slots);
+    if (d.n_chunks > 1) atomicAdd(&sc->multi_slots, slots);
+    if (d.n_chunks == 0) atomicAdd(&sc->n_small, 1ull);
   }
 };
 
@@ -158,24 +164,4 @@ struct OutWinChunk0 {
   WindowDesc *w;
   __device__ void operator()(size_t i, uint32_t ex, uint32_t) const { w[i].chunk0 = ex; }
 };
-struct InWinSmall {
-  const WindowDesc *w;
-  __device__ uint32_t operator()(size_t i) const { return w[i].n_chunks == 0 ? 1u : 0u; }
-};
-struct OutWinSmall {
-  uint32_t *small_list;
-  __device__ void operator()(size_t i, uint32_t ex, uint32_t own) const {
-    if (own) small_list[ex] = (uint32_t)i;
-  }
-};
-struct InWinSlots {
-  const WindowDesc *w;
-  uint32_t logN;
-  bool only_multi;
-  __device__ uint32_t operator()(size_t i) const {
-    if (only_multi && w[i].n_chunks <= 1) return 0;
-    return w[i].m * logN;
-  }
-};
-
 }  // namespace win
