@@ -103,11 +103,12 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise PpcsrError(f"{LIB_PATH} is missing: build it with `python parallel-packed-csr_b200/build.py`")
+    path = os.environ.get("PPCSR_B200_LIB", LIB_PATH)  # development knob: A/B a differently compiled build
+    if not os.path.exists(path):
+        if not build_if_missing or path != LIB_PATH:
+            raise PpcsrError(f"{path} is missing: build it with `python parallel-packed-csr_b200/build.py`")
         _build.build_library()
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(L, name)  # AttributeError if the header and the library disagree
         fn.restype = res

@@ -97,6 +97,18 @@ int alloc_geometry(ppcsr_shard *s, const Geometry &g) {
   return PPCSR_OK;
 }
 
+// development knob: PPCSR_REB_PAD_SMEM=<bytes> of unused dynamic shared memory caps the resident CTAs per SM of
+// k_rebalance (occupancy experiments); unset in production
+size_t reb_pad_smem() {
+  static long pad = -1;
+  if (pad < 0) {
+    const char *e = getenv("PPCSR_REB_PAD_SMEM");
+    pad = e ? atol(e) : 0;
+    if (pad > 0) cudaFuncSetAttribute(reb::k_rebalance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+  }
+  return (size_t)pad;
+}
+
 uint64_t grown_slots(uint64_t N, uint64_t items) {
   uint64_t n2 = N;
   for (;;) {
@@ -174,12 +186,10 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
   PPCSR_TRY(dev_reserve(s->plan, (size_t)hw->n_chunks, s->stream));
   A.plan = s->plan.p;
   reb::k_plan_chunks<<<div_up(hw->n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
-      s->windows.p, 1u, s->rank_off.p, s->ins_off.p, g2.leaf_shift, g2.n_leaves, hw->n_chunks, s->plan.p);
+      s->windows.p, 1u, s->rank_off.p, s->ins_off.p, g.leaf_shift, g2.leaf_shift, g2.n_leaves, hw->n_chunks, s->plan.p);
   s->launches += 6;
   CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
-  CUDA_TRY(cudaFuncSetAttribute(reb::k_rebalance, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)reb::REBALANCE_SMEM));
-  reb::k_rebalance<<<hw->n_chunks, reb::RT, reb::REBALANCE_SMEM, s->stream>>>(A);
+  reb::k_rebalance<<<hw->n_chunks, reb::RT, reb_pad_smem(), s->stream>>>(A);
   CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
   CUDA_TRY(cudaGetLastError());
   std::swap(s->dest, s->dest_alt);
@@ -351,17 +361,15 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
       PPCSR_TRY(dev_reserve(s->plan, (size_t)h.n_chunks, s->stream));
       A.plan = s->plan.p;
       reb::k_plan_chunks<<<div_up(h.n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
-          s->windows.p, (uint32_t)h.n_windows, s->rank_off.p, s->ins_off.p, g.leaf_shift, 0, (uint32_t)h.n_chunks,
-          s->plan.p);
+          s->windows.p, (uint32_t)h.n_windows, s->rank_off.p, s->ins_off.p, g.leaf_shift, g.leaf_shift, 0,
+          (uint32_t)h.n_chunks, s->plan.p);
       s->launches += 2 + (h.multi_slots ? 1 : 0);
-      CUDA_TRY(cudaFuncSetAttribute(reb::k_rebalance, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)reb::REBALANCE_SMEM));
-      reb::k_rebalance<<<(unsigned)h.n_chunks, reb::RT, reb::REBALANCE_SMEM, s->stream>>>(A);
+      reb::k_rebalance<<<(unsigned)h.n_chunks, reb::RT, reb_pad_smem(), s->stream>>>(A);
     }
     CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     if (h.multi_slots) {
-      reb::k_copy_back<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(s->windows.p, s->plan.p, g.leaf_shift,
-                                                                        s->dest_alt.p, s->val_alt.p, s->dest.p, s->val.p);
+      reb::k_copy_back<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(s->plan.p, g.leaf_shift, s->dest_alt.p,
+                                                                        s->val_alt.p, s->dest.p, s->val.p);
     }
     s->launches += 1;
     reb::k_copy_u32<<<div_up(L, 256), 256, 0, s->stream>>>(s->leaf_cnt.p, s->tree.p + L, L);

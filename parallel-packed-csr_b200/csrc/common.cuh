@@ -155,13 +155,16 @@ struct WindowDesc {
 // Where one rebalance CTA (one chunk of CHUNK_SLOTS output slots) finds its work: precomputed by
 // k_plan_chunks so that no CTA runs a serial binary search while 255 threads wait at a barrier.
 struct ChunkPlan {
-  uint32_t win;   // index into the window list
-  uint32_t i_lo;  // first source leaf (relative to the window) feeding the chunk's rank range
-  uint32_t i_hi;  // last source leaf; i_lo > i_hi means the chunk receives no items
-  uint32_t q_lo;  // insert run of the source leaves i_lo..i_hi: [q_lo, q_hi) in the insert list
+  uint32_t leaf0;    // first leaf of the chunk's window
+  uint32_t m_multi;  // source leaves in the window | bit 31: the window spans several chunks (written out of place)
+  uint32_t items;    // live items of the window after the batch
+  uint32_t o_lo;     // first output leaf of the chunk (relative to the window)
+  uint32_t i_lo;     // first source leaf (relative to the window) feeding the chunk's rank range
+  uint32_t i_hi;     // last source leaf; i_lo > i_hi means the chunk receives no items
+  uint32_t q_lo;     // inserts of the source leaves i_lo..i_hi that can rank inside the chunk: [q_lo, q_hi)
   uint32_t q_hi;
-  uint32_t pad[3];
 };
+static_assert(sizeof(ChunkPlan) == 32, "a rebalance CTA starts from one 32-byte plan entry");
 
 struct ppcsr_shard {
   int device = 0;

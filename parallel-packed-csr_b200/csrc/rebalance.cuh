@@ -8,11 +8,18 @@
 // concatenation over source leaves i of merge(kept(i), inserts(i)); its ranks are
 //     rank(kept item at offset f of leaf i) = R[i] + #kept before f + #inserts of i whose predecessor < f
 //     rank(q-th insert of leaf i)           = R[i] + q + #kept items of i at offsets <= offset(pred)
-// with R = exclusive scan of the post-batch leaf counts.  Output leaf o of m_out receives the ranks
-// [floor(o*j/m_out), floor((o+1)*j/m_out)) left-packed, the rest of the leaf is nulled.  Each CTA owns
-// a chunk of CHUNK_SLOTS consecutive output slots: it finds the source leaves that feed its rank range
-// by binary search in R, stages the items in shared memory at (rank - first rank) and writes the chunk
-// with 16-byte stores.  Algorithmic traffic: every window slot is read once and written once.
+// with R = exclusive scan of the post-batch leaf counts.  Output leaf o of m_out (a power of two: windows are
+// nodes of the implicit tree) receives the ranks [(o*j) >> lg(m_out), ((o+1)*j) >> lg(m_out)) left-packed,
+// the rest of the leaf is nulled.
+//
+// Work decomposition: a CTA owns CHUNK_SLOTS consecutive output slots (its source-leaf range comes from
+// k_plan_chunks), and inside it every WARP owns SUB_SLOTS = 256 of them and runs on its own -- no block
+// barrier on the data path, so the resident warps of an SM each keep a tile of 16 independent 128-B
+// loads in flight.  A warp locates its source leaves in the CTA's slice of R (shared memory), computes the
+// rank of every kept item and insert with ballots / popcounts, scatters them into its 2 KB staging buffer
+// ALREADY IN THE FINAL LAYOUT (leaf-packed, null tails), and hands the buffer to the TMA engine: two 1-KB
+// bulk stores (cp.async.bulk shared -> global) write dest[] and val[].
+// Algorithmic traffic: every window slot is read once and written once.
 #pragma once
 #include "common.cuh"
 #include "primitives.cuh"
@@ -21,8 +28,7 @@ namespace reb {
 
 constexpr int RT = 256;
 constexpr int RWARPS = RT / 32;
-constexpr int CHUNK_SLOTS = 2048;  // output slots per CTA (16 KB of staging)
-constexpr int TILE_LEAVES = 64;    // source leaves examined per inner iteration
+constexpr int CHUNK_SLOTS = 2048;               // output slots per CTA
 
 struct Args {
   const uint32_t *src_dest, *src_val;  // source slots
@@ -41,7 +47,6 @@ struct Args {
   const ChunkPlan *plan;    // one entry per CTA
 };
 
-constexpr uint32_t CLAMP_THRESHOLD = 256;  // leaves with more inserts than this get their insert range clamped
 
 __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t *a, uint32_t n, uint32_t key) {
   uint32_t lo = 0, hi = n;  // first index with a[idx] > key
@@ -62,11 +67,21 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t 
   return lo;
 }
 
-// One thread per chunk: which window the chunk belongs to and which source leaves feed its rank range.
+// first rank of output leaf o when j items are spread over 2^lg leaves (rank_begin() with the division as a shift)
+__device__ __forceinline__ uint32_t leaf_rank0(uint32_t o, uint32_t j, uint32_t lg) {
+  return (uint32_t)(((uint64_t)o * j) >> lg);
+}
+
+// One thread per chunk: the window the chunk belongs to, copied into the plan entry so that the rebalance CTA
+// starts from ONE 32-byte load; the source leaves that feed the chunk's rank range [a, b); and the part of their
+// insert run that can rank inside it.  An insert q of leaf i ranks at R[i] + (q - ins_off[i]) + (kept items up to
+// its predecessor, <= one leaf), so the inserts of the FIRST leaf before ins_off + (a - R - leaf) rank below a and
+// those of the LAST leaf from ins_off + (b - R) on rank at or above b: a hub run spanning thousands of chunks is
+// clipped to <= span + leaf inserts per chunk without any search.
 __global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict__ windows, uint32_t n_windows,
                                                     const uint32_t *__restrict__ rank_off,
-                                                    const uint32_t *__restrict__ ins_off, uint32_t ls_dst,
-                                                    uint32_t m_dst_override, uint32_t n_chunks,
+                                                    const uint32_t *__restrict__ ins_off, uint32_t ls_src,
+                                                    uint32_t ls_dst, uint32_t m_dst_override, uint32_t n_chunks,
                                                     ChunkPlan *__restrict__ plan) {
   const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
   if (chunk >= n_chunks) return;
@@ -78,22 +93,27 @@ __global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict
   }
   const WindowDesc w = windows[lo];
   const uint32_t m_dst = m_dst_override ? m_dst_override : w.m;
+  const uint32_t lg = 31u - (uint32_t)__clz(m_dst);
   const uint32_t CL = CHUNK_SLOTS >> ls_dst;
   const uint32_t o_lo = (chunk - w.chunk0) * CL;
   const uint32_t o_hi = min(o_lo + CL, m_dst);
-  const uint64_t j = w.items;
-  const uint32_t a = (uint32_t)rank_begin(o_lo, j, m_dst);
-  const uint32_t b = (uint32_t)rank_begin(o_hi, j, m_dst);
+  const uint32_t a = leaf_rank0(o_lo, w.items, lg);
+  const uint32_t b = leaf_rank0(o_hi, w.items, lg);
+  const uint32_t *R = rank_off + w.leaf0;
+  const uint32_t *IO = ins_off + w.leaf0;
+  const uint32_t R0 = R[0];
   ChunkPlan p;
-  p.win = lo;
-  p.pad[0] = p.pad[1] = p.pad[2] = 0;
+  p.leaf0 = w.leaf0;
+  p.m_multi = w.m | (w.n_chunks > 1 ? 0x80000000u : 0u);
+  p.items = w.items;
+  p.o_lo = o_lo;
   if (b > a) {
-    const uint32_t *R = rank_off + w.leaf0;
-    const uint32_t R0 = R[0];
     p.i_lo = upper_bound_u32(R, w.m, R0 + a) - 1;      // source leaf holding rank a
     p.i_hi = upper_bound_u32(R, w.m, R0 + b - 1) - 1;  // source leaf holding rank b-1
-    p.q_lo = ins_off[w.leaf0 + p.i_lo];
-    p.q_hi = ins_off[w.leaf0 + p.i_hi + 1];
+    const uint32_t below = a - (R[p.i_lo] - R0);        // ranks of the first leaf below the chunk
+    const uint32_t leaf = 1u << ls_src;
+    p.q_lo = min(IO[p.i_lo] + (below > leaf ? below - leaf : 0u), IO[p.i_lo + 1]);
+    p.q_hi = max(p.q_lo, min(IO[p.i_hi] + (b - (R[p.i_hi] - R0)), IO[p.i_hi + 1]));
   } else {
     p.i_lo = 1;
     p.i_hi = 0;
@@ -102,308 +122,226 @@ __global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict
   plan[chunk] = p;
 }
 
-constexpr int LEAVES_PER_WARP = TILE_LEAVES / RWARPS;
-constexpr int MAX_CHUNK_LEAVES = CHUNK_SLOTS / 8;  // smallest leaf is 8 slots (N >= 32)
-
-// ---- TMA (bulk async copy) + mbarrier helpers: sm_90+/sm_100a PTX ----------------------------------------
+// ---- TMA (bulk async copy) helpers: sm_90+/sm_100a PTX -----------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// global -> shared bulk copy (SASS: UBLKCP); dst/src 16-byte aligned, bytes a non-zero multiple of 16
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+// generic-proxy writes to shared memory become visible to the async proxy (the TMA engine)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// shared -> global bulk copy (SASS: UBLKCP); both addresses 16-byte aligned, bytes a non-zero multiple of 16
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+#ifndef PPCSR_REB_CTAS
+#define PPCSR_REB_CTAS 4
+#endif
+#ifndef PPCSR_TMA_STORE
+#define PPCSR_TMA_STORE 1
+#endif
+constexpr int SEG_LEAVES_SLOTS = 2048;  // source slots examined per segment (64 leaves of 32 slots): 2 quads per thread
+constexpr int QPT = SEG_LEAVES_SLOTS / 4 / RT;  // 16-byte quads per thread and segment
+constexpr int INS_PREFETCH = 2;                 // inserts per thread whose loads are issued together with the quads
+
+// inclusive scan of x over runs of `lpl` consecutive lanes (lpl = 2, 4 or 8: the lanes holding one source leaf)
+__device__ __forceinline__ uint32_t leaf_incl_scan(uint32_t x, unsigned lane, uint32_t lpl) {
+  const uint32_t in_leaf = lane & (lpl - 1u);
+#pragma unroll
+  for (uint32_t d = 1; d < 8; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+    if (in_leaf >= d) x += y;
+  }
+  return x;
 }
 
-constexpr uint32_t INS_CAP = 1024;                      // inserts staged per round
-constexpr uint32_t META_CAP = TILE_LEAVES + 8;          // leaf metadata entries staged (alignment slack included)
-constexpr size_t REBALANCE_SMEM = (size_t)CHUNK_SLOTS * 8 /* staged output */ + (size_t)TILE_LEAVES * 32 * 8 /* source */ +
-                                  (size_t)INS_CAP * 12 + (size_t)META_CAP * 12 + (size_t)TILE_LEAVES * 32 * 4 /* s_last */ +
-                                  (size_t)(MAX_CHUNK_LEAVES + 4) * 4 + (size_t)TILE_LEAVES * 4 + 64;
+// One CTA per chunk of CHUNK_SLOTS output slots.  Per segment of <= 2048 source slots:
+//   P1  every thread loads its 16-byte quads of dest[]/val[] (and, in flight with them, its first inserts),
+//       counts the kept items of each leaf with a segmented warp scan            -> s_kupto
+//   P2  the segment's inserts, spread evenly over the CTA: rank, hang marker, placed -> s_last, staging
+//   P3  the kept items (still in registers): rank from s_last's running maximum, placed -> staging
+// then ONE bulk store (TMA) per array writes the chunk.
+__global__ void __launch_bounds__(RT, PPCSR_REB_CTAS) k_rebalance(Args A) {
+  __shared__ __align__(128) uint32_t s_dest[CHUNK_SLOTS];  // the chunk's output slots in their final layout
+  __shared__ __align__(128) uint32_t s_val[CHUNK_SLOTS];
+  __shared__ uint16_t s_pos[CHUNK_SLOTS];                   // chunk-relative rank -> output slot
+  __shared__ uint32_t s_a[CHUNK_SLOTS / 8 + 8];             // first rank of every output leaf of the chunk (+ end)
+  __shared__ uint32_t s_R[SEG_LEAVES_SLOTS / 8 + 1], s_ioff[SEG_LEAVES_SLOTS / 8 + 1];
+  __shared__ __align__(16) uint32_t s_last[SEG_LEAVES_SLOTS];  // 1 + index of the last insert hanging on a slot
+  __shared__ __align__(16) uint8_t s_kupto[SEG_LEAVES_SLOTS];  // kept items of the leaf up to and including a slot
 
-// One CTA per chunk of CHUNK_SLOTS output slots.  One elected thread prefetches everything the chunk needs --
-// the contiguous run of source leaves (dest[], val[]), their leaf_cnt / rank_off / ins_off entries and the insert
-// run -- with bulk async copies (TMA) that signal one mbarrier, so the chunk pays ONE global-memory latency instead
-// of a chain of dependent loads; all rank arithmetic then runs out of shared memory.
-__global__ void __launch_bounds__(RT, 4) k_rebalance(Args A) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint32_t *s_dest = reinterpret_cast<uint32_t *>(smem_raw);              // staged items at (rank - a)
-  uint32_t *s_val = s_dest + CHUNK_SLOTS;
-  uint32_t *s_src_dest = s_val + CHUNK_SLOTS;                             // source leaves of the tile
-  uint32_t *s_src_val = s_src_dest + TILE_LEAVES * 32;
-  uint32_t *s_ins_pred = s_src_val + TILE_LEAVES * 32;                    // one round of inserts
-  uint32_t *s_ins_dst = s_ins_pred + INS_CAP;
-  uint32_t *s_ins_val = s_ins_dst + INS_CAP;
-  uint32_t *s_cnt = s_ins_val + INS_CAP;                                  // metadata, 16-byte aligned windows
-  uint32_t *s_rank = s_cnt + META_CAP;
-  uint32_t *s_ioff = s_rank + META_CAP;
-  uint32_t *s_last = s_ioff + META_CAP;                                   // [TILE_LEAVES][32]
-  uint32_t *s_a = s_last + TILE_LEAVES * 32;                              // [MAX_CHUNK_LEAVES + 1]
-  uint32_t *t_mask = s_a + MAX_CHUNK_LEAVES + 4;                          // [TILE_LEAVES]
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ uint32_t s_qb, s_qe;
+  const ChunkPlan plan = A.plan[blockIdx.x];
+  const unsigned lane = lane_id(), lt = lanemask_lt();
+  const uint32_t ls_src = A.ls_src, ls_dst = A.ls_dst;
+  const uint32_t m_src = plan.m_multi & 0x7FFFFFFFu;
+  const bool multi = (plan.m_multi >> 31) != 0;
+  const uint32_t m_dst = A.m_dst_override ? A.m_dst_override : m_src;
+  const uint32_t lg = 31u - (uint32_t)__clz(m_dst);
+  const uint32_t dst_leaf0 = A.m_dst_override ? 0u : plan.leaf0;
+  const uint32_t j = plan.items;
+  const uint32_t n_out = min(CHUNK_SLOTS >> ls_dst, m_dst - plan.o_lo);  // output leaves of the chunk
+  const uint32_t out_slot0 = (dst_leaf0 + plan.o_lo) << ls_dst;          // N <= 2^31 slots
+  const uint32_t a = leaf_rank0(plan.o_lo, j, lg);
+  const uint32_t span = leaf_rank0(plan.o_lo + n_out, j, lg) - a;  // items the chunk receives
+  const uint32_t nl = span ? plan.i_hi - plan.i_lo + 1u : 0u;       // source leaves feeding the chunk
+  const uint32_t gl0 = plan.leaf0 + plan.i_lo;                      // the chunk's first source leaf
+  const uint32_t seg_leaves = SEG_LEAVES_SLOTS >> ls_src;
+  const uint32_t lpl = 1u << (ls_src - 2u);                          // lanes per source leaf
+  const unsigned gm = ((1u << lpl) - 1u) << (lane & ~(lpl - 1u));    // the lanes of my leaf
+  const uint32_t R0 = nl ? A.rank_off[plan.leaf0] : 0u;
 
-  const uint32_t chunk = blockIdx.x;
-  const ChunkPlan plan = A.plan[chunk];
-  const WindowDesc w = A.windows[plan.win];
-  const uint32_t logN_src = 1u << A.ls_src, logN_dst = 1u << A.ls_dst;
-  const uint32_t m_dst = A.m_dst_override ? A.m_dst_override : w.m;
-  const uint32_t dst_leaf0 = A.m_dst_override ? 0u : w.leaf0;
-  const uint32_t CL = CHUNK_SLOTS >> A.ls_dst;  // output leaves per chunk
-  const uint32_t o_lo = (chunk - w.chunk0) * CL;
-  const uint32_t o_hi = min(o_lo + CL, m_dst);
-  const uint32_t n_out = o_hi - o_lo;
-  const uint64_t j = w.items;
-  const bool multi = w.n_chunks > 1;
-  uint32_t *out_dest = multi ? A.out_dest_multi : A.out_dest_single;
-  uint32_t *out_val = multi ? A.out_val_multi : A.out_val_single;
-  const unsigned warp = threadIdx.x >> 5, lane = lane_id(), lt = lanemask_lt();
-  const uint32_t i_lo = plan.i_lo, i_hi = plan.i_hi;
-  const bool has_items = i_lo <= i_hi;
-  uint32_t phase = 0;
+  // item of window rank r, written straight into its final slot
+  auto place = [&](uint32_t r, uint32_t d, uint32_t v) {
+    const uint32_t t = r - a;
+    if (t < span) {
+      const uint32_t pos = s_pos[t];
+      s_dest[pos] = d;
+      s_val[pos] = v;
+      // fix_sentinel (reference PCSR.cpp:168-183): a sentinel that lands here refreshes its vertex's back pointer
+      if (d == PPCSR_SENT) A.beg[v - 1u] = out_slot0 + pos;
+    }
+  };
 
-  // geometry of one tile's prefetch (all threads compute it; thread 0 issues)
-  auto tile_leaves = [&](uint32_t tile) { return min((uint32_t)TILE_LEAVES, i_hi - tile + 1); };
-
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar, 1);
-    fence_mbar_init();
+  for (uint32_t seg = 0; seg < nl || seg == 0; seg += seg_leaves) {
+    const uint32_t seg_nl = min(seg_leaves, nl - seg);
+    const uint32_t seg_slot0 = (gl0 + seg) << ls_src;  // first source slot of the segment
+    const uint32_t seg_slots = seg_nl << ls_src;
+    if (seg) __syncthreads();  // everybody is done with the previous segment's tables
+    // ---- P1: loads.  Nothing below depends on anything but the plan entry.
+    uint4 D[QPT], V[QPT];
+#pragma unroll
+    for (int u = 0; u < QPT; u++) {
+      const uint32_t rel = (u * RT + threadIdx.x) * 4u;
+      D[u] = make_uint4(0u, 0u, 0u, 0u);
+      V[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (rel < seg_slots) {
+        D[u] = *reinterpret_cast<const uint4 *>(A.src_dest + seg_slot0 + rel);
+        V[u] = *reinterpret_cast<const uint4 *>(A.src_val + seg_slot0 + rel);
+      }
+    }
+    uint32_t ip[INS_PREFETCH], id[INS_PREFETCH], iv[INS_PREFETCH];
+    if (seg == 0) {
+#pragma unroll
+      for (int u = 0; u < INS_PREFETCH; u++) {
+        const uint32_t q = plan.q_lo + u * RT + threadIdx.x;
+        if (q < plan.q_hi) {
+          ip[u] = A.ins_pred[q];
+          id[u] = A.ins_dst[q];
+          iv[u] = A.ins_val[q];
+        }
+      }
+    }
+    for (uint32_t x = threadIdx.x; x <= seg_nl && nl; x += RT) {
+      s_R[x] = A.rank_off[gl0 + seg + x] - R0;
+      s_ioff[x] = A.ins_off[gl0 + seg + x];
+    }
+    {
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < QPT; u++) reinterpret_cast<uint4 *>(s_last)[u * RT + threadIdx.x] = zero;
+    }
+    if (seg == 0) {  // null the staging buffers; first rank of every output leaf
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      uint4 *zd = reinterpret_cast<uint4 *>(s_dest), *zv = reinterpret_cast<uint4 *>(s_val);
+#pragma unroll
+      for (int x = 0; x < CHUNK_SLOTS / 4 / RT; x++) {
+        zd[x * RT + threadIdx.x] = zero;
+        zv[x * RT + threadIdx.x] = zero;
+      }
+      for (uint32_t k = threadIdx.x; k <= n_out; k += RT) s_a[k] = leaf_rank0(plan.o_lo + k, j, lg) - a;
+      __syncthreads();
+      // rank -> slot table, built per output leaf by (RT / max leaves) threads each
+      const uint32_t tpl_shift = ls_dst - 3u;  // threads per leaf: 4, 2, 1 for leaves of 32, 16, 8 slots
+      const uint32_t k = threadIdx.x >> tpl_shift, sub = threadIdx.x & ((1u << tpl_shift) - 1u);
+      if (k < n_out) {
+        const uint32_t a_k = s_a[k], cnt = s_a[k + 1] - a_k;
+        for (uint32_t i = sub; i < cnt; i += 1u << tpl_shift) s_pos[a_k + i] = (uint16_t)((k << ls_dst) + i);
+      }
+    }
+    // kept items (tombstones have val 0 and drop out here) and their running count inside the leaf
+    uint32_t pre[QPT];
+#pragma unroll
+    for (int u = 0; u < QPT; u++) {
+      const uint32_t k0 = V[u].x != 0u, k1 = V[u].y != 0u, k2 = V[u].z != 0u, k3 = V[u].w != 0u;
+      const uint32_t c = k0 + k1 + k2 + k3;
+      pre[u] = leaf_incl_scan(c, lane, lpl) - c;  // kept items of my leaf in lower lanes
+      const uint32_t p0 = pre[u] + k0, p1 = p0 + k1, p2 = p1 + k2, p3 = p2 + k3;
+      reinterpret_cast<uint32_t *>(s_kupto)[u * RT + threadIdx.x] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+    }
+    __syncthreads();
+    // ---- P2: the segment's inserts: rank = R[leaf] + index in the leaf's run + kept items up to the predecessor.
+    // plan.q_lo / q_hi already exclude the inserts of the first / last leaf that cannot rank inside the chunk.
+    {
+      const uint32_t q_begin = max(plan.q_lo, s_ioff[0]), q_end = min(plan.q_hi, s_ioff[seg_nl]);
+      auto insert = [&](uint32_t q, uint32_t pred, uint32_t d, uint32_t v) {
+        const uint32_t rel = pred - seg_slot0;
+        const uint32_t li = rel >> ls_src;
+        const uint32_t t = q - s_ioff[li];
+        atomicMax(&s_last[rel], t + 1u);
+        place(s_R[li] + t + s_kupto[rel], d, v);
+      };
+      uint32_t q = q_begin + threadIdx.x;
+      if (seg == 0) {
+#pragma unroll
+        for (int u = 0; u < INS_PREFETCH; u++, q += RT)
+          if (q < q_end) insert(q, ip[u], id[u], iv[u]);
+      }
+      for (; q < q_end; q += RT) insert(q, A.ins_pred[q], A.ins_dst[q], A.ins_val[q]);
+    }
+    __syncthreads();
+    // ---- P3: kept items: rank = R[leaf] + kept before + inserts hanging on earlier slots of the leaf.  The inserts
+    // of a leaf are ordered by predecessor, so that count is `last` of the nearest earlier slot that has any (a
+    // running maximum); the inserts of the chunk's first leaf that the plan clipped away all rank below the chunk,
+    // i.e. precede every item that is placed.
+    const uint32_t base_lo = (seg == 0 && nl) ? plan.q_lo - s_ioff[0] : 0u;
+#pragma unroll
+    for (int u = 0; u < QPT; u++) {
+      const uint32_t rel = (u * RT + threadIdx.x) * 4u;
+      const uint4 L = reinterpret_cast<const uint4 *>(s_last)[u * RT + threadIdx.x];
+      const uint32_t lane_max = max(max(L.x, L.y), max(L.z, L.w));
+      const unsigned nz = __ballot_sync(0xFFFFFFFFu, lane_max != 0u) & lt & gm;
+      uint32_t carry = __shfl_sync(0xFFFFFFFFu, lane_max, nz ? 31 - __clz(nz) : 0);
+      if (!nz) carry = 0;
+      const uint32_t my_leaf = rel >> ls_src;
+      if (my_leaf == 0) carry = max(carry, base_lo);
+      const uint32_t k0 = V[u].x != 0u, k1 = V[u].y != 0u, k2 = V[u].z != 0u, k3 = V[u].w != 0u;
+      if (k0 | k1 | k2 | k3) {  // implies rel < seg_slots
+        const uint32_t Rl = s_R[my_leaf] + pre[u];
+        const uint32_t ib1 = max(carry, L.x), ib2 = max(ib1, L.y), ib3 = max(ib2, L.z);
+        if (k0) place(Rl + carry, D[u].x, V[u].x);
+        if (k1) place(Rl + k0 + ib1, D[u].y, V[u].y);
+        if (k2) place(Rl + k0 + k1 + ib2, D[u].z, V[u].z);
+        if (k3) place(Rl + k0 + k1 + k2 + ib3, D[u].w, V[u].w);
+      }
+    }
   }
-  __syncthreads();
-
-  // stage 1 of a tile: source leaves + metadata (+ the insert run when it is known and fits: the common case)
-  auto issue_tile = [&](uint32_t tile, bool with_inserts, uint32_t q0, uint32_t q1) {
-    const uint32_t tl_n = tile_leaves(tile);
-    const uint32_t leaf = w.leaf0 + tile;
-    const uint32_t src_bytes = (tl_n << A.ls_src) * 4u;
-    const uint32_t al = leaf & ~3u;                              // metadata windows start 16-byte aligned
-    const uint32_t meta_n = ((leaf - al) + tl_n + 1 + 3) & ~3u;  // +1: ins_off of the leaf after the tile
-    uint32_t bytes = 2 * src_bytes + 3 * meta_n * 4u;
-    uint32_t qa = 0, qn = 0;
-    if (with_inserts && q1 > q0) {
-      qa = q0 & ~3u;
-      qn = ((q1 - qa) + 3) & ~3u;
-      bytes += 3 * qn * 4u;
-    }
-    mbar_expect_tx(&s_bar, bytes);
-    bulk_g2s(s_src_dest, A.src_dest + ((size_t)leaf << A.ls_src), src_bytes, &s_bar);
-    bulk_g2s(s_src_val, A.src_val + ((size_t)leaf << A.ls_src), src_bytes, &s_bar);
-    bulk_g2s(s_cnt, A.leaf_cnt + al, meta_n * 4u, &s_bar);
-    bulk_g2s(s_rank, A.rank_off + al, meta_n * 4u, &s_bar);
-    bulk_g2s(s_ioff, A.ins_off + al, meta_n * 4u, &s_bar);
-    if (qn) {
-      bulk_g2s(s_ins_pred, A.ins_pred + qa, qn * 4u, &s_bar);
-      bulk_g2s(s_ins_dst, A.ins_dst + qa, qn * 4u, &s_bar);
-      bulk_g2s(s_ins_val, A.ins_val + qa, qn * 4u, &s_bar);
-    }
-  };
-  auto issue_inserts = [&](uint32_t q0, uint32_t q1) {  // q1 - (q0 & ~3) <= INS_CAP
-    const uint32_t qa = q0 & ~3u;
-    const uint32_t qn = ((q1 - qa) + 3) & ~3u;
-    mbar_expect_tx(&s_bar, 3 * qn * 4u);
-    bulk_g2s(s_ins_pred, A.ins_pred + qa, qn * 4u, &s_bar);
-    bulk_g2s(s_ins_dst, A.ins_dst + qa, qn * 4u, &s_bar);
-    bulk_g2s(s_ins_val, A.ins_val + qa, qn * 4u, &s_bar);
-  };
-
-  // fast path: the chunk is fed by one tile of source leaves and its whole insert run fits one round
-  const bool one_shot = has_items && (i_hi - i_lo) < TILE_LEAVES && (plan.q_hi - (plan.q_lo & ~3u)) <= INS_CAP;
-  if (has_items && threadIdx.x == 0) issue_tile(i_lo, one_shot, plan.q_lo, plan.q_hi);
-
-  // overlapped with the copies in flight: first rank of every output leaf.  One exact 64-bit division per CTA;
-  // the others add floor((x*j + rem)/m_dst) whose numerator is < 2^40: double reciprocal + a +-1 fix-up is exact.
+  // every source leaf has been read (a single-CTA window is rebalanced in place) and the staging buffers are
+  // complete: write the chunk
   {
-    const uint64_t base_num = (uint64_t)o_lo * j;
-    const uint64_t base_q = base_num / m_dst, base_r = base_num - base_q * m_dst;
-    const double inv_m = 1.0 / (double)m_dst;
-    for (uint32_t x = threadIdx.x; x <= n_out; x += RT) {
-      const uint64_t num = (uint64_t)x * j + base_r;
-      uint64_t q = (uint64_t)((double)num * inv_m);
-      if (q * m_dst > num) q--;
-      else if ((q + 1) * m_dst <= num) q++;
-      s_a[x] = (uint32_t)(base_q + q);
+    uint32_t *out_dest = (multi ? A.out_dest_multi : A.out_dest_single) + out_slot0;
+    uint32_t *out_val = (multi ? A.out_val_multi : A.out_val_single) + out_slot0;
+    const uint32_t out_slots = n_out << ls_dst;
+#if PPCSR_TMA_STORE
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_s2g(out_dest, s_dest, out_slots * 4u);
+      bulk_s2g(out_val, s_val, out_slots * 4u);
+      bulk_commit();
     }
-  }
-  const uint32_t R0 = A.rank_off[w.leaf0];
-  __syncthreads();
-  const uint32_t a = s_a[0], b = s_a[n_out];
-
-  if (has_items) {
-    for (uint32_t tile = i_lo; tile <= i_hi; tile += TILE_LEAVES) {
-      const uint32_t tl_n = tile_leaves(tile);
-      const uint32_t tile_leaf0 = w.leaf0 + tile;
-      const uint32_t mo = tile_leaf0 & 3u;  // offset of the tile's first leaf inside the aligned metadata window
-      if (tile != i_lo) {
-        __syncthreads();  // everyone is done with the previous tile's buffers
-        if (threadIdx.x == 0) issue_tile(tile, false, 0, 0);
-      }
-      for (uint32_t x = threadIdx.x * 4; x < tl_n * 32; x += RT * 4)
-        *reinterpret_cast<uint4 *>(s_last + x) = make_uint4(0u, 0u, 0u, 0u);
-      mbar_wait(&s_bar, phase);
-      phase ^= 1;
-      // A1: one warp per leaf: the live prefix comes from shared memory now; publish the kept mask
-      uint32_t d[LEAVES_PER_WARP], v[LEAVES_PER_WARP];
-#pragma unroll
-      for (int k = 0; k < LEAVES_PER_WARP; k++) {
-        const uint32_t li = warp + k * RWARPS;
-        if (li >= tl_n) break;  // warp-uniform early exit: a 2x expansion feeds a chunk from ~32 leaves, not 64
-        d[k] = 0;
-        v[k] = 0;
-        if (lane < s_cnt[mo + li]) {
-          d[k] = s_src_dest[(li << A.ls_src) + lane];
-          v[k] = s_src_val[(li << A.ls_src) + lane];
-        }
-        const unsigned mask = __ballot_sync(0xFFFFFFFFu, v[k] != 0u);  // tombstones (val 0) drop out here
-        if (lane == 0) t_mask[li] = mask;
-      }
-      __syncthreads();
-      const uint32_t *t_ioff = s_ioff + mo;
-      const uint32_t *t_rank = s_rank + mo;
-      // Only the first and last source leaf of the chunk can straddle its rank range [a,b).  Inserts outside the
-      // range are skipped by the test below, so clamping is only done for hub leaves whose insert run spans many
-      // chunks (CTA-uniform condition).
-      const bool clamp_lo = tile == i_lo && (t_ioff[1] - t_ioff[0]) > CLAMP_THRESHOLD;
-      const bool clamp_hi = tile + tl_n - 1 == i_hi && (t_ioff[tl_n] - t_ioff[tl_n - 1]) > CLAMP_THRESHOLD;
-      uint32_t q_begin = t_ioff[0], q_end = t_ioff[tl_n];
-      if (clamp_lo || clamp_hi) {
-        if (threadIdx.x == 0) {
-          uint32_t qb = t_ioff[0], qe = t_ioff[tl_n];
-          if (clamp_lo) {
-            const uint32_t io = t_ioff[0], ie = t_ioff[1];
-            const uint32_t mask = t_mask[0], Ri = t_rank[0] - R0;
-            uint32_t lo = io, hi = ie;  // first q with rank(q) >= a
-            while (lo < hi) {
-              const uint32_t mid = (lo + hi) >> 1;
-              const uint32_t f = A.ins_pred[mid] & (logN_src - 1u);
-              const uint32_t r = Ri + (mid - io) + (uint32_t)__popc(mask & ((2u << f) - 1u));
-              if (r < a) lo = mid + 1;
-              else hi = mid;
-            }
-            qb = lo;
-          }
-          if (clamp_hi) {
-            const uint32_t io = t_ioff[tl_n - 1], ie = t_ioff[tl_n];
-            const uint32_t mask = t_mask[tl_n - 1], Ri = t_rank[tl_n - 1] - R0;
-            uint32_t lo = io, hi = ie;  // first q with rank(q) >= b
-            while (lo < hi) {
-              const uint32_t mid = (lo + hi) >> 1;
-              const uint32_t f = A.ins_pred[mid] & (logN_src - 1u);
-              const uint32_t r = Ri + (mid - io) + (uint32_t)__popc(mask & ((2u << f) - 1u));
-              if (r < b) lo = mid + 1;
-              else hi = mid;
-            }
-            qe = lo;
-          }
-          s_qb = qb;
-          s_qe = max(qb, qe);
-        }
-        __syncthreads();
-        q_begin = s_qb;
-        q_end = s_qe;
-      }
-      // B: the tile's inserts, one round of <= INS_CAP staged entries at a time (one round in the common case,
-      // already in flight with the tile): rank = R[i] + index in the leaf's run + kept items up to the predecessor
-      for (uint32_t q0 = q_begin; q0 < q_end;) {
-        const uint32_t qa = q0 & ~3u;
-        const uint32_t q1 = min(q_end, qa + INS_CAP);
-        if (!(one_shot && q0 == q_begin)) {
-          __syncthreads();  // previous round consumed
-          if (threadIdx.x == 0) issue_inserts(q0, q1);
-          mbar_wait(&s_bar, phase);
-          phase ^= 1;
-        }
-        const uint32_t sa = one_shot ? (plan.q_lo & ~3u) : qa;  // global index of staged entry 0
-        for (uint32_t q = q0 + threadIdx.x; q < q1; q += RT) {
-          const uint32_t pred = s_ins_pred[q - sa];
-          const uint32_t li = (pred >> A.ls_src) - tile_leaf0;
-          const uint32_t f = pred & (logN_src - 1u);
-          const uint32_t t = q - t_ioff[li];
-          const uint32_t r = t_rank[li] - R0 + t + (uint32_t)__popc(t_mask[li] & ((2u << f) - 1u));
-          atomicMax(&s_last[li * 32 + f], t + 1u);
-          if (r >= a && r < b) {
-            s_dest[r - a] = s_ins_dst[q - sa];
-            s_val[r - a] = s_ins_val[q - sa];
-          }
-        }
-        q0 = q1;
-      }
-      __syncthreads();
-      // A2: kept items: rank = R[i] + kept before + inserts hanging on earlier offsets.  The inserts of a leaf are
-      // ordered by predecessor, so that count is s_last of the nearest earlier offset that has any.
-#pragma unroll
-      for (int k = 0; k < LEAVES_PER_WARP; k++) {
-        const uint32_t li = warp + k * RWARPS;
-        if (li >= tl_n) break;  // warp-uniform
-        const unsigned mask = t_mask[li];
-        const uint32_t last = s_last[li * 32 + lane];
-        const unsigned hang_all = __ballot_sync(0xFFFFFFFFu, last != 0u);
-        uint32_t ib = 0;
-        if (hang_all) {  // warp-uniform: most leaves of a sparse batch have no inserts at all
-          const unsigned hang = hang_all & lt;
-          ib = __shfl_sync(0xFFFFFFFFu, last, hang ? 31 - __clz(hang) : 0);
-          if (!hang) ib = 0;
-        }
-        if ((mask >> lane) & 1u) {
-          if ((li == 0 && clamp_lo) || (li == tl_n - 1 && clamp_hi)) {
-            // clamped leaf: s_last only saw part of its inserts -> count them in the sorted list instead
-            const uint32_t io = t_ioff[li], ic = t_ioff[li + 1] - io;
-            ib = lower_bound_u32(A.ins_pred + io, ic, ((tile_leaf0 + li) << A.ls_src) + lane);
-          }
-          const uint32_t r = t_rank[li] - R0 + (uint32_t)__popc(mask & lt) + ib;
-          if (r >= a && r < b) {
-            s_dest[r - a] = d[k];
-            s_val[r - a] = v[k];
-          }
-        }
-      }
+#else
+    __syncthreads();
+    for (uint32_t x = threadIdx.x * 4u; x < out_slots; x += RT * 4u) {
+      *reinterpret_cast<uint4 *>(out_dest + x) = *reinterpret_cast<const uint4 *>(s_dest + x);
+      *reinterpret_cast<uint4 *>(out_val + x) = *reinterpret_cast<const uint4 *>(s_val + x);
     }
+#endif
   }
-  __syncthreads();
-  // write-out: 4 consecutive slots per thread, 16-byte stores to dest[] and val[]
-  const uint32_t out_slots = n_out << A.ls_dst;
-  const size_t chunk_slot0 = (size_t)(dst_leaf0 + o_lo) << A.ls_dst;
-  for (uint32_t x = threadIdx.x * 4; x < out_slots; x += RT * 4) {
-    const uint32_t ol = x >> A.ls_dst;
-    const uint32_t f0 = x & (logN_dst - 1u);
-    const uint32_t a_o = s_a[ol], b_o = s_a[ol + 1];
-    const uint32_t base = a_o - a + f0;  // staging index of slot f0
-    const uint32_t live_n = b_o - a_o > f0 ? min(4u, b_o - a_o - f0) : 0u;  // live slots among the 4
-    uint4 dd = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
-    if (live_n > 0) { dd.x = s_dest[base]; vv.x = s_val[base]; }
-    if (live_n > 1) { dd.y = s_dest[base + 1]; vv.y = s_val[base + 1]; }
-    if (live_n > 2) { dd.z = s_dest[base + 2]; vv.z = s_val[base + 2]; }
-    if (live_n > 3) { dd.w = s_dest[base + 3]; vv.w = s_val[base + 3]; }
-    // fix_sentinel (reference PCSR.cpp:168-183): a sentinel that lands here refreshes its vertex's back pointer
-    if (max(max(dd.x, dd.y), max(dd.z, dd.w)) == PPCSR_SENT) {  // rare: ~1 slot in 16+ holds a sentinel
-      if (dd.x == PPCSR_SENT) A.beg[vv.x - 1u] = (uint32_t)(chunk_slot0 + x);
-      if (dd.y == PPCSR_SENT) A.beg[vv.y - 1u] = (uint32_t)(chunk_slot0 + x + 1);
-      if (dd.z == PPCSR_SENT) A.beg[vv.z - 1u] = (uint32_t)(chunk_slot0 + x + 2);
-      if (dd.w == PPCSR_SENT) A.beg[vv.w - 1u] = (uint32_t)(chunk_slot0 + x + 3);
-    }
-    *reinterpret_cast<uint4 *>(out_dest + chunk_slot0 + x) = dd;
-    *reinterpret_cast<uint4 *>(out_val + chunk_slot0 + x) = vv;
-  }
-  for (uint32_t x = threadIdx.x; x < n_out; x += RT) A.tree_leaf_out[dst_leaf0 + o_lo + x] = s_a[x + 1] - s_a[x];
+  for (uint32_t k = threadIdx.x; k < n_out; k += RT) A.tree_leaf_out[dst_leaf0 + plan.o_lo + k] = s_a[k + 1] - s_a[k];
+#if PPCSR_TMA_STORE
+  if (threadIdx.x == 0) bulk_wait_read0();  // the staging buffers must outlive the copy
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -522,18 +460,15 @@ __global__ void __launch_bounds__(RT) k_rebalance_small(SmallArgs A) {
 }
 
 // copy the chunks of multi-CTA windows back from the out-of-place target into the live array
-__global__ void __launch_bounds__(RT) k_copy_back(const WindowDesc *__restrict__ windows,
-                                                  const ChunkPlan *__restrict__ plan, uint32_t ls, const uint32_t *__restrict__ alt_dest,
+__global__ void __launch_bounds__(RT) k_copy_back(const ChunkPlan *__restrict__ plan, uint32_t ls,
+                                                  const uint32_t *__restrict__ alt_dest,
                                                   const uint32_t *__restrict__ alt_val, uint32_t *__restrict__ dest,
                                                   uint32_t *__restrict__ val) {
-  const uint32_t chunk = blockIdx.x;
-  const WindowDesc w = windows[plan[chunk].win];
-  if (w.n_chunks <= 1) return;
-  const uint32_t CL = CHUNK_SLOTS >> ls;
-  const uint32_t o_lo = (chunk - w.chunk0) * CL;
-  const uint32_t o_hi = min(o_lo + CL, w.m);
-  const size_t base = (size_t)(w.leaf0 + o_lo) << ls;
-  const uint32_t slots = (o_hi - o_lo) << ls;
+  const ChunkPlan p = plan[blockIdx.x];
+  if (!(p.m_multi >> 31)) return;
+  const uint32_t o_hi = min(p.o_lo + (CHUNK_SLOTS >> ls), p.m_multi & 0x7FFFFFFFu);
+  const size_t base = (size_t)(p.leaf0 + p.o_lo) << ls;
+  const uint32_t slots = (o_hi - p.o_lo) << ls;
   for (uint32_t x = threadIdx.x * 4; x < slots; x += RT * 4) {
     *reinterpret_cast<uint4 *>(dest + base + x) = *reinterpret_cast<const uint4 *>(alt_dest + base + x);
     *reinterpret_cast<uint4 *>(val + base + x) = *reinterpret_cast<const uint4 *>(alt_val + base + x);
