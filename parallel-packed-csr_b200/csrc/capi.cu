@@ -99,6 +99,14 @@ int alloc_geometry(ppcsr_shard *s, const Geometry &g) {
 
 // development knob: PPCSR_REB_PAD_SMEM=<bytes> of unused dynamic shared memory caps the resident CTAs per SM of
 // k_rebalance (occupancy experiments); unset in production
+uint32_t reb_prefetch_dist() {  // development knob: PPCSR_REB_PREFETCH=<chunks>, default one wave of resident CTAs
+  static long d = -1;
+  if (d < 0) {
+    const char *e = getenv("PPCSR_REB_PREFETCH");
+    d = e ? atol(e) : 148 * 4;
+  }
+  return (uint32_t)d;
+}
 size_t reb_pad_smem() {
   static long pad = -1;
   if (pad < 0) {
@@ -183,13 +191,14 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
   A.ls_src = g.leaf_shift;
   A.ls_dst = g2.leaf_shift;
   A.m_dst_override = g2.n_leaves;
+  A.prefetch_dist = reb_prefetch_dist();
   PPCSR_TRY(dev_reserve(s->plan, (size_t)hw->n_chunks, s->stream));
   A.plan = s->plan.p;
   reb::k_plan_chunks<<<div_up(hw->n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
       s->windows.p, 1u, s->rank_off.p, s->ins_off.p, g.leaf_shift, g2.leaf_shift, g2.n_leaves, hw->n_chunks, s->plan.p);
   s->launches += 6;
   CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
-  reb::k_rebalance<<<hw->n_chunks, reb::RT, reb_pad_smem(), s->stream>>>(A);
+  reb::k_rebalance<<<hw->n_chunks, reb::KT, reb_pad_smem(), s->stream>>>(A);
   CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
   CUDA_TRY(cudaGetLastError());
   std::swap(s->dest, s->dest_alt);
@@ -337,6 +346,7 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     A.n_windows = (uint32_t)h.n_windows;
     A.ls_src = A.ls_dst = g.leaf_shift;
     A.m_dst_override = 0;
+    A.prefetch_dist = reb_prefetch_dist();
     CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
     if (h.n_small) {
       reb::SmallArgs S{};
@@ -364,7 +374,7 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
           s->windows.p, (uint32_t)h.n_windows, s->rank_off.p, s->ins_off.p, g.leaf_shift, g.leaf_shift, 0,
           (uint32_t)h.n_chunks, s->plan.p);
       s->launches += 2 + (h.multi_slots ? 1 : 0);
-      reb::k_rebalance<<<(unsigned)h.n_chunks, reb::RT, reb_pad_smem(), s->stream>>>(A);
+      reb::k_rebalance<<<(unsigned)h.n_chunks, reb::KT, reb_pad_smem(), s->stream>>>(A);
     }
     CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     if (h.multi_slots) {

@@ -28,7 +28,17 @@ namespace reb {
 
 constexpr int RT = 256;
 constexpr int RWARPS = RT / 32;
-constexpr int CHUNK_SLOTS = 2048;               // output slots per CTA
+#ifndef PPCSR_CHUNK_SLOTS
+#define PPCSR_CHUNK_SLOTS 2048
+#endif
+#ifndef PPCSR_REB_THREADS
+#define PPCSR_REB_THREADS 256
+#endif
+#ifndef PPCSR_SEG_SLOTS
+#define PPCSR_SEG_SLOTS 2048
+#endif
+constexpr int KT = PPCSR_REB_THREADS;  // threads of a k_rebalance CTA
+constexpr int CHUNK_SLOTS = PPCSR_CHUNK_SLOTS;               // output slots per CTA
 
 struct Args {
   const uint32_t *src_dest, *src_val;  // source slots
@@ -45,6 +55,7 @@ struct Args {
   uint32_t ls_src, ls_dst;
   uint32_t m_dst_override;  // != 0: resize, the single window maps onto this many output leaves from leaf 0
   const ChunkPlan *plan;    // one entry per CTA
+  uint32_t prefetch_dist;   // L2 prefetch distance in chunks (0 = off)
 };
 
 
@@ -132,6 +143,10 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
                "r"(bytes)
                : "memory");
 }
+// pull a byte range into L2 ahead of its consumer (no destination, no completion to wait for)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
@@ -141,8 +156,8 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 #ifndef PPCSR_TMA_STORE
 #define PPCSR_TMA_STORE 1
 #endif
-constexpr int SEG_LEAVES_SLOTS = 2048;  // source slots examined per segment (64 leaves of 32 slots): 2 quads per thread
-constexpr int QPT = SEG_LEAVES_SLOTS / 4 / RT;  // 16-byte quads per thread and segment
+constexpr int SEG_LEAVES_SLOTS = PPCSR_SEG_SLOTS;  // source slots examined per segment (64 leaves of 32 slots): 2 quads per thread
+constexpr int QPT = SEG_LEAVES_SLOTS / 4 / KT;  // 16-byte quads per thread and segment
 constexpr int INS_PREFETCH = 2;                 // inserts per thread whose loads are issued together with the quads
 
 // inclusive scan of x over runs of `lpl` consecutive lanes (lpl = 2, 4 or 8: the lanes holding one source leaf)
@@ -162,7 +177,7 @@ __device__ __forceinline__ uint32_t leaf_incl_scan(uint32_t x, unsigned lane, ui
 //   P2  the segment's inserts, spread evenly over the CTA: rank, hang marker, placed -> s_last, staging
 //   P3  the kept items (still in registers): rank from s_last's running maximum, placed -> staging
 // then ONE bulk store (TMA) per array writes the chunk.
-__global__ void __launch_bounds__(RT, PPCSR_REB_CTAS) k_rebalance(Args A) {
+__global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance(Args A) {
   __shared__ __align__(128) uint32_t s_dest[CHUNK_SLOTS];  // the chunk's output slots in their final layout
   __shared__ __align__(128) uint32_t s_val[CHUNK_SLOTS];
   __shared__ uint16_t s_pos[CHUNK_SLOTS];                   // chunk-relative rank -> output slot
@@ -172,6 +187,24 @@ __global__ void __launch_bounds__(RT, PPCSR_REB_CTAS) k_rebalance(Args A) {
   __shared__ __align__(16) uint8_t s_kupto[SEG_LEAVES_SLOTS];  // kept items of the leaf up to and including a slot
 
   const ChunkPlan plan = A.plan[blockIdx.x];
+  // CTAs start in grid order, so the chunk `prefetch_dist` places ahead is picked up about one wave of resident
+  // CTAs from now: pull its source leaves and insert run into L2 so that its loads do not pay DRAM latency.
+  if (threadIdx.x == 0 && A.prefetch_dist && blockIdx.x + A.prefetch_dist < gridDim.x) {
+    const ChunkPlan nx = A.plan[blockIdx.x + A.prefetch_dist];
+    if (nx.i_lo <= nx.i_hi) {
+      const size_t slot0 = (size_t)(nx.leaf0 + nx.i_lo) << A.ls_src;
+      const uint32_t bytes = min(((nx.i_hi - nx.i_lo + 1u) << A.ls_src) * 4u, 16384u);
+      bulk_prefetch_l2(A.src_dest + slot0, bytes);
+      bulk_prefetch_l2(A.src_val + slot0, bytes);
+      if (nx.q_hi > nx.q_lo) {
+        const uint32_t qa = nx.q_lo & ~3u;
+        const uint32_t ib = min((((nx.q_hi - qa) + 3u) & ~3u) * 4u, 8192u);
+        bulk_prefetch_l2(A.ins_pred + qa, ib);
+        bulk_prefetch_l2(A.ins_dst + qa, ib);
+        bulk_prefetch_l2(A.ins_val + qa, ib);
+      }
+    }
+  }
   const unsigned lane = lane_id(), lt = lanemask_lt();
   const uint32_t ls_src = A.ls_src, ls_dst = A.ls_dst;
   const uint32_t m_src = plan.m_multi & 0x7FFFFFFFu;
@@ -212,7 +245,7 @@ __global__ void __launch_bounds__(RT, PPCSR_REB_CTAS) k_rebalance(Args A) {
     uint4 D[QPT], V[QPT];
 #pragma unroll
     for (int u = 0; u < QPT; u++) {
-      const uint32_t rel = (u * RT + threadIdx.x) * 4u;
+      const uint32_t rel = (u * KT + threadIdx.x) * 4u;
       D[u] = make_uint4(0u, 0u, 0u, 0u);
       V[u] = make_uint4(0u, 0u, 0u, 0u);
       if (rel < seg_slots) {
@@ -224,7 +257,7 @@ __global__ void __launch_bounds__(RT, PPCSR_REB_CTAS) k_rebalance(Args A) {
     if (seg == 0) {
 #pragma unroll
       for (int u = 0; u < INS_PREFETCH; u++) {
-        const uint32_t q = plan.q_lo + u * RT + threadIdx.x;
+        const uint32_t q = plan.q_lo + u * KT + threadIdx.x;
         if (q < plan.q_hi) {
           ip[u] = A.ins_pred[q];
           id[u] = A.ins_dst[q];
@@ -232,27 +265,29 @@ __global__ void __launch_bounds__(RT, PPCSR_REB_CTAS) k_rebalance(Args A) {
         }
       }
     }
-    for (uint32_t x = threadIdx.x; x <= seg_nl && nl; x += RT) {
+    for (uint32_t x = threadIdx.x; x <= seg_nl && nl; x += KT) {
       s_R[x] = A.rank_off[gl0 + seg + x] - R0;
       s_ioff[x] = A.ins_off[gl0 + seg + x];
     }
     {
       const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-      for (int u = 0; u < QPT; u++) reinterpret_cast<uint4 *>(s_last)[u * RT + threadIdx.x] = zero;
+      for (int u = 0; u < QPT; u++) reinterpret_cast<uint4 *>(s_last)[u * KT + threadIdx.x] = zero;
     }
     if (seg == 0) {  // null the staging buffers; first rank of every output leaf
       const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
       uint4 *zd = reinterpret_cast<uint4 *>(s_dest), *zv = reinterpret_cast<uint4 *>(s_val);
 #pragma unroll
-      for (int x = 0; x < CHUNK_SLOTS / 4 / RT; x++) {
-        zd[x * RT + threadIdx.x] = zero;
-        zv[x * RT + threadIdx.x] = zero;
+      for (int x = 0; x < CHUNK_SLOTS / 4 / KT; x++) {
+        zd[x * KT + threadIdx.x] = zero;
+        zv[x * KT + threadIdx.x] = zero;
       }
-      for (uint32_t k = threadIdx.x; k <= n_out; k += RT) s_a[k] = leaf_rank0(plan.o_lo + k, j, lg) - a;
+      for (uint32_t k = threadIdx.x; k <= n_out; k += KT) s_a[k] = leaf_rank0(plan.o_lo + k, j, lg) - a;
       __syncthreads();
-      // rank -> slot table, built per output leaf by (RT / max leaves) threads each
-      const uint32_t tpl_shift = ls_dst - 3u;  // threads per leaf: 4, 2, 1 for leaves of 32, 16, 8 slots
+      // rank -> slot table, built per output leaf by (KT / max leaves) threads each
+      constexpr uint32_t TPL8 = KT / (CHUNK_SLOTS / 8);  // threads per 8-slot leaf (a power of two; 0 = several leaves per thread)
+      static_assert(TPL8 >= 1, "at least one thread per smallest leaf");
+      const uint32_t tpl_shift = (ls_dst - 3u) + (31u - (uint32_t)__clz(TPL8));
       const uint32_t k = threadIdx.x >> tpl_shift, sub = threadIdx.x & ((1u << tpl_shift) - 1u);
       if (k < n_out) {
         const uint32_t a_k = s_a[k], cnt = s_a[k + 1] - a_k;
@@ -267,7 +302,7 @@ __global__ void __launch_bounds__(RT, PPCSR_REB_CTAS) k_rebalance(Args A) {
       const uint32_t c = k0 + k1 + k2 + k3;
       pre[u] = leaf_incl_scan(c, lane, lpl) - c;  // kept items of my leaf in lower lanes
       const uint32_t p0 = pre[u] + k0, p1 = p0 + k1, p2 = p1 + k2, p3 = p2 + k3;
-      reinterpret_cast<uint32_t *>(s_kupto)[u * RT + threadIdx.x] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+      reinterpret_cast<uint32_t *>(s_kupto)[u * KT + threadIdx.x] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
     }
     __syncthreads();
     // ---- P2: the segment's inserts: rank = R[leaf] + index in the leaf's run + kept items up to the predecessor.
@@ -284,10 +319,10 @@ __global__ void __launch_bounds__(RT, PPCSR_REB_CTAS) k_rebalance(Args A) {
       uint32_t q = q_begin + threadIdx.x;
       if (seg == 0) {
 #pragma unroll
-        for (int u = 0; u < INS_PREFETCH; u++, q += RT)
+        for (int u = 0; u < INS_PREFETCH; u++, q += KT)
           if (q < q_end) insert(q, ip[u], id[u], iv[u]);
       }
-      for (; q < q_end; q += RT) insert(q, A.ins_pred[q], A.ins_dst[q], A.ins_val[q]);
+      for (; q < q_end; q += KT) insert(q, A.ins_pred[q], A.ins_dst[q], A.ins_val[q]);
     }
     __syncthreads();
     // ---- P3: kept items: rank = R[leaf] + kept before + inserts hanging on earlier slots of the leaf.  The inserts
@@ -297,8 +332,8 @@ __global__ void __launch_bounds__(RT, PPCSR_REB_CTAS) k_rebalance(Args A) {
     const uint32_t base_lo = (seg == 0 && nl) ? plan.q_lo - s_ioff[0] : 0u;
 #pragma unroll
     for (int u = 0; u < QPT; u++) {
-      const uint32_t rel = (u * RT + threadIdx.x) * 4u;
-      const uint4 L = reinterpret_cast<const uint4 *>(s_last)[u * RT + threadIdx.x];
+      const uint32_t rel = (u * KT + threadIdx.x) * 4u;
+      const uint4 L = reinterpret_cast<const uint4 *>(s_last)[u * KT + threadIdx.x];
       const uint32_t lane_max = max(max(L.x, L.y), max(L.z, L.w));
       const unsigned nz = __ballot_sync(0xFFFFFFFFu, lane_max != 0u) & lt & gm;
       uint32_t carry = __shfl_sync(0xFFFFFFFFu, lane_max, nz ? 31 - __clz(nz) : 0);
@@ -332,13 +367,13 @@ __global__ void __launch_bounds__(RT, PPCSR_REB_CTAS) k_rebalance(Args A) {
     }
 #else
     __syncthreads();
-    for (uint32_t x = threadIdx.x * 4u; x < out_slots; x += RT * 4u) {
+    for (uint32_t x = threadIdx.x * 4u; x < out_slots; x += KT * 4u) {
       *reinterpret_cast<uint4 *>(out_dest + x) = *reinterpret_cast<const uint4 *>(s_dest + x);
       *reinterpret_cast<uint4 *>(out_val + x) = *reinterpret_cast<const uint4 *>(s_val + x);
     }
 #endif
   }
-  for (uint32_t k = threadIdx.x; k < n_out; k += RT) A.tree_leaf_out[dst_leaf0 + plan.o_lo + k] = s_a[k + 1] - s_a[k];
+  for (uint32_t k = threadIdx.x; k < n_out; k += KT) A.tree_leaf_out[dst_leaf0 + plan.o_lo + k] = s_a[k + 1] - s_a[k];
 #if PPCSR_TMA_STORE
   if (threadIdx.x == 0) bulk_wait_read0();  // the staging buffers must outlive the copy
 #endif
