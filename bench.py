@@ -46,7 +46,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="insert", choices=["insert", "delete"])
+    ap.add_argument("--workload", default="insert", choices=["insert", "delete", "skewed", "mixed"],
+                    help="insert: uniform inserts (C2); delete: deletes sampled from the core (C3); skewed: R-MAT "
+                         "inserts (C4); mixed: 3/4 uniform inserts + 1/4 deletes of core edges, per-update op (C5)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --scale and --batch are the GLOBAL graph and batch, split over the ranks")
+    ap.add_argument("--pagerank", action="store_true", help="one PageRank push step after every batch (timed apart)")
     ap.add_argument("--scale", type=int, default=20)
     ap.add_argument("--batch", type=int, default=10_000_000)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="updates in the CPU baseline sample")
@@ -117,18 +122,32 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline
 # ------------------------------------------------------------------------------------------------
+def host_updates(scale, workload, lo, hi, synth, core=None):
+    """Updates [lo, hi) of the workload's global stream on the host: (src, dst, value-or-array)."""
+    total = 16 << scale
+    if workload == "insert":
+        us, ud = synth.uniform(scale, lo, hi, 7)
+        return us, ud, 1
+    if workload == "skewed":
+        us, ud = synth.rmat(scale, lo, hi, 99)
+        return us, ud, 1
+    cs, cd = core if core is not None else synth.rmat(scale, 0, total, 42)
+    idx = synth.sample_without_replacement(total, hi, 7)[lo:hi]
+    if workload == "delete":
+        return cs[idx], cd[idx], 0
+    ops = synth.mixed_ops(lo, hi, 11)
+    us, ud = synth.uniform(scale, lo, hi, 7)
+    return np.where(ops != 0, us, cs[idx]), np.where(ops != 0, ud, cd[idx]), ops
+
+
 def _write_inputs(tmp, scale, workload, sample, synth):
     n = 1 << scale
     cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
     core = os.path.join(tmp, "core.bin")
     synth.write_triples(core, cs, cd, 1)
     upd = os.path.join(tmp, "upd.bin")
-    if workload == "insert":
-        us, ud = synth.uniform(scale, 0, sample, 7)
-        synth.write_triples(upd, us, ud, 1)
-    else:
-        idx = synth.sample_without_replacement(16 << scale, sample, 7)
-        synth.write_triples(upd, cs[idx], cd[idx], 0)
+    us, ud, v = host_updates(scale, workload, 0, sample, synth, core=(cs, cd))
+    synth.write_triples(upd, us, ud, v)
     return n, core, upd
 
 
@@ -150,12 +169,7 @@ def run_port_once(scale, workload, sample, synth):
     cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
     g = O.OraclePCSR(n)
     g.apply(cs, cd, 1)
-    if workload == "insert":
-        us, ud = synth.uniform(scale, 0, sample, 7)
-        v = 1
-    else:
-        idx = synth.sample_without_replacement(16 << scale, sample, 7)
-        us, ud, v = cs[idx], cd[idx], 0
+    us, ud, v = host_updates(scale, workload, 0, sample, synth, core=(cs, cd))
     t0 = time.perf_counter()
     g.apply(us, ud, v)
     return {"update_ms": (time.perf_counter() - t0) * 1e3, "update_ops": sample}
@@ -167,7 +181,7 @@ def cpu_baseline(args, synth, steps=1, warmup=0):
 
     sample = min(args.cpu_sample, args.batch)
     what = (f"R-MAT scale-{args.scale} core loaded through the reference, then the first {sample} of the "
-            f"{args.batch} {'uniform inserts' if args.workload == 'insert' else 'deletes'}; time = start()->stop() of the update phase")
+            f"{args.batch} {WORKLOAD_TEXT[args.workload]}; time = start()->stop() of the update phase")
     times = []
     if O.have_ref():
         threads = os.cpu_count() or 1
@@ -195,7 +209,7 @@ def main_reference(args):
     base, ms = cpu_baseline(args, synth, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": base,
@@ -205,13 +219,27 @@ def main_reference(args):
     return 0
 
 
+WORKLOAD_TEXT = {
+    "insert": "uniform-random edge insertions",
+    "delete": "edge deletions sampled from the core",
+    "skewed": "skewed (R-MAT) edge insertions",
+    "mixed": "mixed updates (3/4 uniform insertions, 1/4 deletions of core edges, per-update op)",
+}
+
+
+def global_shape(args, world):
+    """(scale, updates per rank) of the run: weak scaling grows the graph with the ranks, strong splits it."""
+    if args.strong:
+        return args.scale, args.batch // world
+    return args.scale + (world.bit_length() - 1), args.batch
+
+
 def workload_config(args, world):
-    op = "uniform-random edge insertions" if args.workload == "insert" else "edge deletions sampled from the core"
-    scale = args.scale + (world.bit_length() - 1)
+    scale, B = global_shape(args, world)
     return {
         "workload": f"R-MAT scale-{scale} core ({16 << scale} raw edges, a/b/c/d=.57/.19/.19/.05) + "
-                    f"{args.batch * world} {op}, one batch of {args.batch} per GPU per step",
-        "batch_per_gpu": args.batch, "scale": scale, "slot_bytes": SLOT_BYTES,
+                    f"{B * world} {WORKLOAD_TEXT[args.workload]}, one batch of {B} per GPU per step",
+        "batch_per_gpu": B, "scale": scale, "slot_bytes": SLOT_BYTES,
         "parallelism": "1 shard" if world == 1 else f"{world} vertex-range shards, NCCL all-to-all routing",
         "l2": "shard state is restored from a device snapshot (>400 MB of writes, larger than the 126 MB L2) "
               "before every timed step; the working set (>=270 MB) also exceeds L2",
@@ -244,9 +272,8 @@ def main_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream()
 
-    scale = args.scale + (world.bit_length() - 1)
+    scale, B = global_shape(args, world)
     n = 1 << scale
-    B = args.batch
     router = importlib.import_module("parallel-packed-csr_b200.router")
 
     # ---- core graph: every rank generates its slice of the global R-MAT stream, routes it to the owners
@@ -258,7 +285,7 @@ def main_b200(args):
         # Shard cost model measured at N=1/2: ~0.13 us per routed update (sort + locate) and ~0.016 us per stored
         # item (window selection + rebalance).  A uniform stream sends B*world/n updates to every vertex, so a
         # vertex weighs ~8 * B*world/n "edges"; deletes follow the edge distribution instead.
-        vw = 8.0 * B * world / n if args.workload == "insert" else 0.0
+        vw = 8.0 * B * world / n if args.workload in ("insert", "mixed") else 0.0
         starts = router.edge_balanced_starts(cs, n, world, dist, vertex_weight=vw)
     else:
         starts = np.array([0, n], dtype=np.uint64)
@@ -268,19 +295,27 @@ def main_b200(args):
     core_geo = graph.shard.geometry
     del cs, cd
 
-    # ---- the update batch of this rank
+    # ---- the update batch of this rank: its slice [rank*B, (rank+1)*B) of the workload's global stream
+    uv = None  # per-update op (1 add / 0 delete) of the mixed stream
+    default_val = 1
     if args.workload == "insert":
         us, ud = synth.uniform(scale, rank * B, (rank + 1) * B, 7, device=dev)
-        default_val = 1
+    elif args.workload == "skewed":
+        us, ud = synth.rmat(scale, rank * B, (rank + 1) * B, 99, device=dev)
     else:
+        # deletes: sampled without replacement from the raw core list; only the sampled edges are regenerated
+        # (the stream is a pure function of the element index)
         idx = synth.sample_without_replacement(core_total, B * world, 7, device=dev)[rank * B:(rank + 1) * B]
-        all_s, all_d = synth.rmat(scale, 0, core_total, 42, device=dev) if world == 1 else (None, None)
-        if world == 1:
-            us, ud = all_s[idx], all_d[idx]
-        else:  # regenerate only the sampled edges (pure function of the index)
-            us, ud = synth.rmat_at(scale, idx, 42)
-        default_val = 0
-        del all_s, all_d
+        us, ud = synth.rmat_at(scale, idx, 42)
+        del idx
+        if args.workload == "delete":
+            default_val = 0
+        else:
+            uv = synth.mixed_ops(rank * B, (rank + 1) * B, 11, device=dev)
+            fs, fd = synth.uniform(scale, rank * B, (rank + 1) * B, 7, device=dev)
+            us, ud = torch.where(uv != 0, fs, us), torch.where(uv != 0, fd, ud)
+            uv = uv.to(torch.int32).contiguous()
+            del fs, fd
     us, ud = us.to(torch.int32).contiguous(), ud.to(torch.int32).contiguous()
     graph.shard.reserve(max_slots=core_geo.N * 4, max_batch=int(B * 1.5) + 1024)
     graph.shard.snapshot()
@@ -297,7 +332,7 @@ def main_b200(args):
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     for _ in range(args.warmup):
         graph.shard.restore()
-        graph.apply(us, ud, None, default_val=default_val)
+        graph.apply(us, ud, uv, default_val=default_val)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -306,7 +341,7 @@ def main_b200(args):
         graph.shard.restore()
         torch.cuda.synchronize()
         ev0[k].record(stream)
-        st = graph.apply(us, ud, None, default_val=default_val)
+        st = graph.apply(us, ud, uv, default_val=default_val)
         ev1[k].record(stream)
         stats_acc.append(st)
     barrier()
@@ -330,13 +365,17 @@ def main_b200(args):
     hd = torch.empty(B, dtype=torch.int32).pin_memory()
     hs.copy_(us)
     hd.copy_(ud)
+    hv = None
+    if uv is not None:
+        hv = torch.empty(B, dtype=torch.int32).pin_memory()
+        hv.copy_(uv)
     e2e_ms = 0.0
     e2e_steps = max(2, min(args.steps, 3))
     for k in range(1 + e2e_steps):
         graph.shard.restore()
         barrier()
         t0 = time.perf_counter()
-        graph.apply_host(hs.numpy(), hd.numpy(), None, default_val=default_val)
+        graph.apply_host(hs.numpy(), hd.numpy(), hv.numpy() if hv is not None else None, default_val=default_val)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) * 1e3
         if k > 0:
@@ -347,9 +386,29 @@ def main_b200(args):
     e2e_value = B * world * e2e_steps / (float(t.item()) / 1e3)
 
     # ---- parity guard on the final state (cheap): invariants must hold
-    rep = graph.shard.check(check_lower=args.workload == "delete")
-    if rep.violations(args.workload == "delete"):
+    lower = args.workload in ("delete", "mixed")
+    rep = graph.shard.check(check_lower=lower)
+    if rep.violations(lower):
         raise SystemExit(f"bench.py: PMA invariants violated after the timed steps: {rep.as_dict()}")
+
+    # ---- optional edge scan: PageRank push steps over the updated graph (reference pagerank.h:16-29)
+    pagerank = None
+    if args.pagerank:
+        vals = 1.0 + (torch.arange(n, device=dev, dtype=torch.float64) % 7)
+        graph.pagerank_step(vals)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(args.steps):
+            graph.pagerank_step(vals)
+        p1.record(stream)
+        barrier()
+        pt = torch.tensor([p0.elapsed_time(p1) / args.steps], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        geo = graph.shard.geometry
+        pagerank = {"ms_per_step": float(pt.item()), "slots_rank0": int(geo.N),
+                    "note": "one push step over every shard (+ one all-reduce of the fp64 vector when sharded)"}
 
     if rank != 0:
         if dist is not None:
@@ -373,10 +432,11 @@ def main_b200(args):
     last = stats_acc[-1]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 4 * B, "d2h_bytes_per_step": 2 * 128,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (3 if hv is not None else 2) * 4 * B,
+                "d2h_bytes_per_step": 2 * 128,
                 "steps": e2e_steps},
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats_acc)),
         "roofline": {"bound": "hbm", "kernel": "reb::k_rebalance", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -390,6 +450,8 @@ def main_b200(args):
         "rebalance_bytes_per_update": reb_bytes / B,
         "hbm_roofline_updates_per_sec": peak * 1e9 / (16 + reb_bytes / B),
     }
+    if pagerank is not None:
+        line["pagerank"] = pagerank
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"], _ = cpu_baseline(args, synth)

@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys
                                                uint32_t ls, uint32_t *__restrict__ nn, uint32_t *__restrict__ uloc,
                                                uint8_t *__restrict__ ucls, uint32_t *__restrict__ ins_cnt,
                                                uint32_t *__restrict__ del_cnt, BatchScalars *sc) {
-  __shared__ uint32_t s_stat[5];
-  if (threadIdx.x < 5) s_stat[threadIdx.x] = 0;
+  __shared__ uint32_t s_stat[6];
+  if (threadIdx.x < 6) s_stat[threadIdx.x] = 0;
   __syncthreads();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lt = lanemask_lt();
@@ -196,16 +196,20 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys
       if (sum) atomicAdd(&nn[s], (uint32_t)sum);
     }
   }
-  // per-leaf counts: the batch is key-sorted, so equal leaves are adjacent -> one atomic per warp run
+  // per-leaf counts: the batch is key-sorted, so equal leaves are adjacent -> one atomic per warp run.  The first
+  // update to reach a leaf also counts it as touched (a leaf hit by inserts AND deletes counts twice: the total
+  // only steers the whole-array-versus-windows policy).
+  bool first_touch = false;
   {
     const uint32_t key = (cls == CLS_INSERT) ? leaf : 0xFFFFFFFFu;
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
-    if (key != 0xFFFFFFFFu && (peers & lt) == 0) atomicAdd(&ins_cnt[leaf], (uint32_t)__popc(peers));
+    if (key != 0xFFFFFFFFu && (peers & lt) == 0) first_touch = atomicAdd(&ins_cnt[leaf], (uint32_t)__popc(peers)) == 0u;
   }
   {
     const uint32_t key = (cls == CLS_DELETE) ? leaf : 0xFFFFFFFFu;
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
-    if (key != 0xFFFFFFFFu && (peers & lt) == 0) atomicAdd(&del_cnt[leaf], (uint32_t)__popc(peers));
+    if (key != 0xFFFFFFFFu && (peers & lt) == 0)
+      first_touch |= atomicAdd(&del_cnt[leaf], (uint32_t)__popc(peers)) == 0u;
   }
   {
     const unsigned m0 = __ballot_sync(0xFFFFFFFFu, cls == CLS_INSERT);
@@ -214,7 +218,9 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys
     const unsigned m3 = __ballot_sync(0xFFFFFFFFu, miss_dup);
     const unsigned m5 = __ballot_sync(0xFFFFFFFFu, miss_first);
     const unsigned m4 = __ballot_sync(0xFFFFFFFFu, winner);
+    const unsigned m6 = __ballot_sync(0xFFFFFFFFu, first_touch);
     if (lane_id() == 0) {
+      if (m6) atomicAdd(&s_stat[5], (uint32_t)__popc(m6));
       if (m0) atomicAdd(&s_stat[0], (uint32_t)__popc(m0));
       if (m1) atomicAdd(&s_stat[1], (uint32_t)__popc(m1));
       if (m2) atomicAdd(&s_stat[2], (uint32_t)__popc(m2));
@@ -229,6 +235,7 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys
     if (s_stat[2]) atomicAdd(&sc->n_deleted, (unsigned long long)s_stat[2]);
     if (s_stat[3]) atomicAdd(&sc->n_not_found, (unsigned long long)s_stat[3]);
     if (s_stat[4]) atomicAdd(&sc->n_unique, (unsigned long long)s_stat[4]);
+    if (s_stat[5]) atomicAdd(&sc->n_touched_est, (unsigned long long)s_stat[5]);
   }
 }
 

@@ -262,6 +262,10 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     whole = true;
     st->resized = new_N != g.N ? 2 : 0;
   }
+  // Policy: the per-window path costs ~4x more per slot than streaming the array once (scattered 128-byte leaves,
+  // one warp each, plus the tree walks of window selection), so once a quarter of the leaves is touched the batch
+  // is applied as ONE root window -- before any window is selected.
+  if (!whole && (h.n_inserted || h.n_deleted) && L >= 64 && h.n_touched_est * 4ull >= L) whole = true;
   if (whole) {
     PPCSR_TRY(scan_rank_and_insert_offsets(s, L));
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
