@@ -240,7 +240,8 @@ def workload_config(args, world):
         "workload": f"R-MAT scale-{scale} core ({16 << scale} raw edges, a/b/c/d=.57/.19/.19/.05) + "
                     f"{B * world} {WORKLOAD_TEXT[args.workload]}, one batch of {B} per GPU per step",
         "batch_per_gpu": B, "scale": scale, "slot_bytes": SLOT_BYTES,
-        "parallelism": "1 shard" if world == 1 else f"{world} vertex-range shards, NCCL all-to-all routing",
+        "parallelism": "1 shard" if world == 1 else f"{world} vertex-range shards, updates routed to their owner "
+                       "through NVLink peer memory (fused bin+scatter kernel; NCCL all-to-all when unavailable)",
         "l2": "shard state is restored from a device snapshot (>400 MB of writes, larger than the 126 MB L2) "
               "before every timed step; the working set (>=270 MB) also exceeds L2",
     }
@@ -289,7 +290,9 @@ def main_b200(args):
         starts = router.edge_balanced_starts(cs, n, world, dist, vertex_weight=vw)
     else:
         starts = np.array([0, n], dtype=np.uint64)
-    graph = router.ShardedGraph(n, starts, rank, world, local_rank, dist=dist)
+    peer_cap = 0 if os.environ.get("PPCSR_NO_PEER") else max(B, hi - lo)
+    graph = router.ShardedGraph(n, starts, rank, world, local_rank, dist=dist, peer_cap=peer_cap,
+                                peer_values=args.workload == "mixed")
     graph.shard.set_stream(stream.cuda_stream)
     graph.apply(cs, cd, None, default_val=1)
     core_geo = graph.shard.geometry
@@ -339,7 +342,7 @@ def main_b200(args):
         sampler.start()
     for k in range(args.steps):
         graph.shard.restore()
-        torch.cuda.synchronize()
+        barrier()  # the untimed restore takes a different time on every shard: start the step together
         ev0[k].record(stream)
         st = graph.apply(us, ud, uv, default_val=default_val)
         ev1[k].record(stream)
@@ -352,6 +355,15 @@ def main_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = B * world * args.steps / (total_ms / 1e3)
+    if world > 1 and os.environ.get("PPCSR_ROUTE_TIMING"):
+        graph.route_timing = []
+        for _ in range(3):
+            graph.shard.restore()
+            barrier()
+            graph.apply(us, ud, uv, default_val=default_val)
+        print(f"[rank {rank}] routing stages ms ([bin, counts, all-to-all, apply] over NCCL, [exchange, apply] over "
+              f"peer memory): {graph.route_timing}", file=sys.stderr)
+        graph.route_timing = None
     if world > 1:  # per-rank view (stderr): how many updates each shard received and where its time went
         s0 = stats_acc[-1]
         print(f"[rank {rank}] local ms/step {sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)) / args.steps:.3f} "
@@ -463,6 +475,18 @@ def main_b200(args):
     return 0
 
 
+def _claim_stdout():
+    """Rank 0 must print exactly ONE JSON line on stdout, but libraries (NCCL's version banner) write to fd 1
+    directly.  Point fd 1 at stderr for the whole run and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
+
+
 if __name__ == "__main__":
     a = parse_args()
-    sys.exit(main_reference(a) if a.impl == "reference" else main_b200(a))
+    _claim_stdout()
+    rc = main_reference(a) if a.impl == "reference" else main_b200(a)
+    sys.stdout.flush()
+    sys.exit(rc)

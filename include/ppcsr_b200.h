@@ -139,6 +139,22 @@ int ppcsr_bin_by_owner(int device, void *cuda_stream, const uint64_t *d_starts, 
 int ppcsr_bin_by_owner_packed(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts,
                               const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val, uint64_t count,
                               uint64_t *d_out_packed, uint32_t *d_out_val, uint64_t *h_counts);
+/* Routing fused with the exchange (NVLink / NVSwitch peer memory): bins the batch by owner like
+ * ppcsr_bin_by_owner_packed, but every packed record is stored straight into the OWNING GPU's receive buffer.
+ * h_peer_rec / h_peer_val / h_peer_cnt are HOST arrays of n_parts device pointers (one per rank, peer-mapped, e.g.
+ * the buffer_ptrs of a symmetric allocation): rank r's receive buffer holds n_parts regions of `region_cap` records,
+ * region s written by sender s; its count array holds n_parts u64 counts, entry s written by sender s.  No host
+ * synchronisation; the caller runs a cross-GPU barrier on the same stream before the owners read their buffers.
+ * Replaces the hand-over of reference ThreadPoolPPPCSR::submit_* (src/thread_pool_pppcsr/thread_pool_pppcsr.cpp:96-118). */
+int ppcsr_bin_to_peers(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts, uint32_t my_rank,
+                       const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val, uint64_t count,
+                       const uint64_t *h_peer_rec, const uint64_t *h_peer_val, const uint64_t *h_peer_cnt,
+                       uint64_t region_cap);
+/* Applies what the peers deposited: `n_segments` regions of `region_cap` packed records at d_packed (values at d_val,
+ * nullable), region r holding h_counts[r] valid records (host array). */
+int ppcsr_apply_batch_segments_device(ppcsr_shard *h, const uint64_t *d_packed, const uint32_t *d_val,
+                                      uint64_t region_cap, const uint64_t *h_counts, uint32_t n_segments,
+                                      uint32_t default_val, ppcsr_batch_stats *stats);
 /* Applies a device-resident batch of packed records (src << 32 | dst), e.g. what the all-to-all delivered. */
 int ppcsr_apply_batch_packed_device(ppcsr_shard *h, const uint64_t *d_packed, const uint32_t *d_val, uint64_t count,
                                     uint32_t default_val, ppcsr_batch_stats *stats);

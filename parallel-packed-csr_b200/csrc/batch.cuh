@@ -86,6 +86,55 @@ __global__ void __launch_bounds__(BT) k_build_keys_packed(const uint64_t *__rest
   }
 }
 
+// Records that arrived through peer memory: `n_seg` regions of `cap` records each, region r holding prefix[r+1] -
+// prefix[r] valid records (one region per sending rank, see k_bin_scatter_peers).  Same guards as above.
+struct SegmentTable {
+  uint32_t n_seg;
+  uint64_t cap;
+  uint64_t prefix[65];  // exclusive prefix of the valid counts, prefix[n_seg] = total
+};
+__global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__restrict__ packed,
+                                                            const uint32_t *__restrict__ val, uint32_t default_val,
+                                                            SegmentTable T, uint32_t n, uint64_t *__restrict__ keys,
+                                                            uint32_t *__restrict__ pay, BatchScalars *sc) {
+  __shared__ uint32_t s_or, s_bad;
+  if (threadIdx.x == 0) {
+    s_or = 0;
+    s_bad = 0;
+  }
+  __syncthreads();
+  uint32_t my_or = 0, my_bad = 0;
+  const size_t count = (size_t)T.prefix[T.n_seg];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = T.n_seg;  // last region with prefix <= i
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (T.prefix[mid] <= i) lo = mid;
+      else hi = mid;
+    }
+    const size_t at = (size_t)lo * T.cap + (i - (size_t)T.prefix[lo]);
+    const uint64_t k = packed[at];
+    const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k;
+    const uint32_t v = val ? val[at] : default_val;
+    const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
+    keys[i] = ok ? k : ((uint64_t)n << 32);
+    if (pay) pay[i] = ok ? v : 0u;
+    if (ok) my_or |= d;
+    else my_bad++;
+  }
+  my_or = __reduce_or_sync(0xFFFFFFFFu, my_or);
+  my_bad = __reduce_add_sync(0xFFFFFFFFu, my_bad);
+  if (lane_id() == 0) {
+    if (my_or) atomicOr(&s_or, my_or);
+    if (my_bad) atomicAdd(&s_bad, my_bad);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_or) atomicOr(&sc->dst_or, s_or);
+    if (s_bad) atomicAdd(&sc->n_ignored, (unsigned long long)s_bad);
+  }
+}
+
 // ---- segmented search ----------------------------------------------------------------------------
 // Finds (src,dst) inside vertex src's slot range (beg[src], beg[src+1]).  Two levels: a binary search
 // over the LEAVES of the range on their first item (empty leaves are skipped to the right), then a
@@ -346,6 +395,103 @@ __global__ void __launch_bounds__(BT) k_bin_scatter(const uint32_t *__restrict__
       if (out_val) out_val[pos] = val ? val[i] : 1u;
     }
   }
+}
+
+// Routing fused with the exchange: the stable owner binning of k_bin_scatter, but every record goes STRAIGHT INTO THE
+// OWNING GPU'S RECEIVE BUFFER over NVLink (peer pointers of a symmetric allocation) -- no send buffer, no count
+// exchange before the data moves, no NCCL all-to-all.  Rank `me` owns region `me` (cap records) of every peer's
+// buffer; the tile is first reordered by destination in shared memory so that the peer stores are coalesced runs
+// (a tile of 4096 records gives runs of ~512 records = 4 KB per destination on 8 GPUs), and block 0 deposits the
+// per-destination counts in the peers' count arrays.  A cross-GPU barrier after this kernel publishes everything.
+//   dynamic shared memory: u64 rec[SORT_TILE] | u32 val[SORT_TILE] (when values travel) | u8 owner[SORT_TILE]
+struct PeerTable {
+  uint64_t *rec[BIN_MAX_PARTS];  // receive buffer of every rank (records)
+  uint32_t *val[BIN_MAX_PARTS];  // receive buffer of every rank (values), used when d_val != nullptr
+  uint64_t *cnt[BIN_MAX_PARTS];  // count array of every rank: cnt[dest][sender]
+};
+inline size_t bin_peers_smem(bool has_val) {
+  return (size_t)prim::SORT_TILE * 8 + (has_val ? (size_t)prim::SORT_TILE * 4 : 0) + (size_t)prim::SORT_TILE;
+}
+template <bool HAS_VAL>
+__global__ void __launch_bounds__(BT) k_bin_scatter_peers(const uint32_t *__restrict__ src,
+                                                          const uint32_t *__restrict__ dst,
+                                                          const uint32_t *__restrict__ val, size_t count,
+                                                          const uint64_t *__restrict__ starts, uint32_t parts,
+                                                          const uint32_t *__restrict__ offs, uint32_t nblocks,
+                                                          uint32_t me, uint64_t cap, PeerTable P) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  uint64_t *s_rec = reinterpret_cast<uint64_t *>(s_dyn);
+  uint32_t *s_v = reinterpret_cast<uint32_t *>(s_dyn + (size_t)prim::SORT_TILE * 8);
+  uint8_t *s_own = s_dyn + (size_t)prim::SORT_TILE * 8 + (HAS_VAL ? (size_t)prim::SORT_TILE * 4 : 0);
+  __shared__ uint32_t s_cnt[prim::SORT_WARPS][BIN_MAX_PARTS];
+  __shared__ uint32_t s_tbase[BIN_MAX_PARTS + 1];  // tile-local start of every destination's run
+  __shared__ uint32_t s_gbase[BIN_MAX_PARTS];      // region-relative position of the tile's run
+  __shared__ uint64_t s_st[BIN_MAX_PARTS];
+  for (int d = threadIdx.x; d < prim::SORT_WARPS * BIN_MAX_PARTS; d += BT) (&s_cnt[0][0])[d] = 0;
+  if (threadIdx.x < parts) s_st[threadIdx.x] = starts[threadIdx.x];
+  __syncthreads();
+  const unsigned w = threadIdx.x >> 5, l = lane_id(), lt = lanemask_lt();
+  const size_t wbase = (size_t)blockIdx.x * prim::SORT_TILE + (size_t)w * (32 * prim::SORT_ROUNDS);
+  uint32_t own[prim::SORT_ROUNDS], rank[prim::SORT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < prim::SORT_ROUNDS; r++) {
+    const size_t i = wbase + (size_t)r * 32 + l;
+    const bool valid = i < count;
+    const uint32_t d = valid ? owner_of(s_st, parts, src[i]) : 0x1FFu;
+    own[r] = d;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+    uint32_t base = 0;
+    if (valid) base = s_cnt[w][d];
+    __syncwarp();
+    if (valid && (peers & lt) == 0) s_cnt[w][d] = base + __popc(peers);
+    __syncwarp();
+    rank[r] = base + __popc(peers & lt);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // tile-local layout: destination-major, warp-minor (stable)
+    uint32_t run = 0;
+    for (uint32_t p = 0; p < parts; p++) {
+      s_tbase[p] = run;
+      for (int ww = 0; ww < prim::SORT_WARPS; ww++) {
+        const uint32_t t = s_cnt[ww][p];
+        s_cnt[ww][p] = run;
+        run += t;
+      }
+    }
+    s_tbase[parts] = run;
+  }
+  if (threadIdx.x < parts) {
+    const size_t row = (size_t)threadIdx.x * nblocks;
+    s_gbase[threadIdx.x] = offs[row + blockIdx.x] - offs[row];
+    if (blockIdx.x == 0) {  // this rank's count for destination p, deposited at the destination
+      const uint32_t next = threadIdx.x + 1 < parts ? offs[row + nblocks] : (uint32_t)count;
+      P.cnt[threadIdx.x][me] = next - offs[row];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < prim::SORT_ROUNDS; r++) {
+    const size_t i = wbase + (size_t)r * 32 + l;
+    if (i < count) {
+      const uint32_t d = own[r];
+      const uint32_t at = s_cnt[w][d] + rank[r];
+      s_rec[at] = ((uint64_t)(src[i] - (uint32_t)s_st[d]) << 32) | dst[i];  // shard-local id (PPPCSR.cpp:46-52)
+      if (HAS_VAL) s_v[at] = val[i];
+      s_own[at] = (uint8_t)d;
+    }
+  }
+  __syncthreads();
+  const uint32_t tile_n = s_tbase[parts];
+  for (uint32_t x = threadIdx.x; x < tile_n; x += BT) {
+    const uint32_t d = s_own[x];
+    const size_t at = (size_t)me * cap + s_gbase[d] + (x - s_tbase[d]);
+    P.rec[d][at] = s_rec[x];
+    if (HAS_VAL) P.val[d][at] = s_v[x];
+  }
+}
+// an empty local batch still has to tell every peer "nothing from me"
+__global__ void k_zero_peer_counts(uint32_t parts, uint32_t me, PeerTable P) {
+  if (threadIdx.x < parts) P.cnt[threadIdx.x][me] = 0;
 }
 
 }  // namespace batch

@@ -607,7 +607,8 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
 
 // shared by the (src,dst) and the packed entry points: `packed` != nullptr selects the packed key builder
 static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint32_t *d_dst, const uint64_t *d_packed,
-                               const uint32_t *d_val, uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats) {
+                               const uint32_t *d_val, uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats,
+                               const batch::SegmentTable *segments = nullptr) {
   PPCSR_TRY(set_device(s));
   ppcsr_batch_stats st{};
   st.batch_size = count;
@@ -631,7 +632,10 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   // 1. keys + guards.  With no per-update values every payload is default_val: sort keys only.
   const bool has_pay = d_val != nullptr;
   const unsigned kb = std::min<unsigned>(div_up(count, batch::BT * 8), 148 * 16);
-  if (d_packed) {
+  if (segments) {
+    batch::k_build_keys_segments<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, *segments, s->n,
+                                                                 s->key_a.p, has_pay ? s->pay_a.p : nullptr, sc);
+  } else if (d_packed) {
     batch::k_build_keys_packed<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, count, s->n, s->key_a.p,
                                                                has_pay ? s->pay_a.p : nullptr, sc);
   } else {
@@ -678,6 +682,27 @@ int ppcsr_apply_batch_packed_device(ppcsr_shard *s, const uint64_t *d_packed, co
                                     uint32_t default_val, ppcsr_batch_stats *stats) {
   if (!s || (count && !d_packed)) return PPCSR_ERR_ARG;
   return apply_device_common(s, nullptr, nullptr, d_packed, d_val, count, default_val, stats);
+}
+
+int ppcsr_apply_batch_segments_device(ppcsr_shard *s, const uint64_t *d_packed, const uint32_t *d_val,
+                                      uint64_t region_cap, const uint64_t *h_counts, uint32_t n_segments,
+                                      uint32_t default_val, ppcsr_batch_stats *stats) {
+  if (!s || !h_counts || n_segments == 0 || n_segments > batch::BIN_MAX_PARTS) return PPCSR_ERR_ARG;
+  batch::SegmentTable T{};
+  T.n_seg = n_segments;
+  T.cap = region_cap;
+  uint64_t total = 0;
+  for (uint32_t r = 0; r < n_segments; r++) {
+    if (h_counts[r] > region_cap) {
+      g_ppcsr_error = "segment count exceeds the region capacity";
+      return PPCSR_ERR_ARG;
+    }
+    T.prefix[r] = total;
+    total += h_counts[r];
+  }
+  T.prefix[n_segments] = total;
+  if (total && !d_packed) return PPCSR_ERR_ARG;
+  return apply_device_common(s, nullptr, nullptr, d_packed, d_val, total, default_val, stats, &T);
 }
 
 int ppcsr_apply_batch(ppcsr_shard *s, const uint32_t *src, const uint32_t *dst, const uint32_t *val, uint64_t count,
@@ -818,6 +843,62 @@ static int bin_common(int device, void *cuda_stream, const uint64_t *d_starts, u
     const uint64_t next = p + 1 < n_parts ? bs->h_firsts[p + 1] : count;
     h_counts[p] = next - bs->h_firsts[p];
   }
+  return PPCSR_OK;
+}
+
+int ppcsr_bin_to_peers(int device, void *cuda_stream, const uint64_t *d_starts, uint32_t n_parts, uint32_t my_rank,
+                       const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val, uint64_t count,
+                       const uint64_t *h_peer_rec, const uint64_t *h_peer_val, const uint64_t *h_peer_cnt,
+                       uint64_t region_cap) {
+  if (n_parts == 0 || n_parts > batch::BIN_MAX_PARTS || my_rank >= n_parts || !h_peer_rec || !h_peer_cnt ||
+      (d_val && !h_peer_val) || (count && (!d_src || !d_dst)))
+    return PPCSR_ERR_ARG;
+  if (count > region_cap || count >= (1ull << 32)) {
+    g_ppcsr_error = "bin_to_peers: the batch exceeds the capacity of this rank's region in the peers' buffers";
+    return PPCSR_ERR_CAPACITY;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  batch::PeerTable P{};
+  for (uint32_t p = 0; p < n_parts; p++) {
+    P.rec[p] = reinterpret_cast<uint64_t *>(h_peer_rec[p]);
+    P.val[p] = h_peer_val ? reinterpret_cast<uint32_t *>(h_peer_val[p]) : nullptr;
+    P.cnt[p] = reinterpret_cast<uint64_t *>(h_peer_cnt[p]);
+  }
+  if (count == 0) {
+    batch::k_zero_peer_counts<<<1, batch::BIN_MAX_PARTS, 0, st>>>(n_parts, my_rank, P);
+    CUDA_TRY(cudaGetLastError());
+    return PPCSR_OK;
+  }
+  BinScratch *bs = bin_scratch(device);
+  if (!bs) {
+    g_ppcsr_error = "bin_to_peers: cannot allocate scratch";
+    return PPCSR_ERR_CAPACITY;
+  }
+  ppcsr_shard &tmp = bs->shard;
+  tmp.stream = st;
+  const unsigned nblocks = div_up(count, prim::SORT_TILE);
+  const size_t hn = (size_t)n_parts * nblocks;
+  PPCSR_TRY(dev_reserve(tmp.hist, hn + 1, st));
+  batch::k_bin_count<<<nblocks, batch::BT, 0, st>>>(d_src, count, d_starts, n_parts, tmp.hist.p, nblocks);
+  PPCSR_TRY(prim::device_scan(&tmp, prim::InArray{tmp.hist.p}, prim::OutPrefixWithTotal{tmp.hist.p, hn}, hn, nullptr,
+                              nullptr));
+  static bool attr_done[64] = {};
+  if (device >= 64 || !attr_done[device]) {
+    CUDA_TRY(cudaFuncSetAttribute(batch::k_bin_scatter_peers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)batch::bin_peers_smem(true)));
+    CUDA_TRY(cudaFuncSetAttribute(batch::k_bin_scatter_peers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)batch::bin_peers_smem(false)));
+    if (device < 64) attr_done[device] = true;
+  }
+  if (d_val) {
+    batch::k_bin_scatter_peers<true><<<nblocks, batch::BT, batch::bin_peers_smem(true), st>>>(
+        d_src, d_dst, d_val, count, d_starts, n_parts, tmp.hist.p, nblocks, my_rank, region_cap, P);
+  } else {
+    batch::k_bin_scatter_peers<false><<<nblocks, batch::BT, batch::bin_peers_smem(false), st>>>(
+        d_src, d_dst, nullptr, count, d_starts, n_parts, tmp.hist.p, nblocks, my_rank, region_cap, P);
+  }
+  CUDA_TRY(cudaGetLastError());
   return PPCSR_OK;
 }
 

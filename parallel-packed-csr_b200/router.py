@@ -109,6 +109,74 @@ class CudaBinner:
         return out, out_val, [int(c) for c in counts]
 
 
+class PeerExchange:
+    """Routing fused with the exchange over NVLink / NVSwitch peer memory.
+
+    Every rank owns a symmetric receive buffer (torch.distributed symmetric memory: the plumbing that maps each
+    rank's allocation into every other rank's address space) of 2 x world regions of `cap` packed records; the
+    binning kernel of rank s stores the records owned by rank d straight into region s of d's buffer (C-ABI
+    ppcsr_bin_to_peers) together with the count, one device-side barrier publishes them, and the owner applies the
+    regions in place (ppcsr_apply_batch_segments_device).  Compared with bin -> count exchange -> NCCL all-to-all
+    there is no send buffer, no second copy and ONE host synchronisation (the world counts) instead of three.
+    The two halves of the buffer alternate between batches: a peer can run at most one batch ahead (it cannot pass
+    the next barrier alone), so it never overwrites records that are still being read.
+    """
+
+    def __init__(self, dist, device, world: int, rank: int, cap: int, with_values: bool = False):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import load_library
+
+        self.L = load_library()
+        self.torch, self.dist = torch, dist
+        self.world, self.rank, self.cap = world, rank, int(cap)
+        self.device = device
+        group = dist.group.WORLD
+        self.rec = symm_mem.empty(2 * world * self.cap, dtype=torch.int64, device=device)
+        self.cnt = symm_mem.empty(2 * world, dtype=torch.int64, device=device)
+        self.rec_h = symm_mem.rendezvous(self.rec, group)
+        self.cnt_h = symm_mem.rendezvous(self.cnt, group)
+        self.val = self.val_h = None
+        if with_values:
+            self.val = symm_mem.empty(2 * world * self.cap, dtype=torch.int32, device=device)
+            self.val_h = symm_mem.rendezvous(self.val, group)
+        self.cnt.zero_()
+        self.parity = 0
+        self.h_counts = torch.empty(world, dtype=torch.int64, pin_memory=True)
+        # per parity: host arrays of the peers' base pointers (passed by value into the kernel's parameter block)
+        u64 = C.c_uint64 * world
+        self.rec_ptrs = [u64(*[int(b) + par * world * self.cap * 8 for b in self.rec_h.buffer_ptrs]) for par in (0, 1)]
+        self.cnt_ptrs = [u64(*[int(b) + par * world * 8 for b in self.cnt_h.buffer_ptrs]) for par in (0, 1)]
+        self.val_ptrs = None
+        if with_values:
+            self.val_ptrs = [u64(*[int(b) + par * world * self.cap * 4 for b in self.val_h.buffer_ptrs]) for par in (0, 1)]
+        torch.cuda.synchronize(device)
+        self.rec_h.barrier(channel=0)
+
+    def exchange(self, starts_dev, src, dst, val):
+        """Returns (device pointer of this rank's regions, value pointer or None, per-sender counts)."""
+        torch = self.torch
+        if val is not None and self.val_ptrs is None:
+            raise RuntimeError("PeerExchange was created without value buffers")
+        par = self.parity
+        self.parity ^= 1
+        stream = torch.cuda.current_stream(self.device)
+        rc = self.L.ppcsr_bin_to_peers(self.device.index, stream.cuda_stream, starts_dev.data_ptr(), self.world, self.rank,
+                                       src.data_ptr(), dst.data_ptr(), val.data_ptr() if val is not None else None,
+                                       src.numel(), self.rec_ptrs[par],
+                                       self.val_ptrs[par] if val is not None else None, self.cnt_ptrs[par], self.cap)
+        if rc != 0:
+            raise RuntimeError(f"ppcsr_bin_to_peers failed: {self.L.ppcsr_last_error().decode()}")
+        self.rec_h.barrier(channel=par)  # every peer's stores (records and counts) are visible after this
+        self.h_counts.copy_(self.cnt[par * self.world:(par + 1) * self.world], non_blocking=True)
+        stream.synchronize()
+        counts = self.h_counts.tolist()
+        rec_ptr = self.rec.data_ptr() + par * self.world * self.cap * 8
+        val_ptr = self.val.data_ptr() + par * self.world * self.cap * 4 if val is not None else None
+        return rec_ptr, val_ptr, counts
+
+
 class TorchBinner:
     """Pure-torch statement of the same binning (stable sort by owner).  TEST DOUBLE for the CPU/gloo tests;
     the product path uses CudaBinner."""
@@ -126,7 +194,8 @@ class TorchBinner:
 class ShardedGraph:
     """PPPCSR recast: rank r owns sources [starts[r], starts[r+1]) in a Shard on its GPU."""
 
-    def __init__(self, n, starts, rank, world, device_index, dist=None, shard_factory=None, binner=None):
+    def __init__(self, n, starts, rank, world, device_index, dist=None, shard_factory=None, binner=None,
+                 peer_cap: int = 0, peer_values: bool = False):
         import torch
 
         self.n, self.rank, self.world, self.dist = int(n), rank, world, dist
@@ -144,6 +213,29 @@ class ShardedGraph:
         self.binner = binner if binner is not None else (CudaBinner(device_index) if world > 1 else None)
         self.starts_dev = torch.from_numpy(self.starts.astype(np.int64)).to(self.dev)
         self.last_route = None
+        # peer_cap > 0: route batches of up to peer_cap updates per rank through NVLink peer memory (PeerExchange);
+        # larger batches, or a platform without symmetric memory, take the NCCL all-to-all.  Every rank must make
+        # the same choice, i.e. pass batches on the same side of peer_cap.
+        self.peer = None
+        if peer_cap and world > 1 and on_gpu and isinstance(self.binner, CudaBinner):
+            try:
+                self.peer = PeerExchange(dist, self.dev, world, rank, peer_cap, with_values=peer_values)
+            except Exception as e:  # noqa: BLE001 -- symmetric memory is an optional transport
+                import sys
+
+                print(f"[rank {rank}] peer-memory routing unavailable ({type(e).__name__}: {e}); using NCCL all-to-all",
+                      file=sys.stderr)
+                ok = torch.zeros(1, device=self.dev)
+            else:
+                ok = torch.ones(1, device=self.dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all or nothing: the ranks must agree on the transport
+            if ok.item() == 0:
+                self.peer = None
+        self.route_timing = None  # set to [] to collect per-stage routing times (development aid)
+        # The routed records are produced on torch's current stream (binning kernels, NCCL all-to-all): the shard
+        # must consume them in stream order, not on its private stream.
+        if on_gpu and hasattr(self.shard, "set_stream"):
+            self.shard.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def get_partition(self, v: int) -> int:
         return owner_of(self.starts, v)
@@ -205,7 +297,25 @@ class ShardedGraph:
 
     def apply(self, src, dst, val=None, default_val=1):
         """Device tensors (int32 bit patterns of u32 ids) holding this rank's slice of the global batch."""
+        if self.world > 1 and self.peer is not None and src.numel() <= self.peer.cap and (
+                val is None or self.peer.val_ptrs is not None):
+            if self.route_timing is not None:
+                import time
+
+                self.torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            rec_ptr, val_ptr, counts = self.peer.exchange(self.starts_dev, src, dst, val)
+            if self.route_timing is not None:
+                t1 = time.perf_counter()
+                st = self.shard.apply_segments_device(rec_ptr, val_ptr, self.peer.cap, counts, default_val)
+                self.torch.cuda.synchronize()
+                self.route_timing.append([round((t1 - t0) * 1e3, 3), round((time.perf_counter() - t1) * 1e3, 3)])
+                return st
+            self.last_route = {"recv": counts, "transport": "peer"}
+            return self.shard.apply_segments_device(rec_ptr, val_ptr, self.peer.cap, counts, default_val)
         if self.world > 1 and hasattr(self.binner, "packed"):
+            if self.route_timing is not None:
+                return self._apply_timed(src, dst, val, default_val)
             got, r_val = self.route_packed(src, dst, val)
             return self.shard.apply_packed_device(got.data_ptr(), r_val.data_ptr() if r_val is not None else None,
                                                   got.numel(), default_val)
@@ -214,6 +324,29 @@ class ShardedGraph:
         return self.shard.apply_device(r_src.data_ptr(), r_dst.data_ptr(),
                                        r_val.contiguous().data_ptr() if r_val is not None else None,
                                        r_src.numel(), default_val)
+
+    def _apply_timed(self, src, dst, val, default_val):
+        """Development aid (route_timing = []): wall-clock of each routing stage with a device sync after it."""
+        import time
+
+        torch, dist = self.torch, self.dist
+        t = [time.perf_counter()]
+
+        def mark():
+            torch.cuda.synchronize()
+            t.append(time.perf_counter())
+
+        packed, b_val, send = self.binner.packed(self.starts_dev, self.world, src, dst, val)
+        mark()
+        recv = self._exchange_counts(send, src.device)
+        mark()
+        got = torch.empty(sum(recv), dtype=torch.int64, device=src.device)
+        dist.all_to_all_single(got, packed, output_split_sizes=recv, input_split_sizes=send)
+        mark()
+        st = self.shard.apply_packed_device(got.data_ptr(), None, got.numel(), default_val)
+        mark()
+        self.route_timing.append([round((b - a) * 1e3, 3) for a, b in zip(t, t[1:])])
+        return st
 
     def apply_host(self, src, dst, val=None, default_val=1):
         """Host (pinned) numpy arrays: the public end-to-end call. H2D happens inside."""

@@ -84,7 +84,21 @@ def _free_port():
     return p
 
 
-def _nccl_worker(rank, world, port, scale, n_upd, out):
+def _mixed_stream(scale, lo, hi, device=None):
+    """Updates [lo, hi) of a mixed stream: 3/4 uniform inserts, 1/4 deletes of core edges, with the op as value."""
+    total = 16 << scale
+    ops = synth.mixed_ops(lo, hi, 11, device=device)
+    fs, fd = synth.uniform(scale, lo, hi, 13, device=device)
+    idx = synth.sample_without_replacement(total, hi, 5, device=device)[lo:hi]
+    ds, dd = synth.rmat_at(scale, idx, 42)
+    if device is None:
+        return np.where(ops != 0, fs, ds), np.where(ops != 0, fd, dd), ops
+    import torch
+
+    return torch.where(ops != 0, fs, ds), torch.where(ops != 0, fd, dd), ops
+
+
+def _nccl_worker(rank, world, port, scale, n_upd, out, transport):
     import torch
     import torch.distributed as dist
 
@@ -98,21 +112,30 @@ def _nccl_worker(rank, world, port, scale, n_upd, out):
         cs, cd = synth.rmat(scale, rank * total // world, (rank + 1) * total // world, 42, device=dev)
         cs, cd = cs.to(torch.int32), cd.to(torch.int32)
         starts = router.edge_balanced_starts(cs, n, world, dist)
-        g = router.ShardedGraph(n, starts, rank, world, rank, dist=dist)
+        g = router.ShardedGraph(n, starts, rank, world, rank, dist=dist,
+                                peer_cap=total // world if transport == "peer" else 0, peer_values=True)
+        if transport == "peer":
+            assert g.peer is not None, "symmetric memory (NVLink peer routing) is not available on this box"
         g.apply(cs, cd)
         us, ud = synth.uniform(scale, rank * n_upd // world, (rank + 1) * n_upd // world, 7, device=dev)
         g.apply(us.to(torch.int32), ud.to(torch.int32))
+        ms, md, mv = _mixed_stream(scale, rank * n_upd // world, (rank + 1) * n_upd // world, device=dev)
+        g.apply(ms.to(torch.int32), md.to(torch.int32), mv.to(torch.int32))
+        used = (g.last_route or {}).get("transport", "nccl")
         rep = g.shard.check(False)
         rowptr, col = g.shard.export()
         vals = torch.from_numpy(1.0 + (np.arange(n) % 7)).to(dev)
         pr = g.pagerank_step(vals).cpu().numpy()
         np.savez(out.format(rank=rank), rowptr=rowptr, col=col, nn=g.shard.num_neighbors(), starts=starts,
-                 bad=int(bool(rep.violations(False))), pr=pr)
+                 bad=int(bool(rep.violations(False))), pr=pr, peer=int(used == "peer"))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_gpu_all_to_all_vs_oracle(tmp_path):
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_two_gpu_all_to_all_vs_oracle(tmp_path, transport):
+    """2 shards on 2 GPUs: updates routed to their owner (NVLink peer-memory scatter, or the NCCL all-to-all), the
+    result compared with the sequential oracle on the unsharded graph: adjacency, num_neighbors, PageRank."""
     import torch
     import torch.multiprocessing as mp
 
@@ -120,19 +143,24 @@ def test_two_gpu_all_to_all_vs_oracle(tmp_path):
         pytest.skip("needs 2 GPUs")
     world, scale, n_upd = 2, 12, 40000
     out = str(tmp_path / "rank{rank}.npz")
-    mp.spawn(_nccl_worker, args=(world, _free_port(), scale, n_upd, out), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, _free_port(), scale, n_upd, out, transport), nprocs=world, join=True)
     n = 1 << scale
     cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
     us, ud = synth.uniform(scale, 0, n_upd, 7)
     o = O.OraclePCSR(n)
     o.apply(cs, cd, 1)
     o.apply(us, ud, 1)
+    # the ranks' slices of the mixed stream are applied as ONE batch in rank order: keys are routed by source, and
+    # the per-key order inside the batch is (rank, position), i.e. the order of the concatenated global stream
+    ms, md, mv = _mixed_stream(scale, 0, n_upd)
+    o.apply(ms, md, mv)
     rowptr, col, nn = o.export()
     opr = o.pagerank(1.0 + (np.arange(n) % 7))
     for r in range(world):
         z = np.load(out.format(rank=r))
         lo, hi = int(z["starts"][r]), int(z["starts"][r + 1])
         assert int(z["bad"]) == 0
+        assert int(z["peer"]) == int(transport == "peer")
         assert np.array_equal(z["rowptr"], rowptr[lo:hi + 1] - rowptr[lo])
         assert np.array_equal(z["col"], col[int(rowptr[lo]):int(rowptr[hi])])
         assert np.array_equal(z["nn"], nn[lo:hi])
