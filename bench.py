@@ -293,7 +293,7 @@ def main_b200(args):
     peer_cap = 0 if os.environ.get("PPCSR_NO_PEER") else max(B, hi - lo)
     graph = router.ShardedGraph(n, starts, rank, world, local_rank, dist=dist, peer_cap=peer_cap,
                                 peer_values=args.workload == "mixed")
-    graph.shard.set_stream(stream.cuda_stream)
+    graph.shard.bind_torch_stream(stream)
     graph.apply(cs, cd, None, default_val=1)
     core_geo = graph.shard.geometry
     del cs, cd

@@ -211,7 +211,16 @@ class Shard:
         _check(self.L.ppcsr_reserve(self.h, max_slots, max_batch))
 
     def set_stream(self, stream_ptr: int | None):
+        """cudaStream_t handle; None / 0 = the shard's own stream (C-ABI convention)."""
         _check(self.L.ppcsr_set_stream(self.h, stream_ptr))
+
+    def bind_torch_stream(self, stream=None):
+        """Run the shard's work on a torch stream (default: the current one).  torch's default stream has the
+        handle 0, which the C-ABI reads as "own stream": cudaStreamLegacy (0x1) names the same stream explicitly."""
+        import torch
+
+        stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.set_stream(stream.cuda_stream or 1)
 
     def sync(self):
         _check(self.L.ppcsr_sync(self.h))

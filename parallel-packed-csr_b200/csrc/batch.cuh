@@ -332,9 +332,16 @@ __global__ void __launch_bounds__(BT) k_bin_count(const uint32_t *__restrict__ s
   }
   __syncthreads();
   const size_t base = (size_t)blockIdx.x * prim::SORT_TILE;
+  uint32_t sv[prim::SORT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < prim::SORT_ROUNDS; r++) {  // every load of the tile in flight before the first use
+    const size_t i = base + (size_t)r * BT + threadIdx.x;
+    sv[r] = i < count ? src[i] : 0u;
+  }
+#pragma unroll
   for (int r = 0; r < prim::SORT_ROUNDS; r++) {
     const size_t i = base + (size_t)r * BT + threadIdx.x;
-    if (i < count) atomicAdd(&s_h[owner_of(s_st, parts, src[i])], 1u);
+    if (i < count) atomicAdd(&s_h[owner_of(s_st, parts, sv[r])], 1u);
   }
   __syncthreads();
   if (threadIdx.x < parts) block_hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_h[threadIdx.x];
@@ -413,12 +420,12 @@ inline size_t bin_peers_smem(bool has_val) {
   return (size_t)prim::SORT_TILE * 8 + (has_val ? (size_t)prim::SORT_TILE * 4 : 0) + (size_t)prim::SORT_TILE;
 }
 template <bool HAS_VAL>
-__global__ void __launch_bounds__(BT) k_bin_scatter_peers(const uint32_t *__restrict__ src,
-                                                          const uint32_t *__restrict__ dst,
-                                                          const uint32_t *__restrict__ val, size_t count,
-                                                          const uint64_t *__restrict__ starts, uint32_t parts,
-                                                          const uint32_t *__restrict__ offs, uint32_t nblocks,
-                                                          uint32_t me, uint64_t cap, PeerTable P) {
+__global__ void __launch_bounds__(BT, 4) k_bin_scatter_peers(const uint32_t *__restrict__ src,
+                                                             const uint32_t *__restrict__ dst,
+                                                             const uint32_t *__restrict__ val, size_t count,
+                                                             const uint64_t *__restrict__ starts, uint32_t parts,
+                                                             const uint32_t *__restrict__ offs, uint32_t nblocks,
+                                                             uint32_t me, uint64_t cap, PeerTable P) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   uint64_t *s_rec = reinterpret_cast<uint64_t *>(s_dyn);
   uint32_t *s_v = reinterpret_cast<uint32_t *>(s_dyn + (size_t)prim::SORT_TILE * 8);
@@ -426,46 +433,79 @@ __global__ void __launch_bounds__(BT) k_bin_scatter_peers(const uint32_t *__rest
   __shared__ uint32_t s_cnt[prim::SORT_WARPS][BIN_MAX_PARTS];
   __shared__ uint32_t s_tbase[BIN_MAX_PARTS + 1];  // tile-local start of every destination's run
   __shared__ uint32_t s_gbase[BIN_MAX_PARTS];      // region-relative position of the tile's run
-  __shared__ uint64_t s_st[BIN_MAX_PARTS];
+  __shared__ uint32_t s_st[BIN_MAX_PARTS];         // first vertex of every shard (vertex ids are 32-bit)
   for (int d = threadIdx.x; d < prim::SORT_WARPS * BIN_MAX_PARTS; d += BT) (&s_cnt[0][0])[d] = 0;
-  if (threadIdx.x < parts) s_st[threadIdx.x] = starts[threadIdx.x];
+  if (threadIdx.x < BIN_MAX_PARTS) s_st[threadIdx.x] = threadIdx.x < parts ? (uint32_t)starts[threadIdx.x] : 0xFFFFFFFFu;
   __syncthreads();
   const unsigned w = threadIdx.x >> 5, l = lane_id(), lt = lanemask_lt();
   const size_t wbase = (size_t)blockIdx.x * prim::SORT_TILE + (size_t)w * (32 * prim::SORT_ROUNDS);
-  uint32_t own[prim::SORT_ROUNDS], rank[prim::SORT_ROUNDS];
+  // all of the warp's sources first (16 independent loads in flight), then owner + stable rank of every record,
+  // kept as one packed word per record: owner << 16 | rank inside the warp's run for that owner
+  uint32_t sv[prim::SORT_ROUNDS];
 #pragma unroll
   for (int r = 0; r < prim::SORT_ROUNDS; r++) {
     const size_t i = wbase + (size_t)r * 32 + l;
-    const bool valid = i < count;
-    const uint32_t d = valid ? owner_of(s_st, parts, src[i]) : 0x1FFu;
-    own[r] = d;
+    sv[r] = i < count ? src[i] : 0xFFFFFFFFu;
+  }
+  uint32_t pk[prim::SORT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < prim::SORT_ROUNDS; r++) {
+    const bool valid = wbase + (size_t)r * 32 + l < count;
+    uint32_t d = 0x1FFu;
+    if (valid) {  // last shard whose first vertex is <= src: branch-free over the (padded) table
+      d = 0;
+#pragma unroll
+      for (uint32_t step = BIN_MAX_PARTS / 2; step >= 1; step >>= 1)
+        if (d + step < parts && s_st[d + step] <= sv[r]) d += step;
+    }
     const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
     uint32_t base = 0;
     if (valid) base = s_cnt[w][d];
     __syncwarp();
     if (valid && (peers & lt) == 0) s_cnt[w][d] = base + __popc(peers);
     __syncwarp();
-    rank[r] = base + __popc(peers & lt);
+    pk[r] = (d << 16) | (base + __popc(peers & lt));
   }
   __syncthreads();
-  if (threadIdx.x == 0) {  // tile-local layout: destination-major, warp-minor (stable)
-    uint32_t run = 0;
-    for (uint32_t p = 0; p < parts; p++) {
-      s_tbase[p] = run;
-      for (int ww = 0; ww < prim::SORT_WARPS; ww++) {
-        const uint32_t t = s_cnt[ww][p];
-        s_cnt[ww][p] = run;
-        run += t;
-      }
+  if (threadIdx.x < 32) {  // tile-local layout: destination-major, warp-minor (stable); one warp scans the totals
+    uint32_t tot[BIN_MAX_PARTS / 32];
+#pragma unroll
+    for (int k = 0; k < BIN_MAX_PARTS / 32; k++) {
+      const uint32_t p = k * 32 + l;
+      tot[k] = 0;
+      if (p < parts)
+        for (int ww = 0; ww < prim::SORT_WARPS; ww++) tot[k] += s_cnt[ww][p];
     }
-    s_tbase[parts] = run;
+    uint32_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < BIN_MAX_PARTS / 32; k++) {
+      uint32_t inc = tot[k];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (l >= (unsigned)o) inc += y;
+      }
+      const uint32_t p = k * 32 + l;
+      uint32_t run = carry + inc - tot[k];
+      if (p < parts) {
+        s_tbase[p] = run;
+        for (int ww = 0; ww < prim::SORT_WARPS; ww++) {
+          const uint32_t t = s_cnt[ww][p];
+          s_cnt[ww][p] = run;
+          run += t;
+        }
+      }
+      carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+    }
+    if (l == 0) s_tbase[parts] = carry;
   }
-  if (threadIdx.x < parts) {
-    const size_t row = (size_t)threadIdx.x * nblocks;
-    s_gbase[threadIdx.x] = offs[row + blockIdx.x] - offs[row];
+  if (threadIdx.x >= 32 && threadIdx.x - 32 < parts) {
+    const uint32_t p = threadIdx.x - 32;
+    const size_t row = (size_t)p * nblocks;
+    s_gbase[p] = offs[row + blockIdx.x] - offs[row];
     if (blockIdx.x == 0) {  // this rank's count for destination p, deposited at the destination
-      const uint32_t next = threadIdx.x + 1 < parts ? offs[row + nblocks] : (uint32_t)count;
-      P.cnt[threadIdx.x][me] = next - offs[row];
+      const uint32_t next = p + 1 < parts ? offs[row + nblocks] : (uint32_t)count;
+      P.cnt[p][me] = next - offs[row];
     }
   }
   __syncthreads();
@@ -473,9 +513,9 @@ __global__ void __launch_bounds__(BT) k_bin_scatter_peers(const uint32_t *__rest
   for (int r = 0; r < prim::SORT_ROUNDS; r++) {
     const size_t i = wbase + (size_t)r * 32 + l;
     if (i < count) {
-      const uint32_t d = own[r];
-      const uint32_t at = s_cnt[w][d] + rank[r];
-      s_rec[at] = ((uint64_t)(src[i] - (uint32_t)s_st[d]) << 32) | dst[i];  // shard-local id (PPPCSR.cpp:46-52)
+      const uint32_t d = pk[r] >> 16;
+      const uint32_t at = s_cnt[w][d] + (pk[r] & 0xFFFFu);
+      s_rec[at] = ((uint64_t)(sv[r] - s_st[d]) << 32) | dst[i];  // shard-local id (PPPCSR.cpp:46-52)
       if (HAS_VAL) s_v[at] = val[i];
       s_own[at] = (uint8_t)d;
     }

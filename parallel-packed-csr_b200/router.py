@@ -83,7 +83,7 @@ class CudaBinner:
         out_dst = torch.empty_like(dst)
         out_val = torch.empty_like(src) if val is not None else None
         counts = (C.c_uint64 * parts)()
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = torch.cuda.current_stream().cuda_stream or 1  # 0x1 = cudaStreamLegacy: torch's default stream
         rc = self.L.ppcsr_bin_by_owner(self.device_index, stream, starts_dev.data_ptr(), parts, src.data_ptr(),
                                        dst.data_ptr(), val.data_ptr() if val is not None else None, count,
                                        out_src.data_ptr(), out_dst.data_ptr(),
@@ -100,7 +100,7 @@ class CudaBinner:
         out = torch.empty(count, dtype=torch.int64, device=src.device)
         out_val = torch.empty_like(src) if val is not None else None
         counts = (C.c_uint64 * parts)()
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = torch.cuda.current_stream().cuda_stream or 1
         rc = self.L.ppcsr_bin_by_owner_packed(self.device_index, stream, starts_dev.data_ptr(), parts, src.data_ptr(),
                                               dst.data_ptr(), val.data_ptr() if val is not None else None, count,
                                               out.data_ptr(), out_val.data_ptr() if out_val is not None else None, counts)
@@ -162,7 +162,7 @@ class PeerExchange:
         par = self.parity
         self.parity ^= 1
         stream = torch.cuda.current_stream(self.device)
-        rc = self.L.ppcsr_bin_to_peers(self.device.index, stream.cuda_stream, starts_dev.data_ptr(), self.world, self.rank,
+        rc = self.L.ppcsr_bin_to_peers(self.device.index, stream.cuda_stream or 1, starts_dev.data_ptr(), self.world, self.rank,
                                        src.data_ptr(), dst.data_ptr(), val.data_ptr() if val is not None else None,
                                        src.numel(), self.rec_ptrs[par],
                                        self.val_ptrs[par] if val is not None else None, self.cnt_ptrs[par], self.cap)
@@ -234,8 +234,8 @@ class ShardedGraph:
         self.route_timing = None  # set to [] to collect per-stage routing times (development aid)
         # The routed records are produced on torch's current stream (binning kernels, NCCL all-to-all): the shard
         # must consume them in stream order, not on its private stream.
-        if on_gpu and hasattr(self.shard, "set_stream"):
-            self.shard.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
+        if on_gpu and hasattr(self.shard, "bind_torch_stream"):
+            self.shard.bind_torch_stream(torch.cuda.current_stream(self.dev))
 
     def get_partition(self, v: int) -> int:
         return owner_of(self.starts, v)
