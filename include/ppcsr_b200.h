@@ -151,10 +151,12 @@ int ppcsr_bin_to_peers(int device, void *cuda_stream, const uint64_t *d_starts, 
                        const uint64_t *h_peer_rec, const uint64_t *h_peer_val, const uint64_t *h_peer_cnt,
                        uint64_t region_cap);
 /* Applies what the peers deposited: `n_segments` regions of `region_cap` packed records at d_packed (values at d_val,
- * nullable), region r holding h_counts[r] valid records (host array). */
+ * nullable), region r holding d_counts[r] valid records.  d_counts is a DEVICE array (the senders wrote it): the
+ * batch size reaches the host together with the sort width, so the exchange adds no host synchronisation.
+ * max_total (0 = n_segments * region_cap) bounds the total for the allocation of the key array. */
 int ppcsr_apply_batch_segments_device(ppcsr_shard *h, const uint64_t *d_packed, const uint32_t *d_val,
-                                      uint64_t region_cap, const uint64_t *h_counts, uint32_t n_segments,
-                                      uint32_t default_val, ppcsr_batch_stats *stats);
+                                      uint64_t region_cap, const uint64_t *d_counts, uint32_t n_segments,
+                                      uint64_t max_total, uint32_t default_val, ppcsr_batch_stats *stats);
 /* Applies a device-resident batch of packed records (src << 32 | dst), e.g. what the all-to-all delivered. */
 int ppcsr_apply_batch_packed_device(ppcsr_shard *h, const uint64_t *d_packed, const uint32_t *d_val, uint64_t count,
                                     uint32_t default_val, ppcsr_batch_stats *stats);

@@ -76,7 +76,7 @@ SYMBOLS = {
     "ppcsr_bin_by_owner_packed": (_i, [_i, _vp, _vp, _u32, _vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "ppcsr_apply_batch_packed_device": (_i, [_vp, _vp, _vp, _u64, _u32, C.POINTER(BatchStats)]),
     "ppcsr_bin_to_peers": (_i, [_i, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _u64]),
-    "ppcsr_apply_batch_segments_device": (_i, [_vp, _vp, _vp, _u64, _vp, _u32, _u32, C.POINTER(BatchStats)]),
+    "ppcsr_apply_batch_segments_device": (_i, [_vp, _vp, _vp, _u64, _vp, _u32, _u64, _u32, C.POINTER(BatchStats)]),
     "ppcsr_geometry_of": (_i, [_vp, C.POINTER(Geometry)]),
     "ppcsr_edge_exists": (_i, [_vp, _u32, _u32, C.POINTER(_i), C.POINTER(_u32)]),
     "ppcsr_edges_exist": (_i, [_vp, _vp, _vp, _u64, _vp]),
@@ -188,12 +188,13 @@ class Shard:
         _check(self.L.ppcsr_apply_batch_packed_device(self.h, d_packed, d_val, count, default_val, C.byref(st)))
         return st.as_dict()
 
-    def apply_segments_device(self, d_packed: int, d_val: int | None, region_cap: int, counts, default_val: int = 1) -> dict:
-        """Records deposited by the peers: len(counts) regions of region_cap records, region r holding counts[r]."""
+    def apply_segments_device(self, d_packed: int, d_val: int | None, region_cap: int, d_counts: int, n_segments: int,
+                              max_total: int = 0, default_val: int = 1) -> dict:
+        """Records deposited by the peers: n_segments regions of region_cap records, region r holding d_counts[r]
+        (device array).  The batch size comes back in the stats."""
         st = BatchStats()
-        arr = (C.c_uint64 * len(counts))(*[int(c) for c in counts])
-        _check(self.L.ppcsr_apply_batch_segments_device(self.h, d_packed, d_val, region_cap, arr, len(counts),
-                                                        default_val, C.byref(st)))
+        _check(self.L.ppcsr_apply_batch_segments_device(self.h, d_packed, d_val, region_cap, d_counts, n_segments,
+                                                        max_total, default_val, C.byref(st)))
         return st.as_dict()
 
     def add_edge(self, s, d, v=1):

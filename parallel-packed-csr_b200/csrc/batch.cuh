@@ -13,6 +13,7 @@ namespace batch {
 enum : uint8_t { CLS_INSERT = 0, CLS_OVERWRITE = 1, CLS_DELETE = 2, CLS_MISS = 3 };
 
 constexpr int BT = 256;
+constexpr int BIN_MAX_PARTS = 64;  // shards a batch can be routed to
 
 // ---- keys -------------------------------------------------------------------------------------
 // Guards: add with value != 0 needs src < n (reference PCSR.cpp:1375) and dst != SENT; remove needs
@@ -91,28 +92,36 @@ __global__ void __launch_bounds__(BT) k_build_keys_packed(const uint64_t *__rest
 struct SegmentTable {
   uint32_t n_seg;
   uint64_t cap;
-  uint64_t prefix[65];  // exclusive prefix of the valid counts, prefix[n_seg] = total
+  const uint64_t *counts;  // DEVICE array: valid records of every region (deposited by the senders)
 };
 __global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__restrict__ packed,
                                                             const uint32_t *__restrict__ val, uint32_t default_val,
                                                             SegmentTable T, uint32_t n, uint64_t *__restrict__ keys,
                                                             uint32_t *__restrict__ pay, BatchScalars *sc) {
   __shared__ uint32_t s_or, s_bad;
+  __shared__ uint64_t s_prefix[BIN_MAX_PARTS + 1];  // exclusive prefix of the regions' counts
   if (threadIdx.x == 0) {
     s_or = 0;
     s_bad = 0;
+    uint64_t run = 0;
+    for (uint32_t r = 0; r < T.n_seg; r++) {
+      s_prefix[r] = run;
+      run += min(T.counts[r], T.cap);
+    }
+    s_prefix[T.n_seg] = run;
+    if (blockIdx.x == 0) sc->seg_total = run;  // the host learns the batch size with the sort width
   }
   __syncthreads();
   uint32_t my_or = 0, my_bad = 0;
-  const size_t count = (size_t)T.prefix[T.n_seg];
+  const size_t count = (size_t)s_prefix[T.n_seg];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = T.n_seg;  // last region with prefix <= i
     while (hi - lo > 1) {
       const uint32_t mid = (lo + hi) >> 1;
-      if (T.prefix[mid] <= i) lo = mid;
+      if (s_prefix[mid] <= i) lo = mid;
       else hi = mid;
     }
-    const size_t at = (size_t)lo * T.cap + (i - (size_t)T.prefix[lo]);
+    const size_t at = (size_t)lo * T.cap + (i - (size_t)s_prefix[lo]);
     const uint64_t k = packed[at];
     const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k;
     const uint32_t v = val ? val[at] : default_val;
@@ -319,7 +328,6 @@ __device__ __forceinline__ uint32_t owner_of(const uint64_t *starts, uint32_t pa
   return lo;
 }
 
-constexpr int BIN_MAX_PARTS = 64;
 
 __global__ void __launch_bounds__(BT) k_bin_count(const uint32_t *__restrict__ src, size_t count,
                                                   const uint64_t *__restrict__ starts, uint32_t parts,

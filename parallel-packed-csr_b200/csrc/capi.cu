@@ -623,7 +623,12 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
     return PPCSR_ERR_ARG;
   }
   const Geometry g = s->geo;
-  PPCSR_TRY(reserve_batch_arrays(s, count));
+  if (segments) {  // only an upper bound of the batch size is known: the keys (and values) are sized for it
+    PPCSR_TRY(dev_reserve(s->key_a, count, s->stream));
+    if (d_val) PPCSR_TRY(dev_reserve(s->pay_a, count, s->stream));
+  } else {
+    PPCSR_TRY(reserve_batch_arrays(s, count));
+  }
   BatchScalars *sc = s->d_scalars;
   CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(BatchScalars), s->stream));
   CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
@@ -644,6 +649,20 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   }
   CUDA_TRY(cudaGetLastError());
   PPCSR_TRY(read_scalars(s));
+  if (segments) {  // the real batch size arrives with the sort width
+    if (s->h_scalars->seg_total > count) {
+      g_ppcsr_error = "the peers deposited more records than max_total allows";
+      return PPCSR_ERR_CAPACITY;
+    }
+    count = s->h_scalars->seg_total;
+    st.batch_size = count;
+    if (count == 0) {
+      s->last = st;
+      if (stats) *stats = st;
+      return PPCSR_OK;
+    }
+    PPCSR_TRY(reserve_batch_arrays(s, count));
+  }
   const int lo_bits = std::max(1, bits_of(s->h_scalars->dst_or));
   // rejected updates carry the key (n << 32): they need bits_of(n) source bits, valid ones bits_of(n-1)
   const int hi_bits = std::max(1, s->h_scalars->n_ignored ? bits_of(s->n) : bits_of(s->n ? s->n - 1 : 0));
@@ -685,24 +704,17 @@ int ppcsr_apply_batch_packed_device(ppcsr_shard *s, const uint64_t *d_packed, co
 }
 
 int ppcsr_apply_batch_segments_device(ppcsr_shard *s, const uint64_t *d_packed, const uint32_t *d_val,
-                                      uint64_t region_cap, const uint64_t *h_counts, uint32_t n_segments,
-                                      uint32_t default_val, ppcsr_batch_stats *stats) {
-  if (!s || !h_counts || n_segments == 0 || n_segments > batch::BIN_MAX_PARTS) return PPCSR_ERR_ARG;
+                                      uint64_t region_cap, const uint64_t *d_counts, uint32_t n_segments,
+                                      uint64_t max_total, uint32_t default_val, ppcsr_batch_stats *stats) {
+  if (!s || !d_counts || !d_packed || n_segments == 0 || n_segments > batch::BIN_MAX_PARTS) return PPCSR_ERR_ARG;
   batch::SegmentTable T{};
   T.n_seg = n_segments;
   T.cap = region_cap;
-  uint64_t total = 0;
-  for (uint32_t r = 0; r < n_segments; r++) {
-    if (h_counts[r] > region_cap) {
-      g_ppcsr_error = "segment count exceeds the region capacity";
-      return PPCSR_ERR_ARG;
-    }
-    T.prefix[r] = total;
-    total += h_counts[r];
-  }
-  T.prefix[n_segments] = total;
-  if (total && !d_packed) return PPCSR_ERR_ARG;
-  return apply_device_common(s, nullptr, nullptr, d_packed, d_val, total, default_val, stats, &T);
+  T.counts = d_counts;
+  uint64_t bound = max_total ? std::min<uint64_t>(max_total, (uint64_t)n_segments * region_cap)
+                             : (uint64_t)n_segments * region_cap;
+  bound = std::min<uint64_t>(bound, (1ull << 31) - 1);  // one batch holds < 2^31 updates
+  return apply_device_common(s, nullptr, nullptr, d_packed, d_val, bound, default_val, stats, &T);
 }
 
 int ppcsr_apply_batch(ppcsr_shard *s, const uint32_t *src, const uint32_t *dst, const uint32_t *val, uint64_t count,

@@ -141,6 +141,7 @@ struct BatchScalars {
   unsigned int root_violation;      // bit0: root above upper bound, bit1: root below lower bound
   unsigned int pad0, pad1;
   unsigned long long n_touched_est;  // leaves that received inserts + leaves that lost items (k_locate's tally)
+  unsigned long long seg_total;      // batch size when it is only known on the device (records deposited by peers)
 };
 static_assert(sizeof(BatchScalars) % 8 == 0, "BatchScalars must stay 8-byte sized");
 

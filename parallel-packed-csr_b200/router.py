@@ -143,7 +143,6 @@ class PeerExchange:
             self.val_h = symm_mem.rendezvous(self.val, group)
         self.cnt.zero_()
         self.parity = 0
-        self.h_counts = torch.empty(world, dtype=torch.int64, pin_memory=True)
         # per parity: host arrays of the peers' base pointers (passed by value into the kernel's parameter block)
         u64 = C.c_uint64 * world
         self.rec_ptrs = [u64(*[int(b) + par * world * self.cap * 8 for b in self.rec_h.buffer_ptrs]) for par in (0, 1)]
@@ -155,7 +154,8 @@ class PeerExchange:
         self.rec_h.barrier(channel=0)
 
     def exchange(self, starts_dev, src, dst, val):
-        """Returns (device pointer of this rank's regions, value pointer or None, per-sender counts)."""
+        """Returns device pointers: this rank's regions, their values (or None), the per-sender counts.  No host
+        synchronisation: the owner's key builder reads the counts on the device."""
         torch = self.torch
         if val is not None and self.val_ptrs is None:
             raise RuntimeError("PeerExchange was created without value buffers")
@@ -169,12 +169,10 @@ class PeerExchange:
         if rc != 0:
             raise RuntimeError(f"ppcsr_bin_to_peers failed: {self.L.ppcsr_last_error().decode()}")
         self.rec_h.barrier(channel=par)  # every peer's stores (records and counts) are visible after this
-        self.h_counts.copy_(self.cnt[par * self.world:(par + 1) * self.world], non_blocking=True)
-        stream.synchronize()
-        counts = self.h_counts.tolist()
         rec_ptr = self.rec.data_ptr() + par * self.world * self.cap * 8
         val_ptr = self.val.data_ptr() + par * self.world * self.cap * 4 if val is not None else None
-        return rec_ptr, val_ptr, counts
+        cnt_ptr = self.cnt.data_ptr() + par * self.world * 8
+        return rec_ptr, val_ptr, cnt_ptr
 
 
 class TorchBinner:
@@ -217,6 +215,7 @@ class ShardedGraph:
         # larger batches, or a platform without symmetric memory, take the NCCL all-to-all.  Every rank must make
         # the same choice, i.e. pass batches on the same side of peer_cap.
         self.peer = None
+        self.peer_max_total = 0  # optional bound on what one rank can receive per batch (sizes the key array)
         if peer_cap and world > 1 and on_gpu and isinstance(self.binner, CudaBinner):
             try:
                 self.peer = PeerExchange(dist, self.dev, world, rank, peer_cap, with_values=peer_values)
@@ -304,15 +303,17 @@ class ShardedGraph:
 
                 self.torch.cuda.synchronize()
                 t0 = time.perf_counter()
-            rec_ptr, val_ptr, counts = self.peer.exchange(self.starts_dev, src, dst, val)
+            rec_ptr, val_ptr, cnt_ptr = self.peer.exchange(self.starts_dev, src, dst, val)
             if self.route_timing is not None:
+                self.torch.cuda.synchronize()
                 t1 = time.perf_counter()
-                st = self.shard.apply_segments_device(rec_ptr, val_ptr, self.peer.cap, counts, default_val)
+            st = self.shard.apply_segments_device(rec_ptr, val_ptr, self.peer.cap, cnt_ptr, self.world,
+                                                  self.peer_max_total, default_val)
+            if self.route_timing is not None:
                 self.torch.cuda.synchronize()
                 self.route_timing.append([round((t1 - t0) * 1e3, 3), round((time.perf_counter() - t1) * 1e3, 3)])
-                return st
-            self.last_route = {"recv": counts, "transport": "peer"}
-            return self.shard.apply_segments_device(rec_ptr, val_ptr, self.peer.cap, counts, default_val)
+            self.last_route = {"transport": "peer", "received": st["batch_size"]}
+            return st
         if self.world > 1 and hasattr(self.binner, "packed"):
             if self.route_timing is not None:
                 return self._apply_timed(src, dst, val, default_val)
