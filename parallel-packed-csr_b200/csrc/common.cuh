@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -225,6 +226,8 @@ template <typename T>
 inline int dev_reserve(DevBuf<T> &b, size_t elems, cudaStream_t stream, bool keep = false) {
   if (elems <= b.cap) return PPCSR_OK;
   size_t want = elems + elems / 8 + 64;  // slack so slowly growing batches do not realloc every time
+  static const bool log_alloc = getenv("PPCSR_LOG_ALLOC") != nullptr;  // development aid: who allocates mid-run?
+  if (log_alloc) fprintf(stderr, "[ppcsr] dev_reserve: %zu -> %zu elements of %zu bytes\n", b.cap, want, sizeof(T));
   T *np_ = nullptr;
   cudaError_t e = cudaMalloc((void **)&np_, want * sizeof(T));
   if (e != cudaSuccess) {
