@@ -1,6 +1,7 @@
 // capi.cu -- C-ABI (include/ppcsr_b200.h) and host orchestration of the batch pipeline.
 // Unity build: all kernels are included here and compiled for sm_100a only.
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "batch.cuh"
@@ -117,6 +118,63 @@ size_t reb_pad_smem() {
   return (size_t)pad;
 }
 
+// PPCSR_REB_KERNEL=6 selects the one-chunk-per-CTA kernel (k_rebalance) for A/B runs; the default is the persistent,
+// software-pipelined kernel (k_rebalance_p)
+int reb_kernel() {
+  static int k = -1;
+  if (k < 0) {
+    const char *e = getenv("PPCSR_REB_KERNEL");
+    k = e ? atoi(e) : 9;
+  }
+  return k;
+}
+int launch_rebalance(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
+  if (reb_kernel() == 6) {
+    reb::k_rebalance<<<n_chunks, reb::KT, reb_pad_smem(), s->stream>>>(A);
+    return PPCSR_OK;
+  }
+  // per device, once, and thread-safe: PPPCSR drives its shards from several host threads
+  static std::once_flag once[64];
+  static int sms[64] = {0};
+  static cudaError_t once_err[64];
+  const int dv = s->device & 63;
+  std::call_once(once[dv], [&] {
+    once_err[dv] = cudaDeviceGetAttribute(&sms[dv], cudaDevAttrMultiProcessorCount, s->device);
+    if (once_err[dv] == cudaSuccess)
+      once_err[dv] = cudaFuncSetAttribute(reb::k_rebalance_p, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(reb::PSmem));
+  });
+  CUDA_TRY(once_err[dv]);
+  const int n_sm = sms[dv];
+  static long ctas = -1;  // development knob: resident CTAs per SM the grid is sized for
+  if (ctas < 0) {
+    const char *e = getenv("PPCSR_REB_GRID_CTAS");
+    ctas = e ? atol(e) : PPCSR_REB_CTAS;
+  }
+  const unsigned grid = std::min<unsigned>(n_chunks, (unsigned)(n_sm * ctas));
+  reb::k_rebalance_p<<<grid, reb::KT, sizeof(reb::PSmem), s->stream>>>(A, n_chunks);
+  return PPCSR_OK;
+}
+
+// Output leaves per chunk of a whole-array rebuild.  A chunk's source range is its share of the source leaves plus
+// one or two straddled at the ends; at the full 2048 output slots a 1:1 rebuild reads ~65 source leaves, one more
+// than a segment of the kernel holds, and pays a whole extra round for it.  Chunks of 60 leaves keep the range in
+// one segment (measured on C4: 2.48 -> 2.32 ms); a doubling (33-34 leaves, second round on one warp only) and a
+// halving (2-3 full segments either way) are best at the full size.  PPCSR_REB_CL=<leaves> overrides (development).
+uint32_t whole_array_chunk_leaves(const Geometry &g, const Geometry &g2) {
+  const uint32_t cap = reb::CHUNK_SLOTS >> g2.leaf_shift;
+  static long forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("PPCSR_REB_CL");
+    forced = e ? atol(e) : 0;
+  }
+  if (forced > 0) return std::max<uint32_t>(1u, std::min<uint32_t>(cap, (uint32_t)forced));
+  const double ratio = (double)g2.n_leaves / (double)g.n_leaves;
+  const double per_seg = 0.94 * (double)(reb::SEG_LEAVES_SLOTS >> g.leaf_shift) * ratio;
+  if (per_seg >= 0.75 * cap) return std::min<uint32_t>(cap, (uint32_t)per_seg);
+  return cap;
+}
+
 uint64_t grown_slots(uint64_t N, uint64_t items) {
   uint64_t n2 = N;
   for (;;) {
@@ -163,7 +221,7 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
   PPCSR_TRY(dev_reserve(s->dest_alt, g2.N, s->stream));
   PPCSR_TRY(dev_reserve(s->val_alt, g2.N, s->stream));
   PPCSR_TRY(dev_reserve(s->tree, (size_t)2 * g2.n_leaves, s->stream));
-  const uint32_t CL2 = reb::CHUNK_SLOTS >> g2.leaf_shift;
+  const uint32_t CL2 = whole_array_chunk_leaves(g, g2);
   WindowDesc *hw = reinterpret_cast<WindowDesc *>(s->h_pinned);
   hw->node = 1;
   hw->leaf0 = 0;
@@ -192,13 +250,16 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
   A.ls_dst = g2.leaf_shift;
   A.m_dst_override = g2.n_leaves;
   A.prefetch_dist = reb_prefetch_dist();
+  A.chunk_leaves = CL2;
+  A.ins_sentinels = s->ins_sentinels ? 1u : 0u;
   PPCSR_TRY(dev_reserve(s->plan, (size_t)hw->n_chunks, s->stream));
   A.plan = s->plan.p;
   reb::k_plan_chunks<<<div_up(hw->n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
-      s->windows.p, 1u, s->rank_off.p, s->ins_off.p, g.leaf_shift, g2.leaf_shift, g2.n_leaves, hw->n_chunks, s->plan.p);
+      s->windows.p, 1u, s->rank_off.p, s->ins_off.p, g.leaf_shift, g2.leaf_shift, g2.n_leaves, hw->n_chunks, CL2,
+      s->plan.p);
   s->launches += 6;
   CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
-  reb::k_rebalance<<<hw->n_chunks, reb::KT, reb_pad_smem(), s->stream>>>(A);
+  PPCSR_TRY(launch_rebalance(s, hw->n_chunks, A));
   CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
   CUDA_TRY(cudaGetLastError());
   std::swap(s->dest, s->dest_alt);
@@ -351,6 +412,8 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     A.ls_src = A.ls_dst = g.leaf_shift;
     A.m_dst_override = 0;
     A.prefetch_dist = reb_prefetch_dist();
+    A.chunk_leaves = CL;
+    A.ins_sentinels = s->ins_sentinels ? 1u : 0u;
     CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
     if (h.n_small) {
       reb::SmallArgs S{};
@@ -376,9 +439,9 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
       A.plan = s->plan.p;
       reb::k_plan_chunks<<<div_up(h.n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
           s->windows.p, (uint32_t)h.n_windows, s->rank_off.p, s->ins_off.p, g.leaf_shift, g.leaf_shift, 0,
-          (uint32_t)h.n_chunks, s->plan.p);
+          (uint32_t)h.n_chunks, CL, s->plan.p);
       s->launches += 2 + (h.multi_slots ? 1 : 0);
-      reb::k_rebalance<<<(unsigned)h.n_chunks, reb::KT, reb_pad_smem(), s->stream>>>(A);
+      PPCSR_TRY(launch_rebalance(s, (unsigned)h.n_chunks, A));
     }
     CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     if (h.multi_slots) {
@@ -783,7 +846,10 @@ int ppcsr_add_nodes(ppcsr_shard *s, uint32_t count) {
                                                              s->misc.p, s->ins_cnt.p, g.leaf_shift, sc);
   CUDA_TRY(cudaGetLastError());
   s->n = n_new;  // beg[n_new] = N is (re)written below; sentinel fix-up fills beg[n_old .. n_new)
-  PPCSR_TRY(finish_batch(s, count, &st));
+  s->ins_sentinels = true;
+  const int fb = finish_batch(s, count, &st);
+  s->ins_sentinels = false;
+  PPCSR_TRY(fb);
   reb::k_set_u32<<<1, 1, 0, s->stream>>>(s->beg.p + s->n, (uint32_t)s->geo.N);
   PPCSR_TRY(finalize_stats(s, &st));
   return PPCSR_OK;

@@ -196,6 +196,7 @@ struct ppcsr_shard {
   DevBuf<WindowDesc> windows;          // [n_leaves]
   DevBuf<uint32_t> win_chunk_off;      // [n_leaves+1]
   DevBuf<ChunkPlan> plan;              // [n_chunks]
+  bool ins_sentinels = false;          // the pending insert list holds sentinels (ppcsr_add_nodes)
 
   // per-batch update-granular scratch
   DevBuf<uint64_t> key_a, key_b;       // [batch]

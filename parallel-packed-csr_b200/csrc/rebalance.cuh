@@ -56,6 +56,8 @@ struct Args {
   uint32_t m_dst_override;  // != 0: resize, the single window maps onto this many output leaves from leaf 0
   const ChunkPlan *plan;    // one entry per CTA
   uint32_t prefetch_dist;   // L2 prefetch distance in chunks (0 = off)
+  uint32_t chunk_leaves;    // output leaves per chunk (<= CHUNK_SLOTS >> ls_dst; not necessarily a power of two)
+  uint32_t ins_sentinels;   // != 0: the insert list itself holds sentinels (add_nodes)
 };
 
 
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict
                                                     const uint32_t *__restrict__ rank_off,
                                                     const uint32_t *__restrict__ ins_off, uint32_t ls_src,
                                                     uint32_t ls_dst, uint32_t m_dst_override, uint32_t n_chunks,
-                                                    ChunkPlan *__restrict__ plan) {
+                                                    uint32_t CL, ChunkPlan *__restrict__ plan) {
   const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
   if (chunk >= n_chunks) return;
   uint32_t lo = 0, hi = n_windows;  // last window with chunk0 <= chunk
@@ -105,8 +107,7 @@ __global__ void __launch_bounds__(RT) k_plan_chunks(const WindowDesc *__restrict
   const WindowDesc w = windows[lo];
   const uint32_t m_dst = m_dst_override ? m_dst_override : w.m;
   const uint32_t lg = 31u - (uint32_t)__clz(m_dst);
-  const uint32_t CL = CHUNK_SLOTS >> ls_dst;
-  const uint32_t o_lo = (chunk - w.chunk0) * CL;
+  const uint32_t o_lo = (chunk - w.chunk0) * CL;  // CL output leaves per chunk
   const uint32_t o_hi = min(o_lo + CL, m_dst);
   const uint32_t a = leaf_rank0(o_lo, w.items, lg);
   const uint32_t b = leaf_rank0(o_hi, w.items, lg);
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance(Args A) {
   const uint32_t lg = 31u - (uint32_t)__clz(m_dst);
   const uint32_t dst_leaf0 = A.m_dst_override ? 0u : plan.leaf0;
   const uint32_t j = plan.items;
-  const uint32_t n_out = min(CHUNK_SLOTS >> ls_dst, m_dst - plan.o_lo);  // output leaves of the chunk
+  const uint32_t n_out = min(A.chunk_leaves, m_dst - plan.o_lo);  // output leaves of the chunk
   const uint32_t out_slot0 = (dst_leaf0 + plan.o_lo) << ls_dst;          // N <= 2^31 slots
   const uint32_t a = leaf_rank0(plan.o_lo, j, lg);
   const uint32_t span = leaf_rank0(plan.o_lo + n_out, j, lg) - a;  // items the chunk receives
@@ -377,6 +378,390 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance(Args A) {
 #if PPCSR_TMA_STORE
   if (threadIdx.x == 0) bulk_wait_read0();  // the staging buffers must outlive the copy
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_rebalance_p: the same rank arithmetic as k_rebalance, as a PERSISTENT, software-pipelined kernel (the default).
+//
+// ncu on k_rebalance (profiles/r1_v6c_*): 40 % of the warp stall samples sit on the first use of the chunk's plan
+// entry and of its source quads -- every CTA walks plan -> addresses -> DRAM -> compute -> store with nothing to
+// overlap but the three other CTAs of its SM -- and another 25 % at its five block barriers.  Here one CTA per
+// resident slot (grid = SMs x PPCSR_REB_CTAS) loops over the chunks c, c+G, c+2G, ...; a ROUND is one segment of
+// one chunk, and as soon as the operands of a round sit in registers (after P1) one thread issues the bulk copies
+// (cp.async.bulk global -> shared, completing on an mbarrier) of the next round:
+//   * source quads of the segment, its R / insert-offset slices, and for the first segment of a chunk its first
+//     PINS inserts, R0 and the plan entry of the chunk after it;
+// so DRAM latency hides behind P2/P3 of the previous round, and the bulk store of a chunk drains while the next
+// one runs P1.  Two block barriers per round instead of five:
+//   BT  all placements of the previous round are done (then: bulk store of a finished chunk, wait for the stage)
+//   P1  stage -> registers; markers of the inserts; tables; kept counts; staging buffers re-zeroed
+//   B2  tables complete, stage consumed (then: bulk loads of the next round)
+//   P2  inserts placed;  P3  kept items placed -- no barrier between them: the marker a kept item needs (how many
+//       inserts hang on earlier slots of its leaf) is written in P1 by the LAST insert of each slot (neighbour
+//       compare on the staged predecessors: 16-bit, no shared-memory atomics) and cleared again by its reader.
+// The warps of a CTA do not carry the same load (see "Division of labour" below); the per-chunk housekeeping is
+// dealt to the light ones.
+// Measured (B200, same box as k_rebalance): C2 265 -> 234 us, C4 2.46 -> 2.32 ms, C3 124 -> 124 us.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int PINS = INS_PREFETCH * KT;  // staged inserts per chunk
+constexpr int TBL = SEG_LEAVES_SLOTS / 8 + 1;
+
+struct PSmem {  // dynamic shared memory layout of k_rebalance_p
+  uint32_t s_dest[CHUNK_SLOTS];   // the chunk's output slots in their final layout (128-byte aligned: first member)
+  uint32_t s_val[CHUNK_SLOTS];
+  uint32_t st_d[SEG_LEAVES_SLOTS];  // stage: source quads of the next round
+  uint32_t st_v[SEG_LEAVES_SLOTS];
+  uint16_t s_last[SEG_LEAVES_SLOTS];  // 1 + (index - base) of the last insert hanging on a slot
+  uint16_t s_pos[CHUNK_SLOTS];        // chunk-relative rank -> output slot
+  uint8_t s_kupto[SEG_LEAVES_SLOTS];  // kept items of the leaf up to and including a slot
+  uint32_t s_a[CHUNK_SLOTS / 8 + 8];  // first rank of every output leaf of the chunk (+ end)
+  uint32_t s_R[TBL + 3], s_ioff[TBL + 3];
+  // stage, 16-byte aligned arrays filled by bulk copies that start at the 16-byte boundary below the first element
+  // wanted: entry x of a table sits at [x + (first index & 3)]
+  alignas(16) uint32_t st_R[TBL + 7];     // R slice of the next round's segment
+  alignas(16) uint32_t st_ioff[TBL + 7];  // insert offsets of the same leaves
+  alignas(16) uint32_t st_ip[PINS + 8];   // first inserts of the next chunk (+ one more predecessor)
+  alignas(16) uint32_t st_id[PINS + 8];
+  alignas(16) uint32_t st_iv[PINS + 8];
+  alignas(16) uint32_t st_R0[4];
+  alignas(16) uint4 plan[2][2];           // plan entries: [parity][half]
+  alignas(8) uint64_t mbar;               // completion of the stage's bulk copies
+};
+
+// ---- mbarrier + bulk copy global -> shared (the TMA engine; sm_90+/sm_100a PTX) ------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// both addresses 16-byte aligned, bytes a non-zero multiple of 16 (SASS: UBLKCP.S.G)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ ChunkPlan plan_from(const uint4 lo, const uint4 hi) {
+  ChunkPlan r;
+  r.leaf0 = lo.x; r.m_multi = lo.y; r.items = lo.z; r.o_lo = lo.w;
+  r.i_lo = hi.x; r.i_hi = hi.y; r.q_lo = hi.z; r.q_hi = hi.w;
+  return r;
+}
+
+__global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint32_t n_chunks) {
+  extern __shared__ __align__(128) uint8_t p_smem_raw[];
+  PSmem &S = *reinterpret_cast<PSmem *>(p_smem_raw);
+  const unsigned lane = lane_id(), lt = lanemask_lt();
+  const uint32_t ls_src = A.ls_src, ls_dst = A.ls_dst;
+  const uint32_t seg_leaves = SEG_LEAVES_SLOTS >> ls_src;
+  const uint32_t lpl = 1u << (ls_src - 2u);                        // lanes per source leaf
+  const unsigned gm = ((1u << lpl) - 1u) << (lane & ~(lpl - 1u));  // the lanes of my leaf
+  const uint32_t warp_rel0 = (threadIdx.x & ~31u) * 4u;            // first slot of my warp's quads in round 0
+  const uint32_t G = gridDim.x;
+  constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+  // ONE thread stages a round: a handful of bulk copies that complete on the stage's mbarrier.
+  // Segment: the source quads of `snl` leaves from leaf `gl` on, and their R / insert-offset slices.
+  auto issue_segment = [&](uint32_t gl, uint32_t snl) -> uint32_t {
+    const uint32_t qb = (snl << ls_src) * 4u;
+    const uint32_t sh = gl & 3u;
+    const uint32_t tb = ((snl + 1u + sh + 3u) & ~3u) * 4u;
+    bulk_g2s(S.st_d, A.src_dest + ((size_t)gl << ls_src), qb, &S.mbar);
+    bulk_g2s(S.st_v, A.src_val + ((size_t)gl << ls_src), qb, &S.mbar);
+    bulk_g2s(S.st_R, A.rank_off + (gl - sh), tb, &S.mbar);
+    bulk_g2s(S.st_ioff, A.ins_off + (gl - sh), tb, &S.mbar);
+    return 2u * qb + 2u * tb;
+  };
+  // Chunk: its first segment, its first inserts and R0, and the plan entry of the chunk after it.
+  auto issue_chunk = [&](const ChunkPlan &p, uint32_t c_after, uint32_t slot_after) {
+    uint32_t bytes = 0;
+    const uint32_t nl_n = p.i_lo <= p.i_hi ? p.i_hi - p.i_lo + 1u : 0u;
+    if (nl_n) {
+      bytes += issue_segment(p.leaf0 + p.i_lo, min(seg_leaves, nl_n));
+      const uint32_t nq = p.q_hi - p.q_lo;
+      if (nq) {
+        const uint32_t sh = p.q_lo & 3u;
+        const uint32_t ib = ((min(nq, (uint32_t)PINS + 1u) + sh + 3u) & ~3u) * 4u;
+        bulk_g2s(S.st_ip, A.ins_pred + (p.q_lo - sh), ib, &S.mbar);
+        bulk_g2s(S.st_id, A.ins_dst + (p.q_lo - sh), ib, &S.mbar);
+        bulk_g2s(S.st_iv, A.ins_val + (p.q_lo - sh), ib, &S.mbar);
+        bytes += 3u * ib;
+      }
+      bulk_g2s(S.st_R0, A.rank_off + (p.leaf0 & ~3u), 16u, &S.mbar);
+      bytes += 16u;
+    }
+    if (c_after < n_chunks) {
+      bulk_g2s(&S.plan[slot_after][0], A.plan + c_after, 32u, &S.mbar);
+      bytes += 32u;
+    }
+    mbar_expect_tx(&S.mbar, bytes);
+  };
+
+  uint32_t c = blockIdx.x;
+  if (c >= n_chunks) return;
+  // Division of labour between the warps of the CTA.  The per-item phases are spread over all warps, but not evenly:
+  // a chunk's source range is its share of the leaves plus one or two straddled at the ends, so warp 0 runs a second
+  // round of quads that the others skip, and the inserts beyond the first KT land on one or two warps (they are
+  // dealt from the last thread down so that these are not warp 0 again).  Everybody waits for the slowest warp at
+  // the round's barrier, so the per-chunk housekeeping goes to the others: warp IO_WARP talks to the copy engine
+  // (stage loads, chunk store, re-zeroing of the staging buffers), warps other than 0 and IO_WARP build the tables.
+  const unsigned warp = threadIdx.x >> 5;
+  constexpr unsigned IO_WARP = 3;
+  static_assert(KT >= 128, "k_rebalance_p needs warps 0..3");
+  constexpr uint32_t HK = KT - 64;  // housekeeping threads
+  const bool is_io = warp == IO_WARP, is_io_thread = threadIdx.x == IO_WARP * 32;
+  const bool is_hk = warp != 0 && warp != IO_WARP;
+  const uint32_t hk_tid = threadIdx.x - 32u - (warp > IO_WARP ? 32u : 0u);
+  const uint32_t itid = KT - 1u - threadIdx.x;  // my place in the deal of the inserts
+  {
+    const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(A.plan + c));
+    const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(A.plan + c) + 1);
+    if (is_io_thread) {
+      S.plan[0][0] = lo;
+      S.plan[0][1] = hi;
+      mbar_init(&S.mbar, 1u);
+      issue_chunk(plan_from(lo, hi), c + G, 1u);
+    }
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);  // the markers start out clear; every round clears what it set
+    for (uint32_t x = threadIdx.x; x < (uint32_t)SEG_LEAVES_SLOTS * 2u / 16u; x += KT)
+      reinterpret_cast<uint4 *>(S.s_last)[x] = zero;
+    __syncthreads();  // the mbarrier is initialised before anybody polls it
+  }
+  uint32_t parity = 0;
+
+  // state of the chunk in progress (set by its first segment)
+  ChunkPlan plan;
+  uint32_t k = 0, seg = 0;
+  uint32_t m_dst = 0, lg = 0, dst_leaf0 = 0, j = 0, n_out = 0, out_slot0 = 0, a = 0, span = 0, nl = 0, gl0 = 0, R0 = 0;
+  bool multi = false, store_pending = false;
+
+  // item of window rank r, written straight into its final slot; returns the slot (or CHUNK_SLOTS)
+  auto place = [&](uint32_t r, uint32_t d, uint32_t v) -> uint32_t {
+    const uint32_t t = r - a;
+    uint32_t pos = CHUNK_SLOTS;
+    if (t < span) {
+      pos = S.s_pos[t];
+      S.s_dest[pos] = d;
+      S.s_val[pos] = v;
+    }
+    return pos;
+  };
+  // fix_sentinel (reference PCSR.cpp:168-183): a sentinel that lands in slot pos refreshes its vertex's back pointer
+  auto fix_sentinel = [&](uint32_t d, uint32_t v, uint32_t pos) {
+    if (d == PPCSR_SENT && pos < CHUNK_SLOTS) A.beg[v - 1u] = out_slot0 + pos;
+  };
+
+  for (;;) {  // one round per (chunk, segment of <= SEG_LEAVES_SLOTS source slots)
+    if (store_pending) fence_proxy_async_smem();  // my placements are visible to the bulk-copy engine
+    __syncthreads();                              // BT: previous round's tables free, the chunk's placements done
+    if (store_pending) {
+      if (is_io_thread) {  // the finished chunk leaves: one bulk store per array
+        const uint32_t bytes = (n_out << ls_dst) * 4u;
+        bulk_s2g((multi ? A.out_dest_multi : A.out_dest_single) + out_slot0, S.s_dest, bytes);
+        bulk_s2g((multi ? A.out_val_multi : A.out_val_single) + out_slot0, S.s_val, bytes);
+        bulk_commit();
+      }
+      store_pending = false;
+      if (c >= n_chunks) break;
+    }
+    mbar_wait(&S.mbar, parity);  // this round's operands (and plan entry) have landed in the stage
+    parity ^= 1u;
+    if (seg == 0) {
+      plan = plan_from(S.plan[k & 1u][0], S.plan[k & 1u][1]);
+      const uint32_t m_src = plan.m_multi & 0x7FFFFFFFu;
+      multi = (plan.m_multi >> 31) != 0;
+      m_dst = A.m_dst_override ? A.m_dst_override : m_src;
+      lg = 31u - (uint32_t)__clz(m_dst);
+      dst_leaf0 = A.m_dst_override ? 0u : plan.leaf0;
+      j = plan.items;
+      n_out = min(A.chunk_leaves, m_dst - plan.o_lo);  // output leaves of the chunk
+      out_slot0 = (dst_leaf0 + plan.o_lo) << ls_dst;          // N <= 2^31 slots
+      a = leaf_rank0(plan.o_lo, j, lg);
+      span = leaf_rank0(plan.o_lo + n_out, j, lg) - a;        // items the chunk receives
+      nl = plan.i_lo <= plan.i_hi ? plan.i_hi - plan.i_lo + 1u : 0u;  // source leaves feeding the chunk
+      gl0 = plan.leaf0 + plan.i_lo;                           // the chunk's first source leaf
+      R0 = nl ? S.st_R0[plan.leaf0 & 3u] : 0u;
+    }
+    const uint32_t seg_nl = min(seg_leaves, nl - seg);
+    const uint32_t seg_slot0 = (gl0 + seg) << ls_src;  // first source slot of the segment
+    const uint32_t seg_slots = seg_nl << ls_src;
+    const uint32_t *t_R = S.st_R + ((gl0 + seg) & 3u), *t_ioff = S.st_ioff + ((gl0 + seg) & 3u);  // staged tables
+    // ---- P1: operands from the stage into registers
+    uint4 D[QPT], V[QPT];
+#pragma unroll
+    for (int u = 0; u < QPT; u++) {
+      const uint32_t rel = (u * KT + threadIdx.x) * 4u;
+      D[u] = make_uint4(0u, 0u, 0u, 0u);
+      V[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (rel < seg_slots) {
+        D[u] = *reinterpret_cast<const uint4 *>(S.st_d + rel);
+        V[u] = *reinterpret_cast<const uint4 *>(S.st_v + rel);
+      }
+    }
+    // the segment's inserts: plan.q_lo / q_hi already exclude those of the chunk's first / last leaf that cannot rank
+    // inside the chunk.  First segment: from the stage; later segments: straight from global memory.  The LAST
+    // insert hanging on a slot (its successor has another predecessor) leaves 1 + its index in the leaf's run there
+    // (relative to the clipped start in the chunk's first leaf): P3 needs no more than that, and it costs no barrier.
+    const uint32_t q_begin = nl ? max(plan.q_lo, t_ioff[0]) : 0u;
+    const uint32_t q_end = nl ? min(plan.q_hi, t_ioff[seg_nl]) : 0u;
+    const uint32_t base_lo = (seg == 0 && nl) ? plan.q_lo - t_ioff[0] : 0u;
+    const uint32_t ish = plan.q_lo & 3u;  // staged insert i sits at [i + ish]
+    auto mark = [&](uint32_t q, uint32_t pred, uint32_t nx) {
+      if (nx != pred) {
+        const uint32_t rel = pred - seg_slot0;
+        const uint32_t li = rel >> ls_src;
+        S.s_last[rel] = (uint16_t)(q - t_ioff[li] + 1u - (li == 0u ? base_lo : 0u));
+      }
+    };
+    uint32_t ip[INS_PREFETCH], id[INS_PREFETCH], iv[INS_PREFETCH];
+#pragma unroll
+    for (int u = 0; u < INS_PREFETCH; u++) {
+      const uint32_t i = u * KT + itid;
+      const uint32_t q = q_begin + i;
+      ip[u] = id[u] = iv[u] = 0u;
+      if (q < q_end) {
+        uint32_t nx = NONE;
+        if (seg == 0) {
+          ip[u] = S.st_ip[i + ish];
+          id[u] = S.st_id[i + ish];
+          iv[u] = S.st_iv[i + ish];
+          if (q + 1u < q_end) nx = S.st_ip[i + ish + 1u];
+        } else {
+          ip[u] = A.ins_pred[q];
+          id[u] = A.ins_dst[q];
+          iv[u] = A.ins_val[q];
+          if (q + 1u < q_end) nx = A.ins_pred[q + 1u];
+        }
+        mark(q, ip[u], nx);
+      }
+    }
+    for (uint32_t q = q_begin + PINS + itid; q < q_end; q += KT)  // a long run (hub vertex): beyond the stage
+      mark(q, A.ins_pred[q], q + 1u < q_end ? A.ins_pred[q + 1u] : NONE);
+    if (is_hk) {  // housekeeping: the segment's tables; first rank of every output leaf; rank -> slot table
+      for (uint32_t x = hk_tid; x <= seg_nl && nl; x += HK) {
+        S.s_R[x] = t_R[x] - R0;
+        S.s_ioff[x] = t_ioff[x];
+      }
+      if (seg == 0) {
+        for (uint32_t kk = hk_tid; kk <= n_out; kk += HK) S.s_a[kk] = leaf_rank0(plan.o_lo + kk, j, lg) - a;
+        // (1 << tpl_shift) threads per output leaf; the leaf's rank range is recomputed here rather than read from
+        // s_a: no barrier
+        const uint32_t tpl_shift = ls_dst - 3u;
+        for (uint32_t x = hk_tid; x < (n_out << tpl_shift); x += HK) {
+          const uint32_t kk = x >> tpl_shift, sub = x & ((1u << tpl_shift) - 1u);
+          const uint32_t a_k = leaf_rank0(plan.o_lo + kk, j, lg) - a;
+          const uint32_t cnt = leaf_rank0(plan.o_lo + kk + 1u, j, lg) - a - a_k;
+          for (uint32_t i = sub; i < cnt; i += 1u << tpl_shift) S.s_pos[a_k + i] = (uint16_t)((kk << ls_dst) + i);
+        }
+      }
+    }
+    // kept items (tombstones have val 0 and drop out here) and their running count inside the leaf
+    uint32_t pre[QPT];
+#pragma unroll
+    for (int u = 0; u < QPT; u++) {
+      pre[u] = 0;
+      if (u * KT * 4u + warp_rel0 >= seg_slots) continue;  // warp-uniform: nothing of this round lies in the segment
+      const uint32_t k0 = V[u].x != 0u, k1 = V[u].y != 0u, k2 = V[u].z != 0u, k3 = V[u].w != 0u;
+      const uint32_t cc = k0 + k1 + k2 + k3;
+      pre[u] = leaf_incl_scan(cc, lane, lpl) - cc;  // kept items of my leaf in lower lanes
+      const uint32_t p0 = pre[u] + k0, p1 = p0 + k1, p2 = p1 + k2, p3 = p2 + k3;
+      reinterpret_cast<uint32_t *>(S.s_kupto)[u * KT + threadIdx.x] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+    }
+    if (seg == 0 && is_io) {  // null the staging buffers once the copy engine has read the previous chunk out of them
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      uint4 *z = reinterpret_cast<uint4 *>(S.s_dest);  // s_dest and s_val are adjacent
+#pragma unroll 8
+      for (int x = 0; x < 2 * CHUNK_SLOTS / 4 / 32; x++) z[x * 32 + lane] = zero;
+    }
+    __syncthreads();  // B2: tables, markers, kept counts and nulled staging are complete; the stage has been consumed
+    // ---- the next round's operands: the chunk's next segment, or the first segment of this CTA's next chunk
+    const bool more_seg = seg + seg_leaves < nl;
+    if (is_io_thread) {
+      if (more_seg) {
+        mbar_expect_tx(&S.mbar, issue_segment(gl0 + seg + seg_leaves, min(seg_leaves, nl - seg - seg_leaves)));
+      } else if (c + G < n_chunks) {
+        issue_chunk(plan_from(S.plan[(k + 1u) & 1u][0], S.plan[(k + 1u) & 1u][1]), c + 2u * G, k & 1u);
+      }
+    }
+    // ---- P2: inserts: rank = R[leaf] + index in the leaf's run + kept items up to the predecessor
+    {
+      auto insert = [&](uint32_t q, uint32_t pred, uint32_t d, uint32_t v) {
+        const uint32_t rel = pred - seg_slot0;
+        const uint32_t li = rel >> ls_src;
+        const uint32_t pos = place(S.s_R[li] + (q - S.s_ioff[li]) + S.s_kupto[rel], d, v);
+        if (A.ins_sentinels) fix_sentinel(d, v, pos);
+      };
+      uint32_t q = q_begin + itid;
+#pragma unroll
+      for (int u = 0; u < INS_PREFETCH; u++, q += KT)
+        if (q < q_end) insert(q, ip[u], id[u], iv[u]);
+      for (; q < q_end; q += KT) insert(q, A.ins_pred[q], A.ins_dst[q], A.ins_val[q]);
+    }
+    // ---- P3: kept items: rank = R[leaf] + kept before + inserts hanging on earlier slots of the leaf.  The inserts
+    // of a leaf are ordered by predecessor, so that count is the marker of the nearest earlier slot that has one (a
+    // running maximum); the inserts of the chunk's first leaf that the plan clipped away all rank below the chunk,
+    // i.e. precede every item that is placed (base_lo).
+#pragma unroll
+    for (int u = 0; u < QPT; u++) {
+      if (u * KT * 4u + warp_rel0 >= seg_slots) continue;  // warp-uniform
+      const uint32_t rel = (u * KT + threadIdx.x) * 4u;
+      const uint2 Lw = reinterpret_cast<const uint2 *>(S.s_last)[u * KT + threadIdx.x];
+      if (Lw.x | Lw.y) reinterpret_cast<uint2 *>(S.s_last)[u * KT + threadIdx.x] = make_uint2(0u, 0u);  // clear what was set
+      const uint32_t L0 = Lw.x & 0xFFFFu, L1 = Lw.x >> 16, L2 = Lw.y & 0xFFFFu, L3 = Lw.y >> 16;
+      const uint32_t lane_max = max(max(L0, L1), max(L2, L3));
+      const unsigned nz = __ballot_sync(0xFFFFFFFFu, lane_max != 0u) & lt & gm;
+      uint32_t carry = __shfl_sync(0xFFFFFFFFu, lane_max, nz ? 31 - __clz(nz) : 0);
+      if (!nz) carry = 0;
+      const uint32_t my_leaf = rel >> ls_src;
+      const uint32_t k0 = V[u].x != 0u, k1 = V[u].y != 0u, k2 = V[u].z != 0u, k3 = V[u].w != 0u;
+      if (k0 | k1 | k2 | k3) {  // implies rel < seg_slots
+        const uint32_t Rl = S.s_R[my_leaf] + pre[u] + (my_leaf == 0u ? base_lo : 0u);
+        const uint32_t ib1 = max(carry, L0), ib2 = max(ib1, L1), ib3 = max(ib2, L2);
+        uint32_t p0 = CHUNK_SLOTS, p1 = CHUNK_SLOTS, p2 = CHUNK_SLOTS, p3 = CHUNK_SLOTS;
+        if (k0) p0 = place(Rl + carry, D[u].x, V[u].x);
+        if (k1) p1 = place(Rl + k0 + ib1, D[u].y, V[u].y);
+        if (k2) p2 = place(Rl + k0 + k1 + ib2, D[u].z, V[u].z);
+        if (k3) p3 = place(Rl + k0 + k1 + k2 + ib3, D[u].w, V[u].w);
+        if (D[u].x == PPCSR_SENT || D[u].y == PPCSR_SENT || D[u].z == PPCSR_SENT || D[u].w == PPCSR_SENT) {
+          fix_sentinel(D[u].x, V[u].x, p0);
+          fix_sentinel(D[u].y, V[u].y, p1);
+          fix_sentinel(D[u].z, V[u].z, p2);
+          fix_sentinel(D[u].w, V[u].w, p3);
+        }
+      }
+    }
+    if (more_seg) {
+      seg += seg_leaves;
+      continue;
+    }
+    // every source leaf has been read (a single-CTA window is rebalanced in place) and the staging buffers are
+    // complete: the chunk is stored after the next barrier
+    if (is_hk)
+      for (uint32_t kk = hk_tid; kk < n_out; kk += HK)
+        A.tree_leaf_out[dst_leaf0 + plan.o_lo + kk] = S.s_a[kk + 1] - S.s_a[kk];
+    store_pending = true;
+    c += G;
+    k++;
+    seg = 0;
+  }
+  if (is_io_thread) bulk_wait_read0();  // the staging buffers must outlive the last copy
 }
 
 // ---------------------------------------------------------------------------------------------------------
