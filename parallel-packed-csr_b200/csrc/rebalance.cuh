@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance(Args A) {
 // Measured (B200, same box as k_rebalance): C2 265 -> 234 us, C4 2.46 -> 2.32 ms, C3 124 -> 124 us.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int PINS = INS_PREFETCH * KT;  // staged inserts per chunk
-constexpr int TBL = SEG_LEAVES_SLOTS / 8 + 1;
+constexpr int PSEG_MAX_LEAVES = 128;  // leaves per segment (8-slot leaves only exist in arrays of <= 128 slots)
+constexpr int TBL = PSEG_MAX_LEAVES + 1;
 
 struct PSmem {  // dynamic shared memory layout of k_rebalance_p
   uint32_t s_dest[CHUNK_SLOTS];   // the chunk's output slots in their final layout (128-byte aligned: first member)
@@ -412,9 +413,8 @@ struct PSmem {  // dynamic shared memory layout of k_rebalance_p
   uint32_t st_d[SEG_LEAVES_SLOTS];  // stage: source quads of the next round
   uint32_t st_v[SEG_LEAVES_SLOTS];
   uint16_t s_last[SEG_LEAVES_SLOTS];  // 1 + (index - base) of the last insert hanging on a slot
-  uint16_t s_pos[CHUNK_SLOTS];        // chunk-relative rank -> output slot
+  uint16_t s_pos[2][CHUNK_SLOTS];     // chunk-relative rank -> output slot; [parity of the CTA's chunk count]
   uint8_t s_kupto[SEG_LEAVES_SLOTS];  // kept items of the leaf up to and including a slot
-  uint32_t s_a[CHUNK_SLOTS / 8 + 8];  // first rank of every output leaf of the chunk (+ end)
   uint32_t s_R[TBL + 3], s_ioff[TBL + 3];
   // stage, 16-byte aligned arrays filled by bulk copies that start at the 16-byte boundary below the first element
   // wanted: entry x of a table sits at [x + (first index & 3)]
@@ -468,49 +468,12 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
   PSmem &S = *reinterpret_cast<PSmem *>(p_smem_raw);
   const unsigned lane = lane_id(), lt = lanemask_lt();
   const uint32_t ls_src = A.ls_src, ls_dst = A.ls_dst;
-  const uint32_t seg_leaves = SEG_LEAVES_SLOTS >> ls_src;
+  const uint32_t seg_leaves = min((uint32_t)SEG_LEAVES_SLOTS >> ls_src, (uint32_t)PSEG_MAX_LEAVES);
   const uint32_t lpl = 1u << (ls_src - 2u);                        // lanes per source leaf
   const unsigned gm = ((1u << lpl) - 1u) << (lane & ~(lpl - 1u));  // the lanes of my leaf
   const uint32_t warp_rel0 = (threadIdx.x & ~31u) * 4u;            // first slot of my warp's quads in round 0
   const uint32_t G = gridDim.x;
   constexpr uint32_t NONE = 0xFFFFFFFFu;
-
-  // ONE thread stages a round: a handful of bulk copies that complete on the stage's mbarrier.
-  // Segment: the source quads of `snl` leaves from leaf `gl` on, and their R / insert-offset slices.
-  auto issue_segment = [&](uint32_t gl, uint32_t snl) -> uint32_t {
-    const uint32_t qb = (snl << ls_src) * 4u;
-    const uint32_t sh = gl & 3u;
-    const uint32_t tb = ((snl + 1u + sh + 3u) & ~3u) * 4u;
-    bulk_g2s(S.st_d, A.src_dest + ((size_t)gl << ls_src), qb, &S.mbar);
-    bulk_g2s(S.st_v, A.src_val + ((size_t)gl << ls_src), qb, &S.mbar);
-    bulk_g2s(S.st_R, A.rank_off + (gl - sh), tb, &S.mbar);
-    bulk_g2s(S.st_ioff, A.ins_off + (gl - sh), tb, &S.mbar);
-    return 2u * qb + 2u * tb;
-  };
-  // Chunk: its first segment, its first inserts and R0, and the plan entry of the chunk after it.
-  auto issue_chunk = [&](const ChunkPlan &p, uint32_t c_after, uint32_t slot_after) {
-    uint32_t bytes = 0;
-    const uint32_t nl_n = p.i_lo <= p.i_hi ? p.i_hi - p.i_lo + 1u : 0u;
-    if (nl_n) {
-      bytes += issue_segment(p.leaf0 + p.i_lo, min(seg_leaves, nl_n));
-      const uint32_t nq = p.q_hi - p.q_lo;
-      if (nq) {
-        const uint32_t sh = p.q_lo & 3u;
-        const uint32_t ib = ((min(nq, (uint32_t)PINS + 1u) + sh + 3u) & ~3u) * 4u;
-        bulk_g2s(S.st_ip, A.ins_pred + (p.q_lo - sh), ib, &S.mbar);
-        bulk_g2s(S.st_id, A.ins_dst + (p.q_lo - sh), ib, &S.mbar);
-        bulk_g2s(S.st_iv, A.ins_val + (p.q_lo - sh), ib, &S.mbar);
-        bytes += 3u * ib;
-      }
-      bulk_g2s(S.st_R0, A.rank_off + (p.leaf0 & ~3u), 16u, &S.mbar);
-      bytes += 16u;
-    }
-    if (c_after < n_chunks) {
-      bulk_g2s(&S.plan[slot_after][0], A.plan + c_after, 32u, &S.mbar);
-      bytes += 32u;
-    }
-    mbar_expect_tx(&S.mbar, bytes);
-  };
 
   uint32_t c = blockIdx.x;
   if (c >= n_chunks) return;
@@ -518,29 +481,98 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
   // a chunk's source range is its share of the leaves plus one or two straddled at the ends, so warp 0 runs a second
   // round of quads that the others skip, and the inserts beyond the first KT land on one or two warps (they are
   // dealt from the last thread down so that these are not warp 0 again).  Everybody waits for the slowest warp at
-  // the round's barrier, so the per-chunk housekeeping goes to the others: warp IO_WARP talks to the copy engine
-  // (stage loads, chunk store, re-zeroing of the staging buffers), warps other than 0 and IO_WARP build the tables.
+  // the round's barrier, so the per-chunk housekeeping goes to the others: warp IO_WARP stores the finished chunk and
+  // re-zeroes the staging buffers, the warps other than 0 and IO_WARP ("hk") build the tables -- the rank -> slot
+  // table of the NEXT chunk after their own P3, while warp 0 is still placing -- and lane 0 of four of them issues
+  // the bulk loads of the next round (quads / tables + R0 / inserts / plan entry: one mbarrier arrival each).
   const unsigned warp = threadIdx.x >> 5;
   constexpr unsigned IO_WARP = 3;
-  static_assert(KT >= 128, "k_rebalance_p needs warps 0..3");
+  static_assert(KT == 256, "k_rebalance_p deals its housekeeping to warps 1, 2, 4, 5 (loads), 3 (store) of 8");
   constexpr uint32_t HK = KT - 64;  // housekeeping threads
   const bool is_io = warp == IO_WARP, is_io_thread = threadIdx.x == IO_WARP * 32;
   const bool is_hk = warp != 0 && warp != IO_WARP;
   const uint32_t hk_tid = threadIdx.x - 32u - (warp > IO_WARP ? 32u : 0u);
   const uint32_t itid = KT - 1u - threadIdx.x;  // my place in the deal of the inserts
+  // issuer threads: lane 0 of warp 1 (role 0: quads), 2 (1: tables, R0), 4 (2: inserts), 5 (3: plan entry)
+  const bool is_issuer = lane == 0 && (warp == 1 || warp == 2 || warp == 4 || warp == 5);
+  const uint32_t role = warp < 3 ? warp - 1u : warp - 2u;
+
+  // The bulk copies of one round, complete on the stage's mbarrier (four arrivals).  gl / snl: first leaf and leaf
+  // count of the segment; first_seg: the round opens chunk p (stage its first inserts and R0 too, and fetch the
+  // plan entry of the CTA's chunk after it into plan slot `slot_after`).
+  auto issue_round = [&](bool first_seg, uint32_t gl, uint32_t snl, const ChunkPlan &p, uint32_t c_after,
+                         uint32_t slot_after) {
+    uint32_t bytes = 0;
+    if (role == 0) {
+      if (snl) {
+        const uint32_t qb = (snl << ls_src) * 4u;
+        bulk_g2s(S.st_d, A.src_dest + ((size_t)gl << ls_src), qb, &S.mbar);
+        bulk_g2s(S.st_v, A.src_val + ((size_t)gl << ls_src), qb, &S.mbar);
+        bytes = 2u * qb;
+      }
+    } else if (role == 1) {
+      if (snl) {
+        const uint32_t sh = gl & 3u;
+        const uint32_t tb = ((snl + 1u + sh + 3u) & ~3u) * 4u;
+        bulk_g2s(S.st_R, A.rank_off + (gl - sh), tb, &S.mbar);
+        bulk_g2s(S.st_ioff, A.ins_off + (gl - sh), tb, &S.mbar);
+        bytes = 2u * tb;
+        if (first_seg) {
+          bulk_g2s(S.st_R0, A.rank_off + (p.leaf0 & ~3u), 16u, &S.mbar);
+          bytes += 16u;
+        }
+      }
+    } else if (role == 2) {
+      const uint32_t nq = p.q_hi - p.q_lo;
+      if (first_seg && snl && nq) {
+        const uint32_t sh = p.q_lo & 3u;
+        const uint32_t ib = ((min(nq, (uint32_t)PINS + 1u) + sh + 3u) & ~3u) * 4u;
+        bulk_g2s(S.st_ip, A.ins_pred + (p.q_lo - sh), ib, &S.mbar);
+        bulk_g2s(S.st_id, A.ins_dst + (p.q_lo - sh), ib, &S.mbar);
+        bulk_g2s(S.st_iv, A.ins_val + (p.q_lo - sh), ib, &S.mbar);
+        bytes = 3u * ib;
+      }
+    } else {
+      if (first_seg && c_after < n_chunks) {
+        bulk_g2s(&S.plan[slot_after][0], A.plan + c_after, 32u, &S.mbar);
+        bytes = 32u;
+      }
+    }
+    mbar_expect_tx(&S.mbar, bytes);
+  };
+  auto issue_chunk = [&](const ChunkPlan &p, uint32_t c_after, uint32_t slot_after) {
+    const uint32_t nl_n = p.i_lo <= p.i_hi ? p.i_hi - p.i_lo + 1u : 0u;
+    issue_round(true, p.leaf0 + p.i_lo, min(seg_leaves, nl_n), p, c_after, slot_after);
+  };
+  // rank -> slot table of the chunk with plan entry p, by the hk threads: (1 << tpl_shift) threads per output leaf
+  auto build_pos = [&](const ChunkPlan &p, uint32_t buf) {
+    const uint32_t md = A.m_dst_override ? A.m_dst_override : (p.m_multi & 0x7FFFFFFFu);
+    const uint32_t lgn = 31u - (uint32_t)__clz(md);
+    const uint32_t no = min(A.chunk_leaves, md - p.o_lo);
+    const uint32_t an = leaf_rank0(p.o_lo, p.items, lgn);
+    const uint32_t tpl_shift = ls_dst - 3u;
+    uint16_t *tab = S.s_pos[buf];
+    for (uint32_t x = hk_tid; x < (no << tpl_shift); x += HK) {
+      const uint32_t kk = x >> tpl_shift, sub = x & ((1u << tpl_shift) - 1u);
+      const uint32_t a_k = leaf_rank0(p.o_lo + kk, p.items, lgn) - an;
+      const uint32_t cnt = leaf_rank0(p.o_lo + kk + 1u, p.items, lgn) - an - a_k;
+      for (uint32_t i = sub; i < cnt; i += 1u << tpl_shift) tab[a_k + i] = (uint16_t)((kk << ls_dst) + i);
+    }
+  };
   {
     const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(A.plan + c));
     const uint4 hi = __ldg(reinterpret_cast<const uint4 *>(A.plan + c) + 1);
-    if (is_io_thread) {
+    if (threadIdx.x == 0) {
       S.plan[0][0] = lo;
       S.plan[0][1] = hi;
-      mbar_init(&S.mbar, 1u);
-      issue_chunk(plan_from(lo, hi), c + G, 1u);
+      mbar_init(&S.mbar, 4u);
     }
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);  // the markers start out clear; every round clears what it set
     for (uint32_t x = threadIdx.x; x < (uint32_t)SEG_LEAVES_SLOTS * 2u / 16u; x += KT)
       reinterpret_cast<uint4 *>(S.s_last)[x] = zero;
-    __syncthreads();  // the mbarrier is initialised before anybody polls it
+    if (is_hk) build_pos(plan_from(lo, hi), 0u);
+    __syncthreads();  // the mbarrier is initialised before anybody arrives on it or polls it
+    if (is_issuer) issue_chunk(plan_from(lo, hi), c + G, 1u);
   }
   uint32_t parity = 0;
 
@@ -555,7 +587,7 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
     const uint32_t t = r - a;
     uint32_t pos = CHUNK_SLOTS;
     if (t < span) {
-      pos = S.s_pos[t];
+      pos = S.s_pos[k & 1u][t];
       S.s_dest[pos] = d;
       S.s_val[pos] = v;
     }
@@ -652,22 +684,10 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
     }
     for (uint32_t q = q_begin + PINS + itid; q < q_end; q += KT)  // a long run (hub vertex): beyond the stage
       mark(q, A.ins_pred[q], q + 1u < q_end ? A.ins_pred[q + 1u] : NONE);
-    if (is_hk) {  // housekeeping: the segment's tables; first rank of every output leaf; rank -> slot table
+    if (is_hk) {  // housekeeping: the segment's tables
       for (uint32_t x = hk_tid; x <= seg_nl && nl; x += HK) {
         S.s_R[x] = t_R[x] - R0;
         S.s_ioff[x] = t_ioff[x];
-      }
-      if (seg == 0) {
-        for (uint32_t kk = hk_tid; kk <= n_out; kk += HK) S.s_a[kk] = leaf_rank0(plan.o_lo + kk, j, lg) - a;
-        // (1 << tpl_shift) threads per output leaf; the leaf's rank range is recomputed here rather than read from
-        // s_a: no barrier
-        const uint32_t tpl_shift = ls_dst - 3u;
-        for (uint32_t x = hk_tid; x < (n_out << tpl_shift); x += HK) {
-          const uint32_t kk = x >> tpl_shift, sub = x & ((1u << tpl_shift) - 1u);
-          const uint32_t a_k = leaf_rank0(plan.o_lo + kk, j, lg) - a;
-          const uint32_t cnt = leaf_rank0(plan.o_lo + kk + 1u, j, lg) - a - a_k;
-          for (uint32_t i = sub; i < cnt; i += 1u << tpl_shift) S.s_pos[a_k + i] = (uint16_t)((kk << ls_dst) + i);
-        }
       }
     }
     // kept items (tombstones have val 0 and drop out here) and their running count inside the leaf
@@ -693,9 +713,9 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
     __syncthreads();  // B2: tables, markers, kept counts and nulled staging are complete; the stage has been consumed
     // ---- the next round's operands: the chunk's next segment, or the first segment of this CTA's next chunk
     const bool more_seg = seg + seg_leaves < nl;
-    if (is_io_thread) {
+    if (is_issuer) {
       if (more_seg) {
-        mbar_expect_tx(&S.mbar, issue_segment(gl0 + seg + seg_leaves, min(seg_leaves, nl - seg - seg_leaves)));
+        issue_round(false, gl0 + seg + seg_leaves, min(seg_leaves, nl - seg - seg_leaves), plan, 0u, 0u);
       } else if (c + G < n_chunks) {
         issue_chunk(plan_from(S.plan[(k + 1u) & 1u][0], S.plan[(k + 1u) & 1u][1]), c + 2u * G, k & 1u);
       }
@@ -753,9 +773,12 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
     }
     // every source leaf has been read (a single-CTA window is rebalanced in place) and the staging buffers are
     // complete: the chunk is stored after the next barrier
-    if (is_hk)
+    if (is_hk) {  // post-rebalance leaf counts of this chunk; rank -> slot table of the CTA's next chunk
       for (uint32_t kk = hk_tid; kk < n_out; kk += HK)
-        A.tree_leaf_out[dst_leaf0 + plan.o_lo + kk] = S.s_a[kk + 1] - S.s_a[kk];
+        A.tree_leaf_out[dst_leaf0 + plan.o_lo + kk] =
+            leaf_rank0(plan.o_lo + kk + 1u, j, lg) - leaf_rank0(plan.o_lo + kk, j, lg);
+      if (c + G < n_chunks) build_pos(plan_from(S.plan[(k + 1u) & 1u][0], S.plan[(k + 1u) & 1u][1]), (k + 1u) & 1u);
+    }
     store_pending = true;
     c += G;
     k++;
