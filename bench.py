@@ -438,7 +438,9 @@ def main_b200(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_rebalance_dram_bytes_per_launch")
+            # ncu DRAM bytes of the roofline kernel, captured per workload (null where there is no capture)
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {}).get(
+                f"{args.workload}/scale{args.scale}/batch{args.batch}") if world == 1 and not args.strong else None
         except Exception:
             traffic = None
     last = stats_acc[-1]
@@ -451,7 +453,7 @@ def main_b200(args):
                 "d2h_bytes_per_step": 2 * 128,
                 "steps": e2e_steps},
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats_acc)),
-        "roofline": {"bound": "hbm", "kernel": "reb::k_rebalance", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "reb::k_rebalance_p", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": reb_bytes, "kernel_ms": reb_ms},
         "stages_ms": {k: mean(k) for k in ("ms_total", "ms_sort", "ms_locate", "ms_select", "ms_rebalance",
