@@ -531,6 +531,13 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
         bulk_g2s(S.st_id, A.ins_dst + (p.q_lo - sh), ib, &S.mbar);
         bulk_g2s(S.st_iv, A.ins_val + (p.q_lo - sh), ib, &S.mbar);
         bytes = 3u * ib;
+        if (nq > (uint32_t)PINS) {  // a run longer than the stage is read straight from global memory: pull it into L2
+          const uint32_t q1 = (p.q_lo + PINS) & ~3u;
+          const uint32_t tb = min(((p.q_hi - q1 + 3u) & ~3u) * 4u, 16384u);
+          bulk_prefetch_l2(A.ins_pred + q1, tb);
+          bulk_prefetch_l2(A.ins_dst + q1, tb);
+          bulk_prefetch_l2(A.ins_val + q1, tb);
+        }
       }
     } else {
       if (first_seg && c_after < n_chunks) {
