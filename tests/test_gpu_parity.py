@@ -186,6 +186,64 @@ def test_mixed_stream_vs_oracle(n, m, batch):
     g.close()
 
 
+def _csr_of(n, keys):
+    """rowptr / col of a sorted unique array of (src << 32 | dst) keys: the logical graph (numpy restatement)."""
+    src = (keys >> np.uint64(32)).astype(np.int64)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(src, minlength=n), out=rowptr[1:])
+    return rowptr, (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
+def test_full_size_properties_c2_c3():
+    """BASELINE configs 2 and 3 at FULL size (R-MAT scale-20 core, 10 M uniform inserts, 10 M deletes), where the
+    oracle is too slow: size-independent properties instead.  The logical edge set is a set -- inserts are a union,
+    deletes a difference -- so the expected adjacency is np.unique / np.setdiff1d of the keys; on top of that the PMA
+    invariants after every batch, idempotence (the same inserts again change nothing), the reference's call-count
+    meaning of num_neighbors, and the insert -> delete round trip back to the core graph.  This is also the only test
+    in which every persistent rebalance CTA walks through dozens of chunks (32768 chunks over 592 CTAs)."""
+    scale, n_upd = 20, 10_000_000
+    n = 1 << scale
+    k64 = lambda s, d: (np.asarray(s).astype(np.uint64) << np.uint64(32)) | np.asarray(d).astype(np.uint64)
+    cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
+    us, ud = synth.uniform(scale, 0, n_upd, 7)
+    core = np.unique(k64(cs, cd))
+    upd = np.unique(k64(us, ud))
+    g = pp.Shard(n)
+    g.apply(cs, cd, 1)
+    assert_invariants(g, where="core")
+    assert_same_graph(g, *_csr_of(n, core), where="core")
+    nn_core = np.bincount(np.asarray(cs).astype(np.int64), minlength=n)  # call counts: duplicates count too
+    assert np.array_equal(g.num_neighbors(), nn_core.astype(g.num_neighbors().dtype))
+    # C2: one batch of 10 M inserts (doubles the array: 2^25 -> 2^26 slots)
+    st = g.apply(us, ud)
+    both = np.union1d(core, upd)
+    assert st["n_inserted"] == both.size - core.size and st["n_overwritten"] == upd.size - st["n_inserted"]
+    assert st["resized"] == 1 and st["slots_after"] == 2 * st["slots_before"]
+    assert_invariants(g, where="C2")
+    assert_same_graph(g, *_csr_of(n, both), where="C2")
+    nn = nn_core + np.bincount(np.asarray(us).astype(np.int64), minlength=n)
+    assert np.array_equal(g.num_neighbors().astype(np.int64), nn)
+    # idempotence: the same batch again only overwrites
+    st = g.apply(us, ud)
+    assert st["n_inserted"] == 0 and st["n_overwritten"] == upd.size and st["n_windows"] == 0
+    assert_same_graph(g, *_csr_of(n, both), where="C2 twice")
+    # round trip: deleting exactly what was new gives the core graph back (shrinks the array again)
+    new = np.setdiff1d(both, core, assume_unique=True)
+    st = g.apply((new >> np.uint64(32)).astype(np.uint32), (new & np.uint64(0xFFFFFFFF)).astype(np.uint32), 0)
+    assert st["n_deleted"] == new.size and st["n_not_found"] == 0
+    assert_invariants(g, check_lower=True, where="round trip")
+    assert_same_graph(g, *_csr_of(n, core), where="round trip")
+    # C3: 10 M deletes sampled from the raw core list (duplicates in the list are misses the second time)
+    idx = synth.sample_without_replacement(16 << scale, n_upd, 7)
+    ds, dd = np.asarray(cs)[idx], np.asarray(cd)[idx]
+    gone = np.unique(k64(ds, dd))
+    st = g.apply(ds, dd, 0)
+    assert st["n_deleted"] == gone.size and st["n_not_found"] == n_upd - gone.size
+    assert_invariants(g, check_lower=True, where="C3")
+    assert_same_graph(g, *_csr_of(n, np.setdiff1d(core, gone, assume_unique=True)), where="C3")
+    g.close()
+
+
 def test_hub_vertex_grow_and_shrink():
     """reference test add_remove_edge_1E4_seq shape: 1e4 inserts on vertex 0 (many double_list), then delete
     them all (many half_list)."""
