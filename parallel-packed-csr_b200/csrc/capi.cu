@@ -113,7 +113,9 @@ size_t reb_pad_smem() {
   if (pad < 0) {
     const char *e = getenv("PPCSR_REB_PAD_SMEM");
     pad = e ? atol(e) : 0;
+#if PPCSR_HAVE_V6
     if (pad > 0) cudaFuncSetAttribute(reb::k_rebalance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+#endif
   }
   return (size_t)pad;
 }
@@ -130,8 +132,13 @@ int reb_kernel() {
 }
 int launch_rebalance(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
   if (reb_kernel() == 6) {
+#if PPCSR_HAVE_V6
     reb::k_rebalance<<<n_chunks, reb::KT, reb_pad_smem(), s->stream>>>(A);
     return PPCSR_OK;
+#else
+    g_ppcsr_error = "this build has no one-chunk-per-CTA kernel";
+    return PPCSR_ERR_ARG;
+#endif
   }
   // per device, once, and thread-safe: PPPCSR drives its shards from several host threads
   static std::once_flag once[64];

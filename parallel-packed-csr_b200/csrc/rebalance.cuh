@@ -178,6 +178,8 @@ __device__ __forceinline__ uint32_t leaf_incl_scan(uint32_t x, unsigned lane, ui
 //   P2  the segment's inserts, spread evenly over the CTA: rank, hang marker, placed -> s_last, staging
 //   P3  the kept items (still in registers): rank from s_last's running maximum, placed -> staging
 // then ONE bulk store (TMA) per array writes the chunk.
+#define PPCSR_HAVE_V6 (PPCSR_CHUNK_SLOTS <= 2048 && PPCSR_SEG_SLOTS <= 2048)
+#if PPCSR_HAVE_V6
 __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance(Args A) {
   __shared__ __align__(128) uint32_t s_dest[CHUNK_SLOTS];  // the chunk's output slots in their final layout
   __shared__ __align__(128) uint32_t s_val[CHUNK_SLOTS];
@@ -380,6 +382,8 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance(Args A) {
 #endif
 }
 
+#endif  // PPCSR_HAVE_V6
+
 // ---------------------------------------------------------------------------------------------------------
 // k_rebalance_p: the same rank arithmetic as k_rebalance, as a PERSISTENT, software-pipelined kernel (the default).
 //
@@ -404,7 +408,7 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance(Args A) {
 // Measured (B200, same box as k_rebalance): C2 265 -> 234 us, C4 2.46 -> 2.32 ms, C3 124 -> 124 us.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int PINS = INS_PREFETCH * KT;  // staged inserts per chunk
-constexpr int PSEG_MAX_LEAVES = 128;  // leaves per segment (8-slot leaves only exist in arrays of <= 128 slots)
+constexpr int PSEG_MAX_LEAVES = SEG_LEAVES_SLOTS / 32 > 128 ? SEG_LEAVES_SLOTS / 32 : 128;  // leaves per segment (8-slot leaves only exist in arrays of <= 128 slots)
 constexpr int TBL = PSEG_MAX_LEAVES + 1;
 
 struct PSmem {  // dynamic shared memory layout of k_rebalance_p
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
   // the bulk loads of the next round (quads / tables + R0 / inserts / plan entry: one mbarrier arrival each).
   const unsigned warp = threadIdx.x >> 5;
   constexpr unsigned IO_WARP = 3;
-  static_assert(KT == 256, "k_rebalance_p deals its housekeeping to warps 1, 2, 4, 5 (loads), 3 (store) of 8");
+  static_assert(KT >= 256, "k_rebalance_p deals its housekeeping to warps 1, 2, 4, 5 (loads), 3 (store)");
   constexpr uint32_t HK = KT - 64;  // housekeeping threads
   const bool is_io = warp == IO_WARP, is_io_thread = threadIdx.x == IO_WARP * 32;
   const bool is_hk = warp != 0 && warp != IO_WARP;
