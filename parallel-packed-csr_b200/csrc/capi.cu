@@ -2,6 +2,7 @@
 // Unity build: all kernels are included here and compiled for sm_100a only.
 #include <algorithm>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "batch.cuh"
@@ -517,6 +518,23 @@ __global__ void k_fill_new_nodes(uint32_t *ins_dst, uint32_t *ins_val, uint32_t 
   }
 }
 
+// One PageRank push step over the whole shard.  Default: the leaf walk (k_pagerank_push_leaves, a coalesced stream
+// over the packed array); PPCSR_PR_KERNEL=vertex selects the warp-per-vertex kernel (A/B).
+template <typename W>
+static void launch_pagerank_push(ppcsr_shard *s, const W *d_in, double *d_acc, uint64_t out_len) {
+  static const bool per_vertex = getenv("PPCSR_PR_KERNEL") && std::string(getenv("PPCSR_PR_KERNEL")) == "vertex";
+  if (per_vertex) {
+    const unsigned blocks = std::min<unsigned>(div_up((uint64_t)s->n * 32, qry::QT), 148 * 16);
+    qry::k_pagerank_push<W><<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->leaf_cnt.p, s->beg.p, s->nn.p,
+                                                              s->geo.leaf_shift, s->n, d_in, d_acc, out_len);
+  } else {
+    const unsigned blocks = std::min<unsigned>(div_up(s->geo.N, (uint64_t)qry::QT * qry::PRL_BATCH), 148 * 16);
+    qry::k_pagerank_push_leaves<W><<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p,
+                                                                     s->nn.p, s->geo.leaf_shift, s->n, s->geo.N, d_in,
+                                                                     d_acc, out_len);
+  }
+}
+
 template <typename W>
 static int pagerank_host(ppcsr_shard *s, const W *in, W *out, uint64_t out_len) {
   if (!s || !in || !out) return PPCSR_ERR_ARG;
@@ -528,9 +546,7 @@ static int pagerank_host(ppcsr_shard *s, const W *in, W *out, uint64_t out_len) 
   CUDA_TRY(cudaMemcpyAsync(d_in.p, in, (size_t)s->n * sizeof(W), cudaMemcpyHostToDevice, s->stream));
   CUDA_TRY(cudaMemsetAsync(s->pr_acc.p, 0, (size_t)out_len * sizeof(double), s->stream));
   if (s->n) {
-    const unsigned blocks = std::min<unsigned>(div_up((uint64_t)s->n * 32, qry::QT), 148 * 16);
-    qry::k_pagerank_push<W><<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->leaf_cnt.p, s->beg.p, s->nn.p,
-                                                              s->geo.leaf_shift, s->n, d_in.p, s->pr_acc.p, out_len);
+    launch_pagerank_push<W>(s, d_in.p, s->pr_acc.p, out_len);
   }
   if (out_len) qry::k_cast_out<W><<<div_up(out_len, 256), 256, 0, s->stream>>>(s->pr_acc.p, d_out.p, out_len);
   CUDA_TRY(cudaGetLastError());
@@ -1167,9 +1183,7 @@ int ppcsr_pagerank_push_device(ppcsr_shard *s, const double *d_in, double *d_out
   if (!s || !d_in || !d_out) return PPCSR_ERR_ARG;
   PPCSR_TRY(set_device(s));
   if (s->n == 0) return PPCSR_OK;
-  const unsigned blocks = std::min<unsigned>(div_up((uint64_t)s->n * 32, qry::QT), 148 * 16);
-  qry::k_pagerank_push<double><<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->leaf_cnt.p, s->beg.p, s->nn.p,
-                                                                 s->geo.leaf_shift, s->n, d_in, d_out, out_len);
+  launch_pagerank_push<double>(s, d_in, d_out, out_len);
   CUDA_TRY(cudaGetLastError());
   return PPCSR_OK;
 }

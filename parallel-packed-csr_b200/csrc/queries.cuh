@@ -116,6 +116,72 @@ __global__ void __launch_bounds__(QT) k_pagerank_push(const uint32_t *__restrict
     }
   }
 }
+// ---- PageRank push step, leaf walk: a warp streams a run of consecutive 32-slot groups ----------------------
+// The warp-per-vertex form above pays a dependent chain (beg[v], beg[v+1], in[v], nn[v]) per vertex and leaves most
+// lanes idle on an R-MAT graph (half of the vertices own at most a couple of edges).  The packed array itself
+// carries everything a full scan needs, in order: a sentinel (dest == SENT, val == v + 1) opens vertex v's run, every
+// live slot after it is one of v's edges.  So: one coalesced 128-byte read of dest[] per group, the sentinels of the
+// group fetch their vertex's contribution, a ballot + shuffle hands every edge the contribution of the nearest
+// sentinel below it (or the one carried in from the previous group), and the warp finds the vertex of its first
+// slot with ONE binary search over beg[].  Same arithmetic as k_pagerank_push (contribution in W, accumulation fp64).
+constexpr int PRL_BATCH = 4;  // groups whose loads are issued together
+template <typename W>
+__global__ void __launch_bounds__(QT) k_pagerank_push_leaves(const uint32_t *__restrict__ dest,
+                                                             const uint32_t *__restrict__ val,
+                                                             const uint32_t *__restrict__ leaf_cnt,
+                                                             const uint32_t *__restrict__ beg,
+                                                             const uint32_t *__restrict__ nn, uint32_t ls, uint32_t n,
+                                                             uint64_t n_slots, const W *__restrict__ in,
+                                                             double *__restrict__ acc, uint64_t out_len) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t groups = (uint32_t)(n_slots >> 5);
+  const uint32_t per = (groups + warps - 1) / warps;
+  const uint32_t g0 = min(w * per, groups), g1 = min(g0 + per, groups);
+  if (g0 >= g1 || n == 0) return;
+  // vertex owning the first slot of my run: the last v with beg[v] <= slot (beg[0] == 0)
+  W carry;
+  {
+    const uint32_t s0 = g0 << 5;
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (beg[mid] <= s0) lo = mid;
+      else hi = mid;
+    }
+    carry = in[lo] / (W)nn[lo];
+  }
+  const uint32_t lsm = (1u << ls) - 1u;
+  const unsigned le = lanemask_lt() | (1u << lane);
+  for (uint32_t g = g0; g < g1; g += PRL_BATCH) {
+    uint32_t d[PRL_BATCH];
+    bool live[PRL_BATCH];
+#pragma unroll
+    for (int u = 0; u < PRL_BATCH; u++) {
+      const uint32_t slot = ((g + u) << 5) + lane;
+      live[u] = g + u < g1 && (slot & lsm) < leaf_cnt[slot >> ls];
+      d[u] = live[u] ? dest[slot] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < PRL_BATCH; u++) {
+      if (g + u >= g1) break;  // warp-uniform
+      const bool sent = live[u] && d[u] == PPCSR_SENT;
+      W c = (W)0;
+      if (sent) {
+        const uint32_t v = val[((g + u) << 5) + lane] - 1u;
+        c = in[v] / (W)nn[v];
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, sent);
+      const unsigned below = m & le;
+      W mine = __shfl_sync(0xFFFFFFFFu, c, below ? 31 - __clz(below) : 0);
+      if (!below) mine = carry;
+      if (live[u] && !sent && d[u] < out_len) atomicAdd(&acc[d[u]], (double)mine);
+      if (m) carry = __shfl_sync(0xFFFFFFFFu, c, 31 - __clz(m));
+    }
+  }
+}
+
 template <typename W>
 __global__ void k_cast_out(const double *__restrict__ acc, W *__restrict__ out, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
