@@ -187,6 +187,11 @@ int ppcsr_pagerank_step_f32(ppcsr_shard *h, const float *in, float *out, uint64_
 /* Device-buffer variant used by the multi-GPU path: accumulates (no zeroing) into d_out[out_len] fp64;
  * `d_in` is indexed by shard-local vertex. */
 int ppcsr_pagerank_push_device(ppcsr_shard *h, const double *d_in, double *d_out, uint64_t out_len);
+/* Iterated PageRank with damping on one shard holding the whole graph: `iterations` push steps
+ * of the reference's kernel (src/utility/pagerank.h:16-29, divisor num_neighbors) kept on the device,
+ *     r_0 = 1/n,   r_{t+1}[v] = (1 - damping)/n + damping * sum_{(u,v)} r_t[u] / num_neighbors[u],
+ * out[n] on the host.  No host round trip between the steps. */
+int ppcsr_pagerank(ppcsr_shard *h, uint32_t iterations, double damping, double *out);
 /* reference src/utility/bfs.h:15-36 on one shard holding the whole graph: dist[n], UINT32_MAX = unreached. */
 int ppcsr_bfs(ppcsr_shard *h, uint32_t start, uint32_t *dist);
 

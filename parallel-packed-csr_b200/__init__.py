@@ -88,6 +88,7 @@ SYMBOLS = {
     "ppcsr_pagerank_step_f64": (_i, [_vp, _vp, _vp, _u64]),
     "ppcsr_pagerank_step_f32": (_i, [_vp, _vp, _vp, _u64]),
     "ppcsr_pagerank_push_device": (_i, [_vp, _vp, _vp, _u64]),
+    "ppcsr_pagerank": (_i, [_vp, _u32, C.c_double, _vp]),
     "ppcsr_bfs": (_i, [_vp, _u32, _vp]),
     "ppcsr_check_invariants": (_i, [_vp, _i, C.POINTER(InvariantReport)]),
     "ppcsr_snapshot": (_i, [_vp]),
@@ -300,6 +301,12 @@ class Shard:
         out = np.zeros(out_len, dtype=dtype)
         fn = self.L.ppcsr_pagerank_step_f64 if dtype == np.float64 else self.L.ppcsr_pagerank_step_f32
         _check(fn(self.h, _np_ptr(values), _np_ptr(out), out_len))
+        return out
+
+    def pagerank(self, iterations=20, damping=0.85):
+        """Iterated PageRank with damping, all steps on the device (push semantics of reference pagerank.h:16-29)."""
+        out = np.zeros(self.n, dtype=np.float64)
+        _check(self.L.ppcsr_pagerank(self.h, iterations, float(damping), _np_ptr(out)))
         return out
 
     def bfs(self, start):

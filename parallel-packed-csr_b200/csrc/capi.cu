@@ -1188,6 +1188,28 @@ int ppcsr_pagerank_push_device(ppcsr_shard *s, const double *d_in, double *d_out
   return PPCSR_OK;
 }
 
+int ppcsr_pagerank(ppcsr_shard *s, uint32_t iterations, double damping, double *out) {
+  if (!s || !out) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  const uint64_t n = s->n;
+  if (n == 0) return PPCSR_OK;
+  DevBuf<double> d_r;
+  PPCSR_TRY(dev_reserve(d_r, (size_t)n + 1, s->stream));
+  PPCSR_TRY(dev_reserve(s->pr_acc, (size_t)n + 1, s->stream));
+  const unsigned nb = div_up(n, 256);
+  qry::k_fill_f64<<<nb, 256, 0, s->stream>>>(d_r.p, 1.0 / (double)n, n);
+  CUDA_TRY(cudaMemsetAsync(s->pr_acc.p, 0, (size_t)n * sizeof(double), s->stream));
+  for (uint32_t it = 0; it < iterations; it++) {
+    launch_pagerank_push<double>(s, d_r.p, s->pr_acc.p, n);
+    qry::k_pagerank_finish<<<nb, 256, 0, s->stream>>>(d_r.p, s->pr_acc.p, n, (1.0 - damping) / (double)n, damping);
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, d_r.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  dev_free(d_r);
+  return PPCSR_OK;
+}
+
 int ppcsr_pagerank_step_f64(ppcsr_shard *s, const double *in, double *out, uint64_t out_len) {
   return pagerank_host<double>(s, in, out, out_len);
 }

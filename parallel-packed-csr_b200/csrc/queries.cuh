@@ -182,6 +182,19 @@ __global__ void __launch_bounds__(QT) k_pagerank_push_leaves(const uint32_t *__r
   }
 }
 
+// iterated PageRank: r[v] = base + damping * acc[v]; acc is cleared for the next push step
+__global__ void k_pagerank_finish(double *__restrict__ r, double *__restrict__ acc, uint64_t n, double base,
+                                  double damping) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    r[i] = base + damping * acc[i];
+    acc[i] = 0.0;
+  }
+}
+__global__ void k_fill_f64(double *__restrict__ p, double v, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
 template <typename W>
 __global__ void k_cast_out(const double *__restrict__ acc, W *__restrict__ out, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -310,6 +310,29 @@ def test_bfs_and_read_neighbourhood():
     assert q.all() and not g.edges_exist([1], [1001])[0]
 
 
+def test_iterated_pagerank_matches_numpy():
+    """ppcsr_pagerank (device-resident iterations) against the same recurrence evaluated with numpy on the exported
+    CSR: r <- (1-d)/n + d * push(r), push as in reference pagerank.h:16-29 (divisor = call-count num_neighbors)."""
+    scale = 14
+    n = 1 << scale
+    cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
+    g = pp.Shard(n)
+    g.apply(cs, cd, 1)
+    us, ud = synth.uniform(scale, 0, 50000, 7)
+    g.apply(us, ud)
+    rp, col = g.export()
+    nn = g.num_neighbors().astype(np.float64)
+    src = np.repeat(np.arange(n), np.diff(rp).astype(np.int64))
+    r = np.full(n, 1.0 / n)
+    d = 0.85
+    for _ in range(12):
+        contrib = r[src] / nn[src]
+        r = (1.0 - d) / n + d * np.bincount(col.astype(np.int64), weights=contrib, minlength=n)
+    got = g.pagerank(12, d)
+    assert np.allclose(got, r, rtol=PR_RTOL, atol=0.0)
+    g.close()
+
+
 def test_snapshot_restore_roundtrip():
     n = 1 << 12
     cs, cd = synth.rmat(12, 0, 16 << 12, 42)
