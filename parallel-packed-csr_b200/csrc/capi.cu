@@ -625,6 +625,7 @@ void ppcsr_destroy(ppcsr_shard *s) {
   dev_free(s->in_src); dev_free(s->in_dst); dev_free(s->in_val); dev_free(s->ukey); dev_free(s->uval);
   dev_free(s->uloc); dev_free(s->ucls); dev_free(s->ufirst); dev_free(s->ins_dst); dev_free(s->ins_val); dev_free(s->ins_pred);
   dev_free(s->block_tmp); dev_free(s->hist); dev_free(s->pr_acc); dev_free(s->misc);
+  dev_free(s->scan_state); dev_free(s->scan_ticket);
   dev_free(s->snap.dest); dev_free(s->snap.val); dev_free(s->snap.leaf_cnt); dev_free(s->snap.tree);
   dev_free(s->snap.beg); dev_free(s->snap.nn);
   if (s->d_scalars) cudaFree(s->d_scalars);
@@ -675,6 +676,7 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
     PPCSR_TRY(dev_reserve(s->touched_win, wcap, s->stream));
     PPCSR_TRY(dev_reserve(s->windows, wcap, s->stream));
     PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)div_up(g.N, prim::SCAN_TILE) + 2, s->stream));
+    PPCSR_TRY(prim::reserve_scan_state(s, (size_t)div_up(g.N, prim::SCAN_TILE) + 2));
   } else {
     PPCSR_TRY(dev_reserve(s->dest_alt, s->geo.N, s->stream));
     PPCSR_TRY(dev_reserve(s->val_alt, s->geo.N, s->stream));
@@ -686,6 +688,7 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
     PPCSR_TRY(dev_reserve(s->in_val, max_batch, s->stream));
     PPCSR_TRY(dev_reserve(s->hist, prim::radix_sort_scratch_words(max_batch), s->stream));
     PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)div_up(max_batch, prim::SCAN_TILE) + 2, s->stream));
+    PPCSR_TRY(prim::reserve_scan_state(s, (size_t)div_up(max_batch, prim::SCAN_TILE) + 2));
   }
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   return PPCSR_OK;
@@ -1352,7 +1355,7 @@ int ppcsr_debug_sort_pairs(int device, uint64_t *keys, uint32_t *payload, uint64
   dev_free(tmp.key_a); dev_free(tmp.key_b); dev_free(tmp.pay_a); dev_free(tmp.pay_b);
   dev_free(tmp.ukey); dev_free(tmp.uval); dev_free(tmp.uloc); dev_free(tmp.ucls); dev_free(tmp.ufirst);
   dev_free(tmp.ins_dst); dev_free(tmp.ins_val); dev_free(tmp.ins_pred);
-  dev_free(tmp.hist); dev_free(tmp.block_tmp);
+  dev_free(tmp.hist); dev_free(tmp.block_tmp); dev_free(tmp.scan_state); dev_free(tmp.scan_ticket);
   return rc;
 }
 
@@ -1370,7 +1373,7 @@ int ppcsr_debug_exclusive_scan(int device, const uint32_t *in, uint32_t *out, ui
   int rc = prim::device_scan(&tmp, prim::InArray{a.p}, prim::OutPrefixWithTotal{b.p, (size_t)count}, count, nullptr,
                              nullptr);
   if (rc == PPCSR_OK) CUDA_TRY(cudaMemcpy(out, b.p, (count + 1) * 4, cudaMemcpyDeviceToHost));
-  dev_free(a); dev_free(b); dev_free(tmp.block_tmp);
+  dev_free(a); dev_free(b); dev_free(tmp.block_tmp); dev_free(tmp.scan_state); dev_free(tmp.scan_ticket);
   return rc;
 }
 

@@ -209,6 +209,10 @@ struct ppcsr_shard {
   DevBuf<uint8_t> ufirst;              // [batch] first op of the key in this batch is a remove
   DevBuf<uint32_t> ins_dst, ins_val, ins_pred;  // [batch] compacted pure inserts, key order
   DevBuf<uint32_t> block_tmp;          // scan/sort block scratch
+  DevBuf<unsigned long long> scan_state;   // look-back words of the single-pass scan, epoch-tagged (primitives.cuh)
+  DevBuf<unsigned long long> scan_ticket;  // [1] tile ticket counter of the scans (monotonic)
+  unsigned long long scan_ticket_base = 0; // first ticket of the next scan
+  uint32_t scan_epoch = 0;                 // scans issued since scan_state was last cleared
   DevBuf<uint32_t> hist;               // radix histograms
   DevBuf<double> pr_acc;               // pagerank fp64 accumulator
   DevBuf<uint32_t> misc;               // misc query scratch

@@ -1,6 +1,10 @@
 // primitives.cuh -- device-wide exclusive scan / stream compaction (the radix sort lives in sort.cuh).
-// Hand-written (no CUB/Thrust): three-phase scan (tile reduce -> spine -> tile scan) with functor
-// input/output so the same code serves prefix sums, order-preserving selects and histogram offsets.
+// Hand-written (no CUB/Thrust), with functor input/output so the same code serves prefix sums, order-preserving
+// selects and histogram offsets.  Two forms: up to SCAN_ONEPASS_MAX_TILES tiles ONE kernel -- tiles take tickets,
+// publish their sum and resolve the prefix of all earlier tiles by decoupled look-back (a batch runs seven scans;
+// at three launches each they were half of the launches of a small batch); beyond that the three-phase form (tile
+// reduce -> spine -> tile scan), whose second read of the input is cheaper than the look-back ramp of the first wave
+// of tiles (10 M-element compaction: 98 us against 114 us).
 #pragma once
 #include "common.cuh"
 
@@ -9,6 +13,7 @@ namespace prim {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr unsigned SCAN_ONEPASS_MAX_TILES = 1024;  // 2 M elements
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 #pragma unroll
@@ -38,6 +43,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total,
   return r;
 }
 
+// ---- three-phase scan (tile reduce -> spine -> tile scan): used for LARGE inputs, see device_scan ----
 template <class In>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, size_t n, uint32_t *block_sums) {
   __shared__ uint32_t s_warp[33];
@@ -123,6 +129,113 @@ __global__ void k_zero_totals(uint32_t *total32, unsigned long long *total64) {
   if (total64) *total64 = 0;
 }
 
+// ---- single-pass scan: decoupled look-back --------------------------------------------------------------------
+// One 64-bit word per tile: [63:62] status (1 = the tile's own sum, 2 = inclusive prefix over all tiles up to it),
+// [61:32] epoch of the scan that wrote it, [31:0] the value.  The epoch makes words left behind by earlier scans
+// read as "not there yet", so the array is never cleared between scans; tiles are numbered by a ticket counter that
+// only ever grows (the host passes the first ticket of this scan), so every earlier tile is already running when a
+// tile looks back.
+constexpr unsigned long long SCAN_ST_AGG = 1ull << 62, SCAN_ST_INC = 2ull << 62;
+__device__ __forceinline__ unsigned long long scan_word(unsigned long long status, uint32_t epoch, uint32_t value) {
+  return status | ((unsigned long long)epoch << 32) | value;
+}
+template <class In, class Out>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(In in, Out out, size_t n, unsigned long long *tickets,
+                                                               unsigned long long ticket_base,
+                                                               unsigned long long *state, uint32_t epoch, uint32_t nb,
+                                                               uint32_t *total32, unsigned long long *total64) {
+  __shared__ uint32_t s_warp[33];
+  __shared__ uint32_t s_v[SCAN_TILE + SCAN_TILE / 32];
+  __shared__ uint32_t s_ex[SCAN_TILE + SCAN_TILE / 32];
+  __shared__ uint32_t s_tile, s_prefix;
+  if (threadIdx.x == 0) s_tile = (uint32_t)(atomicAdd(tickets, 1ull) - ticket_base);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const size_t base = (size_t)tile * SCAN_TILE;
+  // loads in coalesced order (item k*256 + tid); the tile is transposed through shared memory so that each thread
+  // scans 8 consecutive items
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const uint32_t j = k * SCAN_THREADS + threadIdx.x;
+    const size_t i = base + j;
+    s_v[scan_pad(j)] = (i < n) ? in(i) : 0u;
+  }
+  __syncthreads();
+  uint32_t v[SCAN_ITEMS];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = s_v[scan_pad(threadIdx.x * SCAN_ITEMS + k)];
+    sum += v[k];
+  }
+  uint32_t total;
+  uint32_t ex = block_excl_scan(sum, &total, s_warp);
+  if (threadIdx.x < 32) {  // warp 0: publish the tile's sum, then add up the tiles before it
+    const unsigned lane = threadIdx.x;
+    volatile unsigned long long *st = state;
+    if (lane == 0) st[tile] = scan_word(tile == 0 ? SCAN_ST_INC : SCAN_ST_AGG, epoch, total);
+    uint32_t prefix = 0;
+    if (tile > 0) {
+      int64_t j = (int64_t)tile - 1;  // lane l examines tile j - l
+      for (;;) {
+        const int64_t t = j - (int64_t)lane;
+        // tiles before the first one count as an inclusive prefix of zero
+        const unsigned long long w = t >= 0 ? st[t] : scan_word(SCAN_ST_INC, epoch, 0u);
+        const bool ready = (uint32_t)((w >> 32) & 0x3FFFFFFFu) == epoch && (w >> 62) != 0ull;
+        const unsigned inc = __ballot_sync(0xFFFFFFFFu, ready && (w >> 62) == 2ull);
+        const unsigned not_ready = __ballot_sync(0xFFFFFFFFu, !ready);
+        const unsigned first_inc = inc ? (unsigned)__ffs(inc) - 1u : 32u;
+        const unsigned need = first_inc < 32u ? (2u << first_inc) - 1u : 0xFFFFFFFFu;  // lanes 0..first_inc
+        if (not_ready & need) continue;  // a tile this window depends on has not published yet: look again
+        uint32_t x = (need >> lane) & 1u ? (uint32_t)w : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
+        prefix += x;
+        if (first_inc < 32u) break;
+        j -= 32;
+      }
+      if (lane == 0) st[tile] = scan_word(SCAN_ST_INC, epoch, prefix + total);
+    }
+    if (lane == 0) {
+      s_prefix = prefix;
+      if (tile + 1 == nb) {
+        if (total32) *total32 = prefix + total;
+        if (total64) *total64 = prefix + total;
+      }
+    }
+  }
+  __syncthreads();
+  ex += s_prefix;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    s_ex[scan_pad(threadIdx.x * SCAN_ITEMS + k)] = ex;
+    ex += v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const uint32_t j = k * SCAN_THREADS + threadIdx.x;
+    const size_t i = base + j;
+    if (i < n) out(i, s_ex[scan_pad(j)], s_v[scan_pad(j)]);
+  }
+}
+
+// look-back words for scans of up to `tiles` tiles (also callable ahead of time, so that a batch never allocates)
+inline int reserve_scan_state(ppcsr_shard *s, size_t tiles) {
+  const size_t cap0 = s->scan_state.cap;
+  PPCSR_TRY(dev_reserve(s->scan_state, tiles + 1, s->stream));
+  if (s->scan_state.cap != cap0 || s->scan_epoch + 1u >= (1u << 30)) {  // fresh memory, or the epoch wraps: no word may look valid
+    CUDA_TRY(cudaMemsetAsync(s->scan_state.p, 0, s->scan_state.cap * sizeof(unsigned long long), s->stream));
+    s->scan_epoch = 0;
+  }
+  if (!s->scan_ticket.p) {
+    PPCSR_TRY(dev_reserve(s->scan_ticket, 1, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->scan_ticket.p, 0, sizeof(unsigned long long), s->stream));
+    s->scan_ticket_base = 0;
+  }
+  return PPCSR_OK;
+}
+
 // Exclusive scan of in(i), i in [0,n): out(i, exclusive_prefix, in(i)) is called once per element.
 // The grand total goes to *d_total32 and/or *d_total64 (device pointers, nullable).
 template <class In, class Out>
@@ -133,11 +246,21 @@ int device_scan(ppcsr_shard *s, In in, Out out, size_t n, uint32_t *d_total32, u
     return PPCSR_OK;
   }
   const unsigned nb = div_up(n, SCAN_TILE);
-  PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)nb + 1, s->stream));
-  s->launches += 3;
-  k_scan_reduce<<<nb, SCAN_THREADS, 0, s->stream>>>(in, n, s->block_tmp.p);
-  k_scan_spine<<<1, 1024, 0, s->stream>>>(s->block_tmp.p, nb, d_total32, d_total64);
-  k_scan_apply<<<nb, SCAN_THREADS, 0, s->stream>>>(in, out, n, s->block_tmp.p);
+  if (nb > SCAN_ONEPASS_MAX_TILES) {
+    PPCSR_TRY(dev_reserve(s->block_tmp, (size_t)nb + 1, s->stream));
+    s->launches += 3;
+    k_scan_reduce<<<nb, SCAN_THREADS, 0, s->stream>>>(in, n, s->block_tmp.p);
+    k_scan_spine<<<1, 1024, 0, s->stream>>>(s->block_tmp.p, nb, d_total32, d_total64);
+    k_scan_apply<<<nb, SCAN_THREADS, 0, s->stream>>>(in, out, n, s->block_tmp.p);
+    CUDA_TRY(cudaGetLastError());
+    return PPCSR_OK;
+  }
+  PPCSR_TRY(reserve_scan_state(s, nb));
+  s->scan_epoch++;
+  s->launches += 1;
+  k_scan_onepass<<<nb, SCAN_THREADS, 0, s->stream>>>(in, out, n, s->scan_ticket.p, s->scan_ticket_base, s->scan_state.p,
+                                                     s->scan_epoch, nb, d_total32, d_total64);
+  s->scan_ticket_base += nb;
   CUDA_TRY(cudaGetLastError());
   return PPCSR_OK;
 }

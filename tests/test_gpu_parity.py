@@ -51,7 +51,7 @@ def assert_pagerank(g, oracle_pr, n):
 # ------------------------------------------------------------------------------------------------
 def test_primitives_scan_and_sort():
     rng = np.random.default_rng(0)
-    for n in (0, 1, 5, 2048, 2049, 100_003, 1_500_000):
+    for n in (0, 1, 5, 2048, 2049, 100_003, 1_500_000, 3_000_001):  # the last one takes the three-phase form
         v = rng.integers(0, 50, n).astype(np.uint32)
         out = pp.debug_exclusive_scan(v)
         ref = np.concatenate([[0], np.cumsum(v, dtype=np.uint64)]).astype(np.uint32)
