@@ -282,8 +282,14 @@ __global__ void __launch_bounds__(QT) k_check_leaves(const uint32_t *__restrict_
   }
   if (bad_layout) atomicAdd(&c->bad_leaf_layout, (unsigned long long)bad_layout);
   if (bad_order) atomicAdd(&c->bad_order, (unsigned long long)bad_order);
-  if (sent) atomicAdd(&c->sentinels, (unsigned long long)sent);
-  if (cnt) atomicAdd(&c->live_items, (unsigned long long)cnt);
+  {  // every leaf adds to the same two words: sum over the warp first
+    const unsigned peers = __activemask();
+    const uint32_t w_sent = __reduce_add_sync(peers, sent), w_cnt = __reduce_add_sync(peers, cnt);
+    if ((peers & ((1u << (threadIdx.x & 31u)) - 1u)) == 0u) {
+      if (w_sent) atomicAdd(&c->sentinels, (unsigned long long)w_sent);
+      if (w_cnt) atomicAdd(&c->live_items, (unsigned long long)w_cnt);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(QT) k_check_vertices(const uint32_t *__restrict__ dest,
