@@ -121,6 +121,10 @@ int ppcsr_apply_batch_device(ppcsr_shard *h, const uint32_t *d_src, const uint32
 /* Single operations = batches of one (reference PCSR::add_edge / remove_edge). Correctness path, slow. */
 int ppcsr_add_edge(ppcsr_shard *h, uint32_t src, uint32_t dst, uint32_t value);
 int ppcsr_remove_edge(ppcsr_shard *h, uint32_t src, uint32_t dst, int *found);
+/* How a batch that leaves the root within its bounds is rebalanced: 0 (default) = cost model -- a list of disjoint
+ * windows, or ONE root window (the whole array streamed once) when that is cheaper; -1 = always the window list;
+ * 1 = always the root window.  Does not change results, only the physical layout (tests run both paths). */
+int ppcsr_set_whole_array_policy(ppcsr_shard *h, int mode);
 /* reference PCSR::add_node (src/pcsr/PCSR.cpp:681-703): appends `count` vertices after the last one. */
 int ppcsr_add_nodes(ppcsr_shard *h, uint32_t count);
 int ppcsr_last_stats(ppcsr_shard *h, ppcsr_batch_stats *stats);

@@ -89,6 +89,7 @@ SYMBOLS = {
     "ppcsr_pagerank_step_f32": (_i, [_vp, _vp, _vp, _u64]),
     "ppcsr_pagerank_push_device": (_i, [_vp, _vp, _vp, _u64]),
     "ppcsr_pagerank": (_i, [_vp, _u32, C.c_double, _vp]),
+    "ppcsr_set_whole_array_policy": (_i, [_vp, _i]),
     "ppcsr_bfs": (_i, [_vp, _u32, _vp]),
     "ppcsr_check_invariants": (_i, [_vp, _i, C.POINTER(InvariantReport)]),
     "ppcsr_snapshot": (_i, [_vp]),
@@ -302,6 +303,10 @@ class Shard:
         fn = self.L.ppcsr_pagerank_step_f64 if dtype == np.float64 else self.L.ppcsr_pagerank_step_f32
         _check(fn(self.h, _np_ptr(values), _np_ptr(out), out_len))
         return out
+
+    def set_whole_array_policy(self, mode: int):
+        """-1: always a window list; 0: cost model (default); 1: always one root window."""
+        _check(self.L.ppcsr_set_whole_array_policy(self.h, int(mode)))
 
     def pagerank(self, iterations=20, damping=0.85):
         """Iterated PageRank with damping, all steps on the device (push semantics of reference pagerank.h:16-29)."""

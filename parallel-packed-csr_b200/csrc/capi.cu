@@ -331,10 +331,26 @@ int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     whole = true;
     st->resized = new_N != g.N ? 2 : 0;
   }
-  // Policy: the per-window path costs ~4x more per slot than streaming the array once (scattered 128-byte leaves,
-  // one warp each, plus the tree walks of window selection), so once a quarter of the leaves is touched the batch
-  // is applied as ONE root window -- before any window is selected.
-  if (!whole && (h.n_inserted || h.n_deleted) && L >= 64 && h.n_touched_est * 4ull >= L) whole = true;
+  // Policy: windows or ONE root window?  Measured on B200 at scale 20 (profiles/README.md, "Batch-size sweep";
+  // window selection + rebalance stages together): the window path costs ~150 us of launches and host round trip,
+  // ~0.012 us per 1000 leaves (its O(leaves) passes: post-batch counts, tree, touched list, the two offset scans)
+  // and ~1.05 us per 1000 touched leaves (path walks, window list, one warp per window): 0.19 / 0.23 / 0.40 ms at
+  // 10 K / 72 K / 224 K windows.  Streaming the whole array through k_rebalance_p costs ~105 us (scans, plan, tree
+  // of the new array) + 16 bytes per slot at ~3.8 TB/s: 0.25 ms at 2^25 slots.  So at scale 20 the root window wins
+  // from ~80 K touched leaves on (8 % of them), at scale 24 from ~1.9 M (11 %); the earlier fixed rule (a quarter
+  // of the leaves) left a 1 M-update batch on the window path (0.61 ms instead of 0.47 ms).
+  // ppcsr_set_whole_array_policy / PPCSR_WHOLE_ARRAY=never|always override it (the tests run every stream under
+  // both paths: on small arrays the model always picks the root window).
+  if (!whole && (h.n_inserted || h.n_deleted) && L >= 64) {
+    static const int env_forced = [] {
+      const char *e = getenv("PPCSR_WHOLE_ARRAY");
+      return !e ? 0 : std::string(e) == "never" ? -1 : std::string(e) == "always" ? 1 : 0;
+    }();
+    const int forced = s->whole_policy ? s->whole_policy : env_forced;  // ppcsr_set_whole_array_policy wins
+    const double windows_us = 150.0 + 0.012e-3 * (double)L + 1.05e-3 * (double)h.n_touched_est;
+    const double whole_us = 105.0 + (double)g.N * 16.0 / 3.8e6;
+    if (forced > 0 || (forced == 0 && windows_us > whole_us)) whole = true;
+  }
   if (whole) {
     PPCSR_TRY(scan_rank_and_insert_offsets(s, L));
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
@@ -878,6 +894,12 @@ int ppcsr_add_nodes(ppcsr_shard *s, uint32_t count) {
   PPCSR_TRY(fb);
   reb::k_set_u32<<<1, 1, 0, s->stream>>>(s->beg.p + s->n, (uint32_t)s->geo.N);
   PPCSR_TRY(finalize_stats(s, &st));
+  return PPCSR_OK;
+}
+
+int ppcsr_set_whole_array_policy(ppcsr_shard *s, int mode) {
+  if (!s || mode < -1 || mode > 1) return PPCSR_ERR_ARG;
+  s->whole_policy = mode;
   return PPCSR_OK;
 }
 

@@ -197,6 +197,7 @@ struct ppcsr_shard {
   DevBuf<uint32_t> win_chunk_off;      // [n_leaves+1]
   DevBuf<ChunkPlan> plan;              // [n_chunks]
   bool ins_sentinels = false;          // the pending insert list holds sentinels (ppcsr_add_nodes)
+  int whole_policy = 0;                // -1 never / 0 cost model / 1 always: one root window instead of a window list
 
   // per-batch update-granular scratch
   DevBuf<uint64_t> key_a, key_b;       // [batch]

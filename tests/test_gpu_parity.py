@@ -82,11 +82,18 @@ def test_create_matches_reference_constructor():
         g.close()
 
 
+# every stream is applied twice: through the window list (policy -1) and with the cost model (0), which on arrays this
+# small always rebuilds ONE root window
+POLICIES = [-1, 0]
+
+
+@pytest.mark.parametrize("policy", POLICIES, ids=["windows", "auto"])
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
-def test_golden_fixture(path):
+def test_golden_fixture(path, policy):
     fx = np.load(path)
     n = int(fx["n"])
     g = pp.Shard(n)
+    g.set_whole_array_policy(policy)
     if fx["core_src"].size:
         g.apply(fx["core_src"], fx["core_dst"], fx["core_val"])
         assert_invariants(g, where="core")
@@ -108,7 +115,8 @@ def _stream(kind, scale, count, seed):
 @pytest.mark.parametrize("scale,n_upd,kind,batches", [
     (12, 20000, "uniform", 1), (12, 20000, "rmat", 7), (14, 100000, "uniform", 3), (16, 100000, "uniform", 1),
 ])
-def test_insert_stream_vs_oracle(scale, n_upd, kind, batches):
+@pytest.mark.parametrize("policy", POLICIES, ids=["windows", "auto"])
+def test_insert_stream_vs_oracle(scale, n_upd, kind, batches, policy):
     """BASELINE config 1 shape: R-MAT core + insert stream, applied as one or several batches."""
     n = 1 << scale
     cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
@@ -118,6 +126,7 @@ def test_insert_stream_vs_oracle(scale, n_upd, kind, batches):
     o.apply(us, ud, 1)
     rowptr, col, nn = o.export()
     g = pp.Shard(n)
+    g.set_whole_array_policy(policy)
     st = g.apply(cs, cd, 1)
     assert st["n_inserted"] == int(rowptr[-1]) - 0 or True
     assert_invariants(g, where="core")
@@ -130,7 +139,8 @@ def test_insert_stream_vs_oracle(scale, n_upd, kind, batches):
 
 
 @pytest.mark.parametrize("scale,n_del,batches", [(12, 30000, 1), (12, 60000, 5), (14, 200000, 2), (16, 100000, 1)])
-def test_delete_stream_vs_oracle(scale, n_del, batches):
+@pytest.mark.parametrize("policy", POLICIES, ids=["windows", "auto"])
+def test_delete_stream_vs_oracle(scale, n_del, batches, policy):
     """BASELINE config 3 shape: deletes sampled without replacement from the raw core list (duplicates in the
     core make ~4% of them misses -> the reference's `not found` path)."""
     n = 1 << scale
@@ -142,6 +152,7 @@ def test_delete_stream_vs_oracle(scale, n_del, batches):
     o.apply(ds, dd, 0)
     rowptr, col, nn = o.export()
     g = pp.Shard(n)
+    g.set_whole_array_policy(policy)
     g.apply(cs, cd, 1)
     misses = 0
     for part in np.array_split(np.arange(n_del), batches):
@@ -155,7 +166,8 @@ def test_delete_stream_vs_oracle(scale, n_del, batches):
 
 
 @pytest.mark.parametrize("n,m,batch", [(1000, 20000, 20000), (1000, 20000, 997), (50, 5000, 64), (3000, 60000, 1)])
-def test_mixed_stream_vs_oracle(n, m, batch):
+@pytest.mark.parametrize("policy", POLICIES, ids=["windows", "auto"])
+def test_mixed_stream_vs_oracle(n, m, batch, policy):
     """Mixed adds (with values) and deletes, 3:1 (reference test add_remove_edge_random_2E4_seq).  A batch is
     applied with last-op-wins, which equals the sequential reference on the same stream."""
     if batch == 1:
@@ -166,6 +178,7 @@ def test_mixed_stream_vs_oracle(n, m, batch):
     val = np.where(rng.integers(0, 4, m) != 0, rng.integers(1, 1 << 20, m), 0)
     o = O.OraclePCSR(n)
     g = pp.Shard(n)
+    g.set_whole_array_policy(policy)
     misses = 0
     for lo in range(0, m, batch):
         sl = slice(lo, min(m, lo + batch))
