@@ -15,75 +15,104 @@ enum : uint8_t { CLS_INSERT = 0, CLS_OVERWRITE = 1, CLS_DELETE = 2, CLS_MISS = 3
 constexpr int BT = 256;
 constexpr int BIN_MAX_PARTS = 64;  // shards a batch can be routed to
 
+// Per-update values ride along as the payload of the sort -- unless they are all the same: a mixed stream of adds (one
+// value, e.g. the thread pools' 1) and removes needs ONE bit per update, and bit 63 of the key word is free as long as
+// vertex ids stay below 2^31 (the sort's digits cover only the live (src,dst) field, so the bit travels with the key
+// without taking part in the order).  The builders set it for removes and report the largest and the smallest
+// non-zero value; the host then sorts keys only when they coincide (8 instead of 12 bytes per update and pass).
+constexpr uint64_t KEY_OP_BIT = 1ull << 63;
+__device__ __forceinline__ uint64_t emit_key(bool ok, uint64_t key, uint32_t v, uint32_t n, uint32_t op_bit) {
+  if (!ok) return (uint64_t)n << 32;  // rejected: sorts behind every valid key
+  return (op_bit && v == 0u) ? (key | KEY_OP_BIT) : key;
+}
+
 // ---- keys -------------------------------------------------------------------------------------
 // Guards: add with value != 0 needs src < n (reference PCSR.cpp:1375) and dst != SENT; remove needs
 // src < n (the reference would read out of bounds, PCSR.cpp:717).  Rejected updates get the key
 // (n << 32), which sorts after every valid key, and are counted.
 __global__ void __launch_bounds__(BT) k_build_keys(const uint32_t *__restrict__ src, const uint32_t *__restrict__ dst,
                                                    const uint32_t *__restrict__ val, uint32_t default_val,
-                                                   size_t count, uint32_t n, uint64_t *__restrict__ keys,
+                                                   size_t count, uint32_t n, uint32_t op_bit, uint64_t *__restrict__ keys,
                                                    uint32_t *__restrict__ pay, BatchScalars *sc) {
-  __shared__ uint32_t s_or, s_bad;
+  __shared__ uint32_t s_or, s_bad, s_vmax, s_vinv;
   if (threadIdx.x == 0) {
     s_or = 0;
     s_bad = 0;
+    s_vmax = 0;
+    s_vinv = 0;
   }
   __syncthreads();
-  uint32_t my_or = 0, my_bad = 0;
+  uint32_t my_or = 0, my_bad = 0, my_vmax = 0, my_vinv = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t s = src[i], d = dst[i];
     const uint32_t v = val ? val[i] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
-    keys[i] = ok ? (((uint64_t)s << 32) | d) : ((uint64_t)n << 32);
+    keys[i] = emit_key(ok, ((uint64_t)s << 32) | d, v, n, op_bit);
     if (pay) pay[i] = ok ? v : 0u;
     if (ok) my_or |= d;
     else my_bad++;
+    if (pay && ok && v) my_vmax = max(my_vmax, v), my_vinv = max(my_vinv, ~v);
   }
   my_or = __reduce_or_sync(0xFFFFFFFFu, my_or);
   my_bad = __reduce_add_sync(0xFFFFFFFFu, my_bad);
+  my_vmax = __reduce_max_sync(0xFFFFFFFFu, my_vmax);
+  my_vinv = __reduce_max_sync(0xFFFFFFFFu, my_vinv);
   if (lane_id() == 0) {
     if (my_or) atomicOr(&s_or, my_or);
     if (my_bad) atomicAdd(&s_bad, my_bad);
+    if (my_vmax) atomicMax(&s_vmax, my_vmax);
+    if (my_vinv) atomicMax(&s_vinv, my_vinv);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     if (s_or) atomicOr(&sc->dst_or, s_or);
     if (s_bad) atomicAdd(&sc->n_ignored, (unsigned long long)s_bad);
+    if (s_vmax) atomicMax(&sc->val_max, s_vmax);
+    if (s_vinv) atomicMax(&sc->val_inv_min, s_vinv);
   }
 }
 
 // same guards for records that arrive already packed as (src << 32 | dst) (the all-to-all payload)
 __global__ void __launch_bounds__(BT) k_build_keys_packed(const uint64_t *__restrict__ packed,
                                                           const uint32_t *__restrict__ val, uint32_t default_val,
-                                                          size_t count, uint32_t n, uint64_t *__restrict__ keys,
+                                                          size_t count, uint32_t n, uint32_t op_bit, uint64_t *__restrict__ keys,
                                                           uint32_t *__restrict__ pay, BatchScalars *sc) {
-  __shared__ uint32_t s_or, s_bad;
+  __shared__ uint32_t s_or, s_bad, s_vmax, s_vinv;
   if (threadIdx.x == 0) {
     s_or = 0;
     s_bad = 0;
+    s_vmax = 0;
+    s_vinv = 0;
   }
   __syncthreads();
-  uint32_t my_or = 0, my_bad = 0;
+  uint32_t my_or = 0, my_bad = 0, my_vmax = 0, my_vinv = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
     const uint64_t k = packed[i];
     const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k;
     const uint32_t v = val ? val[i] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
-    keys[i] = ok ? k : ((uint64_t)n << 32);
+    keys[i] = emit_key(ok, k, v, n, op_bit);
     if (pay) pay[i] = ok ? v : 0u;
     if (ok) my_or |= d;
     else my_bad++;
+    if (pay && ok && v) my_vmax = max(my_vmax, v), my_vinv = max(my_vinv, ~v);
   }
   my_or = __reduce_or_sync(0xFFFFFFFFu, my_or);
   my_bad = __reduce_add_sync(0xFFFFFFFFu, my_bad);
+  my_vmax = __reduce_max_sync(0xFFFFFFFFu, my_vmax);
+  my_vinv = __reduce_max_sync(0xFFFFFFFFu, my_vinv);
   if (lane_id() == 0) {
     if (my_or) atomicOr(&s_or, my_or);
     if (my_bad) atomicAdd(&s_bad, my_bad);
+    if (my_vmax) atomicMax(&s_vmax, my_vmax);
+    if (my_vinv) atomicMax(&s_vinv, my_vinv);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     if (s_or) atomicOr(&sc->dst_or, s_or);
     if (s_bad) atomicAdd(&sc->n_ignored, (unsigned long long)s_bad);
+    if (s_vmax) atomicMax(&sc->val_max, s_vmax);
+    if (s_vinv) atomicMax(&sc->val_inv_min, s_vinv);
   }
 }
 
@@ -96,13 +125,15 @@ struct SegmentTable {
 };
 __global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__restrict__ packed,
                                                             const uint32_t *__restrict__ val, uint32_t default_val,
-                                                            SegmentTable T, uint32_t n, uint64_t *__restrict__ keys,
+                                                            SegmentTable T, uint32_t n, uint32_t op_bit, uint64_t *__restrict__ keys,
                                                             uint32_t *__restrict__ pay, BatchScalars *sc) {
-  __shared__ uint32_t s_or, s_bad;
+  __shared__ uint32_t s_or, s_bad, s_vmax, s_vinv;
   __shared__ uint64_t s_prefix[BIN_MAX_PARTS + 1];  // exclusive prefix of the regions' counts
   if (threadIdx.x == 0) {
     s_or = 0;
     s_bad = 0;
+    s_vmax = 0;
+    s_vinv = 0;
     uint64_t run = 0;
     for (uint32_t r = 0; r < T.n_seg; r++) {
       s_prefix[r] = run;
@@ -112,7 +143,7 @@ __global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__re
     if (blockIdx.x == 0) sc->seg_total = run;  // the host learns the batch size with the sort width
   }
   __syncthreads();
-  uint32_t my_or = 0, my_bad = 0;
+  uint32_t my_or = 0, my_bad = 0, my_vmax = 0, my_vinv = 0;
   const size_t count = (size_t)s_prefix[T.n_seg];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
     uint32_t lo = 0, hi = T.n_seg;  // last region with prefix <= i
@@ -126,21 +157,28 @@ __global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__re
     const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k;
     const uint32_t v = val ? val[at] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
-    keys[i] = ok ? k : ((uint64_t)n << 32);
+    keys[i] = emit_key(ok, k, v, n, op_bit);
     if (pay) pay[i] = ok ? v : 0u;
     if (ok) my_or |= d;
     else my_bad++;
+    if (pay && ok && v) my_vmax = max(my_vmax, v), my_vinv = max(my_vinv, ~v);
   }
   my_or = __reduce_or_sync(0xFFFFFFFFu, my_or);
   my_bad = __reduce_add_sync(0xFFFFFFFFu, my_bad);
+  my_vmax = __reduce_max_sync(0xFFFFFFFFu, my_vmax);
+  my_vinv = __reduce_max_sync(0xFFFFFFFFu, my_vinv);
   if (lane_id() == 0) {
     if (my_or) atomicOr(&s_or, my_or);
     if (my_bad) atomicAdd(&s_bad, my_bad);
+    if (my_vmax) atomicMax(&s_vmax, my_vmax);
+    if (my_vinv) atomicMax(&s_vinv, my_vinv);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     if (s_or) atomicOr(&sc->dst_or, s_or);
     if (s_bad) atomicAdd(&sc->n_ignored, (unsigned long long)s_bad);
+    if (s_vmax) atomicMax(&sc->val_max, s_vmax);
+    if (s_vinv) atomicMax(&sc->val_inv_min, s_vinv);
   }
 }
 
@@ -201,7 +239,7 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys
                                                const uint32_t *__restrict__ leaf_cnt, const uint32_t *__restrict__ beg,
                                                uint32_t ls, uint32_t *__restrict__ nn, uint32_t *__restrict__ uloc,
                                                uint8_t *__restrict__ ucls, uint32_t *__restrict__ ins_cnt,
-                                               uint32_t *__restrict__ del_cnt, BatchScalars *sc) {
+                                               uint32_t *__restrict__ del_cnt, uint32_t op_bit, BatchScalars *sc) {
   __shared__ uint32_t s_stat[6];
   if (threadIdx.x < 6) s_stat[threadIdx.x] = 0;
   __syncthreads();
@@ -211,21 +249,26 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys
   int delta = 0;
   bool miss_dup = false, miss_first = false, winner = false;
   if (i < count) {
-    const uint64_t k = keys[i];
+    // op_bit: bit 63 of a key word marks a remove (KEY_OP_BIT) and is not part of the key
+    const uint64_t km = op_bit ? ~KEY_OP_BIT : ~0ull;
+    auto value_at = [&](size_t x) -> uint32_t {
+      return pay ? pay[x] : (op_bit && (keys[x] & KEY_OP_BIT)) ? 0u : default_val;
+    };
+    const uint64_t k = keys[i] & km;
     if (k < invalid_key) {
       s = (uint32_t)(k >> 32);
-      const uint32_t v = pay ? pay[i] : default_val;
+      const uint32_t v = value_at(i);
       delta = v != 0 ? 1 : -1;
-      const bool same_prev = i > 0 && keys[i - 1] == k;
-      winner = i + 1 == count || keys[i + 1] != k;
+      const bool same_prev = i > 0 && (keys[i - 1] & km) == k;
+      winner = i + 1 == count || (keys[i + 1] & km) != k;
       // a remove right after a remove of the same key: the sequential reference reports `not found`
-      if (v == 0 && same_prev && (pay ? pay[i - 1] : default_val) == 0) miss_dup = true;
+      if (v == 0 && same_prev && value_at(i - 1) == 0) miss_dup = true;
       if (winner) {
         bool first_del = v == 0;  // is the FIRST op of this key's run a remove?
         if (same_prev) {
           size_t h = i - 1;
-          while (h > 0 && keys[h - 1] == k) h--;
-          first_del = (pay ? pay[h] : default_val) == 0;
+          while (h > 0 && (keys[h - 1] & km) == k) h--;
+          first_del = value_at(h) == 0;
         }
         const uint32_t d = (uint32_t)k;
         uint32_t slot;

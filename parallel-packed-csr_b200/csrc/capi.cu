@@ -741,15 +741,18 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
 
   // 1. keys + guards.  With no per-update values every payload is default_val: sort keys only.
   const bool has_pay = d_val != nullptr;
+  // per-update values: removes are also flagged in bit 63 of the key word (free while vertex ids stay below 2^31),
+  // so that a stream whose non-zero values are all equal can be sorted keys-only (see batch::emit_key)
+  const uint32_t op_bit = (has_pay && s->n < (1u << 31)) ? 1u : 0u;
   const unsigned kb = std::min<unsigned>(div_up(count, batch::BT * 8), 148 * 16);
   if (segments) {
-    batch::k_build_keys_segments<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, *segments, s->n,
+    batch::k_build_keys_segments<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, *segments, s->n, op_bit,
                                                                  s->key_a.p, has_pay ? s->pay_a.p : nullptr, sc);
   } else if (d_packed) {
-    batch::k_build_keys_packed<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, count, s->n, s->key_a.p,
+    batch::k_build_keys_packed<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, count, s->n, op_bit, s->key_a.p,
                                                                has_pay ? s->pay_a.p : nullptr, sc);
   } else {
-    batch::k_build_keys<<<kb, batch::BT, 0, s->stream>>>(d_src, d_dst, d_val, default_val, count, s->n, s->key_a.p,
+    batch::k_build_keys<<<kb, batch::BT, 0, s->stream>>>(d_src, d_dst, d_val, default_val, count, s->n, op_bit, s->key_a.p,
                                                         has_pay ? s->pay_a.p : nullptr, sc);
   }
   CUDA_TRY(cudaGetLastError());
@@ -771,10 +774,18 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   const int lo_bits = std::max(1, bits_of(s->h_scalars->dst_or));
   // rejected updates carry the key (n << 32): they need bits_of(n) source bits, valid ones bits_of(n-1)
   const int hi_bits = std::max(1, s->h_scalars->n_ignored ? bits_of(s->n) : bits_of(s->n ? s->n - 1 : 0));
-  // 2. stable radix sort by (src,dst)
+  // 2. stable radix sort by (src,dst); the values travel as payload unless they are all the same
+  bool sort_pay = has_pay;
+  if (op_bit) {
+    const uint32_t vmax = s->h_scalars->val_max, vmin = ~s->h_scalars->val_inv_min;
+    if (vmax == 0u || vmax == vmin) {  // removes only, or ONE non-zero value: the key's op bit says it all
+      sort_pay = false;
+      default_val = vmax ? vmax : 1u;
+    }
+  }
   uint64_t *keys;
   uint32_t *pay;
-  PPCSR_TRY(prim::radix_sort_pairs(s, s->key_a.p, has_pay ? s->pay_a.p : nullptr, s->key_b.p, s->pay_b.p, count,
+  PPCSR_TRY(prim::radix_sort_pairs(s, s->key_a.p, sort_pay ? s->pay_a.p : nullptr, s->key_b.p, s->pay_b.p, count,
                                    lo_bits, hi_bits, &keys, &pay));
   CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
   // 3+4. call counts, last-op-wins, locate, per-leaf counts -- one kernel over the sorted batch
@@ -783,7 +794,7 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
   batch::k_locate<<<div_up(count, batch::BT), batch::BT, 0, s->stream>>>(
       keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
-      s->nn.p, s->uloc.p, s->ucls.p, s->ins_cnt.p, s->del_cnt.p, sc);
+      s->nn.p, s->uloc.p, s->ucls.p, s->ins_cnt.p, s->del_cnt.p, op_bit, sc);
   PPCSR_TRY(prim::device_scan(
       s, batch::InIsInsert{s->ucls.p},
       batch::OutInsert{keys, pay, default_val, s->uloc.p, s->ins_dst.p, s->ins_val.p, s->ins_pred.p}, count, nullptr,

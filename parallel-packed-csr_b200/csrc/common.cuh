@@ -140,7 +140,8 @@ struct BatchScalars {
   unsigned long long n_small;       // windows handled one per warp
   unsigned int dst_or;              // OR of all dst (sort width)
   unsigned int root_violation;      // bit0: root above upper bound, bit1: root below lower bound
-  unsigned int pad0, pad1;
+  unsigned int val_max;             // largest per-update value of the batch (0: none non-zero)
+  unsigned int val_inv_min;         // ~(smallest non-zero value)
   unsigned long long n_touched_est;  // leaves that received inserts + leaves that lost items (k_locate's tally)
   unsigned long long seg_total;      // batch size when it is only known on the device (records deposited by peers)
 };

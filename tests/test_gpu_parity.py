@@ -167,15 +167,17 @@ def test_delete_stream_vs_oracle(scale, n_del, batches, policy):
 
 @pytest.mark.parametrize("n,m,batch", [(1000, 20000, 20000), (1000, 20000, 997), (50, 5000, 64), (3000, 60000, 1)])
 @pytest.mark.parametrize("policy", POLICIES, ids=["windows", "auto"])
-def test_mixed_stream_vs_oracle(n, m, batch, policy):
+@pytest.mark.parametrize("one_value", [False, True], ids=["values", "ops"])
+def test_mixed_stream_vs_oracle(n, m, batch, policy, one_value):
     """Mixed adds (with values) and deletes, 3:1 (reference test add_remove_edge_random_2E4_seq).  A batch is
-    applied with last-op-wins, which equals the sequential reference on the same stream."""
+    applied with last-op-wins, which equals the sequential reference on the same stream.  `ops`: every add carries
+    the same value (what the thread pools submit): the batch is sorted keys-only, the op rides in bit 63 of the key."""
     if batch == 1:
         m = 1500  # single-op batches are slow; still covers every path
     rng = np.random.default_rng(n + m + batch)
     src = rng.integers(0, n + 3, m)  # a few sources >= n: silently ignored (reference PCSR.cpp:1375)
     dst = rng.integers(0, n, m)
-    val = np.where(rng.integers(0, 4, m) != 0, rng.integers(1, 1 << 20, m), 0)
+    val = np.where(rng.integers(0, 4, m) != 0, 7 if one_value else rng.integers(1, 1 << 20, m), 0)
     o = O.OraclePCSR(n)
     g = pp.Shard(n)
     g.set_whole_array_policy(policy)
