@@ -251,6 +251,11 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
   A.out_dest_single = A.out_dest_multi = s->dest_alt.p;
   A.out_val_single = A.out_val_multi = s->val_alt.p;
   A.tree_leaf_out = s->tree.p + g2.n_leaves;
+  // the persistent kernel reads no leaf counts (kept flags come from val[]), so the new counts can go straight into
+  // leaf_cnt[]; sized for the new geometry before the launch (old contents are not needed any more)
+  PPCSR_TRY(dev_reserve(s->leaf_cnt, g2.n_leaves, s->stream));
+  A.leaf_cnt = s->leaf_cnt.p;
+  A.leaf_cnt_out = reb_kernel() == 6 ? nullptr : s->leaf_cnt.p;
   A.beg = s->beg.p;
   A.windows = s->windows.p;
   A.n_windows = 1;
@@ -265,7 +270,7 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
   reb::k_plan_chunks<<<div_up(hw->n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
       s->windows.p, 1u, s->rank_off.p, s->ins_off.p, g.leaf_shift, g2.leaf_shift, g2.n_leaves, hw->n_chunks, CL2,
       s->plan.p);
-  s->launches += 6;
+  s->launches += 4;
   CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
   PPCSR_TRY(launch_rebalance(s, hw->n_chunks, A));
   CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
@@ -273,17 +278,15 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
   std::swap(s->dest, s->dest_alt);
   std::swap(s->val, s->val_alt);
   s->geo = g2;
-  PPCSR_TRY(dev_reserve(s->leaf_cnt, g2.n_leaves, s->stream));
   PPCSR_TRY(reserve_leaf_arrays(s, g2));
-  reb::k_copy_u32<<<div_up(g2.n_leaves, 256), 256, 0, s->stream>>>(s->leaf_cnt.p, s->tree.p + g2.n_leaves,
-                                                                  g2.n_leaves);
+  if (!A.leaf_cnt_out)  // the one-chunk-per-CTA kernel leaves the counts in the tree only
+    reb::k_copy_u32<<<div_up(g2.n_leaves, 256), 256, 0, s->stream>>>(s->leaf_cnt.p, s->tree.p + g2.n_leaves,
+                                                                    g2.n_leaves);
   PPCSR_TRY(win::tree_rebuild(s, s->tree.p, g2.H));
   reb::k_set_u32<<<1, 1, 0, s->stream>>>(s->beg.p + s->n, (uint32_t)g2.N);
-  // every leaf was rewritten: for the invariant checker all of them count as touched by this batch
-  qry::k_fill_u32<<<div_up(g2.n_leaves, 256), 256, 0, s->stream>>>(s->ins_cnt.p, h.n_inserted ? 1u : 0u,
-                                                                  g2.n_leaves);
-  qry::k_fill_u32<<<div_up(g2.n_leaves, 256), 256, 0, s->stream>>>(s->del_cnt.p, h.n_deleted ? 1u : 0u,
-                                                                  g2.n_leaves);
+  // every leaf was rewritten: for the invariant checker all of them count as touched by this batch (a flag, not two
+  // fills of the per-leaf count arrays)
+  s->all_touched = 4u | (h.n_inserted ? 1u : 0u) | (h.n_deleted ? 2u : 0u);
   CUDA_TRY(cudaGetLastError());
   st->n_windows = 1;
   st->whole_array = 1;
@@ -736,6 +739,7 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   }
   BatchScalars *sc = s->d_scalars;
   CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(BatchScalars), s->stream));
+  s->all_touched = 0;
   CUDA_TRY(cudaEventRecord(s->ev[0], s->stream));
   s->launches = 2;  // build_keys, locate
 
@@ -889,6 +893,7 @@ int ppcsr_add_nodes(ppcsr_shard *s, uint32_t count) {
   PPCSR_TRY(reserve_batch_arrays(s, count));
   BatchScalars *sc = s->d_scalars;
   CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(BatchScalars), s->stream));
+  s->all_touched = 0;
   for (int e = 0; e < 3; e++) CUDA_TRY(cudaEventRecord(s->ev[e], s->stream));
   s->launches = 2;
   CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
@@ -1297,8 +1302,8 @@ int ppcsr_check_invariants(ppcsr_shard *s, int check_lower, ppcsr_invariant_repo
   qry::k_check_vertices<<<div_up((uint64_t)s->n + 1, qry::QT), qry::QT, 0, s->stream>>>(
       s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, s->n, g.N, g.leaf_shift, d_c.p);
   if (L > 1) qry::k_check_tree<<<div_up(L, qry::QT), qry::QT, 0, s->stream>>>(s->tree.p, L, d_c.p);
-  qry::k_check_bounds<<<div_up(L, qry::QT), qry::QT, 0, s->stream>>>(s->tree.p, s->ins_cnt.p, s->del_cnt.p, L, g.logN,
-                                                                    (int)g.H, check_lower, d_c.p);
+  qry::k_check_bounds<<<div_up(L, qry::QT), qry::QT, 0, s->stream>>>(s->tree.p, s->ins_cnt.p, s->del_cnt.p, s->all_touched,
+                                                                    L, g.logN, (int)g.H, check_lower, d_c.p);
   CUDA_TRY(cudaGetLastError());
   qry::InvCounters *hc = reinterpret_cast<qry::InvCounters *>(s->h_pinned);
   CUDA_TRY(cudaMemcpyAsync(hc, d_c.p, sizeof(qry::InvCounters), cudaMemcpyDeviceToHost, s->stream));

@@ -198,6 +198,7 @@ struct ppcsr_shard {
   DevBuf<uint32_t> win_chunk_off;      // [n_leaves+1]
   DevBuf<ChunkPlan> plan;              // [n_chunks]
   bool ins_sentinels = false;          // the pending insert list holds sentinels (ppcsr_add_nodes)
+  uint32_t all_touched = 0;            // invariant checker: bit 2 = the last batch rewrote every leaf (bit 0 inserts, bit 1 deletes)
   int whole_policy = 0;                // -1 never / 0 cost model / 1 always: one root window instead of a window list
 
   // per-batch update-granular scratch

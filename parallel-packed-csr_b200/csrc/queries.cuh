@@ -318,14 +318,19 @@ __global__ void __launch_bounds__(QT) k_check_tree(const uint32_t *__restrict__ 
   if (tree[i] != tree[2 * i] + tree[2 * i + 1]) atomicAdd(&c->bad_tree, 1ull);
 }
 
-// density bounds on every path touched by the last batch (ins_cnt/del_cnt still hold its per-leaf counts)
+// density bounds on every path touched by the last batch (ins_cnt/del_cnt still hold its per-leaf counts, unless
+// the batch rebuilt the whole array)
 __global__ void __launch_bounds__(QT) k_check_bounds(const uint32_t *__restrict__ tree,
                                                      const uint32_t *__restrict__ ins_cnt,
-                                                     const uint32_t *__restrict__ del_cnt, uint32_t n_leaves,
-                                                     uint32_t logN, int H, int check_lower, InvCounters *c) {
+                                                     const uint32_t *__restrict__ del_cnt, uint32_t all_touched,
+                                                     uint32_t n_leaves, uint32_t logN, int H, int check_lower,
+                                                     InvCounters *c) {
   const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= n_leaves) return;
-  const bool ins = ins_cnt[l] != 0, del = del_cnt[l] != 0;
+  // all_touched bit 2: the last batch rewrote the whole array -- every leaf counts as touched by its inserts (bit 0)
+  // and deletes (bit 1), and the per-leaf arrays are not meaningful
+  const bool ins = (all_touched & 4u) ? (all_touched & 1u) != 0 : ins_cnt[l] != 0;
+  const bool del = (all_touched & 4u) ? (all_touched & 2u) != 0 : del_cnt[l] != 0;
   if (!ins && !del) return;
   uint32_t node = n_leaves + l;
   uint64_t len = logN;

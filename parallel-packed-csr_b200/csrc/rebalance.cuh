@@ -49,6 +49,7 @@ struct Args {
   uint32_t *out_dest_single, *out_val_single;  // target of single-CTA windows (in place)
   uint32_t *out_dest_multi, *out_val_multi;    // target of multi-CTA windows (out of place)
   uint32_t *tree_leaf_out;                     // post-rebalance leaf counts (leaf level of the tree)
+  uint32_t *leaf_cnt_out;                      // nullable: the same counts, straight into the new leaf_cnt[] (k_rebalance_p)
   uint32_t *beg;
   const WindowDesc *windows;
   uint32_t n_windows;
@@ -785,9 +786,11 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
     // every source leaf has been read (a single-CTA window is rebalanced in place) and the staging buffers are
     // complete: the chunk is stored after the next barrier
     if (is_hk) {  // post-rebalance leaf counts of this chunk; rank -> slot table of the CTA's next chunk
-      for (uint32_t kk = hk_tid; kk < n_out; kk += HK)
-        A.tree_leaf_out[dst_leaf0 + plan.o_lo + kk] =
-            leaf_rank0(plan.o_lo + kk + 1u, j, lg) - leaf_rank0(plan.o_lo + kk, j, lg);
+      for (uint32_t kk = hk_tid; kk < n_out; kk += HK) {
+        const uint32_t c_k = leaf_rank0(plan.o_lo + kk + 1u, j, lg) - leaf_rank0(plan.o_lo + kk, j, lg);
+        A.tree_leaf_out[dst_leaf0 + plan.o_lo + kk] = c_k;
+        if (A.leaf_cnt_out) A.leaf_cnt_out[dst_leaf0 + plan.o_lo + kk] = c_k;
+      }
       if (c + G < n_chunks) build_pos(plan_from(S.plan[(k + 1u) & 1u][0], S.plan[(k + 1u) & 1u][1]), (k + 1u) & 1u);
     }
     store_pending = true;
