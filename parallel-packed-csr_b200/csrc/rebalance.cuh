@@ -392,8 +392,8 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance(Args A) {
 // entry and of its source quads -- every CTA walks plan -> addresses -> DRAM -> compute -> store with nothing to
 // overlap but the three other CTAs of its SM -- and another 25 % at its five block barriers.  Here one CTA per
 // resident slot (grid = SMs x PPCSR_REB_CTAS) loops over the chunks c, c+G, c+2G, ...; a ROUND is one segment of
-// one chunk, and as soon as the operands of a round sit in registers (after P1) one thread issues the bulk copies
-// (cp.async.bulk global -> shared, completing on an mbarrier) of the next round:
+// one chunk, and as soon as the operands of a round sit in registers (after P1) lane 0 of four warps issues the bulk
+// copies (cp.async.bulk global -> shared, completing on ONE mbarrier with four arrivals) of the next round:
 //   * source quads of the segment, its R / insert-offset slices, and for the first segment of a chunk its first
 //     PINS inserts, R0 and the plan entry of the chunk after it;
 // so DRAM latency hides behind P2/P3 of the previous round, and the bulk store of a chunk drains while the next
@@ -404,12 +404,13 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance(Args A) {
 //   P2  inserts placed;  P3  kept items placed -- no barrier between them: the marker a kept item needs (how many
 //       inserts hang on earlier slots of its leaf) is written in P1 by the LAST insert of each slot (neighbour
 //       compare on the staged predecessors: 16-bit, no shared-memory atomics) and cleared again by its reader.
-// The warps of a CTA do not carry the same load (see "Division of labour" below); the per-chunk housekeeping is
-// dealt to the light ones.
-// Measured (B200, same box as k_rebalance): C2 265 -> 234 us, C4 2.46 -> 2.32 ms, C3 124 -> 124 us.
+// The warps of a CTA do not carry the same load (see "Division of labour" below); the per-chunk housekeeping -- the
+// rank -> slot table of the CTA's NEXT chunk (double-buffered), leaf counts, tables, the store -- is dealt to the light
+// ones.  Measured (B200, same box as k_rebalance): C2 265 -> 225 us, C4 2.46 -> 2.23 ms, C3 124 -> 121 us.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int PINS = INS_PREFETCH * KT;  // staged inserts per chunk
-constexpr int PSEG_MAX_LEAVES = SEG_LEAVES_SLOTS / 32 > 128 ? SEG_LEAVES_SLOTS / 32 : 128;  // leaves per segment (8-slot leaves only exist in arrays of <= 128 slots)
+// leaves per segment: 64 of 32 slots; arrays with smaller leaves are tiny, their segments are capped at 128 leaves
+constexpr int PSEG_MAX_LEAVES = SEG_LEAVES_SLOTS / 32 > 128 ? SEG_LEAVES_SLOTS / 32 : 128;
 constexpr int TBL = PSEG_MAX_LEAVES + 1;
 
 struct PSmem {  // dynamic shared memory layout of k_rebalance_p
