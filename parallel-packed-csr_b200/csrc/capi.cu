@@ -1,6 +1,7 @@
 // capi.cu -- C-ABI (include/ppcsr_b200.h) and host orchestration of the batch pipeline.
 // Unity build: all kernels are included here and compiled for sm_100a only.
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -165,10 +166,12 @@ int launch_rebalance(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
 }
 
 // Output leaves per chunk of a whole-array rebuild.  A chunk's source range is its share of the source leaves plus
-// one or two straddled at the ends; at the full 2048 output slots a 1:1 rebuild reads ~65 source leaves, one more
-// than a segment of the kernel holds, and pays a whole extra round for it.  Chunks of 60 leaves keep the range in
-// one segment (measured on C4: 2.48 -> 2.32 ms); a doubling (33-34 leaves, second round on one warp only) and a
-// halving (2-3 full segments either way) are best at the full size.  PPCSR_REB_CL=<leaves> overrides (development).
+// one or two straddled at the ends, and the kernel takes it in segments of 64 leaves: at the full 2048 output slots
+// a 1:1 rebuild reads ~65 source leaves and a halving ~130, i.e. one leaf more than one resp. two segments hold, and
+// pays a whole extra round for it.  Slightly smaller chunks fit the range into one segment fewer (measured: C4, 1:1,
+// 60 leaves: 2.48 -> 2.32 ms; C3, halving, 56 leaves: 123 -> 118 us; the margin covers the local variation of the
+// source density, larger after random deletes).  A doubling (33-34 source leaves) is best at the full size.
+// PPCSR_REB_CL=<leaves> overrides (development).
 uint32_t whole_array_chunk_leaves(const Geometry &g, const Geometry &g2) {
   const uint32_t cap = reb::CHUNK_SLOTS >> g2.leaf_shift;
   static long forced = -1;
@@ -177,9 +180,14 @@ uint32_t whole_array_chunk_leaves(const Geometry &g, const Geometry &g2) {
     forced = e ? atol(e) : 0;
   }
   if (forced > 0) return std::max<uint32_t>(1u, std::min<uint32_t>(cap, (uint32_t)forced));
-  const double ratio = (double)g2.n_leaves / (double)g.n_leaves;
-  const double per_seg = 0.94 * (double)(reb::SEG_LEAVES_SLOTS >> g.leaf_shift) * ratio;
-  if (per_seg >= 0.75 * cap) return std::min<uint32_t>(cap, (uint32_t)per_seg);
+  const double seg = (double)(reb::SEG_LEAVES_SLOTS >> g.leaf_shift);
+  const double src_per_out = (double)g.n_leaves / (double)g2.n_leaves;  // source leaves per output leaf
+  const double margin = src_per_out > 1.0 ? 1.12 : 1.03;
+  const double segments = std::ceil((cap * src_per_out * margin + 2.0) / seg);  // at the full chunk size
+  if (segments > 1.0) {
+    const double fewer = std::floor(((segments - 1.0) * seg - 2.0) / (src_per_out * margin));
+    if (fewer >= 0.75 * cap) return std::min<uint32_t>(cap, (uint32_t)fewer);
+  }
   return cap;
 }
 
