@@ -1,6 +1,6 @@
 // One PageRank push step with the reference's signature (reference src/utility/pagerank.h:16-29):
 //   out[nbr] += values[v] / getNode(v).num_neighbors   for every edge (v, nbr)
-// The edge scan runs on the GPU (warp-per-vertex kernel, fp64 accumulation) through T::pagerank_push.
+// The edge scan runs on the GPU (leaf walk over the packed array, fp64 accumulation) through T::pagerank_push.
 #pragma once
 #include <cstdint>
 #include <vector>
