@@ -202,6 +202,12 @@ int ppcsr_bfs(ppcsr_shard *h, uint32_t start, uint32_t *dist);
 /* ---- checks and snapshots ---- */
 /* PMA invariants I1-I6.  `check_lower` != 0 also counts lower-bound violations. */
 int ppcsr_check_invariants(ppcsr_shard *h, int check_lower, ppcsr_invariant_report *report);
+/* Order-independent checksum of the logical graph: out[0] = edges, out[1] = sum (mod 2^64) of
+ * mix64((vertex_offset + src) << 32 | dst) over all edges, out[2] = sum of num_neighbors[v] * mix64(vertex_offset + v)
+ * (mix64 = the splitmix64 finaliser).  Sums of several shards add up to the checksum of the whole graph when
+ * vertex_offset is the shard's first global vertex (reference PPPCSR.cpp:46-52).  The parity anchor at sizes where
+ * per-vertex get_neighbourhood dumps (reference PCSR.cpp:901-912) are impractical. */
+int ppcsr_checksum(ppcsr_shard *h, uint64_t vertex_offset, uint64_t out[3]);
 /* Device-side copy of the whole shard state (arrays + geometry); restore makes the shard identical
  * to the snapshot again.  One snapshot per shard. */
 int ppcsr_snapshot(ppcsr_shard *h);

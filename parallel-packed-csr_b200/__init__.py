@@ -92,6 +92,7 @@ SYMBOLS = {
     "ppcsr_set_whole_array_policy": (_i, [_vp, _i]),
     "ppcsr_bfs": (_i, [_vp, _u32, _vp]),
     "ppcsr_check_invariants": (_i, [_vp, _i, C.POINTER(InvariantReport)]),
+    "ppcsr_checksum": (_i, [_vp, _u64, _vp]),
     "ppcsr_snapshot": (_i, [_vp]),
     "ppcsr_restore": (_i, [_vp]),
     "ppcsr_debug_dump": (_i, [_vp, _vp, _vp, _vp]),
@@ -323,6 +324,12 @@ class Shard:
         r = InvariantReport()
         _check(self.L.ppcsr_check_invariants(self.h, 1 if check_lower else 0, C.byref(r)))
         return r
+
+    def checksum(self, vertex_offset: int = 0) -> dict:
+        """Order-independent checksum of the logical graph (edges, edge_hash, nn_hash), see ppcsr_checksum."""
+        out = (C.c_uint64 * 3)()
+        _check(self.L.ppcsr_checksum(self.h, vertex_offset, out))
+        return {"edges": int(out[0]), "edge_hash": int(out[1]), "nn_hash": int(out[2])}
 
     def debug_dump(self):
         g = self.geometry

@@ -1329,6 +1329,28 @@ int ppcsr_check_invariants(ppcsr_shard *s, int check_lower, ppcsr_invariant_repo
   return PPCSR_OK;
 }
 
+int ppcsr_checksum(ppcsr_shard *s, uint64_t vertex_offset, uint64_t out[3]) {
+  if (!s || !out) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  out[0] = out[1] = out[2] = 0;
+  if (s->n == 0) return PPCSR_OK;
+  DevBuf<unsigned long long> d_o;
+  PPCSR_TRY(dev_reserve(d_o, 4, s->stream));
+  CUDA_TRY(cudaMemsetAsync(d_o.p, 0, 4 * sizeof(unsigned long long), s->stream));
+  const unsigned blocks = std::min<unsigned>(div_up(s->geo.N, (uint64_t)qry::QT * 4), 148 * 16);
+  qry::k_checksum_leaves<<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p,
+                                                           s->geo.leaf_shift, s->n, s->geo.N, vertex_offset, d_o.p);
+  qry::k_checksum_nn<<<std::min<unsigned>(div_up(s->n, qry::QT), 148 * 8), qry::QT, 0, s->stream>>>(
+      s->nn.p, s->n, vertex_offset, d_o.p);
+  CUDA_TRY(cudaGetLastError());
+  unsigned long long *hp = reinterpret_cast<unsigned long long *>(s->h_pinned);
+  CUDA_TRY(cudaMemcpyAsync(hp, d_o.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  for (int k = 0; k < 3; k++) out[k] = hp[k];
+  dev_free(d_o);
+  return PPCSR_OK;
+}
+
 int ppcsr_snapshot(ppcsr_shard *s) {
   if (!s) return PPCSR_ERR_ARG;
   PPCSR_TRY(set_device(s));

@@ -233,6 +233,80 @@ __global__ void k_fill_u32(uint32_t *p, uint32_t v, size_t n) {
   if (i < n) p[i] = v;
 }
 
+// ---- checksum of the logical graph (parity anchor at sizes where an adjacency dump is impractical) -----------
+// edges, sum of mix64(global_src << 32 | dst) over all edges, sum of num_neighbors[v] * mix64(global v) -- the same
+// order-independent sums oracle/ref_driver.cpp --checksum takes over the reference's get_neighbourhood().  Same leaf
+// walk as the PageRank push: the sentinels carry the source vertex.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 30;
+  x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27;
+  x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+__global__ void __launch_bounds__(QT) k_checksum_leaves(const uint32_t *__restrict__ dest,
+                                                        const uint32_t *__restrict__ val,
+                                                        const uint32_t *__restrict__ leaf_cnt,
+                                                        const uint32_t *__restrict__ beg, uint32_t ls, uint32_t n,
+                                                        uint64_t n_slots, unsigned long long vertex_offset,
+                                                        unsigned long long *__restrict__ out) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = lane_id();
+  const uint32_t groups = (uint32_t)(n_slots >> 5);
+  const uint32_t per = (groups + warps - 1) / warps;
+  const uint32_t g0 = min(w * per, groups), g1 = min(g0 + per, groups);
+  if (g0 >= g1 || n == 0) return;
+  uint32_t carry;  // vertex owning the first slot of my run: the last v with beg[v] <= slot
+  {
+    const uint32_t s0 = g0 << 5;
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (beg[mid] <= s0) lo = mid;
+      else hi = mid;
+    }
+    carry = lo;
+  }
+  const uint32_t lsm = (1u << ls) - 1u;
+  const unsigned le = lanemask_lt() | (1u << lane);
+  unsigned long long cnt = 0, hash = 0;
+  for (uint32_t g = g0; g < g1; g++) {
+    const uint32_t slot = (g << 5) + lane;
+    const bool live = (slot & lsm) < leaf_cnt[slot >> ls];
+    const uint32_t d = live ? dest[slot] : 0u;
+    const bool sent = live && d == PPCSR_SENT;
+    const uint32_t sv = sent ? val[slot] - 1u : 0u;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, sent);
+    const unsigned below = m & le;
+    uint32_t mine = __shfl_sync(0xFFFFFFFFu, sv, below ? 31 - __clz(below) : 0);
+    if (!below) mine = carry;
+    if (live && !sent) {
+      cnt++;
+      hash += mix64(((vertex_offset + mine) << 32) | d);
+    }
+    if (m) carry = __shfl_sync(0xFFFFFFFFu, sv, 31 - __clz(m));
+  }
+  for (int o = 16; o; o >>= 1) {
+    cnt += __shfl_down_sync(0xFFFFFFFFu, cnt, o);
+    hash += __shfl_down_sync(0xFFFFFFFFu, hash, o);
+  }
+  if (lane == 0) {
+    atomicAdd(&out[0], cnt);
+    atomicAdd(&out[1], hash);
+  }
+}
+__global__ void __launch_bounds__(QT) k_checksum_nn(const uint32_t *__restrict__ nn, uint32_t n,
+                                                    unsigned long long vertex_offset,
+                                                    unsigned long long *__restrict__ out) {
+  unsigned long long acc = 0;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
+    acc += (unsigned long long)nn[v] * mix64(vertex_offset + v);
+  for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
+  if (lane_id() == 0 && acc) atomicAdd(&out[2], acc);
+}
+
 // ---- invariants -------------------------------------------------------------------
 struct InvCounters {
   unsigned long long bad_sentinel, bad_order, bad_leaf_layout, bad_upper, bad_lower, bad_tree, live_items, sentinels,

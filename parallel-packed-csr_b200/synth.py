@@ -131,3 +131,32 @@ def write_text(path: str, src, dst, op=None) -> None:
         else:
             for s, d, o in zip(src.tolist(), dst.tolist(), np.asarray(op).tolist()):
                 f.write(f"{s} {d} {o}\n")
+
+
+_M64 = (1 << 64) - 1
+
+
+def mix64(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser on uint64 arrays (the hash of the graph checksum)."""
+    x = np.asarray(x, dtype=np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    return x
+
+
+def graph_checksum(rowptr, col, num_neighbors=None, vertex_offset: int = 0) -> dict:
+    """Host statement of ppcsr_checksum / ref_driver --checksum over a CSR: edges, edge_hash, nn_hash."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    n = rowptr.shape[0] - 1
+    src = np.repeat(np.arange(n, dtype=np.uint64) + np.uint64(vertex_offset), np.diff(rowptr))
+    with np.errstate(over="ignore"):
+        eh = int(mix64((src << np.uint64(32)) | np.asarray(col, dtype=np.uint64)).sum(dtype=np.uint64))
+        nh = 0
+        if num_neighbors is not None:
+            v = np.arange(n, dtype=np.uint64) + np.uint64(vertex_offset)
+            nh = int((np.asarray(num_neighbors, dtype=np.uint64) * mix64(v)).sum(dtype=np.uint64))
+    return {"edges": int(rowptr[-1]), "edge_hash": eh & _M64, "nn_hash": nh & _M64}

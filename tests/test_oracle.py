@@ -101,3 +101,70 @@ def test_oracle_matches_live_reference_random_streams():
         assert np.array_equal(nn, ref["num_neighbors"])
         assert g.geometry == (ref["N"], ref["logN"], ref["H"])
         assert np.array_equal(g.pagerank(1.0 + (np.arange(n) % 7)), ref["pagerank"], equal_nan=True)
+
+
+def test_graph_checksum_host_statement():
+    """synth.graph_checksum (the host statement of ppcsr_checksum / ref_driver --checksum) on a tiny CSR, by hand."""
+    import importlib
+
+    synth = importlib.import_module("parallel-packed-csr_b200.synth")
+
+    def mix(x):
+        m = (1 << 64) - 1
+        x ^= x >> 30
+        x = (x * 0xBF58476D1CE4E5B9) & m
+        x ^= x >> 27
+        x = (x * 0x94D049BB133111EB) & m
+        return x ^ (x >> 31)
+
+    rowptr, col, nn = [0, 2, 2, 3], [1, 2, 0], [5, 0, 1]
+    want_e = (mix((7 << 32) | 1) + mix((7 << 32) | 2) + mix((9 << 32) | 0)) & ((1 << 64) - 1)
+    want_n = (5 * mix(7) + 1 * mix(9)) & ((1 << 64) - 1)
+    got = synth.graph_checksum(rowptr, col, nn, vertex_offset=7)
+    assert got == {"edges": 3, "edge_hash": want_e, "nn_hash": want_n}
+
+
+def test_c4_golden_checksum_fixture():
+    """tests/golden/c4_checksum.json (the reference's checksum of the full-size C4 graph, bench.py's parity anchor):
+    the call-count hash is reproducible from the streams, the edge count is consistent with it."""
+    import json
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_checksum.json")))
+    assert g["workload"] == {"scale": 24, "batch": 100_000_000, "stream": "skewed", "core_edges": 16 << 24,
+                             "core_seed": 42, "update_seed": 99}
+    assert 0 < g["edges"] < (16 << 24) + 100_000_000 and len(g["edge_hash"]) == 16 and len(g["nn_hash_call_count"]) == 16
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_ref_driver_synthetic_streams_and_checksum(tmp_path):
+    """ref_driver's built-in stream generator is bit-identical to synth.py, its --checksum equals the host statement
+    over its own dump, and a --checkpoint dump equals a run that stops there."""
+    import importlib
+    import json
+    import subprocess
+
+    synth = importlib.import_module("parallel-packed-csr_b200.synth")
+    for kind, scale, lo, hi, seed in (("rmat", 24, 5, 20005, 99), ("uniform", 20, 0, 20000, 7),
+                                      ("rmat", 16, (1 << 32) - 10, (1 << 32) + 500, 42)):
+        p = str(tmp_path / "emit.bin")
+        subprocess.run([O.REF_DRIVER, "--threads", "3", "--synth-updates", f"{kind}:{scale}:{lo}:{hi}:{seed}",
+                        "--emit-updates", p], check=True)
+        a = np.fromfile(p, dtype="<u4").reshape(-1, 3)
+        s, d = (synth.rmat if kind == "rmat" else synth.uniform)(scale, lo, hi, seed)
+        assert np.array_equal(a[:, 0], s) and np.array_equal(a[:, 1], d) and (a[:, 2] == 1).all()
+    d1, d2, d3, sp = (str(tmp_path / x) for x in ("ck.bin", "full.bin", "stop.bin", "sum.json"))
+    base = [O.REF_DRIVER, "--mode", "pppcsrnuma", "--api", "pool", "--threads", "1", "--ppd", "2", "--n", str(1 << 12),
+            "--synth-core", "rmat:12:0:65536:42", "--synth-updates", "rmat:12:0:20000:99"]
+    subprocess.run(base + ["--checkpoint", "5000", d1, "--dump", d2, "--checksum", sp], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(base + ["--size", "5000", "--dump", d3], check=True, stdout=subprocess.DEVNULL)
+    ck, full, stop = O.read_dump(d1), O.read_dump(d2), O.read_dump(d3)
+    assert np.array_equal(ck["rowptr"], stop["rowptr"]) and np.array_equal(ck["col"], stop["col"])
+    cs = json.load(open(sp))
+    want = synth.graph_checksum(full["rowptr"], full["col"], full["num_neighbors"])
+    assert cs["edges"] == want["edges"] and int(cs["edge_hash"], 16) == want["edge_hash"]
+    assert int(cs["nn_hash"], 16) == want["nn_hash"]  # threads = 1: the call counts are exact
+    o = O.OraclePCSR(1 << 12)
+    o.apply(*synth.rmat(12, 0, 65536, 42), 1)
+    o.apply(*synth.rmat(12, 0, 20000, 99), 1)
+    rp, col, nn = o.export()
+    assert np.array_equal(rp, full["rowptr"]) and np.array_equal(col, full["col"]) and np.array_equal(nn, full["num_neighbors"])
