@@ -25,6 +25,13 @@
  *     that dst == 0xFFFFFFFF is rejected (it is the sentinel marker, reference PCSR.h:32, PCSR.cpp:64).
  *   - num_neighbors follows the reference's call-count semantics: +1 per accepted add call, -1 per
  *     remove call, duplicates and misses included (reference PCSR.cpp:1392,747).
+ *
+ * Failure atomicity of a batch: everything a batch can need in the worst case (every update a new edge: the grown
+ * array, trees, scratch) is allocated BEFORE the shard is modified, so PPCSR_ERR_CAPACITY from an apply_* / submit /
+ * wait / add_nodes call normally means "nothing was applied, the handle is intact".  The exception is the 2^31-slot
+ * limit, which can only be decided after duplicates have been resolved: a batch that hits it after it has begun leaves
+ * the handle POISONED -- every further update returns PPCSR_ERR_CAPACITY until ppcsr_restore() brings back a snapshot
+ * (or the handle is destroyed).  PPCSR_ERR_CUDA is always fatal for the handle.
  */
 #ifndef PPCSR_B200_H
 #define PPCSR_B200_H
@@ -42,7 +49,7 @@ typedef enum {
   PPCSR_OK = 0,
   PPCSR_ERR_CUDA = -1,     /* a CUDA runtime call failed (fatal for the handle) */
   PPCSR_ERR_ARG = -2,      /* bad argument */
-  PPCSR_ERR_CAPACITY = -3, /* slot count would exceed 2^31 or allocation failed */
+  PPCSR_ERR_CAPACITY = -3, /* slot count would exceed 2^31 or allocation failed (see "Failure atomicity" below) */
   PPCSR_ERR_NO_DEVICE = -4 /* no CUDA device: there is NO CPU fallback */
 } ppcsr_status;
 
@@ -118,6 +125,18 @@ int ppcsr_apply_batch(ppcsr_shard *h, const uint32_t *src, const uint32_t *dst, 
 /* Same, buffers already resident in this shard's device memory (not modified). */
 int ppcsr_apply_batch_device(ppcsr_shard *h, const uint32_t *d_src, const uint32_t *d_dst, const uint32_t *d_val,
                              uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats);
+/* Pipelined form of ppcsr_apply_batch for a stream of batches (replaces a sequence of ThreadPool start()/stop()
+ * regions, reference src/thread_pool/thread_pool.cpp:78-113): ppcsr_submit_batch starts the host->device copy of the
+ * batch into one of TWO staging slots on a copy stream and returns at once with a ticket; ppcsr_wait(ticket) applies
+ * that batch (after its copy) and returns its stats.  With
+ *     submit(b0); for i: { submit(b[i+1]); wait(b[i]); }
+ * the copy of batch i+1 runs under the compute of batch i.  At most two batches in flight; batches are applied in
+ * submission order (wait for the older ticket first).  The host buffers must stay valid until the matching
+ * ppcsr_wait returns; they should be page-locked (cudaHostAlloc / cudaHostRegister) -- a pageable buffer makes the
+ * submit itself block for the duration of the copy. */
+int ppcsr_submit_batch(ppcsr_shard *h, const uint32_t *src, const uint32_t *dst, const uint32_t *val, uint64_t count,
+                       uint32_t default_val, uint64_t *ticket);
+int ppcsr_wait(ppcsr_shard *h, uint64_t ticket, ppcsr_batch_stats *stats);
 /* Single operations = batches of one (reference PCSR::add_edge / remove_edge). Correctness path, slow. */
 int ppcsr_add_edge(ppcsr_shard *h, uint32_t src, uint32_t dst, uint32_t value);
 int ppcsr_remove_edge(ppcsr_shard *h, uint32_t src, uint32_t dst, int *found);

@@ -68,6 +68,8 @@ SYMBOLS = {
     "ppcsr_reserve": (_i, [_vp, _u64, _u64]),
     "ppcsr_apply_batch": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(BatchStats)]),
     "ppcsr_apply_batch_device": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(BatchStats)]),
+    "ppcsr_submit_batch": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_u64)]),
+    "ppcsr_wait": (_i, [_vp, _u64, C.POINTER(BatchStats)]),
     "ppcsr_add_edge": (_i, [_vp, _u32, _u32, _u32]),
     "ppcsr_remove_edge": (_i, [_vp, _u32, _u32, C.POINTER(_i)]),
     "ppcsr_add_nodes": (_i, [_vp, _u32]),
@@ -177,6 +179,26 @@ class Shard:
         st = BatchStats()
         _check(self.L.ppcsr_apply_batch(self.h, _np_ptr(src), _np_ptr(dst), _np_ptr(val), src.shape[0], default_val,
                                         C.byref(st)))
+        return st.as_dict()
+
+    def submit(self, src, dst, val=None, default_val: int = 1) -> int:
+        """Pipelined host submit (ppcsr_submit_batch): starts the H2D copy, returns a ticket for wait().  The arrays
+        must stay alive (and should be pinned) until wait() returns; they are kept referenced here."""
+        src = _u32_array(src)
+        dst = _u32_array(dst, src.shape[0])
+        val = _u32_array(val, src.shape[0]) if val is not None else None
+        t = C.c_uint64()
+        _check(self.L.ppcsr_submit_batch(self.h, _np_ptr(src), _np_ptr(dst), _np_ptr(val), src.shape[0], default_val,
+                                         C.byref(t)))
+        if not hasattr(self, "_inflight"):
+            self._inflight = {}
+        self._inflight[t.value] = (src, dst, val)
+        return t.value
+
+    def wait(self, ticket: int) -> dict:
+        st = BatchStats()
+        _check(self.L.ppcsr_wait(self.h, ticket, C.byref(st)))
+        self._inflight.pop(ticket, None)
         return st.as_dict()
 
     def apply_device(self, d_src: int, d_dst: int, d_val: int | None, count: int, default_val: int = 1) -> dict:

@@ -237,15 +237,19 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys
                                                uint32_t default_val, size_t count, uint64_t invalid_key,
                                                const uint32_t *__restrict__ dest, uint32_t *__restrict__ val,
                                                const uint32_t *__restrict__ leaf_cnt, const uint32_t *__restrict__ beg,
-                                               uint32_t ls, uint32_t *__restrict__ nn, uint32_t *__restrict__ uloc,
-                                               uint8_t *__restrict__ ucls, uint32_t *__restrict__ ins_cnt,
-                                               uint32_t *__restrict__ del_cnt, uint32_t op_bit, BatchScalars *sc) {
+                                               uint32_t ls, uint32_t *__restrict__ nn, uint32_t *__restrict__ ins_dst,
+                                               uint32_t *__restrict__ ins_val, uint32_t *__restrict__ ins_pred,
+                                               unsigned long long *scan_state, uint32_t scan_epoch,
+                                               uint32_t *__restrict__ ins_cnt, uint32_t *__restrict__ del_cnt,
+                                               uint32_t op_bit, BatchScalars *sc) {
+  __shared__ uint32_t s_warp[33];
+  __shared__ uint32_t s_prefix;
   __shared__ uint32_t s_stat[6];
   if (threadIdx.x < 6) s_stat[threadIdx.x] = 0;
   __syncthreads();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lt = lanemask_lt();
-  uint32_t cls = 0xFFu, leaf = 0xFFFFFFFFu, s = 0xFFFFFFFFu;
+  uint32_t cls = 0xFFu, leaf = 0xFFFFFFFFu, s = 0xFFFFFFFFu, my_slot = 0, my_val = 0, my_dst = 0;
   int delta = 0;
   bool miss_dup = false, miss_first = false, winner = false;
   if (i < count) {
@@ -281,11 +285,12 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys
           if (hit) val[slot] = 0;  // tombstone; compacted away by the rebalance of this leaf (PCSR.cpp:605-606)
         }
         if (first_del && !hit) miss_first = true;  // counted on the winner: the run's head op found nothing
-        uloc[i] = slot;
+        my_slot = slot;
+        my_val = v;
+        my_dst = d;
         leaf = slot >> ls;
       }
     }
-    ucls[i] = (uint8_t)cls;
   }
   // call counts: one atomic per run of equal sources inside the warp
   {
@@ -329,36 +334,60 @@ __global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys
       if (m4) atomicAdd(&s_stat[4], (uint32_t)__popc(m4));
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (s_stat[0]) atomicAdd(&sc->n_inserted, (unsigned long long)s_stat[0]);
-    if (s_stat[1]) atomicAdd(&sc->n_overwritten, (unsigned long long)s_stat[1]);
-    if (s_stat[2]) atomicAdd(&sc->n_deleted, (unsigned long long)s_stat[2]);
-    if (s_stat[3]) atomicAdd(&sc->n_not_found, (unsigned long long)s_stat[3]);
-    if (s_stat[4]) atomicAdd(&sc->n_unique, (unsigned long long)s_stat[4]);
-    if (s_stat[5]) atomicAdd(&sc->n_touched_est, (unsigned long long)s_stat[5]);
-  }
-}
-
-// ---- compacted insert list (key order preserved) ---------------------------------------------------
-struct InIsInsert {
-  const uint8_t *ucls;
-  __device__ uint32_t operator()(size_t i) const { return ucls[i] == CLS_INSERT ? 1u : 0u; }
-};
-struct OutInsert {
-  const uint64_t *keys;  // sorted batch
-  const uint32_t *pay;   // nullable: all default_val
-  uint32_t default_val;
-  const uint32_t *uloc;
-  uint32_t *ins_dst, *ins_val, *ins_pred;
-  __device__ void operator()(size_t i, uint32_t ex, uint32_t own) const {
-    if (own) {
-      ins_dst[ex] = (uint32_t)keys[i];
-      ins_val[ex] = pay ? pay[i] : default_val;
-      ins_pred[ex] = uloc[i];
+  // The compacted, key-ordered insert list (dst, value, predecessor slot), written by this kernel itself: exclusive
+  // scan of the insert flags over the block, the block's base from a decoupled look-back over the earlier blocks
+  // (one epoch-tagged word per block in scan_state, same protocol as prim::k_scan_onepass; tiles are the blocks in
+  // launch order, as in the single-pass scans of CUB).  Replaces a separate three-pass compaction (class and slot
+  // arrays written, read twice).
+  {
+    const uint32_t is_ins = cls == CLS_INSERT ? 1u : 0u;
+    uint32_t total;
+    const uint32_t ex = prim::block_excl_scan(is_ins, &total, s_warp);  // ends with a block barrier: s_stat is final too
+    if (threadIdx.x < 32) {
+      const unsigned lane = threadIdx.x;
+      const uint32_t tile = blockIdx.x;
+      volatile unsigned long long *st = scan_state;
+      if (lane == 0) st[tile] = prim::scan_word(tile == 0 ? prim::SCAN_ST_INC : prim::SCAN_ST_AGG, scan_epoch, total);
+      uint32_t prefix = 0;
+      if (tile > 0) {
+        int64_t j = (int64_t)tile - 1;  // lane l examines tile j - l
+        for (;;) {
+          const int64_t t = j - (int64_t)lane;
+          const unsigned long long w = t >= 0 ? st[t] : prim::scan_word(prim::SCAN_ST_INC, scan_epoch, 0u);
+          const bool ready = (uint32_t)((w >> 32) & 0x3FFFFFFFu) == scan_epoch && (w >> 62) != 0ull;
+          const unsigned inc = __ballot_sync(0xFFFFFFFFu, ready && (w >> 62) == 2ull);
+          const unsigned not_ready = __ballot_sync(0xFFFFFFFFu, !ready);
+          const unsigned first_inc = inc ? (unsigned)__ffs(inc) - 1u : 32u;
+          const unsigned need = first_inc < 32u ? (2u << first_inc) - 1u : 0xFFFFFFFFu;  // lanes 0..first_inc
+          if (not_ready & need) continue;  // a block this window depends on has not published yet: look again
+          uint32_t x = (need >> lane) & 1u ? (uint32_t)w : 0u;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
+          prefix += x;
+          if (first_inc < 32u) break;
+          j -= 32;
+        }
+        if (lane == 0) st[tile] = prim::scan_word(prim::SCAN_ST_INC, scan_epoch, prefix + total);
+      }
+      if (lane == 0) {
+        s_prefix = prefix;
+        if (s_stat[0]) atomicAdd(&sc->n_inserted, (unsigned long long)s_stat[0]);
+        if (s_stat[1]) atomicAdd(&sc->n_overwritten, (unsigned long long)s_stat[1]);
+        if (s_stat[2]) atomicAdd(&sc->n_deleted, (unsigned long long)s_stat[2]);
+        if (s_stat[3]) atomicAdd(&sc->n_not_found, (unsigned long long)s_stat[3]);
+        if (s_stat[4]) atomicAdd(&sc->n_unique, (unsigned long long)s_stat[4]);
+        if (s_stat[5]) atomicAdd(&sc->n_touched_est, (unsigned long long)s_stat[5]);
+      }
+    }
+    __syncthreads();
+    if (is_ins) {
+      const uint32_t at = s_prefix + ex;
+      ins_dst[at] = my_dst;
+      ins_val[at] = my_val;
+      ins_pred[at] = my_slot;
     }
   }
-};
+}
 
 // ---- owner binning for the multi-GPU all-to-all (reference PPPCSR::get_partiton, PPPCSR.cpp:58-66) ----
 __device__ __forceinline__ uint32_t owner_of(const uint64_t *starts, uint32_t parts, uint64_t v) {

@@ -46,8 +46,6 @@ int reserve_batch_arrays(ppcsr_shard *s, size_t count) {
   PPCSR_TRY(dev_reserve(s->key_b, count, s->stream));
   PPCSR_TRY(dev_reserve(s->pay_a, count, s->stream));
   PPCSR_TRY(dev_reserve(s->pay_b, count, s->stream));
-  PPCSR_TRY(dev_reserve(s->uloc, count, s->stream));
-  PPCSR_TRY(dev_reserve(s->ucls, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_dst, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_val, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_pred, count, s->stream));
@@ -102,34 +100,34 @@ int alloc_geometry(ppcsr_shard *s, const Geometry &g) {
 
 // development knob: PPCSR_REB_PAD_SMEM=<bytes> of unused dynamic shared memory caps the resident CTAs per SM of
 // k_rebalance (occupancy experiments); unset in production
+// the knobs below are read once; function-local statics with an initialiser are thread-safe (PPPCSR drives its shards
+// from several host threads)
 uint32_t reb_prefetch_dist() {  // development knob: PPCSR_REB_PREFETCH=<chunks>, default one wave of resident CTAs
-  static long d = -1;
-  if (d < 0) {
+  static const long d = [] {
     const char *e = getenv("PPCSR_REB_PREFETCH");
-    d = e ? atol(e) : 148 * 4;
-  }
+    return e ? atol(e) : 148L * 4;
+  }();
   return (uint32_t)d;
 }
 size_t reb_pad_smem() {
-  static long pad = -1;
-  if (pad < 0) {
+  static const long pad = [] {
     const char *e = getenv("PPCSR_REB_PAD_SMEM");
-    pad = e ? atol(e) : 0;
+    const long p = e ? atol(e) : 0;
 #if PPCSR_HAVE_V6
-    if (pad > 0) cudaFuncSetAttribute(reb::k_rebalance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    if (p > 0) cudaFuncSetAttribute(reb::k_rebalance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p);
 #endif
-  }
+    return p;
+  }();
   return (size_t)pad;
 }
 
 // PPCSR_REB_KERNEL=6 selects the one-chunk-per-CTA kernel (k_rebalance) for A/B runs; the default is the persistent,
 // software-pipelined kernel (k_rebalance_p)
 int reb_kernel() {
-  static int k = -1;
-  if (k < 0) {
+  static const int k = [] {
     const char *e = getenv("PPCSR_REB_KERNEL");
-    k = e ? atoi(e) : 9;
-  }
+    return e ? atoi(e) : 9;
+  }();
   return k;
 }
 int launch_rebalance(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
@@ -155,11 +153,10 @@ int launch_rebalance(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
   });
   CUDA_TRY(once_err[dv]);
   const int n_sm = sms[dv];
-  static long ctas = -1;  // development knob: resident CTAs per SM the grid is sized for
-  if (ctas < 0) {
+  static const long ctas = [] {  // development knob: resident CTAs per SM the grid is sized for
     const char *e = getenv("PPCSR_REB_GRID_CTAS");
-    ctas = e ? atol(e) : PPCSR_REB_CTAS;
-  }
+    return e ? atol(e) : (long)PPCSR_REB_CTAS;
+  }();
   const unsigned grid = std::min<unsigned>(n_chunks, (unsigned)(n_sm * ctas));
   reb::k_rebalance_p<<<grid, reb::KT, sizeof(reb::PSmem), s->stream>>>(A, n_chunks);
   return PPCSR_OK;
@@ -174,11 +171,10 @@ int launch_rebalance(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
 // PPCSR_REB_CL=<leaves> overrides (development).
 uint32_t whole_array_chunk_leaves(const Geometry &g, const Geometry &g2) {
   const uint32_t cap = reb::CHUNK_SLOTS >> g2.leaf_shift;
-  static long forced = -1;
-  if (forced < 0) {
+  static const long forced = [] {
     const char *e = getenv("PPCSR_REB_CL");
-    forced = e ? atol(e) : 0;
-  }
+    return e ? atol(e) : 0L;
+  }();
   if (forced > 0) return std::max<uint32_t>(1u, std::min<uint32_t>(cap, (uint32_t)forced));
   const double seg = (double)(reb::SEG_LEAVES_SLOTS >> g.leaf_shift);
   const double src_per_out = (double)g.n_leaves / (double)g2.n_leaves;  // source leaves per output leaf
@@ -210,6 +206,42 @@ uint64_t shrunk_slots(uint64_t N, uint64_t items) {
     n2 /= 2;
   }
   return n2;
+}
+
+// Failure atomicity.  k_locate mutates the shard (values overwritten, tombstones written, num_neighbors bumped) before
+// the back half of the batch knows whether the array has to grow, and growing allocates.  So everything the batch can
+// need in the WORST case (every update a new edge) is reserved here, before the first mutation: the out-of-place
+// target at the grown size, tree / leaf counts (contents kept), the per-leaf scratch, window list, chunk plan and the
+// scan scratch.  An allocation that fails here fails the batch cleanly (PPCSR_ERR_CAPACITY, shard untouched).  The one
+// case that cannot be decided up front -- the worst case would pass 2^31 slots although the real batch (duplicates,
+// overwrites) may not -- reserves up to the limit; if the real batch then needs more, the handle is POISONED: it
+// refuses every further update until ppcsr_restore (or ppcsr_destroy).
+int reserve_worst_case(ppcsr_shard *s, uint64_t count) {
+  const Geometry g = s->geo;
+  const uint64_t items_worst = s->items + count;
+  uint64_t need = g.N;
+  if (!window_ok_upper(items_worst, g.N, g.logN, 0, (int)g.H)) {
+    need = grown_slots(g.N, items_worst);
+    if (need == 0) need = PPCSR_MAX_SLOTS;
+  }
+  const Geometry g2 = make_geometry(need);
+  PPCSR_TRY(dev_reserve(s->dest_alt, g2.N, s->stream));
+  PPCSR_TRY(dev_reserve(s->val_alt, g2.N, s->stream));
+  PPCSR_TRY(dev_reserve(s->tree, (size_t)2 * g2.n_leaves, s->stream, true));
+  PPCSR_TRY(dev_reserve(s->leaf_cnt, g2.n_leaves, s->stream, true));
+  PPCSR_TRY(reserve_leaf_arrays(s, g2));
+  PPCSR_TRY(reserve_window_arrays(s, count));
+  const uint32_t min_cl = std::max<uint32_t>(1u, ((uint32_t)reb::CHUNK_SLOTS >> g2.leaf_shift) * 3u / 4u);
+  PPCSR_TRY(dev_reserve(s->plan, (size_t)g2.n_leaves / min_cl + 2, s->stream));
+  const size_t scan_tiles = (size_t)div_up(std::max<uint64_t>(std::max<uint64_t>(g2.n_leaves, count), 1), prim::SCAN_TILE) + 2;
+  PPCSR_TRY(dev_reserve(s->block_tmp, scan_tiles, s->stream));
+  PPCSR_TRY(prim::reserve_scan_state(s, std::max<size_t>(scan_tiles, (size_t)div_up(count, batch::BT) + 2)));
+  return PPCSR_OK;
+}
+int poisoned_error() {
+  g_ppcsr_error = "the handle was left inconsistent by a batch that failed after it had started to modify the shard; "
+                  "ppcsr_restore a snapshot or destroy it";
+  return PPCSR_ERR_CAPACITY;
 }
 
 // post-batch live count of a leaf, straight from the three per-leaf arrays
@@ -306,7 +338,14 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
 
 // Back half of a batch: s->ins_cnt / del_cnt hold the per-leaf counts, ins_{dst,val,pred} the key-ordered
 // insert list, d_scalars the class counts.  Chooses windows, rebalances, refreshes tree and counts.
+int finish_batch_impl(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st);
+// any failure past this point leaves tombstones / stale counts behind: the handle is poisoned (see reserve_worst_case)
 int finish_batch(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
+  const int rc = finish_batch_impl(s, list_cap, st);
+  if (rc != PPCSR_OK) s->poisoned = true;
+  return rc;
+}
+int finish_batch_impl(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
   const Geometry g = s->geo;
   const uint32_t L = g.n_leaves;
   BatchScalars *sc = s->d_scalars;
@@ -621,21 +660,30 @@ int ppcsr_create(uint32_t init_n, uint32_t src_n, int device, ppcsr_shard **out)
   }
   ppcsr_shard *s = new ppcsr_shard();
   s->device = device;
-  CUDA_TRY(cudaSetDevice(device));
-  CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
-  s->stream = s->own_stream;
-  for (auto &e : s->ev) CUDA_TRY(cudaEventCreate(&e));
-  CUDA_TRY(cudaMalloc((void **)&s->d_scalars, sizeof(BatchScalars)));
-  CUDA_TRY(cudaMallocHost((void **)&s->h_scalars, sizeof(BatchScalars)));
-  s->h_pinned_bytes = 1 << 16;
-  CUDA_TRY(cudaMallocHost(&s->h_pinned, s->h_pinned_bytes));
-  s->n = src_n;
-  s->geo = make_geometry(N);
-  PPCSR_TRY(alloc_geometry(s, s->geo));
-  PPCSR_TRY(dev_reserve(s->beg, (size_t)src_n + 1, s->stream));
-  PPCSR_TRY(dev_reserve(s->nn, (size_t)src_n + 1, s->stream));
-  PPCSR_TRY(init_layout(s));
-  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  const int rc = [&]() -> int {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
+    for (auto &e : s->ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaMalloc((void **)&s->d_scalars, sizeof(BatchScalars)));
+    CUDA_TRY(cudaMallocHost((void **)&s->h_scalars, sizeof(BatchScalars)));
+    s->h_pinned_bytes = 1 << 16;
+    CUDA_TRY(cudaMallocHost(&s->h_pinned, s->h_pinned_bytes));
+    s->n = src_n;
+    s->geo = make_geometry(N);
+    PPCSR_TRY(alloc_geometry(s, s->geo));
+    PPCSR_TRY(dev_reserve(s->beg, (size_t)src_n + 1, s->stream));
+    PPCSR_TRY(dev_reserve(s->nn, (size_t)src_n + 1, s->stream));
+    PPCSR_TRY(init_layout(s));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PPCSR_OK;
+  }();
+  if (rc != PPCSR_OK) {  // release whatever was created so far (streams, events, pinned and device buffers)
+    const std::string why = g_ppcsr_error;
+    ppcsr_destroy(s);
+    g_ppcsr_error = why;
+    return rc;
+  }
   *out = s;
   return PPCSR_OK;
 }
@@ -643,7 +691,7 @@ int ppcsr_create(uint32_t init_n, uint32_t src_n, int device, ppcsr_shard **out)
 void ppcsr_destroy(ppcsr_shard *s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaStreamSynchronize(s->stream);
+  if (s->stream) cudaStreamSynchronize(s->stream);
   dev_free(s->dest); dev_free(s->val); dev_free(s->dest_alt); dev_free(s->val_alt);
   dev_free(s->leaf_cnt); dev_free(s->tree); dev_free(s->beg); dev_free(s->nn);
   dev_free(s->ins_cnt); dev_free(s->del_cnt); dev_free(s->rank_off); dev_free(s->ins_off);
@@ -655,6 +703,14 @@ void ppcsr_destroy(ppcsr_shard *s) {
   dev_free(s->scan_state); dev_free(s->scan_ticket);
   dev_free(s->snap.dest); dev_free(s->snap.val); dev_free(s->snap.leaf_cnt); dev_free(s->snap.tree);
   dev_free(s->snap.beg); dev_free(s->snap.nn);
+  for (auto &P : s->pending) {
+    dev_free(P.src); dev_free(P.dst); dev_free(P.val);
+    if (P.copied) cudaEventDestroy(P.copied);
+  }
+  if (s->copy_stream) {
+    cudaStreamSynchronize(s->copy_stream);
+    cudaStreamDestroy(s->copy_stream);
+  }
   if (s->d_scalars) cudaFree(s->d_scalars);
   if (s->h_scalars) cudaFreeHost(s->h_scalars);
   if (s->h_pinned) cudaFreeHost(s->h_pinned);
@@ -738,7 +794,9 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
     g_ppcsr_error = "batch too large (>= 2^31 updates); split it";
     return PPCSR_ERR_ARG;
   }
+  if (s->poisoned) return poisoned_error();
   const Geometry g = s->geo;
+  PPCSR_TRY(reserve_worst_case(s, count));  // before anything is modified: see reserve_worst_case
   if (segments) {  // only an upper bound of the batch size is known: the keys (and values) are sized for it
     PPCSR_TRY(dev_reserve(s->key_a, count, s->stream));
     if (d_val) PPCSR_TRY(dev_reserve(s->pay_a, count, s->stream));
@@ -804,13 +862,14 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   const uint64_t invalid_key = (uint64_t)s->n << 32;
   CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
   CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
-  batch::k_locate<<<div_up(count, batch::BT), batch::BT, 0, s->stream>>>(
+  // the kernel also compacts the key-ordered insert list (look-back over its blocks: one scan_state word each)
+  const unsigned lblocks = div_up(count, batch::BT);
+  PPCSR_TRY(prim::reserve_scan_state(s, lblocks));
+  s->scan_epoch++;
+  batch::k_locate<<<lblocks, batch::BT, 0, s->stream>>>(
       keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
-      s->nn.p, s->uloc.p, s->ucls.p, s->ins_cnt.p, s->del_cnt.p, op_bit, sc);
-  PPCSR_TRY(prim::device_scan(
-      s, batch::InIsInsert{s->ucls.p},
-      batch::OutInsert{keys, pay, default_val, s->uloc.p, s->ins_dst.p, s->ins_val.p, s->ins_pred.p}, count, nullptr,
-      nullptr));
+      s->nn.p, s->ins_dst.p, s->ins_val.p, s->ins_pred.p, s->scan_state.p, s->scan_epoch, s->ins_cnt.p, s->del_cnt.p,
+      op_bit, sc);
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
   // 5. windows + rebalance
   PPCSR_TRY(finish_batch(s, count, &st));
@@ -861,6 +920,57 @@ int ppcsr_apply_batch(ppcsr_shard *s, const uint32_t *src, const uint32_t *dst, 
   return ppcsr_apply_batch_device(s, s->in_src.p, s->in_dst.p, val ? s->in_val.p : nullptr, count, default_val, stats);
 }
 
+// ---- pipelined host submit: the copy of batch i+1 runs under the compute of batch i -----------------------------
+int ppcsr_submit_batch(ppcsr_shard *s, const uint32_t *src, const uint32_t *dst, const uint32_t *val, uint64_t count,
+                       uint32_t default_val, uint64_t *ticket) {
+  if (!s || !ticket || (count && (!src || !dst))) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  ppcsr_shard::Pending &P = s->pending[s->next_ticket & 1u];
+  if (P.busy) {
+    g_ppcsr_error = "ppcsr_submit_batch: two batches are already in flight; ppcsr_wait for the older one first";
+    return PPCSR_ERR_ARG;
+  }
+  if (!s->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  if (!P.copied) CUDA_TRY(cudaEventCreateWithFlags(&P.copied, cudaEventDisableTiming));
+  PPCSR_TRY(dev_reserve(P.src, count, s->copy_stream));
+  PPCSR_TRY(dev_reserve(P.dst, count, s->copy_stream));
+  if (val) PPCSR_TRY(dev_reserve(P.val, count, s->copy_stream));
+  if (count) {
+    CUDA_TRY(cudaMemcpyAsync(P.src.p, src, count * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(P.dst.p, dst, count * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+    if (val) CUDA_TRY(cudaMemcpyAsync(P.val.p, val, count * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+  }
+  CUDA_TRY(cudaEventRecord(P.copied, s->copy_stream));
+  P.count = count;
+  P.default_val = default_val;
+  P.has_val = val != nullptr;
+  P.busy = true;
+  P.ticket = s->next_ticket++;
+  *ticket = P.ticket;
+  return PPCSR_OK;
+}
+
+int ppcsr_wait(ppcsr_shard *s, uint64_t ticket, ppcsr_batch_stats *stats) {
+  if (!s) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  ppcsr_shard::Pending &P = s->pending[ticket & 1u];
+  if (!P.busy || P.ticket != ticket) {
+    g_ppcsr_error = "ppcsr_wait: no such batch in flight";
+    return PPCSR_ERR_ARG;
+  }
+  // batches are applied in submission order: the other slot must not hold an older batch
+  const ppcsr_shard::Pending &O = s->pending[(ticket & 1u) ^ 1u];
+  if (O.busy && O.ticket < ticket) {
+    g_ppcsr_error = "ppcsr_wait: an older batch is still pending; wait for it first (batches apply in order)";
+    return PPCSR_ERR_ARG;
+  }
+  CUDA_TRY(cudaStreamWaitEvent(s->stream, P.copied, 0));
+  const int rc = apply_device_common(s, P.src.p, P.dst.p, nullptr, P.has_val ? P.val.p : nullptr, P.count,
+                                     P.default_val, stats);
+  P.busy = false;
+  return rc;
+}
+
 int ppcsr_add_edge(ppcsr_shard *s, uint32_t src, uint32_t dst, uint32_t value) {
   if (value == 0) return PPCSR_OK;  // reference PCSR.cpp:1375: a zero value is silently ignored
   return ppcsr_apply_batch(s, &src, &dst, &value, 1, 1, nullptr);
@@ -878,6 +988,7 @@ int ppcsr_add_nodes(ppcsr_shard *s, uint32_t count) {
   if (!s) return PPCSR_ERR_ARG;
   if (count == 0) return PPCSR_OK;
   PPCSR_TRY(set_device(s));
+  if (s->poisoned) return poisoned_error();
   if ((uint64_t)s->n + count >= 0xFFFFFFFEull) return PPCSR_ERR_CAPACITY;
   const uint32_t n_old = s->n, n_new = s->n + count;
   PPCSR_TRY(dev_reserve(s->beg, (size_t)n_new + 1, s->stream, true));
@@ -899,6 +1010,7 @@ int ppcsr_add_nodes(ppcsr_shard *s, uint32_t count) {
   }
   const Geometry g = s->geo;
   PPCSR_TRY(reserve_batch_arrays(s, count));
+  PPCSR_TRY(reserve_worst_case(s, count));
   BatchScalars *sc = s->d_scalars;
   CUDA_TRY(cudaMemsetAsync(sc, 0, sizeof(BatchScalars), s->stream));
   s->all_touched = 0;
@@ -940,21 +1052,25 @@ struct BinScratch {
   uint32_t *d_firsts = nullptr;
   uint32_t *h_firsts = nullptr;  // pinned
 };
-static BinScratch *bin_scratch(int device) {
-  static std::vector<BinScratch *> per_device(64, nullptr);
-  if (device < 0 || device >= 64) return nullptr;
-  if (!per_device[device]) {
-    BinScratch *b = new BinScratch();
-    b->shard.device = device;
-    if (cudaMalloc((void **)&b->d_firsts, (batch::BIN_MAX_PARTS + 1) * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMallocHost((void **)&b->h_firsts, (batch::BIN_MAX_PARTS + 1) * sizeof(uint32_t)) != cudaSuccess) {
-      cudaGetLastError();
-      delete b;
-      return nullptr;
-    }
-    per_device[device] = b;
+// One scratch per (device, stream), created under a lock: the scan inside the binning (ticket counter, look-back words,
+// histogram buffer) is only correct when every use of one scratch is ordered on ONE stream, so two callers on the same
+// device but different streams (or threads) must not share it.  Calls that share a stream are stream-ordered and safe.
+static BinScratch *bin_scratch(int device, cudaStream_t stream) {
+  static std::mutex mu;
+  static std::vector<std::pair<std::pair<int, cudaStream_t>, BinScratch *>> all;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto &e : all)
+    if (e.first.first == device && e.first.second == stream) return e.second;
+  BinScratch *b = new BinScratch();
+  b->shard.device = device;
+  if (cudaMalloc((void **)&b->d_firsts, (batch::BIN_MAX_PARTS + 1) * sizeof(uint32_t)) != cudaSuccess ||
+      cudaMallocHost((void **)&b->h_firsts, (batch::BIN_MAX_PARTS + 1) * sizeof(uint32_t)) != cudaSuccess) {
+    cudaGetLastError();
+    delete b;
+    return nullptr;
   }
-  return per_device[device];
+  all.push_back({{device, stream}, b});
+  return b;
 }
 __global__ void k_gather_firsts(const uint32_t *__restrict__ offs, uint32_t nblocks, uint32_t parts,
                                 uint32_t *__restrict__ firsts) {
@@ -970,7 +1086,7 @@ static int bin_common(int device, void *cuda_stream, const uint64_t *d_starts, u
   if (count == 0) return PPCSR_OK;
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  BinScratch *bs = bin_scratch(device);
+  BinScratch *bs = bin_scratch(device, st);
   if (!bs) {
     g_ppcsr_error = "bin_by_owner: cannot allocate scratch";
     return PPCSR_ERR_CAPACITY;
@@ -1020,7 +1136,7 @@ int ppcsr_bin_to_peers(int device, void *cuda_stream, const uint64_t *d_starts, 
     CUDA_TRY(cudaGetLastError());
     return PPCSR_OK;
   }
-  BinScratch *bs = bin_scratch(device);
+  BinScratch *bs = bin_scratch(device, st);
   if (!bs) {
     g_ppcsr_error = "bin_to_peers: cannot allocate scratch";
     return PPCSR_ERR_CAPACITY;
@@ -1033,13 +1149,19 @@ int ppcsr_bin_to_peers(int device, void *cuda_stream, const uint64_t *d_starts, 
   batch::k_bin_count<<<nblocks, batch::BT, 0, st>>>(d_src, count, d_starts, n_parts, tmp.hist.p, nblocks);
   PPCSR_TRY(prim::device_scan(&tmp, prim::InArray{tmp.hist.p}, prim::OutPrefixWithTotal{tmp.hist.p, hn}, hn, nullptr,
                               nullptr));
-  static bool attr_done[64] = {};
-  if (device >= 64 || !attr_done[device]) {
-    CUDA_TRY(cudaFuncSetAttribute(batch::k_bin_scatter_peers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)batch::bin_peers_smem(true)));
-    CUDA_TRY(cudaFuncSetAttribute(batch::k_bin_scatter_peers<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)batch::bin_peers_smem(false)));
-    if (device < 64) attr_done[device] = true;
+  {  // per device, once, thread-safe
+    static std::once_flag once[64];
+    static cudaError_t once_err[64];
+    const int dv = device & 63;
+    std::call_once(once[dv], [&] {
+      once_err[dv] = cudaFuncSetAttribute(batch::k_bin_scatter_peers<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)batch::bin_peers_smem(true));
+      if (once_err[dv] == cudaSuccess)
+        once_err[dv] = cudaFuncSetAttribute(batch::k_bin_scatter_peers<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)batch::bin_peers_smem(false));
+    });
+    CUDA_TRY(once_err[dv]);
   }
   if (d_val) {
     batch::k_bin_scatter_peers<true><<<nblocks, batch::BT, batch::bin_peers_smem(true), st>>>(
@@ -1387,6 +1509,10 @@ int ppcsr_restore(ppcsr_shard *s) {
   PPCSR_TRY(snap_copy(s, s->nn, k.nn, k.n));
   CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)k.geo.n_leaves * 4, s->stream));
   CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)k.geo.n_leaves * 4, s->stream));
+  // the restored layout was touched by no batch: the checker must not apply the last batch's flags to it
+  s->all_touched = 0;
+  s->last = ppcsr_batch_stats{};
+  s->poisoned = false;
   return PPCSR_OK;
 }
 

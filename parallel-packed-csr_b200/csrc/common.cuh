@@ -200,11 +200,23 @@ struct ppcsr_shard {
   bool ins_sentinels = false;          // the pending insert list holds sentinels (ppcsr_add_nodes)
   uint32_t all_touched = 0;            // invariant checker: bit 2 = the last batch rewrote every leaf (bit 0 inserts, bit 1 deletes)
   int whole_policy = 0;                // -1 never / 0 cost model / 1 always: one root window instead of a window list
+  bool poisoned = false;               // a batch failed after it had begun to modify the shard (capi.cu: reserve_worst_case)
 
   // per-batch update-granular scratch
   DevBuf<uint64_t> key_a, key_b;       // [batch]
   DevBuf<uint32_t> pay_a, pay_b;       // [batch]
   DevBuf<uint32_t> in_src, in_dst, in_val;  // staging of host batches
+  // pipelined host submit (ppcsr_submit_batch / ppcsr_wait): two staging slots filled on a copy stream while the
+  // previous batch computes
+  struct Pending {
+    DevBuf<uint32_t> src, dst, val;
+    uint64_t count = 0, ticket = 0;
+    uint32_t default_val = 1;
+    bool has_val = false, busy = false;
+    cudaEvent_t copied = nullptr;
+  } pending[2];
+  cudaStream_t copy_stream = nullptr;
+  uint64_t next_ticket = 1;
   DevBuf<uint64_t> ukey;               // [batch] unique keys (last op wins)
   DevBuf<uint32_t> uval;               // [batch]
   DevBuf<uint32_t> uloc;               // [batch] slot: predecessor (new insert) or hit (exists)
@@ -230,10 +242,18 @@ struct ppcsr_shard {
   Snapshot snap;
 };
 
+// Every device array comes from dev_reserve and ends with at least DEV_PAD_ELEMS elements beyond the requested count.
+// The bulk (TMA) loads of reb::k_rebalance_p round their length up to 16 bytes and may READ up to 3 elements past the
+// logical end of rank_off / ins_off / ins_pred / ins_dst / ins_val (rebalance.cuh: issue_round): the pad is what makes
+// that legal, whatever size the caller asked for.
+constexpr size_t DEV_PAD_ELEMS = 64;
+static_assert(DEV_PAD_ELEMS >= 4, "the rebalance kernel's 16-byte bulk loads over-read by up to 3 elements");
 template <typename T>
 inline int dev_reserve(DevBuf<T> &b, size_t elems, cudaStream_t stream, bool keep = false) {
   if (elems <= b.cap) return PPCSR_OK;
-  size_t want = elems + elems / 8 + 64;  // slack so slowly growing batches do not realloc every time
+  // slack so slowly growing batches do not realloc every time; b.cap counts the usable elements, the pad lies beyond
+  const size_t cap_new = elems + elems / 8;
+  const size_t want = cap_new + DEV_PAD_ELEMS;
   static const bool log_alloc = getenv("PPCSR_LOG_ALLOC") != nullptr;  // development aid: who allocates mid-run?
   if (log_alloc) fprintf(stderr, "[ppcsr] dev_reserve: %zu -> %zu elements of %zu bytes\n", b.cap, want, sizeof(T));
   T *np_ = nullptr;
@@ -246,14 +266,20 @@ inline int dev_reserve(DevBuf<T> &b, size_t elems, cudaStream_t stream, bool kee
     return PPCSR_ERR_CAPACITY;
   }
   if (keep && b.p && b.cap) {
-    CUDA_TRY(cudaMemcpyAsync(np_, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+    e = cudaMemcpyAsync(np_, b.p, b.cap * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {  // do not leak the new block
+      cudaFree(np_);
+      g_ppcsr_error = std::string("dev_reserve: copy into the grown buffer failed: ") + cudaGetErrorString(e);
+      return PPCSR_ERR_CUDA;
+    }
   }
   if (b.p) {
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaFree(b.p));
   }
   b.p = np_;
-  b.cap = want;
+  b.cap = cap_new;
   return PPCSR_OK;
 }
 

@@ -519,6 +519,7 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
     } else if (role == 1) {
       if (snl) {
         const uint32_t sh = gl & 3u;
+        // 16-byte granules: reads up to 3 entries past rank_off / ins_off [n_leaves] (covered by DEV_PAD_ELEMS)
         const uint32_t tb = ((snl + 1u + sh + 3u) & ~3u) * 4u;
         bulk_g2s(S.st_R, A.rank_off + (gl - sh), tb, &S.mbar);
         bulk_g2s(S.st_ioff, A.ins_off + (gl - sh), tb, &S.mbar);

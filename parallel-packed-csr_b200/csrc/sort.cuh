@@ -19,6 +19,7 @@
 // HBM traffic per pass: 16 B per update (+8 with per-update values) -- the floor for an LSD pass.
 #pragma once
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 #include "primitives.cuh"
@@ -347,11 +348,16 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
   uint32_t *counters = ghist + OS_MAX_PASSES * OS_RADIX;
   uint32_t *lookback = counters + 64;
   CUDA_TRY(cudaMemsetAsync(s->hist.p, 0, words * sizeof(uint32_t), s->stream));
-  static bool attr_done[64] = {};
-  if (s->device >= 64 || !attr_done[s->device]) {  // > 48 KB of dynamic shared memory needs an explicit opt-in
-    CUDA_TRY(cudaFuncSetAttribute(k_os_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(true)));
-    CUDA_TRY(cudaFuncSetAttribute(k_os_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(false)));
-    if (s->device < 64) attr_done[s->device] = true;
+  {  // > 48 KB of dynamic shared memory needs an explicit opt-in: per device, once, thread-safe
+    static std::once_flag once[64];
+    static cudaError_t once_err[64];
+    const int dv = s->device & 63;
+    std::call_once(once[dv], [&] {
+      once_err[dv] = cudaFuncSetAttribute(k_os_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(true));
+      if (once_err[dv] == cudaSuccess)
+        once_err[dv] = cudaFuncSetAttribute(k_os_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(false));
+    });
+    CUDA_TRY(once_err[dv]);
   }
   const unsigned hblocks = (unsigned)std::min<size_t>((n + (size_t)OSH_THREADS * OSH_ITEMS - 1) / ((size_t)OSH_THREADS * OSH_ITEMS), 148 * 4);
   s->launches += 2 + P.n_pass;

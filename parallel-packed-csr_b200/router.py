@@ -212,8 +212,8 @@ class ShardedGraph:
         self.starts_dev = torch.from_numpy(self.starts.astype(np.int64)).to(self.dev)
         self.last_route = None
         # peer_cap > 0: route batches of up to peer_cap updates per rank through NVLink peer memory (PeerExchange);
-        # larger batches, or a platform without symmetric memory, take the NCCL all-to-all.  Every rank must make
-        # the same choice, i.e. pass batches on the same side of peer_cap.
+        # larger batches, or a platform without symmetric memory, take the NCCL all-to-all.  Every rank makes the same
+        # choice: apply() decides from the largest slice of ANY rank (see _largest_slice).
         self.peer = None
         self.peer_max_total = 0  # optional bound on what one rank can receive per batch (sizes the key array)
         if peer_cap and world > 1 and on_gpu and isinstance(self.binner, CudaBinner):
@@ -294,10 +294,28 @@ class ShardedGraph:
             torch.cuda.current_stream().synchronize()
         return self._cnt_back.tolist()
 
-    def apply(self, src, dst, val=None, default_val=1):
-        """Device tensors (int32 bit patterns of u32 ids) holding this rank's slice of the global batch."""
-        if self.world > 1 and self.peer is not None and src.numel() <= self.peer.cap and (
-                val is None or self.peer.val_ptrs is not None):
+    def _largest_slice(self, count: int, global_max):
+        """The largest per-rank slice of this batch, known to EVERY rank: the transport (peer memory or NCCL) must be
+        the same on all ranks, so it may only depend on a value they all share -- the caller's `global_max` (no
+        communication) or, without it, one all-reduce(MAX) of the slice sizes."""
+        if global_max is not None:
+            if count > global_max:
+                raise ValueError(f"this rank's slice ({count}) exceeds the declared global_max ({global_max})")
+            return int(global_max)
+        if self.world == 1 or self.dist is None:
+            return count
+        t = self.torch.tensor([count], dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return int(t.item())
+
+    def apply(self, src, dst, val=None, default_val=1, global_max=None):
+        """Device tensors (int32 bit patterns of u32 ids) holding this rank's slice of the global batch.
+        `global_max` (optional, identical on all ranks): an upper bound of the largest slice any rank holds; see
+        _largest_slice."""
+        use_peer = False
+        if self.world > 1 and self.peer is not None and (val is None or self.peer.val_ptrs is not None):
+            use_peer = self._largest_slice(src.numel(), global_max) <= self.peer.cap
+        if use_peer:
             if self.route_timing is not None:
                 import time
 
@@ -349,7 +367,7 @@ class ShardedGraph:
         self.route_timing.append([round((b - a) * 1e3, 3) for a, b in zip(t, t[1:])])
         return st
 
-    def apply_host(self, src, dst, val=None, default_val=1):
+    def apply_host(self, src, dst, val=None, default_val=1, global_max=None):
         """Host (pinned) numpy arrays: the public end-to-end call. H2D happens inside."""
         if self.world == 1:
             return self.shard.apply(src, dst, val, default_val)
@@ -357,7 +375,54 @@ class ShardedGraph:
         d_src = torch.from_numpy(src).to(self.dev, non_blocking=True)
         d_dst = torch.from_numpy(dst).to(self.dev, non_blocking=True)
         d_val = torch.from_numpy(val).to(self.dev, non_blocking=True) if val is not None else None
-        return self.apply(d_src, d_dst, d_val, default_val)
+        return self.apply(d_src, d_dst, d_val, default_val, global_max=global_max)
+
+    # ---- pipelined end-to-end submit: the H2D copy of batch i+1 runs under the compute of batch i ----
+    def submit_host(self, src, dst, val=None, default_val=1, global_max=None):
+        """Starts the host->device copy of this rank's slice of a batch (pinned numpy arrays) on a copy stream and
+        returns a ticket for wait_host().  One shard: the C-ABI's ppcsr_submit_batch.  Sharded: two device staging
+        slots filled on a side stream; the routing and the apply run in wait_host()."""
+        if self.world == 1:
+            return self.shard.submit(src, dst, val, default_val)
+        torch = self.torch
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.dev)
+            self._slots = [None, None]
+            self._next_ticket = 1
+        t = self._next_ticket
+        self._next_ticket += 1
+        slot = self._slots[t & 1]
+        if slot is not None and slot.get("busy"):
+            raise RuntimeError("two batches are already in flight; wait_host() for the older one first")
+        n = src.shape[0]
+        if slot is None or slot["src"].numel() < n or (val is not None and slot["val"] is None):
+            slot = {"src": torch.empty(n, dtype=torch.int32, device=self.dev),
+                    "dst": torch.empty(n, dtype=torch.int32, device=self.dev),
+                    "val": torch.empty(n, dtype=torch.int32, device=self.dev) if val is not None else None}
+            self._slots[t & 1] = slot
+        with torch.cuda.stream(self._copy_stream):
+            slot["src"][:n].copy_(torch.from_numpy(src.view(np.int32)), non_blocking=True)
+            slot["dst"][:n].copy_(torch.from_numpy(dst.view(np.int32)), non_blocking=True)
+            if val is not None:
+                slot["val"][:n].copy_(torch.from_numpy(val.view(np.int32)), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        slot.update(busy=True, n=n, ev=ev, has_val=val is not None, default_val=default_val, host=(src, dst, val),
+                    global_max=global_max)
+        return t
+
+    def wait_host(self, ticket):
+        if self.world == 1:
+            return self.shard.wait(ticket)
+        slot = self._slots[ticket & 1]
+        assert slot is not None and slot.get("busy"), "no such batch in flight"
+        self.torch.cuda.current_stream(self.dev).wait_event(slot["ev"])
+        n = slot["n"]
+        st = self.apply(slot["src"][:n], slot["dst"][:n], slot["val"][:n] if slot["has_val"] else None,
+                        slot["default_val"], global_max=slot.get("global_max"))
+        slot["busy"] = False
+        slot["host"] = None
+        return st
 
     # ---- PageRank across shards: every shard pushes into a full-length vector, then one all-reduce ----
     def pagerank_step(self, values_global):

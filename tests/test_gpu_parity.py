@@ -442,3 +442,45 @@ def test_snapshot_restore_roundtrip():
     st = g.apply(cs, cd, 1)
     assert st["n_inserted"] == 0 and st["n_windows"] == 0
     assert np.array_equal(g.export()[1], before[1])
+
+
+def test_pipelined_submit_equals_sequential_applies():
+    """ppcsr_submit_batch / ppcsr_wait: a stream of batches submitted two ahead gives the graph (and the per-batch
+    stats) of the same batches applied one by one, and the graph of the oracle."""
+    scale = 13
+    n = 1 << scale
+    cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
+    us, ud = synth.rmat(scale, 0, 60000, 99)
+    ops = synth.mixed_ops(0, 60000, 11)
+    parts = np.array_split(np.arange(60000), 6)
+    a, b, o = pp.Shard(n), pp.Shard(n), O.OraclePCSR(n)
+    for g in (a, b):
+        g.apply(cs, cd, 1)
+    o.apply(cs, cd, 1)
+    seq = [a.apply(us[p], ud[p], ops[p]) for p in parts]
+    for p in parts:
+        o.apply(us[p], ud[p], ops[p])
+    bufs = [(np.ascontiguousarray(us[p], dtype=np.uint32), np.ascontiguousarray(ud[p], dtype=np.uint32),
+             np.ascontiguousarray(ops[p], dtype=np.uint32)) for p in parts]
+    t = b.submit(*bufs[0])
+    piped = []
+    for k in range(len(parts)):
+        nxt = b.submit(*bufs[k + 1]) if k + 1 < len(parts) else None
+        piped.append(b.wait(t))
+        t = nxt
+    for x, y in zip(seq, piped):
+        for key in ("batch_size", "n_unique", "n_inserted", "n_overwritten", "n_deleted", "n_not_found"):
+            assert x[key] == y[key], key
+    rowptr, col, nn = o.export()
+    assert_same_graph(a, rowptr, col, nn, where="sequential")
+    assert_same_graph(b, rowptr, col, nn, where="pipelined")
+    assert_invariants(b, check_lower=True, where="pipelined")
+    with pytest.raises(pp.PpcsrError):  # a third batch in flight is refused
+        t1, t2 = b.submit(*bufs[0]), b.submit(*bufs[1])
+        b.submit(*bufs[2])
+    with pytest.raises(pp.PpcsrError):  # out of order
+        b.wait(t2)
+    b.wait(t1)
+    b.wait(t2)
+    a.close()
+    b.close()
