@@ -137,6 +137,22 @@ int ppcsr_apply_batch_device(ppcsr_shard *h, const uint32_t *d_src, const uint32
 int ppcsr_submit_batch(ppcsr_shard *h, const uint32_t *src, const uint32_t *dst, const uint32_t *val, uint64_t count,
                        uint32_t default_val, uint64_t *ticket);
 int ppcsr_wait(ppcsr_shard *h, uint64_t ticket, ppcsr_batch_stats *stats);
+/* ---- input path (reference src/main.cpp:29-62, read_input) ---- */
+/* Binary edge file: `count` interleaved little-endian (src, dst) u32 pairs (host memory, e.g. an mmap'd file), every
+ * update with value `default_val` (0 = remove).  Same result as ppcsr_apply_batch on the de-interleaved arrays. */
+int ppcsr_apply_batch_pairs(ppcsr_shard *h, const uint32_t *pairs, uint64_t count, uint32_t default_val,
+                            ppcsr_batch_stats *stats);
+/* Text edge list parsed ON THE GPU with the reference reader's rules: one edge per line `src<1 char>dst[<1 char>op]`,
+ * op '1' = add (value 1), '0' = remove (value 0), absent = default_val.  `text` is host memory (the raw file bytes).
+ * Outputs DEVICE arrays of *count entries (one per line; free them with ppcsr_free_device) that feed
+ * ppcsr_apply_batch_device directly; lines without a parsable pair come out as (0xFFFFFFFF, 0xFFFFFFFF), which every
+ * batch entry point ignores.  *n_parsed = lines that parsed, *max_id = largest vertex id seen (reference
+ * main.cpp:44,145,155: n = max id + 1 over both files). */
+int ppcsr_parse_edge_list(int device, const char *text, uint64_t bytes, uint32_t default_val, uint32_t **d_src,
+                          uint32_t **d_dst, uint32_t **d_val, uint64_t *count, uint64_t *n_parsed, uint32_t *max_id);
+int ppcsr_free_device(int device, void *p);
+int ppcsr_copy_to_host(int device, void *host, const void *dev, uint64_t bytes);
+
 /* Single operations = batches of one (reference PCSR::add_edge / remove_edge). Correctness path, slow. */
 int ppcsr_add_edge(ppcsr_shard *h, uint32_t src, uint32_t dst, uint32_t value);
 int ppcsr_remove_edge(ppcsr_shard *h, uint32_t src, uint32_t dst, int *found);
@@ -183,6 +199,22 @@ int ppcsr_apply_batch_segments_device(ppcsr_shard *h, const uint64_t *d_packed, 
 /* Applies a device-resident batch of packed records (src << 32 | dst), e.g. what the all-to-all delivered. */
 int ppcsr_apply_batch_packed_device(ppcsr_shard *h, const uint64_t *d_packed, const uint32_t *d_val, uint64_t count,
                                     uint32_t default_val, ppcsr_batch_stats *stats);
+
+/* ---- several shards on several GPUs driven by ONE process: reference PPPCSR + ThreadPoolPPPCSR
+ *      (src/pppcsr/PPPCSR.cpp:13-66, src/thread_pool_pppcsr/thread_pool_pppcsr.cpp:96-118) ---- */
+typedef struct ppcsr_group ppcsr_group;
+/* shards[r] (already created, on any devices that can address each other) owns the global vertices
+ * [starts[r], starts[r+1]); region_cap = the largest batch / n_shards the group will route (records per sender and
+ * receiver); with_values != 0 if batches carry per-update values. */
+int ppcsr_group_create(ppcsr_shard **shards, uint32_t n_shards, const uint64_t *starts, uint64_t region_cap,
+                       int with_values, ppcsr_group **out);
+void ppcsr_group_destroy(ppcsr_group *g); /* the shards stay alive */
+uint32_t ppcsr_group_owner(const ppcsr_group *g, uint64_t vertex); /* reference PPPCSR::get_partiton */
+/* One batch of GLOBAL updates in host memory: slice r of the batch is copied to GPU r (all PCIe links at once), binned
+ * there by owner and stored straight into the owners' receive buffers over NVLink peer memory (ppcsr_bin_to_peers),
+ * then every shard applies what it received.  stats (nullable) gets one entry per shard. */
+int ppcsr_group_apply(ppcsr_group *g, const uint32_t *src, const uint32_t *dst, const uint32_t *val, uint64_t count,
+                      uint32_t default_val, ppcsr_batch_stats *stats);
 
 /* ---- reads ---- */
 int ppcsr_geometry_of(ppcsr_shard *h, ppcsr_geometry *out);

@@ -70,6 +70,15 @@ SYMBOLS = {
     "ppcsr_apply_batch_device": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(BatchStats)]),
     "ppcsr_submit_batch": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_u64)]),
     "ppcsr_wait": (_i, [_vp, _u64, C.POINTER(BatchStats)]),
+    "ppcsr_apply_batch_pairs": (_i, [_vp, _vp, _u64, _u32, C.POINTER(BatchStats)]),
+    "ppcsr_parse_edge_list": (_i, [_i, _vp, _u64, _u32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                   C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u32)]),
+    "ppcsr_free_device": (_i, [_i, _vp]),
+    "ppcsr_copy_to_host": (_i, [_i, _vp, _vp, _u64]),
+    "ppcsr_group_create": (_i, [C.POINTER(_vp), _u32, _vp, _u64, _i, C.POINTER(_vp)]),
+    "ppcsr_group_destroy": (None, [_vp]),
+    "ppcsr_group_owner": (_u32, [_vp, _u64]),
+    "ppcsr_group_apply": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(BatchStats)]),
     "ppcsr_add_edge": (_i, [_vp, _u32, _u32, _u32]),
     "ppcsr_remove_edge": (_i, [_vp, _u32, _u32, C.POINTER(_i)]),
     "ppcsr_add_nodes": (_i, [_vp, _u32]),
@@ -199,6 +208,13 @@ class Shard:
         st = BatchStats()
         _check(self.L.ppcsr_wait(self.h, ticket, C.byref(st)))
         self._inflight.pop(ticket, None)
+        return st.as_dict()
+
+    def apply_pairs(self, pairs, default_val: int = 1) -> dict:
+        """Interleaved (src, dst) u32 pairs (an [n, 2] array or a flat one): the binary input path."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1)
+        st = BatchStats()
+        _check(self.L.ppcsr_apply_batch_pairs(self.h, _np_ptr(pairs), pairs.shape[0] // 2, default_val, C.byref(st)))
         return st.as_dict()
 
     def apply_device(self, d_src: int, d_dst: int, d_val: int | None, count: int, default_val: int = 1) -> dict:
@@ -376,3 +392,61 @@ def debug_exclusive_scan(values, device=0):
     out = np.zeros(values.shape[0] + 1, dtype=np.uint32)
     _check(L.ppcsr_debug_exclusive_scan(device, _np_ptr(values), _np_ptr(out), values.shape[0]))
     return out
+
+
+def parse_edge_list(text: bytes, default_val: int = 1, device: int = 0):
+    """The reference's text edge-list reader (src/main.cpp:29-62) on the GPU (ppcsr_parse_edge_list).  Returns host
+    arrays (src, dst, val), the number of lines that parsed and the largest vertex id."""
+    L = load_library()
+    ds, dd, dv = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    cnt, ok, mx = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    buf = np.frombuffer(text, dtype=np.uint8)
+    _check(L.ppcsr_parse_edge_list(device, _np_ptr(buf) if buf.size else None, buf.size, default_val, C.byref(ds),
+                                   C.byref(dd), C.byref(dv), C.byref(cnt), C.byref(ok), C.byref(mx)))
+    n = cnt.value
+    out = [np.zeros(n, dtype=np.uint32) for _ in range(3)]
+    for a, d in zip(out, (ds, dd, dv)):
+        if n:
+            _check(L.ppcsr_copy_to_host(device, _np_ptr(a), d, n * 4))
+        _check(L.ppcsr_free_device(device, d))
+    return out[0], out[1], out[2], ok.value, mx.value
+
+
+class Group:
+    """Several shards on several GPUs driven by one process (ppcsr_group_*): the data plane of reference PPPCSR."""
+
+    def __init__(self, n: int, starts, devices, region_cap: int, with_values: bool = False):
+        self.L = load_library()
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        assert starts[0] == 0 and starts[-1] == n and len(starts) == len(devices) + 1
+        self.starts = starts
+        self.shards = [Shard(int(starts[r + 1] - starts[r]), device=devices[r]) for r in range(len(devices))]
+        arr = (C.c_void_p * len(devices))(*[s.h for s in self.shards])
+        g = C.c_void_p()
+        _check(self.L.ppcsr_group_create(arr, len(devices), _np_ptr(starts), region_cap, 1 if with_values else 0,
+                                         C.byref(g)))
+        self.g = g
+
+    def apply(self, src, dst, val=None, default_val: int = 1):
+        src = _u32_array(src)
+        dst = _u32_array(dst, src.shape[0])
+        val = _u32_array(val, src.shape[0]) if val is not None else None
+        st = (BatchStats * len(self.shards))()
+        _check(self.L.ppcsr_group_apply(self.g, _np_ptr(src), _np_ptr(dst), _np_ptr(val), src.shape[0], default_val, st))
+        return [x.as_dict() for x in st]
+
+    def owner(self, v: int) -> int:
+        return int(self.L.ppcsr_group_owner(self.g, v))
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.L.ppcsr_group_destroy(self.g)
+            self.g = None
+            for s in self.shards:
+                s.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(BT) k_build_keys(const uint32_t *__restrict__ 
 __global__ void __launch_bounds__(BT) k_build_keys_packed(const uint64_t *__restrict__ packed,
                                                           const uint32_t *__restrict__ val, uint32_t default_val,
                                                           size_t count, uint32_t n, uint32_t op_bit, uint64_t *__restrict__ keys,
-                                                          uint32_t *__restrict__ pay, BatchScalars *sc) {
+                                                          uint32_t *__restrict__ pay, BatchScalars *sc,
+                                                          uint32_t swap_halves) {
+  // swap_halves: the records are interleaved little-endian (src, dst) pairs read as one word (dst << 32 | src)
   __shared__ uint32_t s_or, s_bad, s_vmax, s_vinv;
   if (threadIdx.x == 0) {
     s_or = 0;
@@ -87,7 +89,8 @@ __global__ void __launch_bounds__(BT) k_build_keys_packed(const uint64_t *__rest
   __syncthreads();
   uint32_t my_or = 0, my_bad = 0, my_vmax = 0, my_vinv = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
-    const uint64_t k = packed[i];
+    uint64_t k = packed[i];
+    if (swap_halves) k = (k << 32) | (k >> 32);
     const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k;
     const uint32_t v = val ? val[i] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
@@ -224,168 +227,330 @@ __device__ __forceinline__ bool find_edge(const uint32_t *__restrict__ dest, con
   return false;
 }
 
-// One thread per SORTED batch element.  Fuses what used to be three passes:
-//   * num_neighbors += (#add calls) - (#remove calls) per source over the whole batch, duplicates included
-//     (reference PCSR.cpp:1392 and :747); sorted by src => one warp-aggregated atomic per run;
-//   * last-op-wins: only the last element of a run of equal keys acts on the structure (the batch result
-//     equals the sequential reference on the same stream);
-//   * the segmented search of the winner and the per-leaf insert/delete counts.
-// `not found` follows the sequential rule (reference PCSR.cpp:750-754): a remove misses iff the previous op
-// on the same key in this batch was a remove, or it is the key's first op and the edge is absent.
-// pay == nullptr: every payload equals default_val (keys-only sort).
-__global__ void __launch_bounds__(BT) k_locate(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay,
+// find_edge over an explicit slot window and through (possibly staged) views of dest[] / leaf_cnt[]:
+//   D[slot - doff] is dest[slot], C[leaf - coff] is leaf_cnt[leaf]; the search covers the slots [b, e) of ONE vertex,
+//   `skip_first` says that slot b is the vertex's sentinel (false when the window was clipped from below: then b is
+//   leaf aligned and its leaf holds an item <= d, see k_locate).  Same result as find_edge on the whole range.
+__device__ __forceinline__ bool find_in(const uint32_t *D, uint32_t doff, const uint32_t *C, uint32_t coff, uint32_t b,
+                                        uint32_t e, bool skip_first, uint32_t ls, uint32_t d, uint32_t *slot) {
+  const uint32_t Lb = b >> ls, Le = (e - 1) >> ls;
+  uint32_t lo = Lb, hi = Le + 1;
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    uint32_t m2 = mid;
+    while (m2 < hi && C[m2 - coff] == 0) m2++;
+    if (m2 == hi) {
+      hi = mid;
+      continue;
+    }
+    if (D[(m2 << ls) - doff] <= d) lo = m2;
+    else hi = mid;
+  }
+  const uint32_t base = lo << ls;
+  const uint32_t cnt = C[lo - coff];
+  const uint32_t f_lo = (lo == Lb) ? (b - base) + (skip_first ? 1u : 0u) : 0u;
+  uint32_t f_hi = cnt;
+  if (lo == (e >> ls) && (e - base) < f_hi) f_hi = e - base;
+  const uint32_t *L = D + (base - doff);
+  uint32_t x = f_lo, y = f_hi;  // lower_bound of d in the leaf's live prefix
+  while (x < y) {
+    const uint32_t mid = (x + y) >> 1;
+    if (L[mid] < d) x = mid + 1;
+    else y = mid;
+  }
+  if (x < f_hi && L[x] == d) {
+    *slot = base + x;
+    return true;
+  }
+  *slot = base + x - 1;
+  return false;
+}
+
+// ---- locate: one CTA per TILE of 512 consecutive sorted updates ------------------------------------------------
+// Fuses, over the sorted batch:
+//   * num_neighbors += (#add calls) - (#remove calls) per source, duplicates included (reference PCSR.cpp:1392,747);
+//     sorted by src => one warp-aggregated atomic per run;
+//   * last-op-wins: only the last element of a run of equal keys acts on the structure (the batch result equals the
+//     sequential reference on the same stream); `not found` by the sequential rule (reference PCSR.cpp:750-754): a
+//     remove misses iff the previous op on the same key in this batch was a remove, or it is the key's first op and
+//     the edge is absent;
+//   * the segmented search of every winner (find_in), overwrite / tombstone in place, per-leaf insert / delete counts;
+//   * the compacted, key-ordered insert list (dst, value, predecessor slot): scan of the insert flags over the tile,
+//     the tile's base from a decoupled look-back over the earlier tiles (one epoch-tagged word per tile in scan_state,
+//     same protocol as prim::k_scan_onepass; tiles are the CTAs in launch order, as in CUB's single-pass scans; every
+//     lane examines LB_DEPTH predecessors per step so that a whole wave of resident CTAs is covered in a few steps).
+// Both sequences are sorted, so the tile's updates land in ONE contiguous slot window of the packed array: from the
+// first key's source vertex to the end of the last key's -- or, when a hub vertex makes that too long, between the
+// positions of the tile's first and last key (two searches by two threads).  A window of <= LCAP slots is STAGED in
+// shared memory with coalesced 16-byte loads and every search of the tile runs there (measured on the per-element
+// kernel: 17 cycles of long-scoreboard stall per issued instruction, ~5 dependent DRAM/L2 round trips per update; the
+// leaf-level loop alone was 28 % of the instructions because a hub's range spans 15 levels -- the window caps it at
+// log2(LCAP / leaf)); longer windows are searched in global memory, clipped to the window all the same.
+constexpr int LT = 256;         // threads of a locate CTA
+constexpr int LI = 2;           // sorted updates per thread
+constexpr int LTILE = LT * LI;  // updates per tile
+#ifndef PPCSR_LOC_CAP
+#define PPCSR_LOC_CAP 8192
+#endif
+constexpr int LCAP = PPCSR_LOC_CAP;    // slots of dest[] a tile can stage (32 KB)
+constexpr int LCAP_LEAVES = LCAP / 8;  // leaves are >= 8 slots
+constexpr int LB_DEPTH = 4;            // look-back: predecessors examined per lane and step
+
+struct LocSmem {
+  uint32_t dest[LCAP];         // staged window of dest[]
+  uint32_t cnt[LCAP_LEAVES];   // leaf counts of the window
+  uint64_t key[LTILE + 2];     // the tile's keys; [0] and [LTILE + 1] are the neighbours' (or ~0: none)
+  uint32_t o_dst[LTILE], o_val[LTILE], o_pred[LTILE];  // the tile's inserts, compacted in key order
+  uint32_t warp[33];
+  uint32_t stat[8];
+  uint32_t win[4];             // window [a, b), mode (0 nothing to search, 1 staged, 2 global), valid keys
+  uint32_t prefix;
+};
+
+__global__ void __launch_bounds__(LT) k_locate(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay,
                                                uint32_t default_val, size_t count, uint64_t invalid_key,
                                                const uint32_t *__restrict__ dest, uint32_t *__restrict__ val,
                                                const uint32_t *__restrict__ leaf_cnt, const uint32_t *__restrict__ beg,
-                                               uint32_t ls, uint32_t *__restrict__ nn, uint32_t *__restrict__ ins_dst,
-                                               uint32_t *__restrict__ ins_val, uint32_t *__restrict__ ins_pred,
-                                               unsigned long long *scan_state, uint32_t scan_epoch,
-                                               uint32_t *__restrict__ ins_cnt, uint32_t *__restrict__ del_cnt,
-                                               uint32_t op_bit, BatchScalars *sc) {
-  __shared__ uint32_t s_warp[33];
-  __shared__ uint32_t s_prefix;
-  __shared__ uint32_t s_stat[6];
-  if (threadIdx.x < 6) s_stat[threadIdx.x] = 0;
-  __syncthreads();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                               uint32_t ls, uint32_t n_slots, uint32_t *__restrict__ nn,
+                                               uint32_t *__restrict__ ins_dst, uint32_t *__restrict__ ins_val,
+                                               uint32_t *__restrict__ ins_pred, unsigned long long *scan_state,
+                                               uint32_t scan_epoch, uint32_t *__restrict__ ins_cnt,
+                                               uint32_t *__restrict__ del_cnt, uint32_t op_bit, BatchScalars *sc) {
+  extern __shared__ __align__(16) unsigned char loc_smem_raw[];
+  LocSmem &S = *reinterpret_cast<LocSmem *>(loc_smem_raw);
+  const uint32_t tid = threadIdx.x;
   const unsigned lt = lanemask_lt();
-  uint32_t cls = 0xFFu, leaf = 0xFFFFFFFFu, s = 0xFFFFFFFFu, my_slot = 0, my_val = 0, my_dst = 0;
-  int delta = 0;
-  bool miss_dup = false, miss_first = false, winner = false;
-  if (i < count) {
-    // op_bit: bit 63 of a key word marks a remove (KEY_OP_BIT) and is not part of the key
-    const uint64_t km = op_bit ? ~KEY_OP_BIT : ~0ull;
-    auto value_at = [&](size_t x) -> uint32_t {
-      return pay ? pay[x] : (op_bit && (keys[x] & KEY_OP_BIT)) ? 0u : default_val;
-    };
-    const uint64_t k = keys[i] & km;
-    if (k < invalid_key) {
-      s = (uint32_t)(k >> 32);
-      const uint32_t v = value_at(i);
-      delta = v != 0 ? 1 : -1;
-      const bool same_prev = i > 0 && (keys[i - 1] & km) == k;
-      winner = i + 1 == count || (keys[i + 1] & km) != k;
-      // a remove right after a remove of the same key: the sequential reference reports `not found`
-      if (v == 0 && same_prev && value_at(i - 1) == 0) miss_dup = true;
-      if (winner) {
-        bool first_del = v == 0;  // is the FIRST op of this key's run a remove?
-        if (same_prev) {
-          size_t h = i - 1;
-          while (h > 0 && (keys[h - 1] & km) == k) h--;
-          first_del = value_at(h) == 0;
+  const size_t base = (size_t)blockIdx.x * LTILE;
+  const uint32_t tile_n = (uint32_t)min((size_t)LTILE, count - base);
+  // op_bit: bit 63 of a key word marks a remove (KEY_OP_BIT) and is not part of the key
+  const uint64_t km = op_bit ? ~KEY_OP_BIT : ~0ull;
+  for (uint32_t x = tid; x < (uint32_t)LTILE + 2u; x += LT) {
+    const size_t g = base + x;  // element g - 1
+    S.key[x] = (g >= 1 && g - 1 < count) ? keys[g - 1] : ~0ull;
+  }
+  if (tid < 8) S.stat[tid] = 0;
+  __syncthreads();
+  // ---- the tile's slot window
+  if (tid == 0) {
+    uint32_t lo = 0, hi = tile_n;  // rejected updates carry invalid_key and sort last: count the valid ones
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if ((S.key[1 + mid] & km) < invalid_key) lo = mid + 1;
+      else hi = mid;
+    }
+    const uint32_t nv = lo;
+    uint32_t a = 0, b = 0, mode = 0;
+    if (nv) {
+      const uint32_t s0 = (uint32_t)((S.key[1] & km) >> 32), s1 = (uint32_t)((S.key[nv] & km) >> 32);
+      const uint32_t leaf = 1u << ls;
+      a = (beg[s0] >> ls) << ls;
+      b = (uint32_t)min((unsigned long long)n_slots, (((unsigned long long)beg[s1 + 1] + leaf - 1u) >> ls) << ls);
+      mode = (b - a <= (uint32_t)LCAP) ? 1u : 3u;  // 3: too long, refine with the positions of the end keys
+    }
+    S.win[0] = a;
+    S.win[1] = b;
+    S.win[2] = mode;
+    S.win[3] = nv;
+  }
+  __syncthreads();
+  if (S.win[2] == 3u) {
+    if (tid == 0 || tid == 32) {  // two warps: the two searches run side by side
+      const uint64_t k = S.key[tid == 0 ? 1u : S.win[3]] & km;
+      const uint32_t s = (uint32_t)(k >> 32);
+      uint32_t slot;
+      find_in(dest, 0u, leaf_cnt, 0u, beg[s], beg[s + 1], true, ls, (uint32_t)k, &slot);
+      if (tid == 0) S.win[0] = (slot >> ls) << ls;  // hit or predecessor of the smallest key: nothing lies below
+      else S.win[1] = ((slot >> ls) + 1u) << ls;    // ... of the largest key: nothing lies above its leaf
+    }
+    __syncthreads();
+    if (tid == 0) S.win[2] = (S.win[1] - S.win[0] <= (uint32_t)LCAP) ? 1u : 2u;
+    __syncthreads();
+  }
+  const uint32_t wa = S.win[0], wb = S.win[1], mode = S.win[2];
+  if (mode == 1u) {  // stage the window: coalesced 16-byte loads (wa is leaf aligned, leaves are >= 32 bytes)
+    for (uint32_t x = tid * 4u; x < wb - wa; x += LT * 4u)
+      *reinterpret_cast<uint4 *>(&S.dest[x]) = *reinterpret_cast<const uint4 *>(&dest[wa + x]);
+    const uint32_t nl = (wb - wa) >> ls, l0 = wa >> ls;
+    for (uint32_t x = tid; x < nl; x += LT) S.cnt[x] = leaf_cnt[l0 + x];
+    __syncthreads();
+  }
+  const uint32_t *D = mode == 1u ? S.dest : dest, *C = mode == 1u ? S.cnt : leaf_cnt;
+  const uint32_t doff = mode == 1u ? wa : 0u, coff = mode == 1u ? wa >> ls : 0u;
+
+  uint32_t is_ins[LI], o_d[LI], o_v[LI], o_p[LI];
+#pragma unroll
+  for (int r = 0; r < LI; r++) {
+    const uint32_t e = r * LT + tid;
+    const size_t i = base + e;
+    uint32_t cls = 0xFFu, leaf = 0xFFFFFFFFu, s = 0xFFFFFFFFu;
+    int delta = 0;
+    bool miss_dup = false, miss_first = false, winner = false;
+    is_ins[r] = 0u;
+    o_d[r] = o_v[r] = o_p[r] = 0u;
+    if (e < tile_n) {
+      auto value_at = [&](size_t x) -> uint32_t {
+        return pay ? pay[x] : (op_bit && (keys[x] & KEY_OP_BIT)) ? 0u : default_val;
+      };
+      const uint64_t kw = S.key[e + 1];
+      const uint64_t k = kw & km;
+      if (k < invalid_key) {
+        s = (uint32_t)(k >> 32);
+        const uint32_t v = pay ? pay[i] : (op_bit && (kw & KEY_OP_BIT)) ? 0u : default_val;
+        delta = v != 0 ? 1 : -1;
+        const bool same_prev = (S.key[e] & km) == k && i > 0;
+        winner = (S.key[e + 2] & km) != k || i + 1 == count;
+        // a remove right after a remove of the same key: the sequential reference reports `not found`
+        if (v == 0 && same_prev && value_at(i - 1) == 0) miss_dup = true;
+        if (winner) {
+          bool first_del = v == 0;  // is the FIRST op of this key's run a remove?
+          if (same_prev) {
+            size_t h = i - 1;
+            while (h > 0 && (keys[h - 1] & km) == k) h--;
+            first_del = value_at(h) == 0;
+          }
+          const uint32_t d = (uint32_t)k;
+          uint32_t bb = beg[s], ee = beg[s + 1], slot;
+          bool skip = true;
+          if (bb < wa) {  // clipped from below: the window starts inside this vertex's range, at a leaf whose first
+            bb = wa;      // item is <= the tile's smallest key
+            skip = false;
+          }
+          ee = min(ee, wb);
+          const bool hit = find_in(D, doff, C, coff, bb, ee, skip, ls, d, &slot);
+          if (v != 0) {
+            cls = hit ? CLS_OVERWRITE : CLS_INSERT;
+            if (hit) val[slot] = v;  // duplicate insert overwrites the value (reference PCSR.cpp:529-532)
+          } else {
+            cls = hit ? CLS_DELETE : CLS_MISS;
+            if (hit) val[slot] = 0;  // tombstone; compacted away by the rebalance of this leaf (PCSR.cpp:605-606)
+          }
+          if (first_del && !hit) miss_first = true;  // counted on the winner: the run's head op found nothing
+          leaf = slot >> ls;
+          if (cls == CLS_INSERT) {
+            is_ins[r] = 1u;
+            o_d[r] = d;
+            o_v[r] = v;
+            o_p[r] = slot;
+          }
         }
-        const uint32_t d = (uint32_t)k;
-        uint32_t slot;
-        const bool hit = find_edge(dest, leaf_cnt, beg[s], beg[s + 1], ls, d, &slot);
-        if (v != 0) {
-          cls = hit ? CLS_OVERWRITE : CLS_INSERT;
-          if (hit) val[slot] = v;  // duplicate insert overwrites the value (reference PCSR.cpp:529-532)
-        } else {
-          cls = hit ? CLS_DELETE : CLS_MISS;
-          if (hit) val[slot] = 0;  // tombstone; compacted away by the rebalance of this leaf (PCSR.cpp:605-606)
-        }
-        if (first_del && !hit) miss_first = true;  // counted on the winner: the run's head op found nothing
-        my_slot = slot;
-        my_val = v;
-        my_dst = d;
-        leaf = slot >> ls;
+      }
+    }
+    // call counts: one atomic per run of equal sources inside the warp
+    {
+      const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
+      const unsigned adds = __ballot_sync(0xFFFFFFFFu, delta > 0);
+      const unsigned dels = __ballot_sync(0xFFFFFFFFu, delta < 0);
+      if (s != 0xFFFFFFFFu && (peers & lt) == 0) {
+        const int sum = __popc(peers & adds) - __popc(peers & dels);
+        if (sum) atomicAdd(&nn[s], (uint32_t)sum);
+      }
+    }
+    // per-leaf counts: the batch is key-sorted, so equal leaves are adjacent -> one atomic per warp run.  The first
+    // update to reach a leaf also counts it as touched (a leaf hit by inserts AND deletes counts twice: the total
+    // only steers the whole-array-versus-windows policy).
+    bool first_touch = false;
+    {
+      const uint32_t key = (cls == CLS_INSERT) ? leaf : 0xFFFFFFFFu;
+      const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+      if (key != 0xFFFFFFFFu && (peers & lt) == 0)
+        first_touch = atomicAdd(&ins_cnt[leaf], (uint32_t)__popc(peers)) == 0u;
+    }
+    {
+      const uint32_t key = (cls == CLS_DELETE) ? leaf : 0xFFFFFFFFu;
+      const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+      if (key != 0xFFFFFFFFu && (peers & lt) == 0)
+        first_touch |= atomicAdd(&del_cnt[leaf], (uint32_t)__popc(peers)) == 0u;
+    }
+    {
+      const unsigned m0 = __ballot_sync(0xFFFFFFFFu, cls == CLS_INSERT);
+      const unsigned m1 = __ballot_sync(0xFFFFFFFFu, cls == CLS_OVERWRITE);
+      const unsigned m2 = __ballot_sync(0xFFFFFFFFu, cls == CLS_DELETE);
+      const unsigned m3 = __ballot_sync(0xFFFFFFFFu, miss_dup);
+      const unsigned m5 = __ballot_sync(0xFFFFFFFFu, miss_first);
+      const unsigned m4 = __ballot_sync(0xFFFFFFFFu, winner);
+      const unsigned m6 = __ballot_sync(0xFFFFFFFFu, first_touch);
+      if (lane_id() == 0) {
+        if (m6) atomicAdd(&S.stat[5], (uint32_t)__popc(m6));
+        if (m0) atomicAdd(&S.stat[0], (uint32_t)__popc(m0));
+        if (m1) atomicAdd(&S.stat[1], (uint32_t)__popc(m1));
+        if (m2) atomicAdd(&S.stat[2], (uint32_t)__popc(m2));
+        if (m3 | m5) atomicAdd(&S.stat[3], (uint32_t)(__popc(m3) + __popc(m5)));
+        if (m4) atomicAdd(&S.stat[4], (uint32_t)__popc(m4));
       }
     }
   }
-  // call counts: one atomic per run of equal sources inside the warp
-  {
-    const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
-    const unsigned adds = __ballot_sync(0xFFFFFFFFu, delta > 0);
-    const unsigned dels = __ballot_sync(0xFFFFFFFFu, delta < 0);
-    if (s != 0xFFFFFFFFu && (peers & lt) == 0) {
-      const int sum = __popc(peers & adds) - __popc(peers & dels);
-      if (sum) atomicAdd(&nn[s], (uint32_t)sum);
+  // ---- the tile's inserts, compacted in element order (element = r * LT + tid)
+  uint32_t total = 0;
+#pragma unroll
+  for (int r = 0; r < LI; r++) {
+    uint32_t t;
+    const uint32_t ex = total + prim::block_excl_scan(is_ins[r], &t, S.warp);  // ends with a block barrier
+    if (is_ins[r]) {
+      S.o_dst[ex] = o_d[r];
+      S.o_val[ex] = o_v[r];
+      S.o_pred[ex] = o_p[r];
     }
+    total += t;
   }
-  // per-leaf counts: the batch is key-sorted, so equal leaves are adjacent -> one atomic per warp run.  The first
-  // update to reach a leaf also counts it as touched (a leaf hit by inserts AND deletes counts twice: the total
-  // only steers the whole-array-versus-windows policy).
-  bool first_touch = false;
-  {
-    const uint32_t key = (cls == CLS_INSERT) ? leaf : 0xFFFFFFFFu;
-    const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
-    if (key != 0xFFFFFFFFu && (peers & lt) == 0) first_touch = atomicAdd(&ins_cnt[leaf], (uint32_t)__popc(peers)) == 0u;
-  }
-  {
-    const uint32_t key = (cls == CLS_DELETE) ? leaf : 0xFFFFFFFFu;
-    const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
-    if (key != 0xFFFFFFFFu && (peers & lt) == 0)
-      first_touch |= atomicAdd(&del_cnt[leaf], (uint32_t)__popc(peers)) == 0u;
-  }
-  {
-    const unsigned m0 = __ballot_sync(0xFFFFFFFFu, cls == CLS_INSERT);
-    const unsigned m1 = __ballot_sync(0xFFFFFFFFu, cls == CLS_OVERWRITE);
-    const unsigned m2 = __ballot_sync(0xFFFFFFFFu, cls == CLS_DELETE);
-    const unsigned m3 = __ballot_sync(0xFFFFFFFFu, miss_dup);
-    const unsigned m5 = __ballot_sync(0xFFFFFFFFu, miss_first);
-    const unsigned m4 = __ballot_sync(0xFFFFFFFFu, winner);
-    const unsigned m6 = __ballot_sync(0xFFFFFFFFu, first_touch);
-    if (lane_id() == 0) {
-      if (m6) atomicAdd(&s_stat[5], (uint32_t)__popc(m6));
-      if (m0) atomicAdd(&s_stat[0], (uint32_t)__popc(m0));
-      if (m1) atomicAdd(&s_stat[1], (uint32_t)__popc(m1));
-      if (m2) atomicAdd(&s_stat[2], (uint32_t)__popc(m2));
-      if (m3 | m5) atomicAdd(&s_stat[3], (uint32_t)(__popc(m3) + __popc(m5)));
-      if (m4) atomicAdd(&s_stat[4], (uint32_t)__popc(m4));
-    }
-  }
-  // The compacted, key-ordered insert list (dst, value, predecessor slot), written by this kernel itself: exclusive
-  // scan of the insert flags over the block, the block's base from a decoupled look-back over the earlier blocks
-  // (one epoch-tagged word per block in scan_state, same protocol as prim::k_scan_onepass; tiles are the blocks in
-  // launch order, as in the single-pass scans of CUB).  Replaces a separate three-pass compaction (class and slot
-  // arrays written, read twice).
-  {
-    const uint32_t is_ins = cls == CLS_INSERT ? 1u : 0u;
-    uint32_t total;
-    const uint32_t ex = prim::block_excl_scan(is_ins, &total, s_warp);  // ends with a block barrier: s_stat is final too
-    if (threadIdx.x < 32) {
-      const unsigned lane = threadIdx.x;
-      const uint32_t tile = blockIdx.x;
-      volatile unsigned long long *st = scan_state;
-      if (lane == 0) st[tile] = prim::scan_word(tile == 0 ? prim::SCAN_ST_INC : prim::SCAN_ST_AGG, scan_epoch, total);
-      uint32_t prefix = 0;
-      if (tile > 0) {
-        int64_t j = (int64_t)tile - 1;  // lane l examines tile j - l
-        for (;;) {
-          const int64_t t = j - (int64_t)lane;
-          const unsigned long long w = t >= 0 ? st[t] : prim::scan_word(prim::SCAN_ST_INC, scan_epoch, 0u);
-          const bool ready = (uint32_t)((w >> 32) & 0x3FFFFFFFu) == scan_epoch && (w >> 62) != 0ull;
-          const unsigned inc = __ballot_sync(0xFFFFFFFFu, ready && (w >> 62) == 2ull);
+  if (tid < 32) {  // warp 0: publish the tile's count, then add up the tiles before it
+    const unsigned lane = tid;
+    const uint32_t tile = blockIdx.x;
+    volatile unsigned long long *st = scan_state;
+    if (lane == 0) st[tile] = prim::scan_word(tile == 0 ? prim::SCAN_ST_INC : prim::SCAN_ST_AGG, scan_epoch, total);
+    uint32_t prefix = 0;
+    if (tile > 0) {
+      int64_t j = (int64_t)tile - 1;  // lane l examines the tiles j - l - 32 u, u < LB_DEPTH
+      for (;;) {
+        unsigned long long w[LB_DEPTH];
+#pragma unroll
+        for (int u = 0; u < LB_DEPTH; u++) {
+          const int64_t t = j - (int64_t)(u * 32 + lane);
+          // tiles before the first one count as an inclusive prefix of zero
+          w[u] = t >= 0 ? st[t] : prim::scan_word(prim::SCAN_ST_INC, scan_epoch, 0u);
+        }
+        uint32_t sum = 0;
+        bool done = false, again = false;
+#pragma unroll
+        for (int u = 0; u < LB_DEPTH; u++) {
+          if (done || again) continue;  // warp-uniform
+          const bool ready = (uint32_t)((w[u] >> 32) & 0x3FFFFFFFu) == scan_epoch && (w[u] >> 62) != 0ull;
+          const unsigned inc = __ballot_sync(0xFFFFFFFFu, ready && (w[u] >> 62) == 2ull);
           const unsigned not_ready = __ballot_sync(0xFFFFFFFFu, !ready);
           const unsigned first_inc = inc ? (unsigned)__ffs(inc) - 1u : 32u;
           const unsigned need = first_inc < 32u ? (2u << first_inc) - 1u : 0xFFFFFFFFu;  // lanes 0..first_inc
-          if (not_ready & need) continue;  // a block this window depends on has not published yet: look again
-          uint32_t x = (need >> lane) & 1u ? (uint32_t)w : 0u;
+          if (not_ready & need) {
+            again = true;  // a tile this window depends on has not published yet: read the window again
+            continue;
+          }
+          uint32_t x = (need >> lane) & 1u ? (uint32_t)w[u] : 0u;
 #pragma unroll
-          for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
-          prefix += x;
-          if (first_inc < 32u) break;
-          j -= 32;
+          for (int dd = 16; dd > 0; dd >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, dd);
+          sum += x;
+          done = first_inc < 32u;
         }
-        if (lane == 0) st[tile] = prim::scan_word(prim::SCAN_ST_INC, scan_epoch, prefix + total);
+        if (again) continue;
+        prefix += sum;
+        if (done) break;
+        j -= 32 * LB_DEPTH;
       }
-      if (lane == 0) {
-        s_prefix = prefix;
-        if (s_stat[0]) atomicAdd(&sc->n_inserted, (unsigned long long)s_stat[0]);
-        if (s_stat[1]) atomicAdd(&sc->n_overwritten, (unsigned long long)s_stat[1]);
-        if (s_stat[2]) atomicAdd(&sc->n_deleted, (unsigned long long)s_stat[2]);
-        if (s_stat[3]) atomicAdd(&sc->n_not_found, (unsigned long long)s_stat[3]);
-        if (s_stat[4]) atomicAdd(&sc->n_unique, (unsigned long long)s_stat[4]);
-        if (s_stat[5]) atomicAdd(&sc->n_touched_est, (unsigned long long)s_stat[5]);
-      }
+      if (lane == 0) st[tile] = prim::scan_word(prim::SCAN_ST_INC, scan_epoch, prefix + total);
     }
-    __syncthreads();
-    if (is_ins) {
-      const uint32_t at = s_prefix + ex;
-      ins_dst[at] = my_dst;
-      ins_val[at] = my_val;
-      ins_pred[at] = my_slot;
+    if (lane == 0) {
+      S.prefix = prefix;
+      if (S.stat[0]) atomicAdd(&sc->n_inserted, (unsigned long long)S.stat[0]);
+      if (S.stat[1]) atomicAdd(&sc->n_overwritten, (unsigned long long)S.stat[1]);
+      if (S.stat[2]) atomicAdd(&sc->n_deleted, (unsigned long long)S.stat[2]);
+      if (S.stat[3]) atomicAdd(&sc->n_not_found, (unsigned long long)S.stat[3]);
+      if (S.stat[4]) atomicAdd(&sc->n_unique, (unsigned long long)S.stat[4]);
+      if (S.stat[5]) atomicAdd(&sc->n_touched_est, (unsigned long long)S.stat[5]);
     }
+  }
+  __syncthreads();
+  const uint32_t at0 = S.prefix;
+  for (uint32_t x = tid; x < total; x += LT) {  // coalesced
+    ins_dst[at0 + x] = S.o_dst[x];
+    ins_val[at0 + x] = S.o_val[x];
+    ins_pred[at0 + x] = S.o_pred[x];
   }
 }
 

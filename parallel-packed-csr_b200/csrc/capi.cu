@@ -4,10 +4,12 @@
 #include <cmath>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "batch.cuh"
 #include "common.cuh"
+#include "parse.cuh"
 #include "primitives.cuh"
 #include "queries.cuh"
 #include "rebalance.cuh"
@@ -235,7 +237,7 @@ int reserve_worst_case(ppcsr_shard *s, uint64_t count) {
   PPCSR_TRY(dev_reserve(s->plan, (size_t)g2.n_leaves / min_cl + 2, s->stream));
   const size_t scan_tiles = (size_t)div_up(std::max<uint64_t>(std::max<uint64_t>(g2.n_leaves, count), 1), prim::SCAN_TILE) + 2;
   PPCSR_TRY(dev_reserve(s->block_tmp, scan_tiles, s->stream));
-  PPCSR_TRY(prim::reserve_scan_state(s, std::max<size_t>(scan_tiles, (size_t)div_up(count, batch::BT) + 2)));
+  PPCSR_TRY(prim::reserve_scan_state(s, std::max<size_t>(scan_tiles, (size_t)div_up(count, batch::LTILE) + 2)));
   return PPCSR_OK;
 }
 int poisoned_error() {
@@ -780,7 +782,7 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
 // shared by the (src,dst) and the packed entry points: `packed` != nullptr selects the packed key builder
 static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint32_t *d_dst, const uint64_t *d_packed,
                                const uint32_t *d_val, uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats,
-                               const batch::SegmentTable *segments = nullptr) {
+                               const batch::SegmentTable *segments = nullptr, bool pairs = false) {
   PPCSR_TRY(set_device(s));
   ppcsr_batch_stats st{};
   st.batch_size = count;
@@ -820,7 +822,7 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
                                                                  s->key_a.p, has_pay ? s->pay_a.p : nullptr, sc);
   } else if (d_packed) {
     batch::k_build_keys_packed<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, count, s->n, op_bit, s->key_a.p,
-                                                               has_pay ? s->pay_a.p : nullptr, sc);
+                                                               has_pay ? s->pay_a.p : nullptr, sc, pairs ? 1u : 0u);
   } else {
     batch::k_build_keys<<<kb, batch::BT, 0, s->stream>>>(d_src, d_dst, d_val, default_val, count, s->n, op_bit, s->key_a.p,
                                                         has_pay ? s->pay_a.p : nullptr, sc);
@@ -862,14 +864,25 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   const uint64_t invalid_key = (uint64_t)s->n << 32;
   CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
   CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
-  // the kernel also compacts the key-ordered insert list (look-back over its blocks: one scan_state word each)
-  const unsigned lblocks = div_up(count, batch::BT);
+  // one CTA per tile of sorted updates; the kernel also compacts the key-ordered insert list (look-back over its
+  // tiles: one scan_state word each)
+  const unsigned lblocks = div_up(count, batch::LTILE);
   PPCSR_TRY(prim::reserve_scan_state(s, lblocks));
   s->scan_epoch++;
-  batch::k_locate<<<lblocks, batch::BT, 0, s->stream>>>(
+  {  // > 48 KB of dynamic shared memory needs an explicit opt-in: per device, once, thread-safe
+    static std::once_flag once[64];
+    static cudaError_t once_err[64];
+    const int dv = s->device & 63;
+    std::call_once(once[dv], [&] {
+      once_err[dv] = cudaFuncSetAttribute(batch::k_locate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(batch::LocSmem));
+    });
+    CUDA_TRY(once_err[dv]);
+  }
+  batch::k_locate<<<lblocks, batch::LT, sizeof(batch::LocSmem), s->stream>>>(
       keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
-      s->nn.p, s->ins_dst.p, s->ins_val.p, s->ins_pred.p, s->scan_state.p, s->scan_epoch, s->ins_cnt.p, s->del_cnt.p,
-      op_bit, sc);
+      (uint32_t)g.N, s->nn.p, s->ins_dst.p, s->ins_val.p, s->ins_pred.p, s->scan_state.p, s->scan_epoch, s->ins_cnt.p,
+      s->del_cnt.p, op_bit, sc);
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
   // 5. windows + rebalance
   PPCSR_TRY(finish_batch(s, count, &st));
@@ -969,6 +982,91 @@ int ppcsr_wait(ppcsr_shard *s, uint64_t ticket, ppcsr_batch_stats *stats) {
                                      P.default_val, stats);
   P.busy = false;
   return rc;
+}
+
+// ---- binary input path: interleaved (src, dst) pairs, e.g. an mmap'd edge file -----------------------------------
+int ppcsr_apply_batch_pairs(ppcsr_shard *s, const uint32_t *pairs, uint64_t count, uint32_t default_val,
+                            ppcsr_batch_stats *stats) {
+  if (!s || (count && !pairs)) return PPCSR_ERR_ARG;
+  PPCSR_TRY(set_device(s));
+  if (count == 0) return ppcsr_apply_batch_device(s, nullptr, nullptr, nullptr, 0, default_val, stats);
+  // staged as u64 words: little-endian (src, dst) reads as dst << 32 | src, the key builder swaps the halves
+  PPCSR_TRY(dev_reserve(s->in_src, 2 * count, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(s->in_src.p, pairs, count * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+  return apply_device_common(s, nullptr, nullptr, reinterpret_cast<const uint64_t *>(s->in_src.p), nullptr, count,
+                             default_val, stats, nullptr, true);
+}
+
+// ---- text input path: the reference's edge-list reader on the GPU (parse.cuh) -----------------------------------
+int ppcsr_parse_edge_list(int device, const char *text, uint64_t bytes, uint32_t default_val, uint32_t **d_src,
+                          uint32_t **d_dst, uint32_t **d_val, uint64_t *count, uint64_t *n_parsed, uint32_t *max_id) {
+  if (!d_src || !d_dst || !d_val || !count || (bytes && !text)) return PPCSR_ERR_ARG;
+  *d_src = *d_dst = *d_val = nullptr;
+  *count = 0;
+  if (n_parsed) *n_parsed = 0;
+  if (max_id) *max_id = 0;
+  if (ppcsr_device_count() <= device || device < 0) return PPCSR_ERR_NO_DEVICE;
+  if (bytes == 0) return PPCSR_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  ppcsr_shard tmp;  // scan scratch only
+  tmp.device = device;
+  tmp.stream = nullptr;
+  DevBuf<char> d_text;
+  DevBuf<unsigned long long> d_starts, d_misc;
+  DevBuf<uint32_t> o_src, o_dst, o_val;
+  int rc = [&]() -> int {
+    PPCSR_TRY(dev_reserve(d_text, bytes, nullptr));
+    CUDA_TRY(cudaMemcpy(d_text.p, text, bytes, cudaMemcpyHostToDevice));
+    PPCSR_TRY(dev_reserve(d_misc, 4, nullptr));
+    CUDA_TRY(cudaMemset(d_misc.p, 0, 4 * sizeof(unsigned long long)));
+    // pass 1: count the newlines (sizes the line table), pass 2: the line starts
+    PPCSR_TRY(prim::device_scan(&tmp, parse::InIsNewline{d_text.p}, prim::OutNothing{}, bytes, nullptr, d_misc.p));
+    unsigned long long newlines = 0;
+    CUDA_TRY(cudaMemcpy(&newlines, d_misc.p, sizeof(newlines), cudaMemcpyDeviceToHost));
+    const unsigned long long n_lines = newlines + (text[bytes - 1] == '\n' ? 0ull : 1ull);
+    if (n_lines == 0) return PPCSR_OK;
+    PPCSR_TRY(dev_reserve(d_starts, newlines + 2, nullptr));
+    CUDA_TRY(cudaMemset(d_starts.p, 0, sizeof(unsigned long long)));  // line 0 starts at byte 0
+    PPCSR_TRY(prim::device_scan(&tmp, parse::InIsNewline{d_text.p}, parse::OutLineStart{d_starts.p}, bytes, nullptr,
+                                nullptr));
+    PPCSR_TRY(dev_reserve(o_src, n_lines, nullptr));
+    PPCSR_TRY(dev_reserve(o_dst, n_lines, nullptr));
+    PPCSR_TRY(dev_reserve(o_val, n_lines, nullptr));
+    parse::k_parse_lines<<<div_up(n_lines, parse::PT), parse::PT>>>(
+        d_text.p, bytes, d_starts.p, n_lines, default_val, o_src.p, o_dst.p, o_val.p,
+        reinterpret_cast<unsigned int *>(d_misc.p + 1), d_misc.p + 2);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long h[4];
+    CUDA_TRY(cudaMemcpy(h, d_misc.p, sizeof(h), cudaMemcpyDeviceToHost));
+    *count = n_lines;
+    if (max_id) *max_id = (uint32_t)h[1];
+    if (n_parsed) *n_parsed = h[2];
+    return PPCSR_OK;
+  }();
+  dev_free(d_text); dev_free(d_starts); dev_free(d_misc);
+  dev_free(tmp.block_tmp); dev_free(tmp.scan_state); dev_free(tmp.scan_ticket);
+  if (rc != PPCSR_OK) {
+    dev_free(o_src); dev_free(o_dst); dev_free(o_val);
+    return rc;
+  }
+  *d_src = o_src.p;
+  *d_dst = o_dst.p;
+  *d_val = o_val.p;
+  return PPCSR_OK;
+}
+
+int ppcsr_free_device(int device, void *p) {
+  if (!p) return PPCSR_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFree(p));
+  return PPCSR_OK;
+}
+
+int ppcsr_copy_to_host(int device, void *host, const void *dev, uint64_t bytes) {
+  if (bytes && (!host || !dev)) return PPCSR_ERR_ARG;
+  CUDA_TRY(cudaSetDevice(device));
+  if (bytes) CUDA_TRY(cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost));
+  return PPCSR_OK;
 }
 
 int ppcsr_add_edge(ppcsr_shard *s, uint32_t src, uint32_t dst, uint32_t value) {
@@ -1570,5 +1668,7 @@ int ppcsr_debug_exclusive_scan(int device, const uint32_t *in, uint32_t *out, ui
   dev_free(a); dev_free(b); dev_free(tmp.block_tmp); dev_free(tmp.scan_state); dev_free(tmp.scan_ticket);
   return rc;
 }
+
+#include "group.inl"
 
 }  // extern "C"

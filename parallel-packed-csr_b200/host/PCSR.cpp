@@ -48,11 +48,11 @@ void PCSR::refresh_geometry() {
     edges.logN = (int)g.logN;
     edges.H = (int)g.H;
     std::cout << "Edges: " << edges.N << " logN: " << edges.logN << " #count: " << edges.N / edges.logN << std::endl;
+    // node_locks[i] of every leaf is ONE always-free stub (no per-leaf locking in a batch design): a per-leaf object
+    // would cost 16 M allocations at scale 24 and an O(leaves) version bump per batch
     const size_t leaves = edges.N / edges.logN;
-    while (lock_store_.size() < leaves) lock_store_.emplace_back(new HybridLock());
-    lock_store_.resize(leaves);
-    lock_ptrs_.resize(leaves);
-    for (size_t i = 0; i < leaves; i++) lock_ptrs_[i] = lock_store_[i].get();
+    if (lock_store_.empty()) lock_store_.emplace_back(new HybridLock());
+    lock_ptrs_.assign(leaves, lock_store_[0].get());
     edges.node_locks = lock_ptrs_.data();
   }
 }
@@ -136,16 +136,33 @@ std::vector<int> PCSR::get_neighbourhood(int src) const {
 
 float PCSR::apply_batch(const std::vector<uint32_t> &src, const std::vector<uint32_t> &dst,
                         const std::vector<uint32_t> &value, ppcsr_batch_stats *stats) {
+  return apply_batch(src.data(), dst.data(), value.empty() ? nullptr : value.data(), src.size(), stats);
+}
+
+float PCSR::apply_batch(const uint32_t *src, const uint32_t *dst, const uint32_t *value, size_t count,
+                        ppcsr_batch_stats *stats) {
   std::lock_guard<std::mutex> g(edges.global_lock->mutex());
   ppcsr_batch_stats st{};
-  if (ppcsr_apply_batch(shard_, src.data(), dst.data(), value.empty() ? nullptr : value.data(), src.size(), 1, &st) !=
-      PPCSR_OK)
-    fail("ppcsr_apply_batch");
-  nodes_dirty_ = true;
-  refresh_geometry();
-  for (auto &l : lock_store_) ++(*l);
+  if (ppcsr_apply_batch(shard_, src, dst, value, count, 1, &st) != PPCSR_OK) fail("ppcsr_apply_batch");
+  batch_applied();
   if (stats) *stats = st;
   return st.ms_total;
+}
+
+float PCSR::apply_batch_pairs(const uint32_t *pairs, size_t count, uint32_t default_val, ppcsr_batch_stats *stats) {
+  std::lock_guard<std::mutex> g(edges.global_lock->mutex());
+  ppcsr_batch_stats st{};
+  if (ppcsr_apply_batch_pairs(shard_, pairs, count, default_val, &st) != PPCSR_OK) fail("ppcsr_apply_batch_pairs");
+  batch_applied();
+  if (stats) *stats = st;
+  return st.ms_total;
+}
+
+// after a batch went through the C-ABI behind this object's back (PPPCSR's group route) or through apply_batch
+void PCSR::batch_applied() {
+  nodes_dirty_ = true;
+  refresh_geometry();
+  ++(*lock_store_[0]);  // the version counter counts the batches that rewrote the structure
 }
 
 void PCSR::pagerank_push(const std::vector<double> &in, std::vector<double> &out) const {

@@ -67,6 +67,11 @@ class PCSR {
   // value[i] != 0 inserts, 0 removes; returns the device milliseconds of the batch
   float apply_batch(const std::vector<uint32_t> &src, const std::vector<uint32_t> &dst,
                     const std::vector<uint32_t> &value, ppcsr_batch_stats *stats = nullptr);
+  float apply_batch(const uint32_t *src, const uint32_t *dst, const uint32_t *value /*nullable: all 1*/, size_t count,
+                    ppcsr_batch_stats *stats = nullptr);
+  // interleaved (src, dst) pairs, e.g. an mmap'd binary edge file; every update carries default_val (0 = remove)
+  float apply_batch_pairs(const uint32_t *pairs, size_t count, uint32_t default_val, ppcsr_batch_stats *stats = nullptr);
+  void batch_applied();  // refresh the host mirror after a batch reached the shard through the C-ABI directly
   // one pagerank push step (reference src/utility/pagerank.h:16-29) accumulated into out[0..out.size())
   void pagerank_push(const std::vector<double> &in, std::vector<double> &out) const;
   std::vector<uint32_t> bfs_levels(uint32_t start) const;

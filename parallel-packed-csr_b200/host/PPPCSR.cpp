@@ -1,6 +1,8 @@
 // PPPCSR host shell: see PPPCSR.h.
 #include "PPPCSR.h"
 
+#include <algorithm>
+#include <cstdlib>
 #include <iostream>
 
 PPPCSR::PPPCSR(uint32_t init_n, uint32_t src_n, bool lock_search, int numDomain, int partitionsPerDomain,
@@ -8,17 +10,64 @@ PPPCSR::PPPCSR(uint32_t init_n, uint32_t src_n, bool lock_search, int numDomain,
     : partitionsPerDomain(partitionsPerDomain) {
   (void)src_n;
   const std::size_t parts = (std::size_t)numDomain * (std::size_t)partitionsPerDomain;
-  partitions.reserve(parts);
-  distribution.reserve(parts);
   // equal vertex counts, the last partition takes the remainder (reference PPPCSR.cpp:20,27-29)
   const std::size_t share = init_n / parts;
+  for (std::size_t p = 0; p < parts; p++) distribution.push_back(p * share);
+  build(init_n, lock_search, use_numa);
+}
+
+PPPCSR::PPPCSR(uint32_t init_n, bool lock_search, int partitionsPerDomain, bool use_numa,
+               const std::vector<size_t> &boundaries)
+    : distribution(boundaries), partitionsPerDomain(partitionsPerDomain) {
+  build(init_n, lock_search, use_numa);
+}
+
+void PPPCSR::build(uint32_t init_n, bool lock_search, bool use_numa) {
+  const std::size_t parts = distribution.size();
+  partitions.reserve(parts);
   for (std::size_t p = 0; p < parts; p++) {
-    distribution.push_back(p * share);
-    const std::size_t size = (p + 1 == parts) ? init_n - p * share : share;
+    const std::size_t size = (p + 1 == parts ? (std::size_t)init_n : distribution[p + 1]) - distribution[p];
     const int gpu = use_numa ? (int)(p / partitionsPerDomain) : 0;
     partitions.emplace_back((uint32_t)size, (uint32_t)size, lock_search, gpu);
   }
   std::cout << "Number of partitions: " << partitions.size() << std::endl;
+}
+
+PPPCSR::~PPPCSR() {
+  if (group_) ppcsr_group_destroy(group_);
+}
+
+void PPPCSR::apply_batch(const uint32_t *src, const uint32_t *dst, const uint32_t *value, size_t count,
+                         std::vector<ppcsr_batch_stats> *stats) {
+  const std::size_t parts = partitions.size();
+  const std::size_t slice = (count + parts - 1) / parts;
+  if (!group_ || slice > group_cap_ || (value && !group_values_)) {  // (re)size the receive buffers
+    if (group_) ppcsr_group_destroy(group_);
+    group_ = nullptr;
+    std::vector<ppcsr_shard *> handles;
+    std::vector<uint64_t> starts;
+    uint64_t n = 0;
+    for (std::size_t p = 0; p < parts; p++) {
+      handles.push_back(partitions[p].handle());
+      starts.push_back(distribution[p]);
+      n = distribution[p] + partitions[p].get_n();
+    }
+    starts.push_back(n);
+    group_cap_ = std::max<std::size_t>(slice + slice / 8, 1024);
+    group_values_ = group_values_ || value != nullptr;
+    if (ppcsr_group_create(handles.data(), (uint32_t)parts, starts.data(), group_cap_, group_values_ ? 1 : 0,
+                           &group_) != PPCSR_OK) {
+      std::cout << "ppcsr_group_create failed: " << ppcsr_last_error() << ". Abort\n";
+      std::exit(EXIT_FAILURE);
+    }
+  }
+  std::vector<ppcsr_batch_stats> st(parts);
+  if (ppcsr_group_apply(group_, src, dst, value, count, 1, st.data()) != PPCSR_OK) {
+    std::cout << "ppcsr_group_apply failed: " << ppcsr_last_error() << ". Abort\n";
+    std::exit(EXIT_FAILURE);
+  }
+  for (auto &part : partitions) part.batch_applied();
+  if (stats) *stats = st;
 }
 
 std::size_t PPPCSR::get_partiton(size_t vertex_id) const {

@@ -14,6 +14,14 @@ class PPPCSR {
   edge_list_t edges;  // present in the reference too, never initialised there (PPPCSR.h:14)
 
   PPPCSR(uint32_t init_n, uint32_t src_n, bool lock_search, int numDomain, int partitionsPerDomain, bool use_numa);
+  // same, with explicit first vertices of the partitions (ascending, boundaries[0] == 0): the reference's
+  // `distribution` vector admits any monotone boundaries (PPPCSR.h:57); edge-balanced ones keep a skewed graph from
+  // putting 44 % of its edges on the first of eight GPUs
+  PPPCSR(uint32_t init_n, bool lock_search, int partitionsPerDomain, bool use_numa,
+         const std::vector<size_t> &boundaries);
+  ~PPPCSR();
+  PPPCSR(const PPPCSR &) = delete;
+  PPPCSR &operator=(const PPPCSR &) = delete;
 
   bool edge_exists(uint32_t src, uint32_t dest);
   void add_node();
@@ -33,9 +41,19 @@ class PPPCSR {
   PCSR &partition(std::size_t p) { return partitions[p]; }
   std::size_t partition_start(std::size_t p) const { return distribution[p]; }
   void pagerank_push(const std::vector<double> &in, std::vector<double> &out) const;
+  // One batch of GLOBAL updates (value 0 = remove, value == nullptr = all adds): the batch is cut into one slice per
+  // partition, every GPU bins its slice by owner ON THE DEVICE and stores the records straight into the owner's receive
+  // buffer over NVLink peer memory, every partition applies what it received (C-ABI ppcsr_group_apply).  Replaces the
+  // per-op hand-over of reference ThreadPoolPPPCSR::submit_* (thread_pool_pppcsr.cpp:96-118).  stats: one per partition.
+  void apply_batch(const uint32_t *src, const uint32_t *dst, const uint32_t *value, size_t count,
+                   std::vector<ppcsr_batch_stats> *stats = nullptr);
 
  private:
+  void build(uint32_t init_n, bool lock_search, bool use_numa);
   std::vector<PCSR> partitions;
   std::vector<size_t> distribution;  // first vertex of every partition
   int partitionsPerDomain;
+  ppcsr_group *group_ = nullptr;     // device-side router over the partitions, (re)created for the largest batch seen
+  size_t group_cap_ = 0;
+  bool group_values_ = false;
 };

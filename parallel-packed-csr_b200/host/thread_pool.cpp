@@ -33,6 +33,13 @@ void ThreadPool::submit_read(int thread_id, int src) {
   reads_.push_back(src);
 }
 
+void ThreadPool::submit_bulk(const uint32_t *src, const uint32_t *dst, const uint32_t *value, size_t count) {
+  src_.insert(src_.end(), src, src + count);
+  dst_.insert(dst_.end(), dst, dst + count);
+  if (value) val_.insert(val_.end(), value, value + count);
+  else val_.insert(val_.end(), count, 1u);
+}
+
 void ThreadPool::start(int threads) {
   (void)threads;
   t0_ = std::chrono::steady_clock::now();

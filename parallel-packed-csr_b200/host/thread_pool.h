@@ -22,6 +22,8 @@ class ThreadPool {
   void submit_add(int thread_id, int src, int dest);
   void submit_delete(int thread_id, int src, int dest);
   void submit_read(int thread_id, int src);
+  // a whole array of updates at once (value 0 = delete, value == nullptr = all adds): what the loaders hand over
+  void submit_bulk(const uint32_t *src, const uint32_t *dst, const uint32_t *value, size_t count);
   void start(int threads);
   void stop();
 

@@ -22,7 +22,22 @@ ThreadPoolPPPCSR::ThreadPoolPPPCSR(const int NUM_OF_THREADS, bool lock_search, u
       firstThreadDomain(available_nodes, 0),
       numThreadsDomain(available_nodes, 0) {
   pcsr = new PPPCSR(init_num_nodes, init_num_nodes, lock_search, available_nodes, partitions_per_domain, use_numa);
-  staged_.resize(pcsr->partition_count());
+  init_tables(NUM_OF_THREADS);
+}
+
+ThreadPoolPPPCSR::ThreadPoolPPPCSR(const int NUM_OF_THREADS, bool lock_search, uint32_t init_num_nodes,
+                                   int partitions_per_domain, bool use_numa, const std::vector<size_t> &boundaries)
+    : finished_(false),
+      available_nodes(usable_gpus(NUM_OF_THREADS)),
+      partitions_per_domain(partitions_per_domain),
+      threadToDomain(NUM_OF_THREADS),
+      firstThreadDomain(available_nodes, 0),
+      numThreadsDomain(available_nodes, 0) {
+  pcsr = new PPPCSR(init_num_nodes, lock_search, partitions_per_domain, use_numa, boundaries);
+  init_tables(NUM_OF_THREADS);
+}
+
+void ThreadPoolPPPCSR::init_tables(int NUM_OF_THREADS) {
   for (std::size_t p = 0; p < pcsr->partition_count(); p++) pcsr->partition(p).print_not_found = false;
   // threads are dealt to domains in contiguous blocks, the first (threads % domains) domains get one more
   const int base = NUM_OF_THREADS / available_nodes, extra = NUM_OF_THREADS % available_nodes;
@@ -37,12 +52,12 @@ ThreadPoolPPPCSR::ThreadPoolPPPCSR(const int NUM_OF_THREADS, bool lock_search, u
 
 ThreadPoolPPPCSR::~ThreadPoolPPPCSR() { delete pcsr; }
 
+// Global ids, submission order: the owner of every op is found ON THE DEVICE when the batch starts (the reference
+// looks it up here, per op: thread_pool_pppcsr.cpp:98).
 void ThreadPoolPPPCSR::stage(int src, int dest, uint32_t value) {
-  const std::size_t p = pcsr->get_partiton((size_t)src);
-  Staged &s = staged_[p];
-  s.src.push_back((uint32_t)src - (uint32_t)pcsr->partition_start(p));  // partition-local id (PPPCSR.cpp:46-52)
-  s.dst.push_back((uint32_t)dest);
-  s.val.push_back(value);
+  src_.push_back((uint32_t)src);
+  dst_.push_back((uint32_t)dest);
+  val_.push_back(value);
 }
 
 void ThreadPoolPPPCSR::submit_add(int thread_id, int src, int dest) {
@@ -57,27 +72,24 @@ void ThreadPoolPPPCSR::submit_read(int thread_id, int src) {
   (void)thread_id;
   reads_.push_back(src);
 }
+void ThreadPoolPPPCSR::submit_bulk(const uint32_t *src, const uint32_t *dst, const uint32_t *value, size_t count) {
+  src_.insert(src_.end(), src, src + count);
+  dst_.insert(dst_.end(), dst, dst + count);
+  if (value) val_.insert(val_.end(), value, value + count);
+  else val_.insert(val_.end(), count, 1u);
+}
 
 void ThreadPoolPPPCSR::start(int threads) {
   (void)threads;
   t0_ = std::chrono::steady_clock::now();
   finished_ = false;
   not_found_ = 0;
-  // one host thread per shard so that shards living on different GPUs overlap
-  std::vector<std::thread> workers;
-  std::vector<ppcsr_batch_stats> stats(staged_.size());
-  for (std::size_t p = 0; p < staged_.size(); p++) {
-    std::cout << "Thread " << p << " has " << staged_[p].src.size() << " tasks, runs on domain "
-              << pcsr->partition(p).device() << std::endl;
-    if (staged_[p].src.empty()) continue;
-    workers.emplace_back([this, p, &stats]() {
-      pcsr->registerThread((int)p);
-      pcsr->partition(p).apply_batch(staged_[p].src, staged_[p].dst, staged_[p].val, &stats[p]);
-      pcsr->unregisterThread((int)p);
-    });
-  }
-  for (auto &w : workers) w.join();
-  for (auto &st : stats) not_found_ += st.n_not_found;
+  std::cout << "Thread 0 has " << src_.size() << " tasks for " << pcsr->partition_count()
+            << " partitions, routed on the device" << std::endl;
+  for (std::size_t p = 0; p < pcsr->partition_count(); p++) pcsr->registerThread((int)p);
+  if (!src_.empty()) pcsr->apply_batch(src_.data(), dst_.data(), val_.data(), src_.size(), &stats_);
+  for (std::size_t p = 0; p < pcsr->partition_count(); p++) pcsr->unregisterThread((int)p);
+  for (auto &st : stats_) not_found_ += st.n_not_found;
   for (int v : reads_) pcsr->read_neighbourhood(v);
 }
 
@@ -94,10 +106,8 @@ void ThreadPoolPPPCSR::stop() {
   if (not_found_) std::cout << "not found " << not_found_ << " edges" << std::endl;
   std::cout << "Elapsed wall clock time: "
             << std::chrono::duration_cast<std::chrono::milliseconds>(t1_ - t0_).count() << std::endl;
-  for (auto &s : staged_) {
-    s.src.clear();
-    s.dst.clear();
-    s.val.clear();
-  }
+  src_.clear();
+  dst_.clear();
+  val_.clear();
   reads_.clear();
 }

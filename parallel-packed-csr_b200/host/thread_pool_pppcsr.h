@@ -18,11 +18,16 @@ class ThreadPoolPPPCSR {
 
   explicit ThreadPoolPPPCSR(const int NUM_OF_THREADS, bool lock_search, uint32_t init_num_nodes,
                             int partitions_per_domain, bool use_numa);
+  // same, with explicit partition boundaries (first vertex of every partition; see PPPCSR.h)
+  explicit ThreadPoolPPPCSR(const int NUM_OF_THREADS, bool lock_search, uint32_t init_num_nodes,
+                            int partitions_per_domain, bool use_numa, const std::vector<size_t> &boundaries);
   ~ThreadPoolPPPCSR();
 
   void submit_add(int thread_id, int src, int dest);
   void submit_delete(int thread_id, int src, int dest);
   void submit_read(int thread_id, int src);
+  // a whole array of updates at once (value 0 = delete, value == nullptr = all adds): what the loaders hand over
+  void submit_bulk(const uint32_t *src, const uint32_t *dst, const uint32_t *value, size_t count);
   void start(int threads);
   void stop();
 
@@ -30,18 +35,18 @@ class ThreadPoolPPPCSR {
   const std::vector<int> &thread_to_domain() const { return threadToDomain; }
   const std::vector<int> &first_thread_of_domain() const { return firstThreadDomain; }
   const std::vector<int> &threads_of_domain() const { return numThreadsDomain; }
+  const std::vector<ppcsr_batch_stats> &last_stats() const { return stats_; }
 
  private:
-  struct Staged {
-    std::vector<uint32_t> src, dst, val;
-  };
   void stage(int src, int dest, uint32_t value);
+  void init_tables(int NUM_OF_THREADS);
 
-  std::vector<Staged> staged_;  // one staging batch per partition, submission order inside
+  std::vector<uint32_t> src_, dst_, val_;  // ONE staging batch of global ids, submission order; routed on the device
   std::vector<int> reads_;
   std::chrono::steady_clock::time_point t0_, t1_;
   std::atomic_bool finished_;
   uint64_t not_found_ = 0;
+  std::vector<ppcsr_batch_stats> stats_;
 
   const int available_nodes;  // GPUs used as "domains"
   int partitions_per_domain = 1;

@@ -166,3 +166,136 @@ def test_two_gpu_all_to_all_vs_oracle(tmp_path, transport):
         assert np.array_equal(z["nn"], nn[lo:hi])
         fin = np.isfinite(opr)
         assert np.allclose(z["pr"][fin], opr[fin], rtol=1e-6, atol=0)
+
+
+def _reference_read_input(text: str, default_val: int):
+    """reference src/main.cpp:29-62 (read_input) restated: stoi / substr(pos + 1) / the op character."""
+    import re
+
+    num = re.compile(r"\s*[+-]?\d+")
+    src, dst, val = [], [], []
+    for line in text.split("\n"):
+        m = num.match(line)
+        if not m:
+            continue
+        m2 = num.match(line[m.end() + 1:])
+        if not m2:
+            continue
+        pos, pos2 = m.end(), m2.end()
+        v = default_val
+        at = pos + 1 + pos2 + 1
+        if at < len(line):
+            v = 1 if line[at] == "1" else 0 if line[at] == "0" else default_val
+        src.append(int(m.group()) & 0xFFFFFFFF)
+        dst.append(int(m2.group()) & 0xFFFFFFFF)
+        val.append(v)
+    return np.array(src, dtype=np.uint32), np.array(dst, dtype=np.uint32), np.array(val, dtype=np.uint32)
+
+
+def test_gpu_text_parser_matches_reference_reader():
+    """ppcsr_parse_edge_list (GPU) against the reference reader's rules on separators, op columns, CRLF, blank and
+    malformed lines, a missing final newline, and a large random file."""
+    rng = np.random.default_rng(5)
+    small = "1 2\n3\t4 1\n5,6,0\n\n7 8 x\n  9   10\n11 12 1\r\n13 14\r\nabc\n15\n16 17"
+    big_s, big_d = rng.integers(0, 1 << 20, 300_000), rng.integers(0, 1 << 20, 300_000)
+    big_o = rng.integers(0, 3, 300_000)
+    big = "".join(f"{s} {d}\n" if o == 2 else f"{s} {d} {o}\n" for s, d, o in zip(big_s, big_d, big_o))
+    for text, dv in ((small, 1), (small, 0), (big, 1), ("", 1), ("42 43", 0)):
+        s, d, v, parsed, top = pp.parse_edge_list(text.encode(), default_val=dv)
+        keep = s != 0xFFFFFFFF  # lines without a parsable pair come out as (SENT, SENT)
+        rs, rd, rv = _reference_read_input(text, dv)
+        assert parsed == rs.size and np.array_equal(s[keep], rs) and np.array_equal(d[keep], rd)
+        assert np.array_equal(v[keep], rv)
+        assert top == (max(int(rs.max()), int(rd.max())) if rs.size else 0)
+
+
+def test_text_binary_and_array_inputs_give_the_same_graph(tmp_path):
+    """the CLI fed with the text file (GPU parser), with the host parser, and with the binary
+    pair file builds the same graph as the arrays through the C-ABI, which equals the oracle's."""
+    build.build_host()
+    scale = 11
+    n = 1 << scale
+    cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
+    us, ud = synth.rmat(scale, 0, 9000, 99)
+    o = O.OraclePCSR(n)
+    o.apply(cs, cd, 1)
+    o.apply(us, ud, 1)
+    rowptr, col, _ = o.export()
+    # arrays vs interleaved pairs through the C-ABI
+    a, b = pp.Shard(n), pp.Shard(n)
+    a.apply(cs, cd, 1)
+    a.apply(us, ud, 1)
+    b.apply_pairs(np.stack([cs, cd], axis=1))
+    b.apply_pairs(np.stack([us, ud], axis=1))
+    for g in (a, b):
+        rp, c = g.export()
+        assert np.array_equal(rp, rowptr) and np.array_equal(c, col)
+    want = a.checksum()
+    # the CLI: text (GPU parse), text (host parse), binary pairs -- same checksum line
+    core_t, upd_t = str(tmp_path / "core.txt"), str(tmp_path / "upd.txt")
+    core_b, upd_b = str(tmp_path / "core.bin"), str(tmp_path / "upd.bin")
+    synth.write_text(core_t, cs, cd)
+    synth.write_text(upd_t, us, ud)
+    np.stack([cs, cd], axis=1).astype("<u4").tofile(core_b)
+    np.stack([us, ud], axis=1).astype("<u4").tofile(upd_b)
+    outs = []
+    for extra, core, upd in (([], core_t, upd_t), (["-host_parse"], core_t, upd_t), ([], core_b, upd_b)):
+        cmd = [build.CLI, "-threads=4", "-insert", "-size=9000", "-ppcsr", *extra, f"-core_graph={core}",
+               f"-update_file={upd}", "-check", "-checksum"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("Graph checksum: ")]
+        assert len(line) == 1 and "PMA invariants: ok" in r.stdout
+        outs.append(line[0])
+    assert outs[0] == outs[1] == outs[2]
+    assert outs[0] == f"Graph checksum: edges {want['edges']} edge_hash {want['edge_hash']:016x}"
+
+
+@pytest.mark.parametrize("parts", [1, 3, 4])
+def test_group_route_on_one_gpu(parts):
+    """ppcsr_group_* (the C++ data plane of PPPCSR / ThreadPoolPPPCSR): several shards driven by one process, the
+    batch binned on the device and stored into the owners' receive buffers.  All shards on GPU 0 here (the peer
+    pointers are then plain device pointers); mixed stream with values; compared with the oracle."""
+    n, m = 5000, 60000
+    rng = np.random.default_rng(parts)
+    src, dst = rng.integers(0, n, m), rng.integers(0, n, m)
+    val = np.where(rng.integers(0, 4, m) != 0, rng.integers(1, 1000, m), 0)
+    starts = np.array([0] + sorted(rng.choice(np.arange(1, n), parts - 1, replace=False).tolist()) + [n], dtype=np.uint64)
+    g = pp.Group(n, starts, [0] * parts, region_cap=m // parts + 1, with_values=True)
+    o = O.OraclePCSR(n)
+    for lo in range(0, m, 20000):
+        sl = slice(lo, lo + 20000)
+        st = g.apply(src[sl], dst[sl], val[sl])
+        assert sum(x["batch_size"] for x in st) == 20000
+        o.apply(src[sl], dst[sl], val[sl])
+    rowptr, col, nn = o.export()
+    for r, sh in enumerate(g.shards):
+        lo, hi = int(starts[r]), int(starts[r + 1])
+        rp, c = sh.export()
+        assert np.array_equal(rp, rowptr[lo:hi + 1] - rowptr[lo]), r
+        assert np.array_equal(c, col[int(rowptr[lo]):int(rowptr[hi])]), r
+        assert np.array_equal(sh.num_neighbors(), nn[lo:hi]), r
+        assert not sh.check(True).violations(True)
+        assert g.owner(lo) == r and g.owner(hi - 1) == r
+    g.close()
+
+
+def test_cli_pppcsr_device_route_matches_ppcsr(tmp_path):
+    """-pppcsrnuma (partitions fed through the device-side group route, reference and -balanced boundaries) builds the
+    same logical graph as -ppcsr: same checksum line."""
+    build.build_host()
+    scale = 12
+    cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
+    idx = synth.sample_without_replacement(16 << scale, 20000, 7)
+    core, upd = str(tmp_path / "core.bin"), str(tmp_path / "upd.bin")
+    np.stack([cs, cd], axis=1).astype("<u4").tofile(core)
+    np.stack([cs[idx], cd[idx]], axis=1).astype("<u4").tofile(upd)
+    sums = []
+    for mode in (["-ppcsr"], ["-pppcsrnuma", "-partitions_per_domain=3"], ["-pppcsr", "-partitions_per_domain=4", "-balanced"]):
+        cmd = [build.CLI, "-threads=8", "-delete", "-size=20000", *mode, f"-core_graph={core}", f"-update_file={upd}",
+               "-check", "-checksum"]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "PMA invariants: ok" in r.stdout
+        sums.append([l for l in r.stdout.splitlines() if l.startswith("Graph checksum: ")][0])
+    assert sums[0] == sums[1] == sums[2]
