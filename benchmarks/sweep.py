@@ -114,7 +114,8 @@ def main():
                 "ms_pagerank": float(t[1]),
                 "stages_ms_rank0": {k: round(stats[k], 4) for k in ("ms_sort", "ms_locate", "ms_select", "ms_rebalance")},
                 "windows_rank0": int(stats["n_windows"]), "whole_array_rank0": int(stats["whole_array"]),
-                "slots_rank0": int(stats["slots_after"]), "kernel_launches_rank0": int(stats["kernel_launches"])}), flush=True)
+                "slots_rank0": int(stats["slots_after"]), "kernel_launches_rank0": int(stats["kernel_launches"]),
+                "sparse_path_rank0": int(stats.get("sparse_path", 0))}), flush=True)
         B *= 10
     if dist is not None:
         dist.destroy_process_group()

@@ -87,7 +87,7 @@ typedef struct {
   float ms_rebalance;      /* scan + scatter rebalance (+ copy back for multi-CTA windows)   */
   float ms_rebalance_kernel; /* the k_rebalance launch alone (roofline numerator: rebalance_bytes / this) */
   uint32_t kernel_launches;  /* kernels launched for this batch                                */
-  uint32_t reserved0;
+  uint32_t sparse_path;      /* 1 if the batch took the small-batch path (O(touched leaves) work, one host sync) */
 } ppcsr_batch_stats;
 
 typedef struct {

@@ -31,7 +31,7 @@ class BatchStats(C.Structure):
         "n_windows", "window_slots", "rebalance_bytes", "slots_before", "slots_after")] + [
         ("resized", C.c_uint32), ("whole_array", C.c_uint32)] + [(n, C.c_float) for n in (
             "ms_total", "ms_sort", "ms_locate", "ms_select", "ms_rebalance", "ms_rebalance_kernel")] + [
-        ("kernel_launches", C.c_uint32), ("reserved0", C.c_uint32)]
+        ("kernel_launches", C.c_uint32), ("sparse_path", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

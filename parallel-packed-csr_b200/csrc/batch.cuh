@@ -275,26 +275,30 @@ __device__ __forceinline__ bool find_in(const uint32_t *D, uint32_t doff, const 
 //     remove misses iff the previous op on the same key in this batch was a remove, or it is the key's first op and
 //     the edge is absent;
 //   * the segmented search of every winner (find_in), overwrite / tombstone in place, per-leaf insert / delete counts;
-//   * the compacted, key-ordered insert list (dst, value, predecessor slot): scan of the insert flags over the tile,
-//     the tile's base from a decoupled look-back over the earlier tiles (one epoch-tagged word per tile in scan_state,
-//     same protocol as prim::k_scan_onepass; tiles are the CTAs in launch order, as in CUB's single-pass scans; every
-//     lane examines LB_DEPTH predecessors per step so that a whole wave of resident CTAs is covered in a few steps).
+//   * the tile's inserts (dst, value, predecessor slot), compacted in key order into the TILE'S OWN region of a scratch
+//     list, and the tile's insert count: a scan over the tile counts and k_gather_inserts then make the global
+//     key-ordered insert list.  (Measured: resolving the global offset inside this kernel by a decoupled look-back
+//     costs far more than the extra copy -- tile times vary widely (hub tiles search global memory), and with a
+//     look-back every tile waits for the slowest tile before it while holding its SM slot: 3.6 -> 5.2..6.9 ms on the
+//     100 M-update batch.)
 // Both sequences are sorted, so the tile's updates land in ONE contiguous slot window of the packed array: from the
 // first key's source vertex to the end of the last key's -- or, when a hub vertex makes that too long, between the
-// positions of the tile's first and last key (two searches by two threads).  A window of <= LCAP slots is STAGED in
-// shared memory with coalesced 16-byte loads and every search of the tile runs there (measured on the per-element
-// kernel: 17 cycles of long-scoreboard stall per issued instruction, ~5 dependent DRAM/L2 round trips per update; the
-// leaf-level loop alone was 28 % of the instructions because a hub's range spans 15 levels -- the window caps it at
-// log2(LCAP / leaf)); longer windows are searched in global memory, clipped to the window all the same.
+// end of the last key's.  A window of <= LCAP slots is STAGED in shared memory with coalesced 16-byte loads and every
+// search of the tile runs there (measured on the per-element kernel: 17 cycles of long-scoreboard stall per issued
+// instruction, ~5 dependent DRAM/L2 round trips per update); longer windows (hub vertices) are searched in global
+// memory like before.
 constexpr int LT = 256;         // threads of a locate CTA
 constexpr int LI = 2;           // sorted updates per thread
 constexpr int LTILE = LT * LI;  // updates per tile
+// Window capacity, measured on B200 (locate stage, ms: 100 M skewed updates into 2^29 slots / 10 M uniform into 2^25 /
+// 10 M deletes): 8192 slots (47 KB of shared memory, 4 CTAs per SM) 4.68 / 0.357 / 0.410; 4096 (7 CTAs) 3.45 / 0.265 /
+// 0.295; 2048 (8 CTAs = all 64 warps) 3.27 / 0.251 / 0.286; the per-element kernel with a separate three-pass
+// compaction it replaces: 3.63 / 0.276 / 0.308.  Resident warps matter more than the share of tiles that is staged.
 #ifndef PPCSR_LOC_CAP
-#define PPCSR_LOC_CAP 8192
+#define PPCSR_LOC_CAP 2048
 #endif
-constexpr int LCAP = PPCSR_LOC_CAP;    // slots of dest[] a tile can stage (32 KB)
+constexpr int LCAP = PPCSR_LOC_CAP;    // slots of dest[] a tile can stage
 constexpr int LCAP_LEAVES = LCAP / 8;  // leaves are >= 8 slots
-constexpr int LB_DEPTH = 4;            // look-back: predecessors examined per lane and step
 
 struct LocSmem {
   uint32_t dest[LCAP];         // staged window of dest[]
@@ -304,7 +308,6 @@ struct LocSmem {
   uint32_t warp[33];
   uint32_t stat[8];
   uint32_t win[4];             // window [a, b), mode (0 nothing to search, 1 staged, 2 global), valid keys
-  uint32_t prefix;
 };
 
 __global__ void __launch_bounds__(LT) k_locate(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay,
@@ -312,10 +315,18 @@ __global__ void __launch_bounds__(LT) k_locate(const uint64_t *__restrict__ keys
                                                const uint32_t *__restrict__ dest, uint32_t *__restrict__ val,
                                                const uint32_t *__restrict__ leaf_cnt, const uint32_t *__restrict__ beg,
                                                uint32_t ls, uint32_t n_slots, uint32_t *__restrict__ nn,
-                                               uint32_t *__restrict__ ins_dst, uint32_t *__restrict__ ins_val,
-                                               uint32_t *__restrict__ ins_pred, unsigned long long *scan_state,
-                                               uint32_t scan_epoch, uint32_t *__restrict__ ins_cnt,
-                                               uint32_t *__restrict__ del_cnt, uint32_t op_bit, BatchScalars *sc) {
+                                               uint32_t *__restrict__ tile_dst, uint32_t *__restrict__ tile_val,
+                                               uint32_t *__restrict__ tile_pred, uint32_t *__restrict__ tile_cnt,
+                                               uint32_t *__restrict__ ins_cnt, uint32_t *__restrict__ del_cnt,
+                                               uint32_t op_bit, BatchScalars *sc, uint32_t *touched,
+                                               uint32_t *touch_stamp, uint32_t touch_epoch, uint32_t dst_mask) {
+  // Small-batch path (touched != nullptr, sparse.cuh): the batch was sorted on a SPECULATED dst width (no host round
+  // trip after the key builder); a dst beyond it means the order is wrong -- leave before anything is modified, the
+  // host runs the batch again the general way.  The first update to reach a leaf appends it to the touched list.
+  if (touched && (sc->dst_or & ~dst_mask)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc->sparse_abort = 1u;
+    return;
+  }
   extern __shared__ __align__(16) unsigned char loc_smem_raw[];
   LocSmem &S = *reinterpret_cast<LocSmem *>(loc_smem_raw);
   const uint32_t tid = threadIdx.x;
@@ -345,27 +356,26 @@ __global__ void __launch_bounds__(LT) k_locate(const uint64_t *__restrict__ keys
       const uint32_t leaf = 1u << ls;
       a = (beg[s0] >> ls) << ls;
       b = (uint32_t)min((unsigned long long)n_slots, (((unsigned long long)beg[s1 + 1] + leaf - 1u) >> ls) << ls);
-      mode = (b - a <= (uint32_t)LCAP) ? 1u : 3u;  // 3: too long, refine with the positions of the end keys
+      mode = (b - a <= (uint32_t)LCAP) ? 1u : 2u;
     }
     S.win[0] = a;
     S.win[1] = b;
     S.win[2] = mode;
     S.win[3] = nv;
   }
-  __syncthreads();
-  if (S.win[2] == 3u) {
-    if (tid == 0 || tid == 32) {  // two warps: the two searches run side by side
-      const uint64_t k = S.key[tid == 0 ? 1u : S.win[3]] & km;
-      const uint32_t s = (uint32_t)(k >> 32);
-      uint32_t slot;
-      find_in(dest, 0u, leaf_cnt, 0u, beg[s], beg[s + 1], true, ls, (uint32_t)k, &slot);
-      if (tid == 0) S.win[0] = (slot >> ls) << ls;  // hit or predecessor of the smallest key: nothing lies below
-      else S.win[1] = ((slot >> ls) + 1u) << ls;    // ... of the largest key: nothing lies above its leaf
+  // the vertex ranges of my updates do not depend on the window: their loads fly while thread 0 finds it
+  uint32_t vb[LI], ve[LI];
+#pragma unroll
+  for (int r = 0; r < LI; r++) {
+    vb[r] = ve[r] = 0u;
+    const uint32_t e = r * LT + tid;
+    const uint64_t k = S.key[e + 1] & km;
+    if (e < tile_n && k < invalid_key) {
+      vb[r] = beg[(uint32_t)(k >> 32)];
+      ve[r] = beg[(uint32_t)(k >> 32) + 1u];
     }
-    __syncthreads();
-    if (tid == 0) S.win[2] = (S.win[1] - S.win[0] <= (uint32_t)LCAP) ? 1u : 2u;
-    __syncthreads();
   }
+  __syncthreads();
   const uint32_t wa = S.win[0], wb = S.win[1], mode = S.win[2];
   if (mode == 1u) {  // stage the window: coalesced 16-byte loads (wa is leaf aligned, leaves are >= 32 bytes)
     for (uint32_t x = tid * 4u; x < wb - wa; x += LT * 4u)
@@ -409,14 +419,8 @@ __global__ void __launch_bounds__(LT) k_locate(const uint64_t *__restrict__ keys
             first_del = value_at(h) == 0;
           }
           const uint32_t d = (uint32_t)k;
-          uint32_t bb = beg[s], ee = beg[s + 1], slot;
-          bool skip = true;
-          if (bb < wa) {  // clipped from below: the window starts inside this vertex's range, at a leaf whose first
-            bb = wa;      // item is <= the tile's smallest key
-            skip = false;
-          }
-          ee = min(ee, wb);
-          const bool hit = find_in(D, doff, C, coff, bb, ee, skip, ls, d, &slot);
+          uint32_t slot;
+          const bool hit = find_in(D, doff, C, coff, vb[r], ve[r], true, ls, d, &slot);
           if (v != 0) {
             cls = hit ? CLS_OVERWRITE : CLS_INSERT;
             if (hit) val[slot] = v;  // duplicate insert overwrites the value (reference PCSR.cpp:529-532)
@@ -469,6 +473,14 @@ __global__ void __launch_bounds__(LT) k_locate(const uint64_t *__restrict__ keys
       const unsigned m5 = __ballot_sync(0xFFFFFFFFu, miss_first);
       const unsigned m4 = __ballot_sync(0xFFFFFFFFu, winner);
       const unsigned m6 = __ballot_sync(0xFFFFFFFFu, first_touch);
+      if (touched) {  // one entry per leaf and batch, whatever touched it first; the warp takes its places in one go
+        const bool fresh = first_touch && atomicExch(&touch_stamp[leaf], touch_epoch) != touch_epoch;
+        const unsigned fm = __ballot_sync(0xFFFFFFFFu, fresh);
+        unsigned long long at = 0;
+        if (fm && lane_id() == (unsigned)(__ffs(fm) - 1)) at = atomicAdd(&sc->n_touched, (unsigned long long)__popc(fm));
+        at = __shfl_sync(0xFFFFFFFFu, at, fm ? __ffs(fm) - 1 : 0);
+        if (fresh) touched[at + __popc(fm & lt)] = leaf;
+      }
       if (lane_id() == 0) {
         if (m6) atomicAdd(&S.stat[5], (uint32_t)__popc(m6));
         if (m0) atomicAdd(&S.stat[0], (uint32_t)__popc(m0));
@@ -492,65 +504,42 @@ __global__ void __launch_bounds__(LT) k_locate(const uint64_t *__restrict__ keys
     }
     total += t;
   }
-  if (tid < 32) {  // warp 0: publish the tile's count, then add up the tiles before it
-    const unsigned lane = tid;
-    const uint32_t tile = blockIdx.x;
-    volatile unsigned long long *st = scan_state;
-    if (lane == 0) st[tile] = prim::scan_word(tile == 0 ? prim::SCAN_ST_INC : prim::SCAN_ST_AGG, scan_epoch, total);
-    uint32_t prefix = 0;
-    if (tile > 0) {
-      int64_t j = (int64_t)tile - 1;  // lane l examines the tiles j - l - 32 u, u < LB_DEPTH
-      for (;;) {
-        unsigned long long w[LB_DEPTH];
-#pragma unroll
-        for (int u = 0; u < LB_DEPTH; u++) {
-          const int64_t t = j - (int64_t)(u * 32 + lane);
-          // tiles before the first one count as an inclusive prefix of zero
-          w[u] = t >= 0 ? st[t] : prim::scan_word(prim::SCAN_ST_INC, scan_epoch, 0u);
-        }
-        uint32_t sum = 0;
-        bool done = false, again = false;
-#pragma unroll
-        for (int u = 0; u < LB_DEPTH; u++) {
-          if (done || again) continue;  // warp-uniform
-          const bool ready = (uint32_t)((w[u] >> 32) & 0x3FFFFFFFu) == scan_epoch && (w[u] >> 62) != 0ull;
-          const unsigned inc = __ballot_sync(0xFFFFFFFFu, ready && (w[u] >> 62) == 2ull);
-          const unsigned not_ready = __ballot_sync(0xFFFFFFFFu, !ready);
-          const unsigned first_inc = inc ? (unsigned)__ffs(inc) - 1u : 32u;
-          const unsigned need = first_inc < 32u ? (2u << first_inc) - 1u : 0xFFFFFFFFu;  // lanes 0..first_inc
-          if (not_ready & need) {
-            again = true;  // a tile this window depends on has not published yet: read the window again
-            continue;
-          }
-          uint32_t x = (need >> lane) & 1u ? (uint32_t)w[u] : 0u;
-#pragma unroll
-          for (int dd = 16; dd > 0; dd >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, dd);
-          sum += x;
-          done = first_inc < 32u;
-        }
-        if (again) continue;
-        prefix += sum;
-        if (done) break;
-        j -= 32 * LB_DEPTH;
-      }
-      if (lane == 0) st[tile] = prim::scan_word(prim::SCAN_ST_INC, scan_epoch, prefix + total);
-    }
-    if (lane == 0) {
-      S.prefix = prefix;
-      if (S.stat[0]) atomicAdd(&sc->n_inserted, (unsigned long long)S.stat[0]);
-      if (S.stat[1]) atomicAdd(&sc->n_overwritten, (unsigned long long)S.stat[1]);
-      if (S.stat[2]) atomicAdd(&sc->n_deleted, (unsigned long long)S.stat[2]);
-      if (S.stat[3]) atomicAdd(&sc->n_not_found, (unsigned long long)S.stat[3]);
-      if (S.stat[4]) atomicAdd(&sc->n_unique, (unsigned long long)S.stat[4]);
-      if (S.stat[5]) atomicAdd(&sc->n_touched_est, (unsigned long long)S.stat[5]);
-    }
+  if (tid == 0) {
+    tile_cnt[blockIdx.x] = total;
+    if (S.stat[0]) atomicAdd(&sc->n_inserted, (unsigned long long)S.stat[0]);
+    if (S.stat[1]) atomicAdd(&sc->n_overwritten, (unsigned long long)S.stat[1]);
+    if (S.stat[2]) atomicAdd(&sc->n_deleted, (unsigned long long)S.stat[2]);
+    if (S.stat[3]) atomicAdd(&sc->n_not_found, (unsigned long long)S.stat[3]);
+    if (S.stat[4]) atomicAdd(&sc->n_unique, (unsigned long long)S.stat[4]);
+    if (S.stat[5]) atomicAdd(&sc->n_touched_est, (unsigned long long)S.stat[5]);
   }
   __syncthreads();
-  const uint32_t at0 = S.prefix;
-  for (uint32_t x = tid; x < total; x += LT) {  // coalesced
-    ins_dst[at0 + x] = S.o_dst[x];
-    ins_val[at0 + x] = S.o_val[x];
-    ins_pred[at0 + x] = S.o_pred[x];
+  for (uint32_t x = tid; x < total; x += LT) {  // coalesced, into the tile's own region
+    tile_dst[base + x] = S.o_dst[x];
+    tile_val[base + x] = S.o_val[x];
+    tile_pred[base + x] = S.o_pred[x];
+  }
+}
+
+// the tiles' insert runs, moved to their place in the global key-ordered insert list (tile_off = exclusive scan of the
+// tile counts)
+__global__ void __launch_bounds__(LT) k_gather_inserts(const uint32_t *__restrict__ tile_dst,
+                                                       const uint32_t *__restrict__ tile_val,
+                                                       const uint32_t *__restrict__ tile_pred,
+                                                       const uint32_t *__restrict__ tile_off,
+                                                       uint32_t *__restrict__ ins_dst, uint32_t *__restrict__ ins_val,
+                                                       uint32_t *__restrict__ ins_pred, uint32_t *ins_first,
+                                                       uint32_t ls, const BatchScalars *sc) {
+  if (ins_first && sc->sparse_abort) return;  // small-batch path: k_locate left without doing anything
+  const uint32_t off = tile_off[blockIdx.x], cnt = tile_off[blockIdx.x + 1] - off;
+  const size_t base = (size_t)blockIdx.x * LTILE;
+  for (uint32_t x = threadIdx.x; x < cnt; x += LT) {
+    const uint32_t pred = tile_pred[base + x];
+    ins_dst[off + x] = tile_dst[base + x];
+    ins_val[off + x] = tile_val[base + x];
+    ins_pred[off + x] = pred;
+    // small-batch path: where the inserts of every leaf begin (instead of a scan over all leaves)
+    if (ins_first && (x == 0 || (tile_pred[base + x - 1] >> ls) != (pred >> ls))) atomicMin(&ins_first[pred >> ls], off + x);
   }
 }
 

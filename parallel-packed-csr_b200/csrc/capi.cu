@@ -14,11 +14,15 @@
 #include "queries.cuh"
 #include "rebalance.cuh"
 #include "sort.cuh"
+#include "sparse.cuh"
 #include "windows.cuh"
 
 thread_local std::string g_ppcsr_error;
 
 namespace {
+
+constexpr uint64_t SPARSE_MAX_BATCH = 1ull << 17;  // largest batch the small-batch path (sparse.cuh) takes
+
 
 int bits_of(uint64_t x) { return x == 0 ? 0 : ppcsr_bsr(x) + 1; }
 
@@ -34,6 +38,15 @@ int reserve_leaf_arrays(ppcsr_shard *s, const Geometry &g) {
   PPCSR_TRY(dev_reserve(s->del_cnt, L, s->stream));
   PPCSR_TRY(dev_reserve(s->rank_off, L + 1, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_off, L + 1, s->stream));
+  const uint32_t *old_ins = s->ins_first.p;
+  PPCSR_TRY(dev_reserve(s->ins_first, L, s->stream));
+  if (s->ins_first.p != old_ins) s->cnt_clean = false;  // fresh counters: the next small batch clears them first
+  const size_t old_stamp = s->touch_stamp.cap;
+  PPCSR_TRY(dev_reserve(s->touch_stamp, L, s->stream));
+  if (s->touch_stamp.cap != old_stamp) {
+    CUDA_TRY(cudaMemsetAsync(s->touch_stamp.p, 0, s->touch_stamp.cap * sizeof(uint32_t), s->stream));
+    s->touch_epoch = 0;
+  }
   const size_t old_mark = s->mark.cap;
   PPCSR_TRY(dev_reserve(s->mark, 2 * L, s->stream));
   if (s->mark.cap != old_mark) {
@@ -44,8 +57,9 @@ int reserve_leaf_arrays(ppcsr_shard *s, const Geometry &g) {
 }
 
 int reserve_batch_arrays(ppcsr_shard *s, size_t count) {
-  PPCSR_TRY(dev_reserve(s->key_a, count, s->stream));
-  PPCSR_TRY(dev_reserve(s->key_b, count, s->stream));
+  // the key buffers double as the locate tiles' scratch list (whole tiles): room for one more tile
+  PPCSR_TRY(dev_reserve(s->key_a, count + batch::LTILE, s->stream));
+  PPCSR_TRY(dev_reserve(s->key_b, count + batch::LTILE, s->stream));
   PPCSR_TRY(dev_reserve(s->pay_a, count, s->stream));
   PPCSR_TRY(dev_reserve(s->pay_b, count, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_dst, count, s->stream));
@@ -320,6 +334,7 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
   std::swap(s->dest, s->dest_alt);
   std::swap(s->val, s->val_alt);
   s->geo = g2;
+  s->cnt_clean = false;
   PPCSR_TRY(reserve_leaf_arrays(s, g2));
   if (!A.leaf_cnt_out)  // the one-chunk-per-CTA kernel leaves the counts in the tree only
     reb::k_copy_u32<<<div_up(g2.n_leaves, 256), 256, 0, s->stream>>>(s->leaf_cnt.p, s->tree.p + g2.n_leaves,
@@ -702,7 +717,8 @@ void ppcsr_destroy(ppcsr_shard *s) {
   dev_free(s->in_src); dev_free(s->in_dst); dev_free(s->in_val); dev_free(s->ukey); dev_free(s->uval);
   dev_free(s->uloc); dev_free(s->ucls); dev_free(s->ufirst); dev_free(s->ins_dst); dev_free(s->ins_val); dev_free(s->ins_pred);
   dev_free(s->block_tmp); dev_free(s->hist); dev_free(s->pr_acc); dev_free(s->misc);
-  dev_free(s->scan_state); dev_free(s->scan_ticket);
+  dev_free(s->scan_state); dev_free(s->scan_ticket); dev_free(s->tile_cnt);
+  dev_free(s->touch_stamp); dev_free(s->ins_first); dev_free(s->touched_flags);
   dev_free(s->snap.dest); dev_free(s->snap.val); dev_free(s->snap.leaf_cnt); dev_free(s->snap.tree);
   dev_free(s->snap.beg); dev_free(s->snap.nn);
   for (auto &P : s->pending) {
@@ -751,6 +767,11 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
     PPCSR_TRY(dev_reserve(s->tree, (size_t)2 * g.n_leaves, s->stream, true));
     PPCSR_TRY(dev_reserve(s->ins_cnt, g.n_leaves, s->stream, true));
     PPCSR_TRY(dev_reserve(s->del_cnt, g.n_leaves, s->stream, true));
+    PPCSR_TRY(dev_reserve(s->ins_first, g.n_leaves, s->stream));
+    PPCSR_TRY(dev_reserve(s->touch_stamp, g.n_leaves, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->touch_stamp.p, 0, s->touch_stamp.cap * sizeof(uint32_t), s->stream));
+    s->touch_epoch = 0;
+    s->cnt_clean = false;
     PPCSR_TRY(dev_reserve(s->rank_off, (size_t)g.n_leaves + 1, s->stream));
     PPCSR_TRY(dev_reserve(s->ins_off, (size_t)g.n_leaves + 1, s->stream));
     PPCSR_TRY(dev_reserve(s->mark, (size_t)2 * g.n_leaves, s->stream));
@@ -782,7 +803,8 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
 // shared by the (src,dst) and the packed entry points: `packed` != nullptr selects the packed key builder
 static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint32_t *d_dst, const uint64_t *d_packed,
                                const uint32_t *d_val, uint64_t count, uint32_t default_val, ppcsr_batch_stats *stats,
-                               const batch::SegmentTable *segments = nullptr, bool pairs = false) {
+                               const batch::SegmentTable *segments = nullptr, bool pairs = false,
+                               bool no_sparse = false) {
   PPCSR_TRY(set_device(s));
   ppcsr_batch_stats st{};
   st.batch_size = count;
@@ -800,7 +822,7 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   const Geometry g = s->geo;
   PPCSR_TRY(reserve_worst_case(s, count));  // before anything is modified: see reserve_worst_case
   if (segments) {  // only an upper bound of the batch size is known: the keys (and values) are sized for it
-    PPCSR_TRY(dev_reserve(s->key_a, count, s->stream));
+    PPCSR_TRY(dev_reserve(s->key_a, count + batch::LTILE, s->stream));
     if (d_val) PPCSR_TRY(dev_reserve(s->pay_a, count, s->stream));
   } else {
     PPCSR_TRY(reserve_batch_arrays(s, count));
@@ -828,33 +850,50 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
                                                         has_pay ? s->pay_a.p : nullptr, sc);
   }
   CUDA_TRY(cudaGetLastError());
-  PPCSR_TRY(read_scalars(s));
-  if (segments) {  // the real batch size arrives with the sort width
-    if (s->h_scalars->seg_total > count) {
-      g_ppcsr_error = "the peers deposited more records than max_total allows";
-      return PPCSR_ERR_CAPACITY;
-    }
-    count = s->h_scalars->seg_total;
-    st.batch_size = count;
-    if (count == 0) {
-      s->last = st;
-      if (stats) *stats = st;
-      return PPCSR_OK;
-    }
-    PPCSR_TRY(reserve_batch_arrays(s, count));
-  }
-  const int lo_bits = std::max(1, bits_of(s->h_scalars->dst_or));
-  // rejected updates carry the key (n << 32): they need bits_of(n) source bits, valid ones bits_of(n-1)
-  const int hi_bits = std::max(1, s->h_scalars->n_ignored ? bits_of(s->n) : bits_of(s->n ? s->n - 1 : 0));
-  // 2. stable radix sort by (src,dst); the values travel as payload unless they are all the same
+  // Small-batch path (sparse.cuh): no host round trip here -- the sort width is speculated from the dsts seen so far
+  // (k_locate checks it on the device) -- and none for the windows; see below.
+  static const int env_sparse = [] {
+    const char *e = getenv("PPCSR_SPARSE");
+    return !e ? 0 : std::string(e) == "never" ? -1 : std::string(e) == "always" ? 1 : 0;
+  }();
+  const bool sparse = !no_sparse && !segments && env_sparse >= 0 && s->sparse_policy >= 0 && s->whole_policy <= 0 &&
+                      g.n_leaves >= 1024 && count <= SPARSE_MAX_BATCH && (count * 4 <= g.n_leaves || env_sparse > 0);
+  const uint32_t dst_spec = s->dst_or_seen | (s->n ? s->n - 1u : 0u);
+  int lo_bits, hi_bits;
   bool sort_pay = has_pay;
-  if (op_bit) {
-    const uint32_t vmax = s->h_scalars->val_max, vmin = ~s->h_scalars->val_inv_min;
-    if (vmax == 0u || vmax == vmin) {  // removes only, or ONE non-zero value: the key's op bit says it all
-      sort_pay = false;
-      default_val = vmax ? vmax : 1u;
+  if (sparse) {
+    lo_bits = std::max(1, bits_of(dst_spec));
+    hi_bits = std::max(1, bits_of(s->n));  // wide enough for the rejected key (n << 32) too
+  } else {
+    PPCSR_TRY(read_scalars(s));
+    s->dst_or_seen |= s->h_scalars->dst_or;
+    if (segments) {  // the real batch size arrives with the sort width
+      if (s->h_scalars->seg_total > count) {
+        g_ppcsr_error = "the peers deposited more records than max_total allows";
+        return PPCSR_ERR_CAPACITY;
+      }
+      count = s->h_scalars->seg_total;
+      st.batch_size = count;
+      if (count == 0) {
+        s->last = st;
+        if (stats) *stats = st;
+        return PPCSR_OK;
+      }
+      PPCSR_TRY(reserve_batch_arrays(s, count));
+    }
+    lo_bits = std::max(1, bits_of(s->h_scalars->dst_or));
+    // rejected updates carry the key (n << 32): they need bits_of(n) source bits, valid ones bits_of(n-1)
+    hi_bits = std::max(1, s->h_scalars->n_ignored ? bits_of(s->n) : bits_of(s->n ? s->n - 1 : 0));
+    // the values travel as payload unless they are all the same
+    if (op_bit) {
+      const uint32_t vmax = s->h_scalars->val_max, vmin = ~s->h_scalars->val_inv_min;
+      if (vmax == 0u || vmax == vmin) {  // removes only, or ONE non-zero value: the key's op bit says it all
+        sort_pay = false;
+        default_val = vmax ? vmax : 1u;
+      }
     }
   }
+  // 2. stable radix sort by (src,dst)
   uint64_t *keys;
   uint32_t *pay;
   PPCSR_TRY(prim::radix_sort_pairs(s, s->key_a.p, sort_pay ? s->pay_a.p : nullptr, s->key_b.p, s->pay_b.p, count,
@@ -862,13 +901,33 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
   // 3+4. call counts, last-op-wins, locate, per-leaf counts -- one kernel over the sorted batch
   const uint64_t invalid_key = (uint64_t)s->n << 32;
-  CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
-  CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
-  // one CTA per tile of sorted updates; the kernel also compacts the key-ordered insert list (look-back over its
-  // tiles: one scan_state word each)
+  if (sparse) {  // the per-leaf batch counters are kept clear between small batches: no O(leaves) fill per batch
+    PPCSR_TRY(dev_reserve(s->touched_flags, std::min<size_t>(g.n_leaves, count) + 1, s->stream));
+    if (!s->cnt_clean) {
+      CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+      CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+      CUDA_TRY(cudaMemsetAsync(s->ins_first.p, 0xFF, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+      s->cnt_clean = true;
+    }
+    if (++s->touch_epoch == 0u) {  // the stamps wrapped: no old stamp may look current
+      CUDA_TRY(cudaMemsetAsync(s->touch_stamp.p, 0, s->touch_stamp.cap * sizeof(uint32_t), s->stream));
+      s->touch_epoch = 1u;
+    }
+  } else {
+    CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
+    s->cnt_clean = false;
+  }
+  s->last_sparse = false;
+  // one CTA per tile of sorted updates; every tile leaves its inserts, compacted, in its own region of a scratch list
+  // (the sort's spare key buffer holds dst and value, uloc the predecessor slots); a scan of the tile counts and a
+  // gather make the global key-ordered insert list
   const unsigned lblocks = div_up(count, batch::LTILE);
-  PPCSR_TRY(prim::reserve_scan_state(s, lblocks));
-  s->scan_epoch++;
+  const size_t padded = (size_t)lblocks * batch::LTILE;
+  uint64_t *spare = keys == s->key_a.p ? s->key_b.p : s->key_a.p;
+  uint32_t *tile_dst = reinterpret_cast<uint32_t *>(spare), *tile_val = tile_dst + padded;
+  PPCSR_TRY(dev_reserve(s->uloc, padded, s->stream));
+  PPCSR_TRY(dev_reserve(s->tile_cnt, (size_t)lblocks + 1, s->stream));
   {  // > 48 KB of dynamic shared memory needs an explicit opt-in: per device, once, thread-safe
     static std::once_flag once[64];
     static cudaError_t once_err[64];
@@ -881,9 +940,82 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   }
   batch::k_locate<<<lblocks, batch::LT, sizeof(batch::LocSmem), s->stream>>>(
       keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
-      (uint32_t)g.N, s->nn.p, s->ins_dst.p, s->ins_val.p, s->ins_pred.p, s->scan_state.p, s->scan_epoch, s->ins_cnt.p,
-      s->del_cnt.p, op_bit, sc);
+      (uint32_t)g.N, s->nn.p, tile_dst, tile_val, s->uloc.p, s->tile_cnt.p, s->ins_cnt.p, s->del_cnt.p, op_bit, sc,
+      sparse ? s->touched.p : nullptr, s->touch_stamp.p, s->touch_epoch,
+      lo_bits >= 32 ? 0xFFFFFFFFu : ((1u << lo_bits) - 1u));
+  PPCSR_TRY(prim::device_scan(s, prim::InArray{s->tile_cnt.p}, prim::OutPrefixWithTotal{s->tile_cnt.p, lblocks},
+                              lblocks, nullptr, nullptr));
+  s->launches++;
+  batch::k_gather_inserts<<<lblocks, batch::LT, 0, s->stream>>>(tile_dst, tile_val, s->uloc.p, s->tile_cnt.p,
+                                                               s->ins_dst.p, s->ins_val.p, s->ins_pred.p,
+                                                               sparse ? s->ins_first.p : nullptr, g.leaf_shift, sc);
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+  if (sparse) {
+    // 5s. tree, windows and rebalance of the small-batch path, then the ONE host synchronisation of the batch
+    const unsigned tb = div_up(std::min<uint64_t>(count, g.n_leaves), sp::ST);
+    s->epoch++;
+    s->launches += 5;
+    sp::k_sp_tree<<<tb, sp::ST, 0, s->stream>>>(s->touched.p, sc, s->ins_cnt.p, s->del_cnt.p, g.n_leaves, s->tree.p,
+                                               s->touched_flags.p);
+    win::k_select<<<tb, win::WT, 0, s->stream>>>(s->touched.p, &sc->n_touched, s->ins_cnt.p, s->del_cnt.p, s->tree.p,
+                                                g.n_leaves, g.logN, (int)g.H, s->mark.p, s->epoch, sc);
+    win::k_touched_windows<<<tb, win::WT, 0, s->stream>>>(s->touched.p, &sc->n_touched, s->mark.p, s->epoch, g.n_leaves,
+                                                         sc, s->touched_win.p);
+    sp::k_sp_emit_windows<<<tb, sp::ST, 0, s->stream>>>(s->touched_win.p, s->mark.p, s->epoch, s->tree.p, g.n_leaves,
+                                                       g.logN, s->windows.p, sc);
+    CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
+    sp::RebArgs R{};
+    R.dest = s->dest.p;
+    R.val = s->val.p;
+    R.leaf_cnt = s->leaf_cnt.p;
+    R.tree = s->tree.p;
+    R.ins_cnt = s->ins_cnt.p;
+    R.del_cnt = s->del_cnt.p;
+    R.ins_first = s->ins_first.p;
+    R.ins_dst = s->ins_dst.p;
+    R.ins_val = s->ins_val.p;
+    R.ins_pred = s->ins_pred.p;
+    R.beg = s->beg.p;
+    R.windows = s->windows.p;
+    R.sc = sc;
+    R.n_leaves = g.n_leaves;
+    R.ls = g.leaf_shift;
+    sp::k_sp_rebalance<<<std::max(1u, div_up(std::min<uint64_t>(count, g.n_leaves), reb::RWARPS)), reb::RT, 0,
+                         s->stream>>>(R);
+    CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev[4], s->stream));
+    CUDA_TRY(cudaGetLastError());
+    PPCSR_TRY(read_scalars(s));
+    const BatchScalars h = *s->h_scalars;
+    s->dst_or_seen |= h.dst_or;
+    if (h.sparse_abort)  // a dst wider than the speculated sort width: nothing was modified, run the batch the general way
+      return apply_device_common(s, d_src, d_dst, d_packed, d_val, count, default_val, stats, segments, pairs, true);
+    if (h.sparse_done) {
+      st.n_ignored = h.n_ignored;
+      st.n_unique = h.n_unique;
+      st.n_inserted = h.n_inserted;
+      st.n_overwritten = h.n_overwritten;
+      st.n_deleted = h.n_deleted;
+      st.n_not_found = h.n_not_found;
+      st.n_windows = h.n_windows;
+      st.window_slots = h.window_slots;
+      st.rebalance_bytes = 2ull * h.window_slots * 8ull;
+      st.sparse_path = 1;
+      s->items += h.n_inserted - h.n_deleted;
+      s->last_sparse = true;
+      s->last_touched = (uint32_t)h.n_touched;
+      PPCSR_TRY(finalize_stats(s, &st));
+      if (stats) *stats = st;
+      return PPCSR_OK;
+    }
+    // a window larger than one warp handles, or the root out of bounds: the general path takes over from the per-leaf
+    // counts and the insert list (its own window list, scans and tree)
+    CUDA_TRY(cudaMemsetAsync(&sc->n_touched, 0, offsetof(BatchScalars, dst_or) - offsetof(BatchScalars, n_touched),
+                             s->stream));
+    CUDA_TRY(cudaMemsetAsync(&sc->root_violation, 0, sizeof(unsigned int), s->stream));
+    s->cnt_clean = false;
+  }
   // 5. windows + rebalance
   PPCSR_TRY(finish_batch(s, count, &st));
   PPCSR_TRY(finalize_stats(s, &st));
@@ -1122,6 +1254,8 @@ int ppcsr_add_nodes(ppcsr_shard *s, uint32_t count) {
                                                              s->misc.p, s->ins_cnt.p, g.leaf_shift, sc);
   CUDA_TRY(cudaGetLastError());
   s->n = n_new;  // beg[n_new] = N is (re)written below; sentinel fix-up fills beg[n_old .. n_new)
+  s->cnt_clean = false;
+  s->last_sparse = false;
   s->ins_sentinels = true;
   const int fb = finish_batch(s, count, &st);
   s->ins_sentinels = false;
@@ -1530,8 +1664,16 @@ int ppcsr_check_invariants(ppcsr_shard *s, int check_lower, ppcsr_invariant_repo
   qry::k_check_vertices<<<div_up((uint64_t)s->n + 1, qry::QT), qry::QT, 0, s->stream>>>(
       s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, s->n, g.N, g.leaf_shift, d_c.p);
   if (L > 1) qry::k_check_tree<<<div_up(L, qry::QT), qry::QT, 0, s->stream>>>(s->tree.p, L, d_c.p);
-  qry::k_check_bounds<<<div_up(L, qry::QT), qry::QT, 0, s->stream>>>(s->tree.p, s->ins_cnt.p, s->del_cnt.p, s->all_touched,
-                                                                    L, g.logN, (int)g.H, check_lower, d_c.p);
+  if (s->last_sparse) {  // the small-batch path cleared the per-leaf counters: it left the list of touched leaves
+    if (s->last_touched)
+      sp::k_sp_check_bounds<<<div_up(s->last_touched, sp::ST), sp::ST, 0, s->stream>>>(
+          s->tree.p, s->touched.p, s->touched_flags.p, s->last_touched, L, g.logN, (int)g.H, check_lower,
+          &d_c.p->bad_upper, &d_c.p->bad_lower);
+  } else {
+    qry::k_check_bounds<<<div_up(L, qry::QT), qry::QT, 0, s->stream>>>(s->tree.p, s->ins_cnt.p, s->del_cnt.p,
+                                                                      s->all_touched, L, g.logN, (int)g.H, check_lower,
+                                                                      d_c.p);
+  }
   CUDA_TRY(cudaGetLastError());
   qry::InvCounters *hc = reinterpret_cast<qry::InvCounters *>(s->h_pinned);
   CUDA_TRY(cudaMemcpyAsync(hc, d_c.p, sizeof(qry::InvCounters), cudaMemcpyDeviceToHost, s->stream));
@@ -1609,6 +1751,8 @@ int ppcsr_restore(ppcsr_shard *s) {
   CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)k.geo.n_leaves * 4, s->stream));
   // the restored layout was touched by no batch: the checker must not apply the last batch's flags to it
   s->all_touched = 0;
+  s->last_sparse = false;
+  s->cnt_clean = false;
   s->last = ppcsr_batch_stats{};
   s->poisoned = false;
   return PPCSR_OK;

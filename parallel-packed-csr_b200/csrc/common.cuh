@@ -144,6 +144,8 @@ struct BatchScalars {
   unsigned int val_inv_min;         // ~(smallest non-zero value)
   unsigned long long n_touched_est;  // leaves that received inserts + leaves that lost items (k_locate's tally)
   unsigned long long seg_total;      // batch size when it is only known on the device (records deposited by peers)
+  unsigned int sparse_abort;         // small-batch path: a dst is wider than the speculated sort width -- nothing was modified
+  unsigned int sparse_done;          // small-batch path: every window was small, the batch is complete
 };
 static_assert(sizeof(BatchScalars) % 8 == 0, "BatchScalars must stay 8-byte sized");
 
@@ -200,6 +202,16 @@ struct ppcsr_shard {
   bool ins_sentinels = false;          // the pending insert list holds sentinels (ppcsr_add_nodes)
   uint32_t all_touched = 0;            // invariant checker: bit 2 = the last batch rewrote every leaf (bit 0 inserts, bit 1 deletes)
   int whole_policy = 0;                // -1 never / 0 cost model / 1 always: one root window instead of a window list
+  // small-batch path (sparse.cuh)
+  DevBuf<uint32_t> touch_stamp;        // [n_leaves] epoch of the last batch that touched the leaf
+  DevBuf<uint32_t> ins_first;          // [n_leaves] index of the leaf's first insert in the insert list (0xFFFFFFFF: none)
+  DevBuf<uint32_t> touched_flags;      // [touched] bit 0 inserts, bit 1 deletes (for the invariant checker)
+  uint32_t touch_epoch = 0;
+  bool cnt_clean = false;              // ins_cnt / del_cnt are all zero and ins_first all ones (left so by a sparse batch)
+  bool last_sparse = false;            // the last batch took the small-batch path: `touched` lists its leaves
+  uint32_t last_touched = 0;
+  uint32_t dst_or_seen = 0;            // OR of every dst of every batch so far (speculated sort width of small batches)
+  int sparse_policy = 0;               // -1 never, 0 automatic (PPCSR_SPARSE=never|always overrides)
   bool poisoned = false;               // a batch failed after it had begun to modify the shard (capi.cu: reserve_worst_case)
 
   // per-batch update-granular scratch
@@ -219,7 +231,8 @@ struct ppcsr_shard {
   uint64_t next_ticket = 1;
   DevBuf<uint64_t> ukey;               // [batch] unique keys (last op wins)
   DevBuf<uint32_t> uval;               // [batch]
-  DevBuf<uint32_t> uloc;               // [batch] slot: predecessor (new insert) or hit (exists)
+  DevBuf<uint32_t> uloc;               // [batch, whole tiles] predecessor slots of the locate tiles' inserts
+  DevBuf<uint32_t> tile_cnt;           // [tiles + 1] inserts per locate tile -> exclusive scan
   DevBuf<uint8_t> ucls;                // [batch] class
   DevBuf<uint8_t> ufirst;              // [batch] first op of the key in this batch is a remove
   DevBuf<uint32_t> ins_dst, ins_val, ins_pred;  // [batch] compacted pure inserts, key order

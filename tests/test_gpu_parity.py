@@ -484,3 +484,82 @@ def test_pipelined_submit_equals_sequential_applies():
     b.wait(t2)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("kind", ["insert", "delete", "mixed"])
+def test_small_batch_path_vs_oracle(kind):
+    """The small-batch path (sparse.cuh: touched list from the locate kernel, incremental count tree, windows claimed
+    by compare-and-swap, one warp per window, ONE host synchronisation) on a scale-16 graph: many batches of 1 .. 16 K
+    updates, compared with the oracle after every few batches; every batch must really take that path
+    (stats.sparse_path) unless it needs a window larger than a warp handles."""
+    scale = 16
+    n = 1 << scale
+    cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
+    g, o = pp.Shard(n), O.OraclePCSR(n)
+    g.apply(cs, cd, 1)
+    o.apply(cs, cd, 1)
+    assert g.geometry.N // g.geometry.logN >= 1024
+    rng = np.random.default_rng(3)
+    sizes = [1, 7, 100, 1000, 1024, 4096, 16000, 333, 16384, 2500, 1, 9000]
+    us, ud = synth.rmat(scale, 0, sum(sizes), 99)
+    idx = synth.sample_without_replacement(16 << scale, sum(sizes), 7)
+    ops = synth.mixed_ops(0, sum(sizes), 11)
+    lo, sparse_batches, misses = 0, 0, 0
+    for bi, b in enumerate(sizes):
+        sl = slice(lo, lo + b)
+        lo += b
+        if kind == "insert":
+            s_, d_, v_ = us[sl], ud[sl], np.ones(b, dtype=np.uint32)
+        elif kind == "delete":
+            s_, d_, v_ = cs[idx[sl]], cd[idx[sl]], np.zeros(b, dtype=np.uint32)
+        else:  # adds carry distinct values: the payload travels through the sort
+            s_ = np.where(ops[sl] != 0, us[sl], cs[idx[sl]])
+            d_ = np.where(ops[sl] != 0, ud[sl], cd[idx[sl]])
+            v_ = np.where(ops[sl] != 0, rng.integers(1, 1 << 20, b), 0).astype(np.uint32)
+        st = g.apply(s_, d_, v_)
+        o.apply(s_, d_, v_)
+        sparse_batches += st["sparse_path"]
+        misses += st["n_not_found"]
+        assert st["whole_array"] == 0 or not st["sparse_path"]
+        assert_invariants(g, check_lower=kind != "insert", where=f"{kind} batch {bi} ({b})")
+        if bi % 3 == 2 or bi + 1 == len(sizes):
+            assert_same_graph(g, *o.export(), where=f"{kind} after batch {bi}")
+    assert sparse_batches >= len(sizes) - 2, sparse_batches  # (a hub leaf may ask for a window of more than 8 leaves)
+    assert misses == o.not_found
+    assert_pagerank(g, o.pagerank(1.0 + (np.arange(n) % 7)), n)
+    # a dst wider than anything seen so far: the speculated sort width is wrong, the batch is redone the general way
+    wide = np.array([n - 1, 5, 5], dtype=np.uint32), np.array([(1 << 30) + 7, 3, (1 << 29) + 1], dtype=np.uint32)
+    st = g.apply(*wide, 1)
+    o.apply(*wide, 1)
+    assert st["sparse_path"] == 0 and st["n_inserted"] == 3
+    assert_same_graph(g, *o.export(), where="wide dst")
+    st = g.apply(us[:50], ud[:50], 1)  # and the next small batch is sparse again (all overwrites here)
+    assert st["sparse_path"] == 1 and st["n_inserted"] == 0
+    g.close()
+
+
+def test_small_batch_path_scale20_vs_reference_stream():
+    """Window path at scale 20: the 10 M skewed stream's first 300 K updates applied as batches of
+    1 K .. 100 K through the small-batch path give the graph of the same updates applied as ONE batch through the general
+    path (itself compared with the reference's dump in test_full_size_vs_reference_dump)."""
+    scale = 20
+    n = 1 << scale
+    cs, cd = synth.rmat(scale, 0, 16 << scale, 42)
+    us, ud = synth.rmat(scale, 0, 300_000, 99)
+    a, b = pp.Shard(n), pp.Shard(n)
+    for g in (a, b):
+        g.apply(cs, cd, 1)
+    a.apply(us, ud, 1)
+    lo, taken = 0, 0
+    for size in (1000, 100_000, 10_000, 50_000, 1000, 100_000, 38_000):
+        st = b.apply(us[lo:lo + size], ud[lo:lo + size], 1)
+        taken += st["sparse_path"]
+        lo += size
+        assert_invariants(b, where=f"batch of {size}")
+    assert lo == 300_000 and taken >= 5
+    ra, rb = a.export(), b.export()
+    assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1])
+    assert np.array_equal(a.num_neighbors(), b.num_neighbors())
+    assert a.checksum() == b.checksum()
+    a.close()
+    b.close()
