@@ -309,8 +309,12 @@ struct LocSmem {
   uint32_t stat[8];
   uint32_t win[4];             // window [a, b), mode (0 nothing to search, 1 staged, 2 global), valid keys
 };
+static_assert(sizeof(LocSmem) <= 48 * 1024, "k_locate is launched without a shared-memory opt-in");
 
-__global__ void __launch_bounds__(LT) k_locate(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay,
+// SPARSE: the small-batch variant (appends the touched leaves); a template so that the general instantiation keeps its
+// 32 registers -- 8 CTAs = all 64 warps of an SM (at 40 registers: 6 CTAs, locate stage 3.27 -> 4.02 ms on C4).
+template <bool SPARSE>
+__global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay,
                                                uint32_t default_val, size_t count, uint64_t invalid_key,
                                                const uint32_t *__restrict__ dest, uint32_t *__restrict__ val,
                                                const uint32_t *__restrict__ leaf_cnt, const uint32_t *__restrict__ beg,
@@ -320,10 +324,10 @@ __global__ void __launch_bounds__(LT) k_locate(const uint64_t *__restrict__ keys
                                                uint32_t *__restrict__ ins_cnt, uint32_t *__restrict__ del_cnt,
                                                uint32_t op_bit, BatchScalars *sc, uint32_t *touched,
                                                uint32_t *touch_stamp, uint32_t touch_epoch, uint32_t dst_mask) {
-  // Small-batch path (touched != nullptr, sparse.cuh): the batch was sorted on a SPECULATED dst width (no host round
+  // Small-batch path (SPARSE, sparse.cuh): the batch was sorted on a SPECULATED dst width (no host round
   // trip after the key builder); a dst beyond it means the order is wrong -- leave before anything is modified, the
   // host runs the batch again the general way.  The first update to reach a leaf appends it to the touched list.
-  if (touched && (sc->dst_or & ~dst_mask)) {
+  if (SPARSE && (sc->dst_or & ~dst_mask)) {
     if (blockIdx.x == 0 && threadIdx.x == 0) sc->sparse_abort = 1u;
     return;
   }
@@ -473,7 +477,7 @@ __global__ void __launch_bounds__(LT) k_locate(const uint64_t *__restrict__ keys
       const unsigned m5 = __ballot_sync(0xFFFFFFFFu, miss_first);
       const unsigned m4 = __ballot_sync(0xFFFFFFFFu, winner);
       const unsigned m6 = __ballot_sync(0xFFFFFFFFu, first_touch);
-      if (touched) {  // one entry per leaf and batch, whatever touched it first; the warp takes its places in one go
+      if (SPARSE) {  // one entry per leaf and batch, whatever touched it first; the warp takes its places in one go
         const bool fresh = first_touch && atomicExch(&touch_stamp[leaf], touch_epoch) != touch_epoch;
         const unsigned fm = __ballot_sync(0xFFFFFFFFu, fresh);
         unsigned long long at = 0;
@@ -528,18 +532,14 @@ __global__ void __launch_bounds__(LT) k_gather_inserts(const uint32_t *__restric
                                                        const uint32_t *__restrict__ tile_pred,
                                                        const uint32_t *__restrict__ tile_off,
                                                        uint32_t *__restrict__ ins_dst, uint32_t *__restrict__ ins_val,
-                                                       uint32_t *__restrict__ ins_pred, uint32_t *ins_first,
-                                                       uint32_t ls, const BatchScalars *sc) {
-  if (ins_first && sc->sparse_abort) return;  // small-batch path: k_locate left without doing anything
+                                                       uint32_t *__restrict__ ins_pred, const BatchScalars *sc) {
+  if (sc->sparse_abort) return;  // small-batch path: k_locate left without doing anything
   const uint32_t off = tile_off[blockIdx.x], cnt = tile_off[blockIdx.x + 1] - off;
   const size_t base = (size_t)blockIdx.x * LTILE;
   for (uint32_t x = threadIdx.x; x < cnt; x += LT) {
-    const uint32_t pred = tile_pred[base + x];
     ins_dst[off + x] = tile_dst[base + x];
     ins_val[off + x] = tile_val[base + x];
-    ins_pred[off + x] = pred;
-    // small-batch path: where the inserts of every leaf begin (instead of a scan over all leaves)
-    if (ins_first && (x == 0 || (tile_pred[base + x - 1] >> ls) != (pred >> ls))) atomicMin(&ins_first[pred >> ls], off + x);
+    ins_pred[off + x] = tile_pred[base + x];
   }
 }
 

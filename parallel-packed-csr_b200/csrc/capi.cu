@@ -34,13 +34,12 @@ int set_device(ppcsr_shard *s) {
 // (re)allocate every leaf-granular array for geometry g; contents undefined afterwards except mark (zeroed)
 int reserve_leaf_arrays(ppcsr_shard *s, const Geometry &g) {
   const size_t L = g.n_leaves;
+  const uint32_t *old_ins = s->ins_cnt.p, *old_del = s->del_cnt.p;
   PPCSR_TRY(dev_reserve(s->ins_cnt, L, s->stream));
   PPCSR_TRY(dev_reserve(s->del_cnt, L, s->stream));
+  if (s->ins_cnt.p != old_ins || s->del_cnt.p != old_del) s->cnt_clean = false;  // fresh counters are not clear
   PPCSR_TRY(dev_reserve(s->rank_off, L + 1, s->stream));
   PPCSR_TRY(dev_reserve(s->ins_off, L + 1, s->stream));
-  const uint32_t *old_ins = s->ins_first.p;
-  PPCSR_TRY(dev_reserve(s->ins_first, L, s->stream));
-  if (s->ins_first.p != old_ins) s->cnt_clean = false;  // fresh counters: the next small batch clears them first
   const size_t old_stamp = s->touch_stamp.cap;
   PPCSR_TRY(dev_reserve(s->touch_stamp, L, s->stream));
   if (s->touch_stamp.cap != old_stamp) {
@@ -718,7 +717,7 @@ void ppcsr_destroy(ppcsr_shard *s) {
   dev_free(s->uloc); dev_free(s->ucls); dev_free(s->ufirst); dev_free(s->ins_dst); dev_free(s->ins_val); dev_free(s->ins_pred);
   dev_free(s->block_tmp); dev_free(s->hist); dev_free(s->pr_acc); dev_free(s->misc);
   dev_free(s->scan_state); dev_free(s->scan_ticket); dev_free(s->tile_cnt);
-  dev_free(s->touch_stamp); dev_free(s->ins_first); dev_free(s->touched_flags);
+  dev_free(s->touch_stamp); dev_free(s->touched_flags);
   dev_free(s->snap.dest); dev_free(s->snap.val); dev_free(s->snap.leaf_cnt); dev_free(s->snap.tree);
   dev_free(s->snap.beg); dev_free(s->snap.nn);
   for (auto &P : s->pending) {
@@ -767,7 +766,6 @@ int ppcsr_reserve(ppcsr_shard *s, uint64_t max_slots, uint64_t max_batch) {
     PPCSR_TRY(dev_reserve(s->tree, (size_t)2 * g.n_leaves, s->stream, true));
     PPCSR_TRY(dev_reserve(s->ins_cnt, g.n_leaves, s->stream, true));
     PPCSR_TRY(dev_reserve(s->del_cnt, g.n_leaves, s->stream, true));
-    PPCSR_TRY(dev_reserve(s->ins_first, g.n_leaves, s->stream));
     PPCSR_TRY(dev_reserve(s->touch_stamp, g.n_leaves, s->stream));
     CUDA_TRY(cudaMemsetAsync(s->touch_stamp.p, 0, s->touch_stamp.cap * sizeof(uint32_t), s->stream));
     s->touch_epoch = 0;
@@ -906,7 +904,6 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
     if (!s->cnt_clean) {
       CUDA_TRY(cudaMemsetAsync(s->ins_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
       CUDA_TRY(cudaMemsetAsync(s->del_cnt.p, 0, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
-      CUDA_TRY(cudaMemsetAsync(s->ins_first.p, 0xFF, (size_t)g.n_leaves * sizeof(uint32_t), s->stream));
       s->cnt_clean = true;
     }
     if (++s->touch_epoch == 0u) {  // the stamps wrapped: no old stamp may look current
@@ -928,41 +925,40 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   uint32_t *tile_dst = reinterpret_cast<uint32_t *>(spare), *tile_val = tile_dst + padded;
   PPCSR_TRY(dev_reserve(s->uloc, padded, s->stream));
   PPCSR_TRY(dev_reserve(s->tile_cnt, (size_t)lblocks + 1, s->stream));
-  {  // > 48 KB of dynamic shared memory needs an explicit opt-in: per device, once, thread-safe
-    static std::once_flag once[64];
-    static cudaError_t once_err[64];
-    const int dv = s->device & 63;
-    std::call_once(once[dv], [&] {
-      once_err[dv] = cudaFuncSetAttribute(batch::k_locate, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(batch::LocSmem));
-    });
-    CUDA_TRY(once_err[dv]);
+  // a batch of ONE tile needs no scan and no gather: the tile's run is the insert list
+  uint32_t *t_dst = lblocks == 1 ? s->ins_dst.p : tile_dst, *t_val = lblocks == 1 ? s->ins_val.p : tile_val;
+  uint32_t *t_pred = lblocks == 1 ? s->ins_pred.p : s->uloc.p;
+  const uint32_t dst_mask = lo_bits >= 32 ? 0xFFFFFFFFu : ((1u << lo_bits) - 1u);
+  if (sparse) {
+    batch::k_locate<true><<<lblocks, batch::LT, sizeof(batch::LocSmem), s->stream>>>(
+        keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
+        (uint32_t)g.N, s->nn.p, t_dst, t_val, t_pred, s->tile_cnt.p, s->ins_cnt.p, s->del_cnt.p, op_bit, sc,
+        s->touched.p, s->touch_stamp.p, s->touch_epoch, dst_mask);
+  } else {
+    batch::k_locate<false><<<lblocks, batch::LT, sizeof(batch::LocSmem), s->stream>>>(
+        keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
+        (uint32_t)g.N, s->nn.p, t_dst, t_val, t_pred, s->tile_cnt.p, s->ins_cnt.p, s->del_cnt.p, op_bit, sc, nullptr,
+        nullptr, 0u, dst_mask);
   }
-  batch::k_locate<<<lblocks, batch::LT, sizeof(batch::LocSmem), s->stream>>>(
-      keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
-      (uint32_t)g.N, s->nn.p, tile_dst, tile_val, s->uloc.p, s->tile_cnt.p, s->ins_cnt.p, s->del_cnt.p, op_bit, sc,
-      sparse ? s->touched.p : nullptr, s->touch_stamp.p, s->touch_epoch,
-      lo_bits >= 32 ? 0xFFFFFFFFu : ((1u << lo_bits) - 1u));
-  PPCSR_TRY(prim::device_scan(s, prim::InArray{s->tile_cnt.p}, prim::OutPrefixWithTotal{s->tile_cnt.p, lblocks},
-                              lblocks, nullptr, nullptr));
-  s->launches++;
-  batch::k_gather_inserts<<<lblocks, batch::LT, 0, s->stream>>>(tile_dst, tile_val, s->uloc.p, s->tile_cnt.p,
-                                                               s->ins_dst.p, s->ins_val.p, s->ins_pred.p,
-                                                               sparse ? s->ins_first.p : nullptr, g.leaf_shift, sc);
+  if (lblocks > 1) {
+    PPCSR_TRY(prim::device_scan(s, prim::InArray{s->tile_cnt.p}, prim::OutPrefixWithTotal{s->tile_cnt.p, lblocks},
+                                lblocks, nullptr, nullptr));
+    s->launches++;
+    batch::k_gather_inserts<<<lblocks, batch::LT, 0, s->stream>>>(tile_dst, tile_val, s->uloc.p, s->tile_cnt.p,
+                                                                 s->ins_dst.p, s->ins_val.p, s->ins_pred.p, sc);
+  }
   CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
   if (sparse) {
     // 5s. tree, windows and rebalance of the small-batch path, then the ONE host synchronisation of the batch
     const unsigned tb = div_up(std::min<uint64_t>(count, g.n_leaves), sp::ST);
     s->epoch++;
-    s->launches += 5;
+    s->launches += 4;
     sp::k_sp_tree<<<tb, sp::ST, 0, s->stream>>>(s->touched.p, sc, s->ins_cnt.p, s->del_cnt.p, g.n_leaves, s->tree.p,
                                                s->touched_flags.p);
     win::k_select<<<tb, win::WT, 0, s->stream>>>(s->touched.p, &sc->n_touched, s->ins_cnt.p, s->del_cnt.p, s->tree.p,
                                                 g.n_leaves, g.logN, (int)g.H, s->mark.p, s->epoch, sc);
-    win::k_touched_windows<<<tb, win::WT, 0, s->stream>>>(s->touched.p, &sc->n_touched, s->mark.p, s->epoch, g.n_leaves,
-                                                         sc, s->touched_win.p);
-    sp::k_sp_emit_windows<<<tb, sp::ST, 0, s->stream>>>(s->touched_win.p, s->mark.p, s->epoch, s->tree.p, g.n_leaves,
-                                                       g.logN, s->windows.p, sc);
+    sp::k_sp_windows<<<tb, sp::ST, 0, s->stream>>>(s->touched.p, s->mark.p, s->epoch, s->tree.p, g.n_leaves, g.logN,
+                                                  s->windows.p, sc);
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
     sp::RebArgs R{};
@@ -972,7 +968,6 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
     R.tree = s->tree.p;
     R.ins_cnt = s->ins_cnt.p;
     R.del_cnt = s->del_cnt.p;
-    R.ins_first = s->ins_first.p;
     R.ins_dst = s->ins_dst.p;
     R.ins_val = s->ins_val.p;
     R.ins_pred = s->ins_pred.p;

@@ -146,6 +146,8 @@ struct BatchScalars {
   unsigned long long seg_total;      // batch size when it is only known on the device (records deposited by peers)
   unsigned int sparse_abort;         // small-batch path: a dst is wider than the speculated sort width -- nothing was modified
   unsigned int sparse_done;          // small-batch path: every window was small, the batch is complete
+  unsigned int sp_blocks_done;       // small-batch path: CTAs of k_sp_tree that have finished (the last one sums the top)
+  unsigned int pad0;
 };
 static_assert(sizeof(BatchScalars) % 8 == 0, "BatchScalars must stay 8-byte sized");
 
@@ -204,10 +206,9 @@ struct ppcsr_shard {
   int whole_policy = 0;                // -1 never / 0 cost model / 1 always: one root window instead of a window list
   // small-batch path (sparse.cuh)
   DevBuf<uint32_t> touch_stamp;        // [n_leaves] epoch of the last batch that touched the leaf
-  DevBuf<uint32_t> ins_first;          // [n_leaves] index of the leaf's first insert in the insert list (0xFFFFFFFF: none)
   DevBuf<uint32_t> touched_flags;      // [touched] bit 0 inserts, bit 1 deletes (for the invariant checker)
   uint32_t touch_epoch = 0;
-  bool cnt_clean = false;              // ins_cnt / del_cnt are all zero and ins_first all ones (left so by a sparse batch)
+  bool cnt_clean = false;              // ins_cnt / del_cnt are all zero (left so by a sparse batch)
   bool last_sparse = false;            // the last batch took the small-batch path: `touched` lists its leaves
   uint32_t last_touched = 0;
   uint32_t dst_or_seen = 0;            // OR of every dst of every batch so far (speculated sort width of small batches)

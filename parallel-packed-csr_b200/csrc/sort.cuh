@@ -320,6 +320,107 @@ __global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(const uint64_t *__res
   }
 }
 
+// ---- small batches: ONE CTA, every pass inside the kernel ---------------------------------------------------------
+// A batch of a few thousand keys spends its time in launch and dependency latency, not in bandwidth: the multi-kernel
+// sort above needs 3 + n_pass dependent launches of ~7 us each (63 us for 1 K keys, measured).  Here the keys stay in
+// registers, a pass is rank -> scatter through shared memory -> read back, and the whole sort is one launch.
+// Same stable ranking as k_os_pass (warp-contiguous sub-tiles, per-bit ballots).
+constexpr int SS_THREADS = 1024;
+constexpr int SS_WARPS = SS_THREADS / 32;
+constexpr uint32_t SS_MAX = SS_THREADS * 16;  // 16384 keys
+inline size_t sort_small_smem(int items, bool has_pay) {
+  return (size_t)SS_THREADS * items * (8 + (has_pay ? 4 : 0)) + (size_t)SS_WARPS * OS_RADIX * 2;
+}
+template <int ITEMS, bool HAS_PAY>
+__global__ void __launch_bounds__(SS_THREADS, 1) k_sort_small(const uint64_t *__restrict__ keys,
+                                                               const uint32_t *__restrict__ pay, uint32_t n,
+                                                               SortPasses P, uint64_t *__restrict__ out_keys,
+                                                               uint32_t *__restrict__ out_pay) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  constexpr uint32_t TILE = SS_THREADS * ITEMS;
+  uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_dyn);
+  uint32_t *s_pay = reinterpret_cast<uint32_t *>(s_dyn + (size_t)TILE * 8);
+  uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_dyn + (size_t)TILE * (8 + (HAS_PAY ? 4 : 0)));
+  __shared__ uint32_t s_warp[33];
+  const unsigned w = threadIdx.x >> 5, l = lane_id(), lt = lanemask_lt();
+  uint16_t *my_cnt = s_cnt + (size_t)w * OS_RADIX;
+  const uint32_t wbase = w * (32 * ITEMS);
+  uint64_t k[ITEMS];
+  uint32_t v[ITEMS];
+#pragma unroll
+  for (int r = 0; r < ITEMS; r++) {
+    const uint32_t i = wbase + r * 32 + l;
+    k[r] = i < n ? keys[i] : ~0ull;  // padding carries the largest digit of every pass and sits behind every real key
+    v[r] = (HAS_PAY && i < n) ? pay[i] : 0u;
+  }
+  for (int p = 0; p < P.n_pass; p++) {
+    const int shift = P.shift[p];
+    const uint32_t mask = P.mask[p];
+    for (uint32_t d = threadIdx.x; d < SS_WARPS * OS_RADIX / 2; d += SS_THREADS) reinterpret_cast<uint32_t *>(s_cnt)[d] = 0;
+    __syncthreads();
+    uint32_t rank[ITEMS];
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+      const uint32_t d = sort_digit(k[r], P.lo_bits, shift, mask);
+      const unsigned peers = match_digit(d);
+      const uint32_t base = my_cnt[d];
+      __syncwarp();
+      if ((peers & lt) == 0) my_cnt[d] = (uint16_t)(base + __popc(peers));
+      __syncwarp();
+      rank[r] = base + __popc(peers & lt);
+    }
+    __syncthreads();
+    uint32_t tot = 0;  // thread t < 256: keys of digit t in the tile
+    if (threadIdx.x < OS_RADIX)
+      for (int ww = 0; ww < SS_WARPS; ww++) tot += s_cnt[ww * OS_RADIX + threadIdx.x];
+    uint32_t all;
+    uint32_t run = block_excl_scan(tot, &all, s_warp);
+    if (threadIdx.x < OS_RADIX) {  // s_cnt[w][d] := first position of warp w's keys of digit d
+      for (int ww = 0; ww < SS_WARPS; ww++) {
+        const uint32_t t = s_cnt[ww * OS_RADIX + threadIdx.x];
+        s_cnt[ww * OS_RADIX + threadIdx.x] = (uint16_t)run;
+        run += t;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+      const uint32_t pos = my_cnt[sort_digit(k[r], P.lo_bits, shift, mask)] + rank[r];
+      s_keys[pos] = k[r];
+      if (HAS_PAY) s_pay[pos] = v[r];
+    }
+    __syncthreads();
+    if (p + 1 < P.n_pass) {
+#pragma unroll
+      for (int r = 0; r < ITEMS; r++) {
+        const uint32_t i = wbase + r * 32 + l;
+        k[r] = s_keys[i];
+        if (HAS_PAY) v[r] = s_pay[i];
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t i = threadIdx.x; i < n; i += SS_THREADS) {
+    out_keys[i] = s_keys[i];
+    if (HAS_PAY) out_pay[i] = s_pay[i];
+  }
+}
+
+template <int ITEMS, bool HAS_PAY>
+inline int launch_sort_small(ppcsr_shard *s, const uint64_t *ka, const uint32_t *pa, uint32_t n, const SortPasses &P,
+                             uint64_t *kb, uint32_t *pb) {
+  static std::once_flag once[64];
+  static cudaError_t once_err[64];
+  const int dv = s->device & 63;
+  std::call_once(once[dv], [&] {
+    once_err[dv] = cudaFuncSetAttribute(k_sort_small<ITEMS, HAS_PAY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sort_small_smem(ITEMS, HAS_PAY));
+  });
+  CUDA_TRY(once_err[dv]);
+  k_sort_small<ITEMS, HAS_PAY><<<1, SS_THREADS, sort_small_smem(ITEMS, HAS_PAY), s->stream>>>(ka, pa, n, P, kb, pb);
+  return PPCSR_OK;
+}
+
 // scratch (u32 words) the sort needs in s->hist for `n` keys
 inline size_t radix_sort_scratch_words(size_t n) {
   const size_t ntiles = (n + OS_TILE - 1) / OS_TILE;
@@ -339,6 +440,21 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
   }
   const bool has_pay = pa != nullptr;
   const SortPasses P = make_sort_passes(lo_bits, hi_bits);
+  if (n <= SS_MAX) {  // one CTA, one launch
+    s->launches += 1;
+    const uint32_t m = (uint32_t)n;
+    if (n <= SS_THREADS) {
+      PPCSR_TRY(has_pay ? (launch_sort_small<1, true>(s, ka, pa, m, P, kb, pb)) : (launch_sort_small<1, false>(s, ka, pa, m, P, kb, pb)));
+    } else if (n <= SS_THREADS * 4) {
+      PPCSR_TRY(has_pay ? (launch_sort_small<4, true>(s, ka, pa, m, P, kb, pb)) : (launch_sort_small<4, false>(s, ka, pa, m, P, kb, pb)));
+    } else {
+      PPCSR_TRY(has_pay ? (launch_sort_small<16, true>(s, ka, pa, m, P, kb, pb)) : (launch_sort_small<16, false>(s, ka, pa, m, P, kb, pb)));
+    }
+    CUDA_TRY(cudaGetLastError());
+    *rk = kb;
+    *rp = has_pay ? pb : nullptr;
+    return PPCSR_OK;
+  }
   const size_t ntiles = (n + OS_TILE - 1) / OS_TILE;
   // scratch layout in s->hist: ghist[8][256] | tile counters[64] | lookback[n_pass][OS_LB_DEPTH + ntiles][256]
   const size_t rows = ntiles + OS_LB_DEPTH;

@@ -4,14 +4,16 @@
 // Same decisions as the general path -- reference PCSR::insert / remove walk-ups (src/pcsr/PCSR.cpp:578-591,616-628)
 // through win::k_select -- on the same data; only how the inputs of the selection are produced differs:
 //   * touched leaves: appended by k_locate itself (the first update to reach a leaf in this batch, epoch stamps);
-//   * count tree: the touched leaves add their (inserted - deleted) to every ancestor (k_sp_tree), the tree is never
-//     rebuilt;
+//   * count tree: the touched leaves add their (inserted - deleted) to their ancestors below the top TOP_LEVELS levels
+//     (k_sp_tree); the top levels, where every leaf would hit the same few words, are summed again from the level below
+//     by the last CTA to finish; the tree is never rebuilt;
 //   * windows: the highest marked ancestor of every touched leaf, de-duplicated by a compare-and-swap on its mark
-//     (k_sp_emit_windows) instead of adjacency in a sorted list;
+//     (k_sp_windows) instead of adjacency in a sorted list;
 //   * rebalance: when every chosen window is small (<= reb::SMALL_MAX_LEAVES leaves, the overwhelmingly common case)
-//     one warp per window computes the window-relative ranks and insert offsets on the fly (k_sp_rebalance) -- no
-//     global rank / insert-offset scans -- rewrites the window in place and restores the "all per-leaf batch counters
-//     are clear" state for the next batch.
+//     one warp per window computes the window-relative ranks and insert offsets on the fly (k_sp_rebalance) -- a prefix
+//     over the window's leaf counts, and a binary search for the window's first insert: its inserts are one contiguous
+//     run of the key-ordered list -- instead of global rank / insert-offset scans, rewrites the window in place and
+//     restores the "all per-leaf batch counters are clear" state for the next batch.
 // Anything else (a window larger than that, a root out of bounds, a dst wider than the speculated sort width) leaves the
 // shard as the general path expects it and the host continues there.
 #pragma once
@@ -23,50 +25,101 @@ namespace sp {
 constexpr int ST = 256;
 constexpr uint32_t CLAIMED = 0x80000000u;  // mark[w] == epoch | CLAIMED: the window of node w has been emitted
 
-// every touched leaf adds its net change to all of its ancestors; records what touched it for the invariant checker
-__global__ void __launch_bounds__(ST) k_sp_tree(const uint32_t *__restrict__ touched, const BatchScalars *sc,
+constexpr uint32_t TOP_LEVELS = 8;         // tree levels 0 .. TOP_LEVELS - 1 (255 nodes) are summed, not incremented
+constexpr uint32_t TOP_NODES = 1u << TOP_LEVELS;  // nodes of level TOP_LEVELS: heap indices TOP_NODES .. 2 TOP_NODES - 1
+
+// Every touched leaf adds its net change to its ancestors from the leaf level up to level TOP_LEVELS and records what
+// touched it for the invariant checker; the last CTA to finish sums levels TOP_LEVELS - 1 .. 0 from level TOP_LEVELS
+// (with 100 K touched leaves the root alone would take 100 K serialised atomics).  Needs n_leaves >= 2 TOP_NODES.
+__global__ void __launch_bounds__(ST) k_sp_tree(const uint32_t *__restrict__ touched, BatchScalars *sc,
                                                 const uint32_t *__restrict__ ins_cnt,
                                                 const uint32_t *__restrict__ del_cnt, uint32_t n_leaves,
                                                 uint32_t *__restrict__ tree, uint32_t *__restrict__ touched_flags) {
+  __shared__ uint32_t s_lvl[TOP_NODES];
+  __shared__ bool s_last;
   if (sc->sparse_abort) return;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (size_t)sc->n_touched) return;
-  const uint32_t l = touched[t];
-  const uint32_t ic = ins_cnt[l], dc = del_cnt[l];
-  touched_flags[t] = (ic ? 1u : 0u) | (dc ? 2u : 0u);
-  const uint32_t delta = ic - dc;  // modular: a net loss adds 2^32 - k
-  if (delta == 0u) return;
-  for (uint32_t node = n_leaves + l; node >= 1u; node >>= 1) atomicAdd(&tree[node], delta);
+  if (t < (size_t)sc->n_touched) {
+    const uint32_t l = touched[t];
+    const uint32_t ic = ins_cnt[l], dc = del_cnt[l];
+    touched_flags[t] = (ic ? 1u : 0u) | (dc ? 2u : 0u);
+    const uint32_t delta = ic - dc;  // modular: a net loss adds 2^32 - k
+    if (delta != 0u)
+      for (uint32_t node = n_leaves + l; node >= TOP_NODES; node >>= 1) atomicAdd(&tree[node], delta);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&sc->sp_blocks_done, 1u) + 1u == gridDim.x;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  static_assert(ST == TOP_NODES, "one thread per node of level TOP_LEVELS");
+  s_lvl[threadIdx.x] = __ldcg(&tree[TOP_NODES + threadIdx.x]);
+  __syncthreads();
+  for (uint32_t w = TOP_NODES >> 1; w >= 1u; w >>= 1) {  // level of w nodes: heap indices w .. 2 w - 1
+    uint32_t v = 0;
+    if (threadIdx.x < w) v = s_lvl[2 * threadIdx.x] + s_lvl[2 * threadIdx.x + 1];
+    __syncthreads();
+    if (threadIdx.x < w) {
+      s_lvl[threadIdx.x] = v;
+      tree[w + threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
 }
 
-// one window per maximal marked node: the first touched leaf to claim it emits its descriptor
-__global__ void __launch_bounds__(ST) k_sp_emit_windows(const uint32_t *__restrict__ touched_win, uint32_t *mark,
-                                                        uint32_t epoch, const uint32_t *__restrict__ tree,
-                                                        uint32_t n_leaves, uint32_t logN, WindowDesc *windows,
-                                                        BatchScalars *sc) {
+__device__ __forceinline__ uint32_t highest_marked_any(const uint32_t *__restrict__ mark, uint32_t epoch, uint32_t node) {
+  uint32_t best = 0;
+  while (node >= 1) {
+    if ((mark[node] & ~CLAIMED) == epoch) best = node;  // claimed by a concurrent thread or not: it is marked
+    node >>= 1;
+  }
+  return best;
+}
+
+// One window per maximal marked node: every touched leaf finds its highest marked ancestor; the first one to claim it
+// (compare-and-swap on the mark) emits the descriptor.  The three counters are summed per warp first.
+__global__ void __launch_bounds__(ST) k_sp_windows(const uint32_t *__restrict__ touched, uint32_t *mark, uint32_t epoch,
+                                                   const uint32_t *__restrict__ tree, uint32_t n_leaves, uint32_t logN,
+                                                   WindowDesc *windows, BatchScalars *sc) {
   if (sc->sparse_abort || sc->root_violation) return;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (size_t)sc->n_touched) return;
-  const uint32_t w = touched_win[t];
-  if (atomicCAS(&mark[w], epoch, epoch | CLAIMED) != epoch) return;
-  const uint32_t depth = 31u - (uint32_t)__clz(w);
-  const uint32_t m = n_leaves >> depth;
-  WindowDesc d;
-  d.node = w;
-  d.m = m;
-  d.leaf0 = (w - (1u << depth)) * m;
-  d.items = tree[w];
-  d.n_chunks = m <= (uint32_t)reb::SMALL_MAX_LEAVES ? 0u : 1u;  // != 0: not a one-warp window (the host falls back)
-  d.chunk0 = 0;
-  const unsigned long long at = atomicAdd(&sc->n_windows, 1ull);
-  windows[at] = d;
-  atomicAdd(&sc->window_slots, (unsigned long long)m * logN);
-  if (d.n_chunks == 0) atomicAdd(&sc->n_small, 1ull);
+  bool mine = false;
+  uint32_t w = 0;
+  if (t < (size_t)sc->n_touched) {
+    w = highest_marked_any(mark, epoch, n_leaves + touched[t]);
+    mine = atomicCAS(&mark[w], epoch, epoch | CLAIMED) == epoch;
+  }
+  const unsigned mm = __ballot_sync(0xFFFFFFFFu, mine);
+  if (!mm) return;
+  const uint32_t depth = mine ? 31u - (uint32_t)__clz(w) : 0u;
+  const uint32_t m = mine ? n_leaves >> depth : 0u;
+  const bool small = m <= (uint32_t)reb::SMALL_MAX_LEAVES;
+  const uint32_t all_m = __reduce_add_sync(0xFFFFFFFFu, m);
+  const uint32_t n_small = __reduce_add_sync(0xFFFFFFFFu, mine && small ? 1u : 0u);
+  unsigned long long at = 0;
+  const unsigned leader = (unsigned)__ffs(mm) - 1u;
+  if (lane_id() == leader) {
+    at = atomicAdd(&sc->n_windows, (unsigned long long)__popc(mm));
+    atomicAdd(&sc->window_slots, (unsigned long long)all_m * logN);
+    if (n_small) atomicAdd(&sc->n_small, (unsigned long long)n_small);
+  }
+  at = __shfl_sync(0xFFFFFFFFu, at, leader);
+  if (mine) {
+    WindowDesc d;
+    d.node = w;
+    d.m = m;
+    d.leaf0 = (w - (1u << depth)) * m;
+    d.items = tree[w];
+    d.n_chunks = small ? 0u : 1u;  // != 0: not a one-warp window (the host falls back to the general path)
+    d.chunk0 = 0;
+    windows[at + __popc(mm & lanemask_lt())] = d;
+  }
 }
 
 struct RebArgs {
   uint32_t *dest, *val;  // rebalanced in place
-  uint32_t *leaf_cnt, *tree, *ins_cnt, *del_cnt, *ins_first;
+  uint32_t *leaf_cnt, *tree, *ins_cnt, *del_cnt;
   const uint32_t *ins_dst, *ins_val, *ins_pred;
   uint32_t *beg;
   const WindowDesc *windows;
@@ -97,15 +150,14 @@ __global__ void __launch_bounds__(reb::RT) k_sp_rebalance(RebArgs A) {
   uint32_t *sd = s_dest[warp], *sv = s_val[warp];
 
   // per-leaf metadata: lane k < m owns leaf k
-  uint32_t my_cnt = 0, my_ins = 0, my_new = 0, my_first = 0xFFFFFFFFu;
+  uint32_t my_cnt = 0, my_ins = 0, my_new = 0;
   if (lane < m) {
     const uint32_t i = w.leaf0 + lane;
     my_cnt = A.leaf_cnt[i];
     my_ins = A.ins_cnt[i];
     my_new = my_cnt + my_ins - A.del_cnt[i];
-    if (my_ins) my_first = A.ins_first[i];
   }
-  uint32_t rank_incl = my_new, ins_incl = my_ins, first = my_first;
+  uint32_t rank_incl = my_new, ins_incl = my_ins;
 #pragma unroll
   for (int d = 1; d < SMALL_MAX_LEAVES; d <<= 1) {
     const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, rank_incl, d), b = __shfl_up_sync(0xFFFFFFFFu, ins_incl, d);
@@ -114,10 +166,20 @@ __global__ void __launch_bounds__(reb::RT) k_sp_rebalance(RebArgs A) {
       ins_incl += b;
     }
   }
-#pragma unroll
-  for (int d = SMALL_MAX_LEAVES / 2; d > 0; d >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, d));
   const uint32_t ins_total = __shfl_sync(0xFFFFFFFFu, ins_incl, SMALL_MAX_LEAVES - 1);
-  if (first == 0xFFFFFFFFu) first = 0u;  // a window without inserts (deletes only)
+  // the window's inserts are one contiguous run of the key-ordered insert list (sorted by predecessor slot): its first
+  // element is the first insert whose predecessor lies at or beyond the window's first slot
+  uint32_t first = 0u;
+  if (ins_total) {  // warp-uniform
+    const uint32_t slot0 = w.leaf0 << A.ls;
+    uint32_t lo = 0, hi = (uint32_t)A.sc->n_inserted;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (A.ins_pred[mid] < slot0) lo = mid + 1;
+      else hi = mid;
+    }
+    first = lo;
+  }
   if (lane < m) {
     s_rank[warp][lane] = rank_incl - my_new;
     s_ioff[warp][lane] = first + ins_incl - my_ins;
@@ -201,7 +263,6 @@ __global__ void __launch_bounds__(reb::RT) k_sp_rebalance(RebArgs A) {
     A.tree[A.n_leaves + i] = c;
     A.ins_cnt[i] = 0u;
     A.del_cnt[i] = 0u;
-    A.ins_first[i] = 0xFFFFFFFFu;
   }
   for (uint32_t s = 1, sh = 1; s < m; s <<= 1, sh++) {  // m is a power of two <= 8
     c += __shfl_down_sync(0xFFFFFFFFu, c, s);

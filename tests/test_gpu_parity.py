@@ -533,8 +533,10 @@ def test_small_batch_path_vs_oracle(kind):
     o.apply(*wide, 1)
     assert st["sparse_path"] == 0 and st["n_inserted"] == 3
     assert_same_graph(g, *o.export(), where="wide dst")
-    st = g.apply(us[:50], ud[:50], 1)  # and the next small batch is sparse again (all overwrites here)
-    assert st["sparse_path"] == 1 and st["n_inserted"] == 0
+    st = g.apply(us[:50], ud[:50], 1)  # and the next small batch is sparse again
+    o.apply(us[:50], ud[:50], 1)
+    assert st["sparse_path"] == 1
+    assert_same_graph(g, *o.export(), where="after the wide batch")
     g.close()
 
 
