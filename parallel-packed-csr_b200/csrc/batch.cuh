@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "primitives.cuh"
+#include "sort.cuh"
 
 namespace batch {
 
@@ -26,6 +27,30 @@ __device__ __forceinline__ uint64_t emit_key(bool ok, uint64_t key, uint32_t v, 
   return (op_bit && v == 0u) ? (key | KEY_OP_BIT) : key;
 }
 
+// The key builders can also take the sort's digit histograms (all passes, prim::k_os_hist's job) while the keys pass
+// through their registers: the host SPECULATES the sort layout from the widest dst seen so far and the vertex count,
+// and falls back to prim::k_os_hist when the batch turns out wider (capi.cu).  Saves one read of the batch.
+struct HistArgs {
+  prim::SortPasses P;
+  uint32_t *ghist;  // nullptr: no histogram
+};
+__device__ __forceinline__ void hist_init(uint32_t *s_h, const HistArgs &H) {
+  if (H.ghist)
+    for (int i = threadIdx.x; i < H.P.n_pass * prim::OS_RADIX; i += blockDim.x) s_h[i] = 0;
+}
+__device__ __forceinline__ void hist_add(uint32_t *s_h, const HistArgs &H, uint64_t key) {
+  if (!H.ghist) return;
+  const uint64_t ck = prim::sort_compact(key, H.P.lo_bits);
+#pragma unroll
+  for (int p = 0; p < prim::OS_MAX_PASSES; p++)
+    if (p < H.P.n_pass) atomicAdd(&s_h[p * prim::OS_RADIX + ((uint32_t)(ck >> H.P.shift[p]) & H.P.mask[p])], 1u);
+}
+__device__ __forceinline__ void hist_flush(const uint32_t *s_h, const HistArgs &H) {  // after a block barrier
+  if (H.ghist)
+    for (int i = threadIdx.x; i < H.P.n_pass * prim::OS_RADIX; i += blockDim.x)
+      if (s_h[i]) atomicAdd(&H.ghist[i], s_h[i]);
+}
+
 // ---- keys -------------------------------------------------------------------------------------
 // Guards: add with value != 0 needs src < n (reference PCSR.cpp:1375) and dst != SENT; remove needs
 // src < n (the reference would read out of bounds, PCSR.cpp:717).  Rejected updates get the key
@@ -33,8 +58,10 @@ __device__ __forceinline__ uint64_t emit_key(bool ok, uint64_t key, uint32_t v, 
 __global__ void __launch_bounds__(BT) k_build_keys(const uint32_t *__restrict__ src, const uint32_t *__restrict__ dst,
                                                    const uint32_t *__restrict__ val, uint32_t default_val,
                                                    size_t count, uint32_t n, uint32_t op_bit, uint64_t *__restrict__ keys,
-                                                   uint32_t *__restrict__ pay, BatchScalars *sc) {
+                                                   uint32_t *__restrict__ pay, BatchScalars *sc, HistArgs H) {
   __shared__ uint32_t s_or, s_bad, s_vmax, s_vinv;
+  __shared__ uint32_t s_h[prim::OS_MAX_PASSES * prim::OS_RADIX];
+  hist_init(s_h, H);
   if (threadIdx.x == 0) {
     s_or = 0;
     s_bad = 0;
@@ -47,7 +74,9 @@ __global__ void __launch_bounds__(BT) k_build_keys(const uint32_t *__restrict__ 
     const uint32_t s = src[i], d = dst[i];
     const uint32_t v = val ? val[i] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
-    keys[i] = emit_key(ok, ((uint64_t)s << 32) | d, v, n, op_bit);
+    const uint64_t kq = emit_key(ok, ((uint64_t)s << 32) | d, v, n, op_bit);
+    keys[i] = kq;
+    hist_add(s_h, H, kq);
     if (pay) pay[i] = ok ? v : 0u;
     if (ok) my_or |= d;
     else my_bad++;
@@ -64,6 +93,7 @@ __global__ void __launch_bounds__(BT) k_build_keys(const uint32_t *__restrict__ 
     if (my_vinv) atomicMax(&s_vinv, my_vinv);
   }
   __syncthreads();
+  hist_flush(s_h, H);
   if (threadIdx.x == 0) {
     if (s_or) atomicOr(&sc->dst_or, s_or);
     if (s_bad) atomicAdd(&sc->n_ignored, (unsigned long long)s_bad);
@@ -77,9 +107,11 @@ __global__ void __launch_bounds__(BT) k_build_keys_packed(const uint64_t *__rest
                                                           const uint32_t *__restrict__ val, uint32_t default_val,
                                                           size_t count, uint32_t n, uint32_t op_bit, uint64_t *__restrict__ keys,
                                                           uint32_t *__restrict__ pay, BatchScalars *sc,
-                                                          uint32_t swap_halves) {
+                                                          uint32_t swap_halves, HistArgs H) {
   // swap_halves: the records are interleaved little-endian (src, dst) pairs read as one word (dst << 32 | src)
   __shared__ uint32_t s_or, s_bad, s_vmax, s_vinv;
+  __shared__ uint32_t s_h[prim::OS_MAX_PASSES * prim::OS_RADIX];
+  hist_init(s_h, H);
   if (threadIdx.x == 0) {
     s_or = 0;
     s_bad = 0;
@@ -94,7 +126,9 @@ __global__ void __launch_bounds__(BT) k_build_keys_packed(const uint64_t *__rest
     const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k;
     const uint32_t v = val ? val[i] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
-    keys[i] = emit_key(ok, k, v, n, op_bit);
+    const uint64_t kq = emit_key(ok, k, v, n, op_bit);
+    keys[i] = kq;
+    hist_add(s_h, H, kq);
     if (pay) pay[i] = ok ? v : 0u;
     if (ok) my_or |= d;
     else my_bad++;
@@ -111,6 +145,7 @@ __global__ void __launch_bounds__(BT) k_build_keys_packed(const uint64_t *__rest
     if (my_vinv) atomicMax(&s_vinv, my_vinv);
   }
   __syncthreads();
+  hist_flush(s_h, H);
   if (threadIdx.x == 0) {
     if (s_or) atomicOr(&sc->dst_or, s_or);
     if (s_bad) atomicAdd(&sc->n_ignored, (unsigned long long)s_bad);
@@ -129,8 +164,10 @@ struct SegmentTable {
 __global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__restrict__ packed,
                                                             const uint32_t *__restrict__ val, uint32_t default_val,
                                                             SegmentTable T, uint32_t n, uint32_t op_bit, uint64_t *__restrict__ keys,
-                                                            uint32_t *__restrict__ pay, BatchScalars *sc) {
+                                                            uint32_t *__restrict__ pay, BatchScalars *sc, HistArgs H) {
   __shared__ uint32_t s_or, s_bad, s_vmax, s_vinv;
+  __shared__ uint32_t s_h[prim::OS_MAX_PASSES * prim::OS_RADIX];
+  hist_init(s_h, H);
   __shared__ uint64_t s_prefix[BIN_MAX_PARTS + 1];  // exclusive prefix of the regions' counts
   if (threadIdx.x == 0) {
     s_or = 0;
@@ -160,7 +197,9 @@ __global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__re
     const uint32_t s = (uint32_t)(k >> 32), d = (uint32_t)k;
     const uint32_t v = val ? val[at] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
-    keys[i] = emit_key(ok, k, v, n, op_bit);
+    const uint64_t kq = emit_key(ok, k, v, n, op_bit);
+    keys[i] = kq;
+    hist_add(s_h, H, kq);
     if (pay) pay[i] = ok ? v : 0u;
     if (ok) my_or |= d;
     else my_bad++;
@@ -177,6 +216,7 @@ __global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__re
     if (my_vinv) atomicMax(&s_vinv, my_vinv);
   }
   __syncthreads();
+  hist_flush(s_h, H);
   if (threadIdx.x == 0) {
     if (s_or) atomicOr(&sc->dst_or, s_or);
     if (s_bad) atomicAdd(&sc->n_ignored, (unsigned long long)s_bad);

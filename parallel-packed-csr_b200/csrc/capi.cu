@@ -551,11 +551,16 @@ int finish_batch_impl(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
   return PPCSR_OK;
 }
 
-int finalize_stats(ppcsr_shard *s, ppcsr_batch_stats *st) {
+int finalize_stats(ppcsr_shard *s, ppcsr_batch_stats *st, bool stages = true) {
   CUDA_TRY(cudaEventSynchronize(s->ev[4]));
   float t;
   CUDA_TRY(cudaEventElapsedTime(&t, s->ev[0], s->ev[4]));
   st->ms_total = t;
+  if (!stages) {  // small-batch path: only the two events around the batch were recorded
+    st->kernel_launches = s->launches;
+    s->last = *st;
+    return PPCSR_OK;
+  }
   CUDA_TRY(cudaEventElapsedTime(&t, s->ev[0], s->ev[1]));
   st->ms_sort = t;
   CUDA_TRY(cudaEventElapsedTime(&t, s->ev[1], s->ev[2]));
@@ -836,16 +841,27 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   // per-update values: removes are also flagged in bit 63 of the key word (free while vertex ids stay below 2^31),
   // so that a stream whose non-zero values are all equal can be sorted keys-only (see batch::emit_key)
   const uint32_t op_bit = (has_pay && s->n < (1u << 31)) ? 1u : 0u;
-  const unsigned kb = std::min<unsigned>(div_up(count, batch::BT * 8), 148 * 16);
+  // Speculated sort layout: the widest dst seen so far (at least the vertex ids) and, for the sources, "nothing is
+  // rejected".  The key builder takes the digit histograms of that layout along (batch::HistArgs); if the batch turns
+  // out wider, or needs fewer passes, prim::k_os_hist runs on the real layout as before.
+  const uint32_t dst_spec = s->dst_or_seen | (s->n ? s->n - 1u : 0u);
+  const int lo_spec = std::max(1, bits_of(dst_spec));
+  const int hi_spec = std::max(1, bits_of(s->n ? s->n - 1 : 0));
+  batch::HistArgs H{};
+  H.P = prim::make_sort_passes(lo_spec, hi_spec);
+  H.ghist = nullptr;
+  const bool fused_hist = count > prim::SS_MAX;  // (smaller batches are sorted by one CTA: no global histograms)
+  if (fused_hist) PPCSR_TRY(prim::radix_sort_prepare(s, count, H.P, &H.ghist));
+  const unsigned kb = std::min<unsigned>(div_up(count, batch::BT * 8), 148 * (fused_hist ? 8 : 16));
   if (segments) {
     batch::k_build_keys_segments<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, *segments, s->n, op_bit,
-                                                                 s->key_a.p, has_pay ? s->pay_a.p : nullptr, sc);
+                                                                 s->key_a.p, has_pay ? s->pay_a.p : nullptr, sc, H);
   } else if (d_packed) {
     batch::k_build_keys_packed<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, count, s->n, op_bit, s->key_a.p,
-                                                               has_pay ? s->pay_a.p : nullptr, sc, pairs ? 1u : 0u);
+                                                               has_pay ? s->pay_a.p : nullptr, sc, pairs ? 1u : 0u, H);
   } else {
     batch::k_build_keys<<<kb, batch::BT, 0, s->stream>>>(d_src, d_dst, d_val, default_val, count, s->n, op_bit, s->key_a.p,
-                                                        has_pay ? s->pay_a.p : nullptr, sc);
+                                                        has_pay ? s->pay_a.p : nullptr, sc, H);
   }
   CUDA_TRY(cudaGetLastError());
   // Small-batch path (sparse.cuh): no host round trip here -- the sort width is speculated from the dsts seen so far
@@ -856,12 +872,16 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   }();
   const bool sparse = !no_sparse && !segments && env_sparse >= 0 && s->sparse_policy >= 0 && s->whole_policy <= 0 &&
                       g.n_leaves >= 1024 && count <= SPARSE_MAX_BATCH && (count * 4 <= g.n_leaves || env_sparse > 0);
-  const uint32_t dst_spec = s->dst_or_seen | (s->n ? s->n - 1u : 0u);
+  // every API call counts on a batch of a thousand updates: the small-batch path records the per-stage events only on
+  // request (PPCSR_STAGE_TIMING=1); ms_total is always measured
+  static const bool env_stage = getenv("PPCSR_STAGE_TIMING") != nullptr;
+  const bool stage_ev = !sparse || env_stage;
   int lo_bits, hi_bits;
-  bool sort_pay = has_pay;
+  bool sort_pay = has_pay, hist_done = false;
   if (sparse) {
-    lo_bits = std::max(1, bits_of(dst_spec));
+    lo_bits = lo_spec;
     hi_bits = std::max(1, bits_of(s->n));  // wide enough for the rejected key (n << 32) too
+    hist_done = fused_hist && hi_bits == hi_spec;
   } else {
     PPCSR_TRY(read_scalars(s));
     s->dst_or_seen |= s->h_scalars->dst_or;
@@ -890,13 +910,20 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
         default_val = vmax ? vmax : 1u;
       }
     }
+    // the speculated layout holds if the batch is no wider and would not get away with fewer passes
+    if (fused_hist && count > prim::SS_MAX && lo_bits <= lo_spec && hi_bits <= hi_spec &&
+        prim::make_sort_passes(lo_bits, hi_bits).n_pass == H.P.n_pass) {
+      lo_bits = lo_spec;
+      hi_bits = hi_spec;
+      hist_done = true;
+    }
   }
   // 2. stable radix sort by (src,dst)
   uint64_t *keys;
   uint32_t *pay;
   PPCSR_TRY(prim::radix_sort_pairs(s, s->key_a.p, sort_pay ? s->pay_a.p : nullptr, s->key_b.p, s->pay_b.p, count,
-                                   lo_bits, hi_bits, &keys, &pay));
-  CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
+                                   lo_bits, hi_bits, &keys, &pay, hist_done));
+  if (stage_ev) CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
   // 3+4. call counts, last-op-wins, locate, per-leaf counts -- one kernel over the sorted batch
   const uint64_t invalid_key = (uint64_t)s->n << 32;
   if (sparse) {  // the per-leaf batch counters are kept clear between small batches: no O(leaves) fill per batch
@@ -947,7 +974,7 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
     batch::k_gather_inserts<<<lblocks, batch::LT, 0, s->stream>>>(tile_dst, tile_val, s->uloc.p, s->tile_cnt.p,
                                                                  s->ins_dst.p, s->ins_val.p, s->ins_pred.p, sc);
   }
-  CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+  if (stage_ev) CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
   if (sparse) {
     // 5s. tree, windows and rebalance of the small-batch path, then the ONE host synchronisation of the batch
     const unsigned tb = div_up(std::min<uint64_t>(count, g.n_leaves), sp::ST);
@@ -959,8 +986,10 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
                                                 g.n_leaves, g.logN, (int)g.H, s->mark.p, s->epoch, sc);
     sp::k_sp_windows<<<tb, sp::ST, 0, s->stream>>>(s->touched.p, s->mark.p, s->epoch, s->tree.p, g.n_leaves, g.logN,
                                                   s->windows.p, sc);
-    CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
-    CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
+    if (stage_ev) {
+      CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
+      CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
+    }
     sp::RebArgs R{};
     R.dest = s->dest.p;
     R.val = s->val.p;
@@ -978,7 +1007,7 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
     R.ls = g.leaf_shift;
     sp::k_sp_rebalance<<<std::max(1u, div_up(std::min<uint64_t>(count, g.n_leaves), reb::RWARPS)), reb::RT, 0,
                          s->stream>>>(R);
-    CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
+    if (stage_ev) CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     CUDA_TRY(cudaEventRecord(s->ev[4], s->stream));
     CUDA_TRY(cudaGetLastError());
     PPCSR_TRY(read_scalars(s));
@@ -1000,7 +1029,7 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
       s->items += h.n_inserted - h.n_deleted;
       s->last_sparse = true;
       s->last_touched = (uint32_t)h.n_touched;
-      PPCSR_TRY(finalize_stats(s, &st));
+      PPCSR_TRY(finalize_stats(s, &st, stage_ev));
       if (stats) *stats = st;
       return PPCSR_OK;
     }
@@ -1010,6 +1039,10 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
                              s->stream));
     CUDA_TRY(cudaMemsetAsync(&sc->root_violation, 0, sizeof(unsigned int), s->stream));
     s->cnt_clean = false;
+    if (!stage_ev) {  // the general path's statistics read every stage event
+      CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
+      CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
+    }
   }
   // 5. windows + rebalance
   PPCSR_TRY(finish_batch(s, count, &st));

@@ -427,10 +427,27 @@ inline size_t radix_sort_scratch_words(size_t n) {
   return (size_t)OS_MAX_PASSES * OS_RADIX + 64 + (size_t)OS_MAX_PASSES * (ntiles + OS_LB_DEPTH) * OS_RADIX;
 }
 
+// scratch layout in s->hist: ghist[8][256] | tile counters[64] | lookback[n_pass][OS_LB_DEPTH + ntiles][256]
+inline size_t radix_sort_words(size_t n, int n_pass) {
+  const size_t ntiles = (n + OS_TILE - 1) / OS_TILE;
+  return (size_t)OS_MAX_PASSES * OS_RADIX + 64 + (size_t)n_pass * (ntiles + OS_LB_DEPTH) * OS_RADIX;
+}
+// Reserves and clears the scratch of a sort of up to n keys in P.n_pass passes.  Called BEFORE the key builder when the
+// builder takes the histograms itself (see batch::HistArgs); *ghist = where they go.
+inline int radix_sort_prepare(ppcsr_shard *s, size_t n, const SortPasses &P, uint32_t **ghist) {
+  const size_t words = radix_sort_words(n, P.n_pass);
+  PPCSR_TRY(dev_reserve(s->hist, words, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->hist.p, 0, words * sizeof(uint32_t), s->stream));
+  *ghist = s->hist.p;
+  return PPCSR_OK;
+}
+
 // Sorts n (key,payload) pairs by the key bits [0,lo_bits) and [32, 32+hi_bits).  Input in (ka,pa); the
 // sorted result ends up in *rk / *rp which point at either buffer pair.  pa == nullptr sorts keys only.
+// hist_done: the scratch was prepared (radix_sort_prepare, for at least n keys and this layout) and already holds the
+// digit histograms of this layout: no clearing, no k_os_hist.
 inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t *kb, uint32_t *pb, size_t n,
-                            int lo_bits, int hi_bits, uint64_t **rk, uint32_t **rp) {
+                            int lo_bits, int hi_bits, uint64_t **rk, uint32_t **rp, bool hist_done = false) {
   *rk = ka;
   *rp = pa;
   if (n <= 1) return PPCSR_OK;
@@ -456,14 +473,14 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
     return PPCSR_OK;
   }
   const size_t ntiles = (n + OS_TILE - 1) / OS_TILE;
-  // scratch layout in s->hist: ghist[8][256] | tile counters[64] | lookback[n_pass][OS_LB_DEPTH + ntiles][256]
   const size_t rows = ntiles + OS_LB_DEPTH;
-  const size_t words = (size_t)OS_MAX_PASSES * OS_RADIX + 64 + (size_t)P.n_pass * rows * OS_RADIX;
-  PPCSR_TRY(dev_reserve(s->hist, words, s->stream));
+  if (!hist_done) {
+    uint32_t *g;
+    PPCSR_TRY(radix_sort_prepare(s, n, P, &g));
+  }
   uint32_t *ghist = s->hist.p;
   uint32_t *counters = ghist + OS_MAX_PASSES * OS_RADIX;
   uint32_t *lookback = counters + 64;
-  CUDA_TRY(cudaMemsetAsync(s->hist.p, 0, words * sizeof(uint32_t), s->stream));
   {  // > 48 KB of dynamic shared memory needs an explicit opt-in: per device, once, thread-safe
     static std::once_flag once[64];
     static cudaError_t once_err[64];
@@ -475,9 +492,12 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
     });
     CUDA_TRY(once_err[dv]);
   }
-  const unsigned hblocks = (unsigned)std::min<size_t>((n + (size_t)OSH_THREADS * OSH_ITEMS - 1) / ((size_t)OSH_THREADS * OSH_ITEMS), 148 * 4);
-  s->launches += 2 + P.n_pass;
-  k_os_hist<<<hblocks, OSH_THREADS, 0, s->stream>>>(ka, n, P, ghist);
+  s->launches += 1 + P.n_pass;
+  if (!hist_done) {
+    const unsigned hblocks = (unsigned)std::min<size_t>((n + (size_t)OSH_THREADS * OSH_ITEMS - 1) / ((size_t)OSH_THREADS * OSH_ITEMS), 148 * 4);
+    s->launches += 1;
+    k_os_hist<<<hblocks, OSH_THREADS, 0, s->stream>>>(ka, n, P, ghist);
+  }
   k_os_scan<<<P.n_pass, OS_RADIX, 0, s->stream>>>(ghist, lookback, rows);
   uint64_t *src_k = ka, *dst_k = kb;
   uint32_t *src_p = pa, *dst_p = pb;
