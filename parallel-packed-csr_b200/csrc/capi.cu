@@ -1652,27 +1652,40 @@ int ppcsr_bfs(ppcsr_shard *s, uint32_t start, uint32_t *dist) {
   if (!s || (s->n && !dist)) return PPCSR_ERR_ARG;
   PPCSR_TRY(set_device(s));
   if (s->n == 0) return PPCSR_OK;
-  DevBuf<uint32_t> d_dist;
-  PPCSR_TRY(dev_reserve(d_dist, (size_t)s->n + 1, s->stream));
-  PPCSR_TRY(dev_reserve(s->misc, 16, s->stream));
-  qry::k_fill_u32<<<div_up(s->n, 256), 256, 0, s->stream>>>(d_dist.p, 0xFFFFFFFFu, s->n);
-  if (start < s->n) {
-    reb::k_set_u32<<<1, 1, 0, s->stream>>>(d_dist.p + start, 0u);
-    uint32_t *hp = reinterpret_cast<uint32_t *>(s->h_pinned);
-    const unsigned blocks = std::min<unsigned>(div_up((uint64_t)s->n * 32, qry::QT), 148 * 16);
-    for (uint32_t level = 0; level < s->n; level++) {
-      CUDA_TRY(cudaMemsetAsync(s->misc.p, 0, 4, s->stream));
-      qry::k_bfs_level<<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->leaf_cnt.p, s->beg.p, s->geo.leaf_shift, s->n,
-                                                         d_dist.p, level, s->misc.p);
-      CUDA_TRY(cudaMemcpyAsync(hp, s->misc.p, 4, cudaMemcpyDeviceToHost, s->stream));
-      CUDA_TRY(cudaStreamSynchronize(s->stream));
-      if (hp[0] == 0) break;
+  DevBuf<uint32_t> d_dist, d_fa, d_fb;
+  const int rc = [&]() -> int {
+    PPCSR_TRY(dev_reserve(d_dist, (size_t)s->n + 1, s->stream));
+    PPCSR_TRY(dev_reserve(d_fa, (size_t)s->n + 1, s->stream));
+    PPCSR_TRY(dev_reserve(d_fb, (size_t)s->n + 1, s->stream));
+    PPCSR_TRY(dev_reserve(s->misc, 16, s->stream));
+    qry::k_fill_u32<<<div_up(s->n, 256), 256, 0, s->stream>>>(d_dist.p, 0xFFFFFFFFu, s->n);
+    if (start < s->n) {
+      reb::k_set_u32<<<1, 1, 0, s->stream>>>(d_dist.p + start, 0u);
+      reb::k_set_u32<<<1, 1, 0, s->stream>>>(d_fa.p, start);
+      uint32_t *hp = reinterpret_cast<uint32_t *>(s->h_pinned);
+      uint32_t n_front = 1;
+      uint32_t *cur = d_fa.p, *nxt = d_fb.p;
+      // one launch and one 4-byte read-back (the size of the next frontier) per level
+      for (uint32_t level = 0; n_front != 0 && level < s->n; level++) {
+        CUDA_TRY(cudaMemsetAsync(s->misc.p, 0, 4, s->stream));
+        const unsigned blocks = std::max(1u, std::min<unsigned>(div_up((uint64_t)n_front * 32, qry::QT), 148 * 16));
+        qry::k_bfs_frontier<<<blocks, qry::QT, 0, s->stream>>>(s->dest.p, s->leaf_cnt.p, s->beg.p, s->geo.leaf_shift,
+                                                              s->n, d_dist.p, level, cur, n_front, nxt, s->misc.p);
+        CUDA_TRY(cudaMemcpyAsync(hp, s->misc.p, 4, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        n_front = hp[0];
+        std::swap(cur, nxt);
+      }
     }
-  }
-  CUDA_TRY(cudaMemcpyAsync(dist, d_dist.p, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream));
-  CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(dist, d_dist.p, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return PPCSR_OK;
+  }();
   dev_free(d_dist);
-  return PPCSR_OK;
+  dev_free(d_fa);
+  dev_free(d_fb);
+  return rc;
 }
 
 // ---- checks and snapshots ---------------------------------------------------------------------------

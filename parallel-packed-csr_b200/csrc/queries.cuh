@@ -206,24 +206,37 @@ __global__ void k_cast_in(const W *__restrict__ in, double *__restrict__ out, ui
   if (i < n) out[i] = (double)in[i];
 }
 
-// ---- BFS (level synchronous, warp per frontier vertex) ------------------------------------------------
-__global__ void __launch_bounds__(QT) k_bfs_level(const uint32_t *__restrict__ dest,
-                                                  const uint32_t *__restrict__ leaf_cnt,
-                                                  const uint32_t *__restrict__ beg, uint32_t ls, uint32_t n,
-                                                  uint32_t *__restrict__ dist, uint32_t level, uint32_t *changed) {
+// ---- BFS (level synchronous, frontier queues; reference src/utility/bfs.h:15-36) -------------------------------
+// One warp per vertex of the current frontier scans its slot range; a neighbour reached for the first time
+// (compare-and-swap on its distance) joins the next frontier, the warp takes its places in the queue with one atomic.
+// Work per level is O(frontier edges), not O(n).
+__global__ void __launch_bounds__(QT) k_bfs_frontier(const uint32_t *__restrict__ dest,
+                                                     const uint32_t *__restrict__ leaf_cnt,
+                                                     const uint32_t *__restrict__ beg, uint32_t ls, uint32_t n,
+                                                     uint32_t *__restrict__ dist, uint32_t level,
+                                                     const uint32_t *__restrict__ frontier, uint32_t n_frontier,
+                                                     uint32_t *__restrict__ next, uint32_t *n_next) {
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = lane_id();
-  for (uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n; v += warps) {
-    if (dist[v] != level) continue;
+  const unsigned lt = lanemask_lt();
+  for (uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < n_frontier; f += warps) {
+    const uint32_t v = frontier[f];
     const uint32_t b = beg[v], e = beg[v + 1];
-    for (uint32_t slot = b + 1 + lane; slot < e; slot += 32) {
-      const uint32_t f = slot & ((1u << ls) - 1u);
-      if (f < leaf_cnt[slot >> ls]) {
-        const uint32_t d = dest[slot];
-        if (d < n && dist[d] == 0xFFFFFFFFu) {
-          dist[d] = level + 1;  // benign race: every writer stores the same value
-          *changed = 1;
-        }
+    for (uint32_t base = b + 1; base < e; base += 32) {
+      const uint32_t slot = base + lane;
+      bool fresh = false;
+      uint32_t d = 0;
+      if (slot < e && (slot & ((1u << ls) - 1u)) < leaf_cnt[slot >> ls]) {
+        d = dest[slot];
+        fresh = d < n && atomicCAS(&dist[d], 0xFFFFFFFFu, level + 1u) == 0xFFFFFFFFu;
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, fresh);
+      if (m) {
+        uint32_t at = 0;
+        const unsigned leader = (unsigned)__ffs(m) - 1u;
+        if (lane == leader) at = atomicAdd(n_next, (uint32_t)__popc(m));
+        at = __shfl_sync(0xFFFFFFFFu, at, leader);
+        if (fresh) next[at + __popc(m & lt)] = d;
       }
     }
   }
