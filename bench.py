@@ -387,7 +387,10 @@ def build_core(synth, torch, router, scale, rank, world, local_rank, dev, dist, 
         # Shard cost model measured at N=1/2: ~0.13 us per routed update (sort + locate) and ~0.016 us per stored
         # item (window selection + rebalance).  A uniform stream sends B/n updates to every vertex, so a vertex
         # weighs ~8 * B/n "edges"; skewed inserts and deletes follow the edge distribution instead.
-        vw = 8.0 * B_rank * world / n if workload in ("insert", "mixed") else 0.0
+        # Every vertex also stores one sentinel (an item like an edge), so it weighs at least 1: with weight 0 the shard
+        # of the low-degree tail of an R-MAT graph holds millions of sentinels more than the others and is the one that
+        # has to double its array (measured at 8 GPUs: 7.3 M vertices, 2^26 -> 2^27 slots, +0.13 ms on that rank).
+        vw = 8.0 * B_rank * world / n + 1.0 if workload in ("insert", "mixed") else 1.0
         starts = router.edge_balanced_starts(cs, n, world, dist, vertex_weight=vw)
     else:
         starts = np.array([0, n], dtype=np.uint64)

@@ -5,7 +5,7 @@ src/benchmarking/benchmark-strong-scaling.sh:83-156, with the GPU count in place
 The reference script runs its CLI for every core count / variant / partitions-per-domain / repetition, scrapes the
 second `Elapsed wall clock time:` line (the update phase) and writes one CSV row per core count
     #CORES INS_<variant>0 .. INS_<variant>_Avg INS_<variant>_Stddev DEL_<variant>0 ..
-plus a plot-data file `cores avg_ins stddev_ins avg_del stddev_del`.  Here every cell is one `bench.py --strong` run
+plus a plot-data file `cores avg_ins stddev_ins avg_del stddev_del`.  Here every cell is one `bench.py` run
 (a FIXED graph and batch split over N vertex-range shards, one process per GPU, launched exactly like the driver
 launches bench.py), the scraped number is the time of the batch in milliseconds (`ms_per_step`), and the layout of
 the two output files is the same, so the reference's gnuplot scripts read them unchanged:
@@ -32,7 +32,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def bench_command(gpus: int, workload: str, scale: int, batch: int, steps: int, warmup: int, port: int) -> list[str]:
     """The command line of one cell: plain python at one GPU, torchrun (one rank per GPU) above."""
     tail = [os.path.join(ROOT, "bench.py"), "--gpus", str(gpus), "--steps", str(steps), "--warmup", str(warmup),
-            "--workload", workload, "--scale", str(scale), "--batch", str(batch), "--strong", "--no-cpu-baseline"]
+            "--workload", workload, "--scale", str(scale), "--batch", str(batch), "--only-headline", "--no-cpu-baseline"]
     if gpus == 1:
         return [sys.executable] + tail
     return [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(gpus),

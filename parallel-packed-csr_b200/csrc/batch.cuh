@@ -27,6 +27,74 @@ __device__ __forceinline__ uint64_t emit_key(bool ok, uint64_t key, uint32_t v, 
   return (op_bit && v == 0u) ? (key | KEY_OP_BIT) : key;
 }
 
+// ---- raw key sources: the sort's first pass (prim::k_os_pass / k_os_hist / k_sort_small) builds the key word of
+// update i straight from the caller's arrays, guards included, so the unsorted batch is never written as a key array.
+// Same arithmetic as the builders below (which then only take the scalars and the histograms).
+__device__ __forceinline__ bool update_ok(uint32_t s, uint32_t d, uint32_t v, uint32_t n) {
+  return s < n && !(v != 0 && d == PPCSR_SENT);
+}
+struct RawArrays {
+  const uint32_t *src, *dst, *val;  // val nullable: every update carries default_val
+  uint32_t default_val, n, op_bit;
+  __device__ __forceinline__ uint64_t key(size_t i) const {
+    const uint32_t s = src[i], d = dst[i], v = val ? val[i] : default_val;
+    return emit_key(update_ok(s, d, v, n), ((uint64_t)s << 32) | d, v, n, op_bit);
+  }
+  __device__ __forceinline__ uint32_t payload(size_t i) const {
+    const uint32_t v = val[i];
+    return update_ok(src[i], dst[i], v, n) ? v : 0u;
+  }
+};
+struct RawPacked {
+  const uint64_t *packed;
+  const uint32_t *val;
+  uint32_t default_val, n, op_bit, swap_halves;
+  __device__ __forceinline__ uint64_t word(size_t i) const {
+    const uint64_t k = packed[i];
+    return swap_halves ? (k << 32) | (k >> 32) : k;
+  }
+  __device__ __forceinline__ uint64_t key(size_t i) const {
+    const uint64_t k = word(i);
+    const uint32_t v = val ? val[i] : default_val;
+    return emit_key(update_ok((uint32_t)(k >> 32), (uint32_t)k, v, n), k, v, n, op_bit);
+  }
+  __device__ __forceinline__ uint32_t payload(size_t i) const {
+    const uint64_t k = word(i);
+    const uint32_t v = val[i];
+    return update_ok((uint32_t)(k >> 32), (uint32_t)k, v, n) ? v : 0u;
+  }
+};
+// records deposited by the peers: n_seg regions of `cap` records, region r holding prefix[r + 1] - prefix[r] of them
+// (prefix: a DEVICE array written by k_build_keys_segments)
+struct RawSegments {
+  const uint64_t *packed;
+  const uint32_t *val;
+  const unsigned long long *prefix;
+  unsigned long long cap;
+  uint32_t n_seg, default_val, n, op_bit;
+  __device__ __forceinline__ size_t at(size_t i) const {
+    uint32_t lo = 0, hi = n_seg;  // last region with prefix <= i
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (prefix[mid] <= i) lo = mid;
+      else hi = mid;
+    }
+    return (size_t)lo * cap + (i - (size_t)prefix[lo]);
+  }
+  __device__ __forceinline__ uint64_t key(size_t i) const {
+    const size_t a = at(i);
+    const uint64_t k = packed[a];
+    const uint32_t v = val ? val[a] : default_val;
+    return emit_key(update_ok((uint32_t)(k >> 32), (uint32_t)k, v, n), k, v, n, op_bit);
+  }
+  __device__ __forceinline__ uint32_t payload(size_t i) const {
+    const size_t a = at(i);
+    const uint64_t k = packed[a];
+    const uint32_t v = val[a];
+    return update_ok((uint32_t)(k >> 32), (uint32_t)k, v, n) ? v : 0u;
+  }
+};
+
 // The key builders can also take the sort's digit histograms (all passes, prim::k_os_hist's job) while the keys pass
 // through their registers: the host SPECULATES the sort layout from the widest dst seen so far and the vertex count,
 // and falls back to prim::k_os_hist when the batch turns out wider (capi.cu).  Saves one read of the batch.
@@ -75,9 +143,9 @@ __global__ void __launch_bounds__(BT) k_build_keys(const uint32_t *__restrict__ 
     const uint32_t v = val ? val[i] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
     const uint64_t kq = emit_key(ok, ((uint64_t)s << 32) | d, v, n, op_bit);
-    keys[i] = kq;
+    if (keys) keys[i] = kq;  // nullptr: the sort reads the raw arrays itself (RawArrays)
     hist_add(s_h, H, kq);
-    if (pay) pay[i] = ok ? v : 0u;
+    if (pay && keys) pay[i] = ok ? v : 0u;
     if (ok) my_or |= d;
     else my_bad++;
     if (pay && ok && v) my_vmax = max(my_vmax, v), my_vinv = max(my_vinv, ~v);
@@ -127,9 +195,9 @@ __global__ void __launch_bounds__(BT) k_build_keys_packed(const uint64_t *__rest
     const uint32_t v = val ? val[i] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
     const uint64_t kq = emit_key(ok, k, v, n, op_bit);
-    keys[i] = kq;
+    if (keys) keys[i] = kq;  // nullptr: the sort reads the raw records itself (RawPacked / RawSegments)
     hist_add(s_h, H, kq);
-    if (pay) pay[i] = ok ? v : 0u;
+    if (pay && keys) pay[i] = ok ? v : 0u;
     if (ok) my_or |= d;
     else my_bad++;
     if (pay && ok && v) my_vmax = max(my_vmax, v), my_vinv = max(my_vinv, ~v);
@@ -160,6 +228,7 @@ struct SegmentTable {
   uint32_t n_seg;
   uint64_t cap;
   const uint64_t *counts;  // DEVICE array: valid records of every region (deposited by the senders)
+  unsigned long long *prefix_out;  // DEVICE array of n_seg + 1 entries (nullable): exclusive prefix of the counts
 };
 __global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__restrict__ packed,
                                                             const uint32_t *__restrict__ val, uint32_t default_val,
@@ -180,7 +249,11 @@ __global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__re
       run += min(T.counts[r], T.cap);
     }
     s_prefix[T.n_seg] = run;
-    if (blockIdx.x == 0) sc->seg_total = run;  // the host learns the batch size with the sort width
+    if (blockIdx.x == 0) {
+      sc->seg_total = run;  // the host learns the batch size with the sort width
+      if (T.prefix_out)
+        for (uint32_t r = 0; r <= T.n_seg; r++) T.prefix_out[r] = s_prefix[r];  // for RawSegments
+    }
   }
   __syncthreads();
   uint32_t my_or = 0, my_bad = 0, my_vmax = 0, my_vinv = 0;
@@ -198,9 +271,9 @@ __global__ void __launch_bounds__(BT) k_build_keys_segments(const uint64_t *__re
     const uint32_t v = val ? val[at] : default_val;
     const bool ok = s < n && !(v != 0 && d == PPCSR_SENT);
     const uint64_t kq = emit_key(ok, k, v, n, op_bit);
-    keys[i] = kq;
+    if (keys) keys[i] = kq;  // nullptr: the sort reads the raw records itself (RawPacked / RawSegments)
     hist_add(s_h, H, kq);
-    if (pay) pay[i] = ok ? v : 0u;
+    if (pay && keys) pay[i] = ok ? v : 0u;
     if (ok) my_or |= d;
     else my_bad++;
     if (pay && ok && v) my_vmax = max(my_vmax, v), my_vinv = max(my_vinv, ~v);

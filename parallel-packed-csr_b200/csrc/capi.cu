@@ -722,7 +722,7 @@ void ppcsr_destroy(ppcsr_shard *s) {
   dev_free(s->uloc); dev_free(s->ucls); dev_free(s->ufirst); dev_free(s->ins_dst); dev_free(s->ins_val); dev_free(s->ins_pred);
   dev_free(s->block_tmp); dev_free(s->hist); dev_free(s->pr_acc); dev_free(s->misc);
   dev_free(s->scan_state); dev_free(s->scan_ticket); dev_free(s->tile_cnt);
-  dev_free(s->touch_stamp); dev_free(s->touched_flags);
+  dev_free(s->touch_stamp); dev_free(s->touched_flags); dev_free(s->seg_prefix);
   dev_free(s->snap.dest); dev_free(s->snap.val); dev_free(s->snap.leaf_cnt); dev_free(s->snap.tree);
   dev_free(s->snap.beg); dev_free(s->snap.nn);
   for (auto &P : s->pending) {
@@ -852,15 +852,24 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   H.ghist = nullptr;
   const bool fused_hist = count > prim::SS_MAX;  // (smaller batches are sorted by one CTA: no global histograms)
   if (fused_hist) PPCSR_TRY(prim::radix_sort_prepare(s, count, H.P, &H.ghist));
+  // The unsorted batch is not written out as a key array: the first pass of the sort builds the key words from the
+  // caller's arrays itself (batch::RawArrays / RawPacked / RawSegments), the builder only takes the scalars and the
+  // histograms.  Only a batch small enough for the one-CTA sort whose size is known here is materialised.
+  const bool materialize = !segments && count <= prim::SS_MAX;
+  uint64_t *key_out = materialize ? s->key_a.p : nullptr;
+  const uint32_t src_default = default_val;  // (default_val may be replaced below when the values are all equal)
   const unsigned kb = std::min<unsigned>(div_up(count, batch::BT * 8), 148 * (fused_hist ? 8 : 16));
   if (segments) {
-    batch::k_build_keys_segments<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, *segments, s->n, op_bit,
-                                                                 s->key_a.p, has_pay ? s->pay_a.p : nullptr, sc, H);
+    PPCSR_TRY(dev_reserve(s->seg_prefix, (size_t)segments->n_seg + 2, s->stream));
+    batch::SegmentTable T = *segments;
+    T.prefix_out = s->seg_prefix.p;
+    batch::k_build_keys_segments<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, T, s->n, op_bit, key_out,
+                                                                 has_pay ? s->pay_a.p : nullptr, sc, H);
   } else if (d_packed) {
-    batch::k_build_keys_packed<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, count, s->n, op_bit, s->key_a.p,
+    batch::k_build_keys_packed<<<kb, batch::BT, 0, s->stream>>>(d_packed, d_val, default_val, count, s->n, op_bit, key_out,
                                                                has_pay ? s->pay_a.p : nullptr, sc, pairs ? 1u : 0u, H);
   } else {
-    batch::k_build_keys<<<kb, batch::BT, 0, s->stream>>>(d_src, d_dst, d_val, default_val, count, s->n, op_bit, s->key_a.p,
+    batch::k_build_keys<<<kb, batch::BT, 0, s->stream>>>(d_src, d_dst, d_val, default_val, count, s->n, op_bit, key_out,
                                                         has_pay ? s->pay_a.p : nullptr, sc, H);
   }
   CUDA_TRY(cudaGetLastError());
@@ -921,8 +930,22 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   // 2. stable radix sort by (src,dst)
   uint64_t *keys;
   uint32_t *pay;
-  PPCSR_TRY(prim::radix_sort_pairs(s, s->key_a.p, sort_pay ? s->pay_a.p : nullptr, s->key_b.p, s->pay_b.p, count,
-                                   lo_bits, hi_bits, &keys, &pay, hist_done));
+  if (materialize) {
+    PPCSR_TRY(prim::radix_sort_pairs(s, s->key_a.p, sort_pay ? s->pay_a.p : nullptr, s->key_b.p, s->pay_b.p, count,
+                                     lo_bits, hi_bits, &keys, &pay, hist_done));
+  } else if (segments) {
+    const batch::RawSegments R{d_packed, d_val, s->seg_prefix.p, segments->cap, segments->n_seg, src_default, s->n, op_bit};
+    PPCSR_TRY(prim::radix_sort_from(s, R, sort_pay, s->key_a.p, s->pay_a.p, s->key_b.p, s->pay_b.p, count, lo_bits,
+                                    hi_bits, &keys, &pay, hist_done));
+  } else if (d_packed) {
+    const batch::RawPacked R{d_packed, d_val, src_default, s->n, op_bit, pairs ? 1u : 0u};
+    PPCSR_TRY(prim::radix_sort_from(s, R, sort_pay, s->key_a.p, s->pay_a.p, s->key_b.p, s->pay_b.p, count, lo_bits,
+                                    hi_bits, &keys, &pay, hist_done));
+  } else {
+    const batch::RawArrays R{d_src, d_dst, d_val, src_default, s->n, op_bit};
+    PPCSR_TRY(prim::radix_sort_from(s, R, sort_pay, s->key_a.p, s->pay_a.p, s->key_b.p, s->pay_b.p, count, lo_bits,
+                                    hi_bits, &keys, &pay, hist_done));
+  }
   if (stage_ev) CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
   // 3+4. call counts, last-op-wins, locate, per-leaf counts -- one kernel over the sorted batch
   const uint64_t invalid_key = (uint64_t)s->n << 32;

@@ -234,6 +234,7 @@ struct ppcsr_shard {
   DevBuf<uint32_t> uval;               // [batch]
   DevBuf<uint32_t> uloc;               // [batch, whole tiles] predecessor slots of the locate tiles' inserts
   DevBuf<uint32_t> tile_cnt;           // [tiles + 1] inserts per locate tile -> exclusive scan
+  DevBuf<unsigned long long> seg_prefix;  // [segments + 1] prefix of the peers' record counts (batch::RawSegments)
   DevBuf<uint8_t> ucls;                // [batch] class
   DevBuf<uint8_t> ufirst;              // [batch] first op of the key in this batch is a remove
   DevBuf<uint32_t> ins_dst, ins_val, ins_pred;  // [batch] compacted pure inserts, key order

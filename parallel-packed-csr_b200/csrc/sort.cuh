@@ -69,11 +69,22 @@ __device__ __forceinline__ uint32_t sort_digit(uint64_t key, int lo_bits, int sh
   return (uint32_t)(sort_compact(key, lo_bits) >> shift) & mask;
 }
 
+// Where the FIRST pass of a sort (and the histogram kernel) takes its keys from: an array of key words, or the raw
+// update arrays themselves (batch.cuh: RawArrays / RawPacked / RawSegments build the key word on the fly, so the batch
+// is never materialised as an unsorted key array: one write and one read of the batch less).
+struct KeyArray {
+  const uint64_t *keys;
+  const uint32_t *pay;
+  __device__ __forceinline__ uint64_t key(size_t i) const { return keys[i]; }
+  __device__ __forceinline__ uint32_t payload(size_t i) const { return pay[i]; }
+};
+
 // ---- global histograms of every pass, one read of the keys --------------------------------------------
 constexpr int OSH_THREADS = 512;
 constexpr int OSH_ITEMS = 8;
 
-__global__ void __launch_bounds__(OSH_THREADS) k_os_hist(const uint64_t *__restrict__ keys, size_t n, SortPasses P,
+template <class Src>
+__global__ void __launch_bounds__(OSH_THREADS) k_os_hist(Src src, size_t n, SortPasses P,
                                                          uint32_t *__restrict__ ghist) {
   __shared__ uint32_t s_h[OS_MAX_PASSES * OS_RADIX];
   for (int i = threadIdx.x; i < P.n_pass * OS_RADIX; i += OSH_THREADS) s_h[i] = 0;
@@ -84,7 +95,7 @@ __global__ void __launch_bounds__(OSH_THREADS) k_os_hist(const uint64_t *__restr
 #pragma unroll
     for (int r = 0; r < OSH_ITEMS; r++) {
       const size_t i = base + (size_t)r * OSH_THREADS + threadIdx.x;
-      k[r] = i < n ? keys[i] : 0;
+      k[r] = i < n ? src.key(i) : 0;
     }
 #pragma unroll
     for (int r = 0; r < OSH_ITEMS; r++) {
@@ -202,9 +213,8 @@ inline size_t os_pass_smem(bool has_pay) {
          (size_t)OS_RADIX * 4;
 }
 
-template <bool HAS_PAY>
-__global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(const uint64_t *__restrict__ keys,
-                                                           const uint32_t *__restrict__ pay, size_t n, DigitSel sel,
+template <bool HAS_PAY, class Src = KeyArray>
+__global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(Src src, size_t n, DigitSel sel,
                                                            const uint32_t *__restrict__ gbase,
                                                            uint32_t *__restrict__ lookback, uint32_t *tile_counter,
                                                            uint64_t *__restrict__ out_keys,
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(const uint64_t *__res
 #pragma unroll
   for (int r = 0; r < OS_ITEMS; r++) {
     const size_t i = wbase + (size_t)r * 32 + l;
-    k[r] = (i < n) ? keys[i] : ~0ull;
+    k[r] = (i < n) ? src.key(i) : ~0ull;
   }
   // early counts: the tile's digit histogram by shared-memory atomics, published BEFORE the (long) ranking phase,
   // so that by the time this tile looks back most of its predecessors have already resolved their prefix
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(const uint64_t *__res
     s_keys[pos] = k[r];
     if (HAS_PAY) {
       const size_t i = wbase + (size_t)r * 32 + l;
-      s_pay[pos] = i < n ? pay[i] : 0u;
+      s_pay[pos] = i < n ? src.payload(i) : 0u;
     }
   }
   // decoupled look-back: sum the counts of the earlier tiles until one with an inclusive prefix is met.
@@ -331,10 +341,9 @@ constexpr uint32_t SS_MAX = SS_THREADS * 16;  // 16384 keys
 inline size_t sort_small_smem(int items, bool has_pay) {
   return (size_t)SS_THREADS * items * (8 + (has_pay ? 4 : 0)) + (size_t)SS_WARPS * OS_RADIX * 2;
 }
-template <int ITEMS, bool HAS_PAY>
-__global__ void __launch_bounds__(SS_THREADS, 1) k_sort_small(const uint64_t *__restrict__ keys,
-                                                               const uint32_t *__restrict__ pay, uint32_t n,
-                                                               SortPasses P, uint64_t *__restrict__ out_keys,
+template <int ITEMS, bool HAS_PAY, class Src>
+__global__ void __launch_bounds__(SS_THREADS, 1) k_sort_small(Src src, uint32_t n, SortPasses P,
+                                                               uint64_t *__restrict__ out_keys,
                                                                uint32_t *__restrict__ out_pay) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   constexpr uint32_t TILE = SS_THREADS * ITEMS;
@@ -350,8 +359,8 @@ __global__ void __launch_bounds__(SS_THREADS, 1) k_sort_small(const uint64_t *__
 #pragma unroll
   for (int r = 0; r < ITEMS; r++) {
     const uint32_t i = wbase + r * 32 + l;
-    k[r] = i < n ? keys[i] : ~0ull;  // padding carries the largest digit of every pass and sits behind every real key
-    v[r] = (HAS_PAY && i < n) ? pay[i] : 0u;
+    k[r] = i < n ? src.key(i) : ~0ull;  // padding carries the largest digit of every pass and sits behind every real key
+    v[r] = (HAS_PAY && i < n) ? src.payload(i) : 0u;
   }
   for (int p = 0; p < P.n_pass; p++) {
     const int shift = P.shift[p];
@@ -406,19 +415,26 @@ __global__ void __launch_bounds__(SS_THREADS, 1) k_sort_small(const uint64_t *__
   }
 }
 
-template <int ITEMS, bool HAS_PAY>
-inline int launch_sort_small(ppcsr_shard *s, const uint64_t *ka, const uint32_t *pa, uint32_t n, const SortPasses &P,
-                             uint64_t *kb, uint32_t *pb) {
+template <int ITEMS, bool HAS_PAY, class Src>
+inline int launch_sort_small(ppcsr_shard *s, const Src &src, uint32_t n, const SortPasses &P, uint64_t *kb,
+                             uint32_t *pb) {
   static std::once_flag once[64];
   static cudaError_t once_err[64];
   const int dv = s->device & 63;
   std::call_once(once[dv], [&] {
-    once_err[dv] = cudaFuncSetAttribute(k_sort_small<ITEMS, HAS_PAY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    once_err[dv] = cudaFuncSetAttribute(k_sort_small<ITEMS, HAS_PAY, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sort_small_smem(ITEMS, HAS_PAY));
   });
   CUDA_TRY(once_err[dv]);
-  k_sort_small<ITEMS, HAS_PAY><<<1, SS_THREADS, sort_small_smem(ITEMS, HAS_PAY), s->stream>>>(ka, pa, n, P, kb, pb);
+  k_sort_small<ITEMS, HAS_PAY, Src><<<1, SS_THREADS, sort_small_smem(ITEMS, HAS_PAY), s->stream>>>(src, n, P, kb, pb);
   return PPCSR_OK;
+}
+template <bool HAS_PAY, class Src>
+inline int sort_small_dispatch(ppcsr_shard *s, const Src &src, uint32_t n, const SortPasses &P, uint64_t *kb,
+                               uint32_t *pb) {
+  if (n <= SS_THREADS) return launch_sort_small<1, HAS_PAY, Src>(s, src, n, P, kb, pb);
+  if (n <= SS_THREADS * 4) return launch_sort_small<4, HAS_PAY, Src>(s, src, n, P, kb, pb);
+  return launch_sort_small<16, HAS_PAY, Src>(s, src, n, P, kb, pb);
 }
 
 // scratch (u32 words) the sort needs in s->hist for `n` keys
@@ -442,31 +458,29 @@ inline int radix_sort_prepare(ppcsr_shard *s, size_t n, const SortPasses &P, uin
   return PPCSR_OK;
 }
 
-// Sorts n (key,payload) pairs by the key bits [0,lo_bits) and [32, 32+hi_bits).  Input in (ka,pa); the
-// sorted result ends up in *rk / *rp which point at either buffer pair.  pa == nullptr sorts keys only.
+// Sorts n (key,payload) pairs by the key bits [0,lo_bits) and [32, 32+hi_bits).  The keys come from `src` (see
+// KeyArray); ka / kb (pa / pb) are the two buffer pairs the passes alternate between -- with a KeyArray source ka / pa
+// are its arrays, with a raw source ka / pa are scratch.  The sorted result ends up in *rk / *rp, which point at either
+// pair.  has_pay == false sorts keys only.
 // hist_done: the scratch was prepared (radix_sort_prepare, for at least n keys and this layout) and already holds the
 // digit histograms of this layout: no clearing, no k_os_hist.
-inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t *kb, uint32_t *pb, size_t n,
-                            int lo_bits, int hi_bits, uint64_t **rk, uint32_t **rp, bool hist_done = false) {
+template <class Src>
+inline int radix_sort_from(ppcsr_shard *s, const Src &src, bool has_pay, uint64_t *ka, uint32_t *pa, uint64_t *kb,
+                           uint32_t *pb, size_t n, int lo_bits, int hi_bits, uint64_t **rk, uint32_t **rp,
+                           bool hist_done = false) {
   *rk = ka;
-  *rp = pa;
-  if (n <= 1) return PPCSR_OK;
+  *rp = has_pay ? pa : nullptr;
+  if (n == 0) return PPCSR_OK;
   if (n > OS_MAX_COUNT) {
     g_ppcsr_error = "batch too large for one sort (>= 2^30 updates); split it";
     return PPCSR_ERR_ARG;
   }
-  const bool has_pay = pa != nullptr;
   const SortPasses P = make_sort_passes(lo_bits, hi_bits);
   if (n <= SS_MAX) {  // one CTA, one launch
     s->launches += 1;
     const uint32_t m = (uint32_t)n;
-    if (n <= SS_THREADS) {
-      PPCSR_TRY(has_pay ? (launch_sort_small<1, true>(s, ka, pa, m, P, kb, pb)) : (launch_sort_small<1, false>(s, ka, pa, m, P, kb, pb)));
-    } else if (n <= SS_THREADS * 4) {
-      PPCSR_TRY(has_pay ? (launch_sort_small<4, true>(s, ka, pa, m, P, kb, pb)) : (launch_sort_small<4, false>(s, ka, pa, m, P, kb, pb)));
-    } else {
-      PPCSR_TRY(has_pay ? (launch_sort_small<16, true>(s, ka, pa, m, P, kb, pb)) : (launch_sort_small<16, false>(s, ka, pa, m, P, kb, pb)));
-    }
+    PPCSR_TRY(has_pay ? (sort_small_dispatch<true, Src>(s, src, m, P, kb, pb))
+                      : (sort_small_dispatch<false, Src>(s, src, m, P, kb, pb)));
     CUDA_TRY(cudaGetLastError());
     *rk = kb;
     *rp = has_pay ? pb : nullptr;
@@ -481,14 +495,18 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
   uint32_t *ghist = s->hist.p;
   uint32_t *counters = ghist + OS_MAX_PASSES * OS_RADIX;
   uint32_t *lookback = counters + 64;
-  {  // > 48 KB of dynamic shared memory needs an explicit opt-in: per device, once, thread-safe
+  {  // > 48 KB of dynamic shared memory needs an explicit opt-in: per device and source type, once, thread-safe
     static std::once_flag once[64];
     static cudaError_t once_err[64];
     const int dv = s->device & 63;
     std::call_once(once[dv], [&] {
-      once_err[dv] = cudaFuncSetAttribute(k_os_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(true));
+      once_err[dv] = cudaFuncSetAttribute(k_os_pass<true, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(true));
       if (once_err[dv] == cudaSuccess)
-        once_err[dv] = cudaFuncSetAttribute(k_os_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(false));
+        once_err[dv] = cudaFuncSetAttribute(k_os_pass<false, Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(false));
+      if (once_err[dv] == cudaSuccess)
+        once_err[dv] = cudaFuncSetAttribute(k_os_pass<true, KeyArray>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(true));
+      if (once_err[dv] == cudaSuccess)
+        once_err[dv] = cudaFuncSetAttribute(k_os_pass<false, KeyArray>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(false));
     });
     CUDA_TRY(once_err[dv]);
   }
@@ -496,20 +514,22 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
   if (!hist_done) {
     const unsigned hblocks = (unsigned)std::min<size_t>((n + (size_t)OSH_THREADS * OSH_ITEMS - 1) / ((size_t)OSH_THREADS * OSH_ITEMS), 148 * 4);
     s->launches += 1;
-    k_os_hist<<<hblocks, OSH_THREADS, 0, s->stream>>>(ka, n, P, ghist);
+    k_os_hist<Src><<<hblocks, OSH_THREADS, 0, s->stream>>>(src, n, P, ghist);
   }
   k_os_scan<<<P.n_pass, OS_RADIX, 0, s->stream>>>(ghist, lookback, rows);
+  // pass 0 reads the source and writes (kb, pb); the later passes alternate between the two buffer pairs
   uint64_t *src_k = ka, *dst_k = kb;
   uint32_t *src_p = pa, *dst_p = pb;
   for (int p = 0; p < P.n_pass; p++) {
-    if (has_pay) {
-      k_os_pass<true><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(true), s->stream>>>(
-          src_k, src_p, n, make_digit_sel(lo_bits, P.shift[p], P.mask[p]), ghist + p * OS_RADIX,
-          lookback + ((size_t)p * rows + OS_LB_DEPTH) * OS_RADIX, counters + p, dst_k, dst_p);
+    const DigitSel sel = make_digit_sel(lo_bits, P.shift[p], P.mask[p]);
+    uint32_t *gb = ghist + p * OS_RADIX, *lb = lookback + ((size_t)p * rows + OS_LB_DEPTH) * OS_RADIX;
+    if (p == 0) {
+      if (has_pay) k_os_pass<true, Src><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(true), s->stream>>>(src, n, sel, gb, lb, counters + p, dst_k, dst_p);
+      else k_os_pass<false, Src><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(false), s->stream>>>(src, n, sel, gb, lb, counters + p, dst_k, nullptr);
     } else {
-      k_os_pass<false><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(false), s->stream>>>(
-          src_k, nullptr, n, make_digit_sel(lo_bits, P.shift[p], P.mask[p]), ghist + p * OS_RADIX,
-          lookback + ((size_t)p * rows + OS_LB_DEPTH) * OS_RADIX, counters + p, dst_k, nullptr);
+      const KeyArray a{src_k, src_p};
+      if (has_pay) k_os_pass<true, KeyArray><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(true), s->stream>>>(a, n, sel, gb, lb, counters + p, dst_k, dst_p);
+      else k_os_pass<false, KeyArray><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(false), s->stream>>>(a, n, sel, gb, lb, counters + p, dst_k, nullptr);
     }
     std::swap(src_k, dst_k);
     std::swap(src_p, dst_p);
@@ -518,6 +538,12 @@ inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t
   *rk = src_k;
   *rp = has_pay ? src_p : nullptr;
   return PPCSR_OK;
+}
+
+// the keys (and payloads) are the arrays ka / pa themselves; pa == nullptr sorts keys only
+inline int radix_sort_pairs(ppcsr_shard *s, uint64_t *ka, uint32_t *pa, uint64_t *kb, uint32_t *pb, size_t n,
+                            int lo_bits, int hi_bits, uint64_t **rk, uint32_t **rp, bool hist_done = false) {
+  return radix_sort_from(s, KeyArray{ka, pa}, pa != nullptr, ka, pa, kb, pb, n, lo_bits, hi_bits, rk, rp, hist_done);
 }
 
 }  // namespace prim

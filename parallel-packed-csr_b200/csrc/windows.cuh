@@ -34,11 +34,27 @@ __global__ void __launch_bounds__(WT) k_tree_up5(uint32_t *__restrict__ tree, ui
   }
 }
 
+// The levels above TOP_D (<= 2^TOP_D nodes) in ONE launch: a single CTA sums level by level from level TOP_D (every
+// further k_tree_up5 launch would be pure launch latency: 4 more dependent launches at 2^21 leaves).
+constexpr uint32_t TOP_D = 12;
+__global__ void __launch_bounds__(1024) k_tree_top(uint32_t *__restrict__ tree, uint32_t D) {
+  for (uint32_t d = D; d >= 1u; d--) {  // level d - 1 from level d
+    const uint32_t nodes = 1u << (d - 1u);
+    for (uint32_t i = threadIdx.x; i < nodes; i += blockDim.x) tree[nodes + i] = tree[2u * (nodes + i)] + tree[2u * (nodes + i) + 1u];
+    __syncthreads();
+  }
+}
+
 inline int tree_rebuild(ppcsr_shard *s, uint32_t *tree, uint32_t H) {
-  for (int D = (int)H; D > 0; D -= 5) {
+  int D = (int)H;
+  for (; D > (int)TOP_D; D -= 5) {
     const uint32_t nodes = 1u << D;
     s->launches++;
     k_tree_up5<<<div_up(nodes, WT), WT, 0, s->stream>>>(tree, (uint32_t)D);
+  }
+  if (D > 0) {
+    s->launches++;
+    k_tree_top<<<1, 1024, 0, s->stream>>>(tree, (uint32_t)D);
   }
   CUDA_TRY(cudaGetLastError());
   return PPCSR_OK;

@@ -299,3 +299,30 @@ def test_cli_pppcsr_device_route_matches_ppcsr(tmp_path):
         assert "PMA invariants: ok" in r.stdout
         sums.append([l for l in r.stdout.splitlines() if l.startswith("Graph checksum: ")][0])
     assert sums[0] == sums[1] == sums[2]
+
+
+def test_benchmark_harnesses_run_on_the_gpu(tmp_path):
+    """the partitions sweep (reference benchmark-partitioning.sh layout) driven through the C++ CLI,
+    and one cell of the GPU-count strong-scaling harness (bench.py launched as the driver launches it), at toy sizes."""
+    import importlib.util
+    import sys
+
+    build.build_host()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("partitioning", os.path.join(root, "benchmarks", "partitioning.py"))
+    pt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pt)
+    prefix = str(tmp_path / "part")
+    assert pt.main(["--scale", "12", "--size", "20000", "--partitions", "1", "3", "--reps", "2", "--out-prefix", prefix,
+                    "--workdir", str(tmp_path)]) == 0
+    rows = open(prefix + "_all_results.csv").read().strip().splitlines()
+    assert rows[0] == pt.header(2) and [r.split()[0] for r in rows[1:]] == ["1", "3"]
+    dev = open(prefix + "_device_ms.csv").read().strip().splitlines()
+    assert all(float(x) > 0 for x in dev[1].split()[1:3])  # the device time of the insert batches was scraped
+    assert open(prefix + "_plot_data.dat").read().splitlines()[0] == "partitions ins del ins-NUMA del-NUMA"
+    r = subprocess.run([sys.executable, os.path.join(root, "benchmarks", "strong_scaling.py"), "--gpus", "1", "--reps", "1",
+                        "--scale", "14", "--batch", "100000", "--steps", "2", "--warmup", "1", "--out-prefix",
+                        str(tmp_path / "ss")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    row = open(str(tmp_path / "ss.csv")).read().strip().splitlines()[1].split()
+    assert row[0] == "1" and float(row[1]) > 0 and float(row[4]) > 0
