@@ -852,10 +852,13 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   H.ghist = nullptr;
   const bool fused_hist = count > prim::SS_MAX;  // (smaller batches are sorted by one CTA: no global histograms)
   if (fused_hist) PPCSR_TRY(prim::radix_sort_prepare(s, count, H.P, &H.ghist));
-  // The unsorted batch is not written out as a key array: the first pass of the sort builds the key words from the
-  // caller's arrays itself (batch::RawArrays / RawPacked / RawSegments), the builder only takes the scalars and the
-  // histograms.  Only a batch small enough for the one-CTA sort whose size is known here is materialised.
-  const bool materialize = !segments && count <= prim::SS_MAX;
+  // The builder writes the batch out as an array of key words.  PPCSR_RAW_FIRST_PASS=1 (development knob) skips that:
+  // the first pass of the sort then builds the key words from the caller's arrays itself (batch::RawArrays / RawPacked /
+  // RawSegments).  Measured on B200: one write and one read of the batch less, but two 4-byte streams and the guards
+  // inside the instruction-bound sort pass cost more than they save -- sort stage 3.35 -> 3.69 ms on C4, 0.364 -> 0.403 ms
+  // on C2 -- so it is off by default.
+  static const bool raw_first_pass = getenv("PPCSR_RAW_FIRST_PASS") != nullptr;
+  const bool materialize = !raw_first_pass || (!segments && count <= prim::SS_MAX);
   uint64_t *key_out = materialize ? s->key_a.p : nullptr;
   const uint32_t src_default = default_val;  // (default_val may be replaced below when the values are all equal)
   const unsigned kb = std::min<unsigned>(div_up(count, batch::BT * 8), 148 * (fused_hist ? 8 : 16));
