@@ -62,7 +62,7 @@ def main():
     del cs, cd
     # a streaming system reaches its working size once: allocate it up front so that no batch pays cudaMalloc
     geo = graph.shard.geometry
-    expect = sum((args.reps if B <= 10_000_000 else max(1, args.reps // 2)) * B
+    expect = sum((1 + (args.reps if B <= 10_000_000 else max(1, args.reps // 2))) * B
                  for B in (args.min_batch * 10 ** k for k in range(12)) if B <= args.max_batch)
     max_slots = int(geo.N)
     while max_slots < min(4 * (geo.N // 2 + expect // world), 1 << 31):
@@ -76,7 +76,7 @@ def main():
         b = B // world
         reps = args.reps if B <= 10_000_000 else max(1, args.reps // 2)
         t_upd, t_pr, stats = 0.0, 0.0, None
-        for _ in range(reps):
+        for rep in range(reps + 1):  # the first batch of every size is a warm-up (allocations for the new size)
             base = offset + rank * b
             us, ud = synth.uniform(scale, base, base + b, 7, device=dev)
             uv = None
@@ -99,8 +99,9 @@ def main():
                 graph.pagerank_step(vals)
             e2.record(stream)
             torch.cuda.synchronize()
-            t_upd += e0.elapsed_time(e1)
-            t_pr += e1.elapsed_time(e2)
+            if rep > 0:
+                t_upd += e0.elapsed_time(e1)
+                t_pr += e1.elapsed_time(e2)
         t = torch.tensor([t_upd / reps, t_pr / reps], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -493,15 +493,17 @@ __global__ void __launch_bounds__(KT, PPCSR_REB_CTAS) k_rebalance_p(Args A, uint
   // the bulk loads of the next round (quads / tables + R0 / inserts / plan entry: one mbarrier arrival each).
   const unsigned warp = threadIdx.x >> 5;
   constexpr unsigned IO_WARP = 3;
-  static_assert(KT >= 256, "k_rebalance_p deals its housekeeping to warps 1, 2, 4, 5 (loads), 3 (store)");
+  static_assert(KT >= 128, "k_rebalance_p deals its housekeeping to warps 1, 2 (4, 5) (loads) and 3 (store)");
   constexpr uint32_t HK = KT - 64;  // housekeeping threads
   const bool is_io = warp == IO_WARP, is_io_thread = threadIdx.x == IO_WARP * 32;
   const bool is_hk = warp != 0 && warp != IO_WARP;
   const uint32_t hk_tid = threadIdx.x - 32u - (warp > IO_WARP ? 32u : 0u);
   const uint32_t itid = KT - 1u - threadIdx.x;  // my place in the deal of the inserts
   // issuer threads: lane 0 of warp 1 (role 0: quads), 2 (1: tables, R0), 4 (2: inserts), 5 (3: plan entry)
-  const bool is_issuer = lane == 0 && (warp == 1 || warp == 2 || warp == 4 || warp == 5);
-  const uint32_t role = warp < 3 ? warp - 1u : warp - 2u;
+  // (a CTA of 128 threads has no warps 4 and 5: lanes 0 and 1 of warps 1 and 2 issue instead)
+  const bool is_issuer = KT >= 256 ? lane == 0 && (warp == 1 || warp == 2 || warp == 4 || warp == 5)
+                                   : lane < 2 && (warp == 1 || warp == 2);
+  const uint32_t role = KT >= 256 ? (warp < 3 ? warp - 1u : warp - 2u) : (warp - 1u) * 2u + lane;
 
   // The bulk copies of one round, complete on the stage's mbarrier (four arrivals).  gl / snl: first leaf and leaf
   // count of the segment; first_seg: the round opens chunk p (stage its first inserts and R0 too, and fetch the
