@@ -13,6 +13,7 @@
 #include "primitives.cuh"
 #include "queries.cuh"
 #include "rebalance.cuh"
+#include "rebalance_m.cuh"
 #include "sort.cuh"
 #include "sparse.cuh"
 #include "windows.cuh"
@@ -136,16 +137,55 @@ size_t reb_pad_smem() {
   return (size_t)pad;
 }
 
-// PPCSR_REB_KERNEL=6 selects the one-chunk-per-CTA kernel (k_rebalance) for A/B runs; the default is the persistent,
-// software-pipelined kernel (k_rebalance_p)
+// The default is the rank-dense persistent kernel (k_rebalance_m, rebalance_m.cuh).  PPCSR_REB_KERNEL=9 selects the
+// slot-dealt persistent kernel of round 1 (k_rebalance_p), =6 the one-chunk-per-CTA kernel (k_rebalance), for A/B runs.
 int reb_kernel() {
   static const int k = [] {
     const char *e = getenv("PPCSR_REB_KERNEL");
-    return e ? atoi(e) : 9;
+    return e ? atoi(e) : 10;
   }();
   return k;
 }
-int launch_rebalance(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
+bool reb_kernel_m() { return reb_kernel() != 6 && reb_kernel() != 9; }
+// plan entries are 32 bytes (ChunkPlan) or 64 (ChunkPlanM): the buffer is kept in units of ChunkPlan
+int reserve_plan(ppcsr_shard *s, size_t n_chunks) {
+  return dev_reserve(s->plan, reb_kernel_m() ? 2 * n_chunks : n_chunks, s->stream);
+}
+void launch_plan(ppcsr_shard *s, const WindowDesc *windows, uint32_t n_windows, uint32_t ls_src, uint32_t ls_dst,
+                 uint32_t m_dst_override, uint32_t n_chunks, uint32_t CL) {
+  if (reb_kernel_m())
+    reb::k_plan_chunks_m<<<div_up(n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
+        windows, n_windows, s->rank_off.p, s->ins_off.p, ls_src, ls_dst, m_dst_override, n_chunks, CL,
+        reinterpret_cast<reb::ChunkPlanM *>(s->plan.p));
+  else
+    reb::k_plan_chunks<<<div_up(n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
+        windows, n_windows, s->rank_off.p, s->ins_off.p, ls_src, ls_dst, m_dst_override, n_chunks, CL, s->plan.p);
+}
+template <bool TOMB>
+int launch_rebalance_m(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
+  static std::once_flag once[64];
+  static int sms[64] = {0};
+  static cudaError_t once_err[64];
+  const int dv = s->device & 63;
+  std::call_once(once[dv], [&] {
+    once_err[dv] = cudaDeviceGetAttribute(&sms[dv], cudaDevAttrMultiProcessorCount, s->device);
+    if (once_err[dv] == cudaSuccess)
+      once_err[dv] = cudaFuncSetAttribute(reb::k_rebalance_m<TOMB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(reb::MSmem<TOMB>));
+  });
+  CUDA_TRY(once_err[dv]);
+  static const long ctas = [] {  // development knob: resident CTAs per SM the grid is sized for
+    const char *e = getenv("PPCSR_REB_GRID_CTAS");
+    return e ? atol(e) : (long)PPCSR_M_CTAS;
+  }();
+  const unsigned grid = std::min<unsigned>(n_chunks, (unsigned)(sms[dv] * ctas));
+  reb::k_rebalance_m<TOMB><<<grid, reb::MT, sizeof(reb::MSmem<TOMB>), s->stream>>>(
+      A, reinterpret_cast<const reb::ChunkPlanM *>(s->plan.p), n_chunks);
+  return PPCSR_OK;
+}
+// tomb: the batch wrote tombstones (it deleted edges); without, the leaves are still left-packed
+int launch_rebalance(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A, bool tomb) {
+  if (reb_kernel_m()) return tomb ? launch_rebalance_m<true>(s, n_chunks, A) : launch_rebalance_m<false>(s, n_chunks, A);
   if (reb_kernel() == 6) {
 #if PPCSR_HAVE_V6
     reb::k_rebalance<<<n_chunks, reb::KT, reb_pad_smem(), s->stream>>>(A);
@@ -247,7 +287,7 @@ int reserve_worst_case(ppcsr_shard *s, uint64_t count) {
   PPCSR_TRY(reserve_leaf_arrays(s, g2));
   PPCSR_TRY(reserve_window_arrays(s, count));
   const uint32_t min_cl = std::max<uint32_t>(1u, ((uint32_t)reb::CHUNK_SLOTS >> g2.leaf_shift) * 3u / 4u);
-  PPCSR_TRY(dev_reserve(s->plan, (size_t)g2.n_leaves / min_cl + 2, s->stream));
+  PPCSR_TRY(reserve_plan(s, (size_t)g2.n_leaves / min_cl + 2));
   const size_t scan_tiles = (size_t)div_up(std::max<uint64_t>(std::max<uint64_t>(g2.n_leaves, count), 1), prim::SCAN_TILE) + 2;
   PPCSR_TRY(dev_reserve(s->block_tmp, scan_tiles, s->stream));
   PPCSR_TRY(prim::reserve_scan_state(s, std::max<size_t>(scan_tiles, (size_t)div_up(count, batch::LTILE) + 2)));
@@ -320,14 +360,12 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
   A.prefetch_dist = reb_prefetch_dist();
   A.chunk_leaves = CL2;
   A.ins_sentinels = s->ins_sentinels ? 1u : 0u;
-  PPCSR_TRY(dev_reserve(s->plan, (size_t)hw->n_chunks, s->stream));
+  PPCSR_TRY(reserve_plan(s, (size_t)hw->n_chunks));
   A.plan = s->plan.p;
-  reb::k_plan_chunks<<<div_up(hw->n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
-      s->windows.p, 1u, s->rank_off.p, s->ins_off.p, g.leaf_shift, g2.leaf_shift, g2.n_leaves, hw->n_chunks, CL2,
-      s->plan.p);
+  launch_plan(s, s->windows.p, 1u, g.leaf_shift, g2.leaf_shift, g2.n_leaves, hw->n_chunks, CL2);
   s->launches += 4;
   CUDA_TRY(cudaEventRecord(s->ev[5], s->stream));
-  PPCSR_TRY(launch_rebalance(s, hw->n_chunks, A));
+  PPCSR_TRY(launch_rebalance(s, hw->n_chunks, A, h.n_deleted != 0));
   CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
   CUDA_TRY(cudaGetLastError());
   std::swap(s->dest, s->dest_alt);
@@ -525,18 +563,21 @@ int finish_batch_impl(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
       reb::k_rebalance_small<<<div_up(h.n_windows, reb::RWARPS), reb::RT, 0, s->stream>>>(S);
     }
     if (h.n_chunks) {
-      PPCSR_TRY(dev_reserve(s->plan, (size_t)h.n_chunks, s->stream));
+      PPCSR_TRY(reserve_plan(s, (size_t)h.n_chunks));
       A.plan = s->plan.p;
-      reb::k_plan_chunks<<<div_up(h.n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
-          s->windows.p, (uint32_t)h.n_windows, s->rank_off.p, s->ins_off.p, g.leaf_shift, g.leaf_shift, 0,
-          (uint32_t)h.n_chunks, CL, s->plan.p);
+      launch_plan(s, s->windows.p, (uint32_t)h.n_windows, g.leaf_shift, g.leaf_shift, 0, (uint32_t)h.n_chunks, CL);
       s->launches += 2 + (h.multi_slots ? 1 : 0);
-      PPCSR_TRY(launch_rebalance(s, (unsigned)h.n_chunks, A));
+      PPCSR_TRY(launch_rebalance(s, (unsigned)h.n_chunks, A, h.n_deleted != 0));
     }
     CUDA_TRY(cudaEventRecord(s->ev[6], s->stream));
     if (h.multi_slots) {
-      reb::k_copy_back<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(s->plan.p, g.leaf_shift, s->dest_alt.p,
-                                                                        s->val_alt.p, s->dest.p, s->val.p);
+      if (reb_kernel_m())
+        reb::k_copy_back_m<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(
+            reinterpret_cast<const reb::ChunkPlanM *>(s->plan.p), g.leaf_shift, s->dest_alt.p, s->val_alt.p, s->dest.p,
+            s->val.p);
+      else
+        reb::k_copy_back<<<(unsigned)h.n_chunks, reb::RT, 0, s->stream>>>(s->plan.p, g.leaf_shift, s->dest_alt.p,
+                                                                          s->val_alt.p, s->dest.p, s->val.p);
     }
     s->launches += 1;
     reb::k_copy_u32<<<div_up(L, 256), 256, 0, s->stream>>>(s->leaf_cnt.p, s->tree.p + L, L);

@@ -1,0 +1,470 @@
+// rebalance_m.cuh -- reb::k_rebalance_m: the rebalance kernel in its RANK-DENSE form (the default since round 2).
+// Same job, same plan (one chunk of <= CHUNK_SLOTS output slots per round trip) and same rank arithmetic as
+// k_rebalance_p (rebalance.cuh) -- replaces reference PCSR::redistribute + fix_sentinel + slide_right/slide_left +
+// double_list/half_list (src/pcsr/PCSR.cpp:222-249, 168-183, 326-390, 251-320) -- but the work is dealt by OUTPUT
+// RANK, not by source slot:
+//
+//   k_rebalance_p gives every thread a quad of SOURCE slots: at the 50-65 % density of a PMA half of those lanes
+//   hold nothing, every kept item pays a segmented scan, a marker look-up and a running maximum, every insert a
+//   marker store, and a warp runs ~760 instructions per chunk whatever the chunk holds (ncu: 1.7 G warp
+//   instructions for the 2^29-slot rebuild, issue-bound at 0.76 slots per cycle).
+//
+//   Here a warp takes 32 CONSECUTIVE RANKS of the merged sequence per step ("unit"): every lane has an item.
+//   Two bit masks over the chunk's ranks say what a rank is:
+//     B   bit t set <=> rank t is one of the batch's inserts      (one shared-memory atomicOr per insert)
+//     HB  bit t set <=> a source leaf's merged run begins at t    (one atomicOr per non-empty source leaf)
+//   and popcounts turn them into addresses:  q = (#B bits below t) + first insert index  is the insert a rank holds
+//   or -- for a kept item -- the number of inserts before it; (#HB bits up to t) names its source leaf x, and
+//       source slot = (t - q) + D[x],   D[x] = (x << ls) + a - R[x] + ins_off[x]
+//   because the leaves are LEFT-PACKED: the kept items of a leaf are the first ones of its line.  (Tombstones of
+//   this batch break that; batches with deletes run the TOMB instantiation, whose pre-pass maps kept index -> slot
+//   per leaf.)  An item is read straight from the staged source line or the staged insert list and stored into its
+//   final slot of the staging buffer through the rank -> slot table; ONE bulk store (TMA) per array writes the chunk.
+//   ~28 instructions per unit of 32 items; the per-leaf and per-insert work is one atomicOr each.
+//
+// Pipeline: persistent CTAs (grid = SMs x M_CTAS), a ROUND = one segment of <= 64 source leaves of one chunk; the
+// bulk loads (cp.async.bulk -> mbarrier) of round r+1 -- source lines, R / insert-offset slices, the chunk's first
+// 512 inserts -- are issued at the top of round r into the other half of a double buffer, a full round ahead.
+// Two block barriers per round (three with tombstones).
+#pragma once
+#include "rebalance.cuh"
+
+namespace reb {
+
+struct ChunkPlanM {  // one 64-byte entry per chunk (k_plan_chunks_m)
+  uint32_t leaf0;      // first leaf of the chunk's window
+  uint32_t multi;      // != 0: the window spans several chunks (written out of place)
+  uint32_t o_lo;       // first output leaf of the chunk, relative to the window
+  uint32_t n_out;      // output leaves of the chunk
+  uint32_t i_lo;       // first source leaf (relative to the window) feeding the chunk
+  uint32_t nl;         // source leaves feeding the chunk (0: the chunk receives no items)
+  uint32_t q_lo, q_hi; // inserts of those leaves that can rank inside the chunk
+  uint32_t R0;         // rank_off[leaf0]
+  uint32_t a;          // first window rank of the chunk
+  uint32_t span;       // items the chunk receives
+  uint32_t out_slot0;  // first output slot
+  uint32_t items;      // live items of the window after the batch
+  uint32_t lg;         // log2(output leaves of the window)
+  uint32_t dst_leaf;   // first output leaf (absolute)
+  uint32_t pad;
+};
+static_assert(sizeof(ChunkPlanM) == 64, "four 16-byte loads");
+
+__global__ void __launch_bounds__(RT) k_plan_chunks_m(const WindowDesc *__restrict__ windows, uint32_t n_windows,
+                                                      const uint32_t *__restrict__ rank_off,
+                                                      const uint32_t *__restrict__ ins_off, uint32_t ls_src,
+                                                      uint32_t ls_dst, uint32_t m_dst_override, uint32_t n_chunks,
+                                                      uint32_t CL, ChunkPlanM *__restrict__ plan) {
+  const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk >= n_chunks) return;
+  uint32_t lo = 0, hi = n_windows;  // last window with chunk0 <= chunk
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (windows[mid].chunk0 <= chunk) lo = mid;
+    else hi = mid;
+  }
+  const WindowDesc w = windows[lo];
+  const uint32_t m_dst = m_dst_override ? m_dst_override : w.m;
+  const uint32_t lg = 31u - (uint32_t)__clz(m_dst);
+  const uint32_t o_lo = (chunk - w.chunk0) * CL;
+  const uint32_t o_hi = min(o_lo + CL, m_dst);
+  const uint32_t a = leaf_rank0(o_lo, w.items, lg);
+  const uint32_t b = leaf_rank0(o_hi, w.items, lg);
+  const uint32_t *R = rank_off + w.leaf0;
+  const uint32_t *IO = ins_off + w.leaf0;
+  const uint32_t R0 = R[0];
+  ChunkPlanM p;
+  p.leaf0 = w.leaf0;
+  p.multi = w.n_chunks > 1 ? 1u : 0u;
+  p.o_lo = o_lo;
+  p.n_out = o_hi - o_lo;
+  p.R0 = R0;
+  p.a = a;
+  p.span = b - a;
+  const uint32_t dst_leaf0 = m_dst_override ? 0u : w.leaf0;
+  p.dst_leaf = dst_leaf0 + o_lo;
+  p.out_slot0 = (dst_leaf0 + o_lo) << ls_dst;
+  p.items = w.items;
+  p.lg = lg;
+  p.pad = 0;
+  if (b > a) {
+    const uint32_t i_lo = upper_bound_u32(R, w.m, R0 + a) - 1;      // source leaf holding rank a
+    const uint32_t i_hi = upper_bound_u32(R, w.m, R0 + b - 1) - 1;  // source leaf holding rank b-1
+    const uint32_t below = a - (R[i_lo] - R0);                      // ranks of the first leaf below the chunk
+    const uint32_t leaf = 1u << ls_src;
+    // an insert ranks at R[leaf] + (its index in the leaf's run) + (kept items up to its predecessor, <= one leaf):
+    // those of the first leaf before IO + (below - leaf) rank below a, those of the last from IO + (b - R) on at or
+    // above b (the clip k_plan_chunks makes, rebalance.cuh)
+    p.i_lo = i_lo;
+    p.nl = i_hi - i_lo + 1u;
+    p.q_lo = min(IO[i_lo] + (below > leaf ? below - leaf : 0u), IO[i_lo + 1]);
+    p.q_hi = max(p.q_lo, min(IO[i_hi] + (b - (R[i_hi] - R0)), IO[i_hi + 1]));
+  } else {
+    p.i_lo = 0;
+    p.nl = 0;
+    p.q_lo = p.q_hi = 0;
+  }
+  plan[chunk] = p;
+}
+
+#ifndef PPCSR_M_CTAS
+#define PPCSR_M_CTAS 3
+#endif
+#ifndef PPCSR_M_PINS
+#define PPCSR_M_PINS 512
+#endif
+constexpr int MT = 256;                        // threads of a k_rebalance_m CTA
+constexpr int MCHUNK = CHUNK_SLOTS;            // output slots per chunk
+constexpr int MSEG = SEG_LEAVES_SLOTS;         // source slots per round
+constexpr int MSEG_MAX_LEAVES = PSEG_MAX_LEAVES;
+constexpr int MTBL = MSEG_MAX_LEAVES + 1;
+constexpr int MPINS = PPCSR_M_PINS;            // staged inserts per chunk
+constexpr int MWORDS = MCHUNK / 32;            // mask words
+static_assert(MT == 256, "k_rebalance_m deals its phases to eight warps");
+static_assert(MCHUNK <= 65536, "rank -> slot table entries are 16-bit");
+
+template <bool TOMB>
+struct MSmem {
+  uint32_t out_d[MCHUNK];  // the chunk's output slots in their final layout (128-byte aligned: first member)
+  uint32_t out_v[MCHUNK];
+  // one word-indexed region W: the source lines and staged inserts.  st_v - st_d == st_iv - st_id (== VOFF words), so
+  // an item's value sits VOFF words behind its dest whichever it is
+  uint32_t st_d[2][MSEG];        // [round parity]
+  uint32_t st_id[2][MPINS + 8];  // [chunk parity]
+  uint32_t st_v[2][MSEG];
+  uint32_t st_iv[2][MPINS + 8];
+  uint32_t st_ip[2][MPINS + 8];
+  alignas(16) uint32_t st_R[2][MTBL + 7];     // R slice of the round's leaves; entry x sits at [x + (first leaf & 3)]
+  alignas(16) uint32_t st_ioff[2][MTBL + 7];  // insert offsets of the same leaves
+  alignas(16) uint32_t B[2][MWORDS];          // [round parity] insert ranks
+  alignas(16) uint32_t HB[2][MWORDS];         // leaf heads
+  uint32_t D[MSEG_MAX_LEAVES];                // per non-empty leaf of the round, in order: source slot - (rank - inserts before)
+  uint16_t pos[MCHUNK];                       // chunk-relative rank -> output slot
+  uint8_t kmap[TOMB ? MSEG : 16];             // [leaf base + kept index] -> offset of that kept item in its leaf
+  uint8_t kupto[TOMB ? MSEG : 16];            // kept items of the leaf up to and including a slot
+  alignas(16) uint4 plan[2][4];               // [chunk parity]
+  uint32_t n_below[2];                        // [chunk parity] staged inserts of the chunk's first leaf that rank below it
+  alignas(8) uint64_t full[2];                // [round parity] the round's bulk loads have landed
+};
+
+template <bool TOMB>
+__global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const ChunkPlanM *__restrict__ gplan,
+                                                                 uint32_t n_chunks) {
+  extern __shared__ __align__(128) uint8_t m_smem_raw[];
+  using SM = MSmem<TOMB>;
+  SM &S = *reinterpret_cast<SM *>(m_smem_raw);
+  constexpr uint32_t VOFF = (uint32_t)(offsetof(SM, st_v) - offsetof(SM, st_d)) / 4u;
+  static_assert(offsetof(SM, st_iv) - offsetof(SM, st_id) == offsetof(SM, st_v) - offsetof(SM, st_d), "VOFF");
+  constexpr uint32_t INS_W = (uint32_t)(offsetof(SM, st_id) - offsetof(SM, st_d)) / 4u;  // word index of st_id[0][0]
+  const uint32_t *W = &S.st_d[0][0];
+
+  const unsigned lane = lane_id(), lt = lanemask_lt(), le = lt | (1u << lane);
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t ls_src = A.ls_src, ls_dst = A.ls_dst;
+  const uint32_t leaf_mask = (1u << ls_src) - 1u;
+  const uint32_t seg_leaves = min((uint32_t)MSEG >> ls_src, (uint32_t)MSEG_MAX_LEAVES);
+  const uint32_t G = gridDim.x;
+  uint32_t c = blockIdx.x;
+  if (c >= n_chunks) return;
+  const bool is_issuer = threadIdx.x == 3u * 32u;  // lane 0 of the IO warp
+
+  // ---- the bulk loads of one round (issuer only): source lines + table slices of the leaves [gl, gl + snl), and, when
+  // the round opens a chunk, the chunk's first MPINS inserts
+  auto issue_round = [&](uint32_t rpar, uint32_t gl, uint32_t snl, bool first_seg, uint32_t cpar, uint32_t q_lo,
+                         uint32_t q_hi) {
+    uint64_t *bar = &S.full[rpar];
+    if (snl == 0) {
+      mbar_expect_tx(bar, 0u);
+      return;
+    }
+    const uint32_t qb = (snl << ls_src) * 4u;
+    const uint32_t sh = gl & 3u;
+    // 16-byte granules: reads up to 3 entries past the logical end of the arrays (covered by DEV_PAD_ELEMS)
+    const uint32_t tb = ((snl + 1u + sh + 3u) & ~3u) * 4u;
+    const uint32_t nq = first_seg ? min(q_hi - q_lo, (uint32_t)MPINS) : 0u;
+    const uint32_t ish = q_lo & 3u;
+    const uint32_t ib = nq ? ((nq + ish + 3u) & ~3u) * 4u : 0u;
+    mbar_expect_tx(bar, 2u * qb + 2u * tb + 3u * ib);
+    bulk_g2s(S.st_d[rpar], A.src_dest + ((size_t)gl << ls_src), qb, bar);
+    bulk_g2s(S.st_v[rpar], A.src_val + ((size_t)gl << ls_src), qb, bar);
+    bulk_g2s(S.st_R[rpar], A.rank_off + (gl - sh), tb, bar);
+    bulk_g2s(S.st_ioff[rpar], A.ins_off + (gl - sh), tb, bar);
+    if (ib) {
+      bulk_g2s(S.st_ip[cpar], A.ins_pred + (q_lo - ish), ib, bar);
+      bulk_g2s(S.st_id[cpar], A.ins_dst + (q_lo - ish), ib, bar);
+      bulk_g2s(S.st_iv[cpar], A.ins_val + (q_lo - ish), ib, bar);
+      if (q_hi - q_lo > (uint32_t)MPINS) {  // a longer run is read straight from global memory: pull it into L2
+        const uint32_t q1 = (q_lo + MPINS) & ~3u;
+        const uint32_t pb = min(((q_hi - q1 + 3u) & ~3u) * 4u, 16384u);
+        bulk_prefetch_l2(A.ins_pred + q1, pb);
+        bulk_prefetch_l2(A.ins_dst + q1, pb);
+        bulk_prefetch_l2(A.ins_val + q1, pb);
+      }
+    }
+  };
+  auto load_plan = [&](uint32_t chunk, uint4 (&p)[4]) {
+    const uint4 *g = reinterpret_cast<const uint4 *>(gplan + chunk);
+    p[0] = __ldg(g);
+    p[1] = __ldg(g + 1);
+    p[2] = __ldg(g + 2);
+    p[3] = __ldg(g + 3);
+  };
+
+  // ---- prologue: the first chunk's plan entry, clear masks, arm the barriers, loads of round 0
+  uint4 pn[4];  // issuer: plan entry of this CTA's NEXT chunk
+  {
+    uint4 p0[4];
+    load_plan(c, p0);
+    if (threadIdx.x == 0) {
+      S.plan[0][0] = p0[0];
+      S.plan[0][1] = p0[1];
+      S.plan[0][2] = p0[2];
+      S.plan[0][3] = p0[3];
+    }
+    if (threadIdx.x < 2u * MWORDS) {
+      (&S.B[0][0])[threadIdx.x] = 0u;
+      (&S.HB[0][0])[threadIdx.x] = 0u;
+    }
+    if (threadIdx.x == 0) {
+      S.n_below[0] = S.n_below[1] = 0u;
+      mbar_init(&S.full[0], 1u);
+      mbar_init(&S.full[1], 1u);
+    }
+    __syncthreads();
+    if (is_issuer) {
+      const ChunkPlanM &P = *reinterpret_cast<const ChunkPlanM *>(p0);
+      issue_round(0u, P.leaf0 + P.i_lo, min(seg_leaves, P.nl), true, 0u, P.q_lo, P.q_hi);
+      if (c + G < n_chunks) load_plan(c + G, pn);
+    }
+  }
+
+  uint32_t k = 0, seg = 0, r = 0;  // chunks done by this CTA, first leaf of the segment within the chunk, round
+  bool store_pending = false;
+  uint32_t st_out_slot0 = 0, st_n_out = 0, st_multi = 0;  // the finished chunk waiting for its store
+
+  for (;;) {
+    if (store_pending) fence_proxy_async_smem();  // my placements are visible to the bulk-copy engine
+    __syncthreads();                              // B0: everybody has left round r-1
+    if (store_pending) {
+      if (is_issuer) {  // the finished chunk leaves: one bulk store per array
+        const uint32_t bytes = (st_n_out << ls_dst) * 4u;
+        bulk_s2g((st_multi ? A.out_dest_multi : A.out_dest_single) + st_out_slot0, S.out_d, bytes);
+        bulk_s2g((st_multi ? A.out_val_multi : A.out_val_single) + st_out_slot0, S.out_v, bytes);
+        bulk_commit();
+      }
+      store_pending = false;
+      if (c >= n_chunks) break;
+    }
+    const uint32_t rpar = r & 1u, cpar = k & 1u;
+    const ChunkPlanM &P = *reinterpret_cast<const ChunkPlanM *>(&S.plan[cpar][0]);
+    const uint32_t nl = P.nl, q_lo = P.q_lo, q_hi = P.q_hi, a = P.a, span = P.span, R0 = P.R0;
+    const uint32_t gl0 = P.leaf0 + P.i_lo;
+    const bool first_seg = seg == 0, last_seg = seg + seg_leaves >= nl;
+    // ---- the next round's operands
+    if (is_issuer) {
+      if (!last_seg) {
+        issue_round(rpar ^ 1u, gl0 + seg + seg_leaves, min(seg_leaves, nl - seg - seg_leaves), false, cpar, 0u, 0u);
+      } else if (c + G < n_chunks) {
+        S.plan[cpar ^ 1u][0] = pn[0];
+        S.plan[cpar ^ 1u][1] = pn[1];
+        S.plan[cpar ^ 1u][2] = pn[2];
+        S.plan[cpar ^ 1u][3] = pn[3];
+        const ChunkPlanM &N = *reinterpret_cast<const ChunkPlanM *>(pn);
+        issue_round(rpar ^ 1u, N.leaf0 + N.i_lo, min(seg_leaves, N.nl), true, cpar ^ 1u, N.q_lo, N.q_hi);
+        if (c + 2u * G < n_chunks) load_plan(c + 2u * G, pn);
+      }
+    }
+    mbar_wait(&S.full[rpar], (r >> 1) & 1u);  // this round's operands have landed
+
+    const uint32_t snl = min(seg_leaves, nl - seg);  // nl == 0: seg == 0, snl == 0
+    const uint32_t seg_slot0 = (gl0 + seg) << ls_src;
+    const uint32_t seg_slots = snl << ls_src;
+    const uint32_t *t_R = S.st_R[rpar] + ((gl0 + seg) & 3u), *t_ioff = S.st_ioff[rpar] + ((gl0 + seg) & 3u);
+    const uint32_t ish = q_lo & 3u;
+    const uint32_t qa = snl ? max(q_lo, t_ioff[0]) : 0u, qb = snl ? min(q_hi, t_ioff[snl]) : 0u;
+    // chunk-relative rank range of the segment
+    uint32_t ta = 0, tb = 0;
+    if (snl) {
+      const uint32_t r_lo = t_R[0] - R0, r_hi = t_R[snl] - R0;
+      ta = r_lo > a ? r_lo - a : 0u;
+      tb = min(span, r_hi > a ? r_hi - a : 0u);
+      if (tb < ta) tb = ta;
+    }
+
+    if (TOMB) {
+      // ---- pre-pass: kept flags of the staged lines (tombstones have val 0), per leaf: kept index -> offset (kmap) and
+      // kept items up to each slot (kupto).  One 16-byte quad per thread and step, a leaf = 2, 4 or 8 lanes.
+      const uint32_t lpl = 1u << (ls_src - 2u);
+      const uint32_t warp_rel0 = (threadIdx.x & ~31u) * 4u;
+#pragma unroll
+      for (int u = 0; u < MSEG / 4 / MT; u++) {
+        if (u * MT * 4u + warp_rel0 >= seg_slots) continue;  // warp-uniform
+        const uint32_t rel = (u * MT + threadIdx.x) * 4u;
+        uint4 V = make_uint4(0u, 0u, 0u, 0u);
+        if (rel < seg_slots) V = *reinterpret_cast<const uint4 *>(&S.st_v[rpar][rel]);
+        const uint32_t k0 = V.x != 0u, k1 = V.y != 0u, k2 = V.z != 0u, k3 = V.w != 0u;
+        const uint32_t cc = k0 + k1 + k2 + k3;
+        const uint32_t pre = leaf_incl_scan(cc, lane, lpl) - cc;  // kept items of my leaf in lower lanes
+        const uint32_t p0 = pre + k0, p1 = p0 + k1, p2 = p1 + k2, p3 = p2 + k3;
+        if (rel < seg_slots) {
+          *reinterpret_cast<uint32_t *>(&S.kupto[rel]) = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+          const uint32_t lb = rel & ~leaf_mask, f0 = rel & leaf_mask;
+          if (k0) S.kmap[lb + pre] = (uint8_t)f0;
+          if (k1) S.kmap[lb + p0] = (uint8_t)(f0 + 1u);
+          if (k2) S.kmap[lb + p1] = (uint8_t)(f0 + 2u);
+          if (k3) S.kmap[lb + p2] = (uint8_t)(f0 + 3u);
+        }
+      }
+      __syncthreads();  // the inserts below read kupto
+    }
+
+    // ---- phase 1, dealt by warp:
+    if (warp == 0) {
+      // leaf heads + per-leaf address offsets; the other parity's masks are cleared for the next round
+      static_assert(MWORDS == 64, "16 lanes x 16 bytes clear one mask");
+      if (lane < 16u) reinterpret_cast<uint4 *>(S.B[rpar ^ 1u])[lane] = make_uint4(0u, 0u, 0u, 0u);
+      else reinterpret_cast<uint4 *>(S.HB[rpar ^ 1u])[lane - 16u] = make_uint4(0u, 0u, 0u, 0u);
+      if (lane == 0) S.n_below[cpar ^ 1u] = 0u;
+      uint32_t base = 0;
+      for (uint32_t x0 = 0; x0 < snl; x0 += 32u) {
+        const uint32_t x = x0 + lane;
+        bool ne = false;
+        uint32_t p = 0, dv = 0;
+        if (x < snl) {
+          const uint32_t Rx = t_R[x] - R0, Rx1 = t_R[x + 1u] - R0;
+          // the leaf's merged run [Rx, Rx1) meets the chunk's ranks [a, a + span)
+          ne = Rx1 > Rx && Rx1 > a && Rx < a + span;
+          p = Rx > a ? Rx - a : 0u;
+          dv = (x << ls_src) + a - Rx + t_ioff[x];
+        }
+        const unsigned nm = __ballot_sync(0xFFFFFFFFu, ne);
+        if (ne) {
+          atomicOr(&S.HB[rpar][p >> 5], 1u << (p & 31u));
+          S.D[base + __popc(nm & lt)] = dv;
+        }
+        base += __popc(nm);
+      }
+    } else if (warp <= 2) {
+      if (first_seg) {  // rank -> slot table and post-rebalance leaf counts of the chunk: one thread per output leaf
+        for (uint32_t kk = threadIdx.x - 32u; kk < P.n_out; kk += 64u) {
+          const uint32_t a_k = leaf_rank0(P.o_lo + kk, P.items, P.lg) - a;
+          const uint32_t c_k = leaf_rank0(P.o_lo + kk + 1u, P.items, P.lg) - a - a_k;
+          const uint32_t b_k = kk << ls_dst;
+          for (uint32_t i = 0; i < c_k; i++) S.pos[a_k + i] = (uint16_t)(b_k + i);
+          A.tree_leaf_out[P.dst_leaf + kk] = c_k;
+          if (A.leaf_cnt_out) A.leaf_cnt_out[P.dst_leaf + kk] = c_k;
+        }
+      }
+    } else if (warp == 3) {
+      if (first_seg) {  // null the staging buffers once the copy engine has read the previous chunk out of them
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *z = reinterpret_cast<uint4 *>(S.out_d);  // out_d and out_v are adjacent
+#pragma unroll 8
+        for (int x = 0; x < 2 * MCHUNK / 4 / 32; x++) z[x * 32 + lane] = zero;
+      }
+    } else {
+      // the segment's inserts: rank = R[leaf] + index in the leaf's run + kept items up to the predecessor -> B
+      uint32_t below = 0;
+      for (uint32_t q = qa + (threadIdx.x - 128u); q < qb; q += 128u) {
+        const uint32_t qi = q - q_lo;
+        const uint32_t pred = qi < (uint32_t)MPINS ? S.st_ip[cpar][qi + ish] : A.ins_pred[q];
+        const uint32_t rel = pred - seg_slot0;
+        const uint32_t x = rel >> ls_src;
+        const uint32_t kup = TOMB ? (uint32_t)S.kupto[rel] : (rel & leaf_mask) + 1u;
+        const uint32_t tt = (t_R[x] - R0) + (q - t_ioff[x]) + kup - a;
+        if (tt < span) atomicOr(&S.B[rpar][tt >> 5], 1u << (tt & 31u));
+        else if ((int32_t)tt < 0) below++;
+      }
+      if (first_seg) {
+        below = __reduce_add_sync(0xFFFFFFFFu, below);
+        if (lane == 0 && below) atomicAdd(&S.n_below[cpar], below);
+      }
+    }
+    __syncthreads();  // B1: masks, tables and the nulled staging buffers are complete
+
+    // ---- phase 2: the segment's ranks [ta, tb), 32 per warp and step, each warp a contiguous run of units
+    {
+      const uint32_t wa = ta >> 5, wb = (tb + 31u) >> 5;
+      const uint32_t per = (wb - wa + 7u) >> 3;
+      const uint32_t w0 = min(wa + warp * per, wb), w1 = min(w0 + per, wb);
+      if (w0 < w1) {
+        // inserts / leaf heads before my first unit
+        uint32_t cnt = 0;
+        if (lane < w0) cnt = __popc(S.B[rpar][lane]) | (__popc(S.HB[rpar][lane]) << 16);
+        if (MWORDS > 32 && lane + 32u < w0) cnt += __popc(S.B[rpar][lane + 32u]) | (__popc(S.HB[rpar][lane + 32u]) << 16);
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        uint32_t pbase = (first_seg ? q_lo + S.n_below[cpar] : qa) + (cnt & 0xFFFFu);
+        uint32_t fbase = (cnt >> 16) - 1u;
+        const uint32_t sbase = rpar * (uint32_t)MSEG;
+        const uint32_t insb = INS_W + cpar * (uint32_t)(MPINS + 8) + ish - q_lo;  // + q = word index of staged insert q
+        const uint32_t out_slot0 = P.out_slot0;
+        for (uint32_t w = w0; w < w1; w++) {
+          const uint32_t bw = S.B[rpar][w], hb = S.HB[rpar][w];
+          const uint32_t t = (w << 5) + lane;
+          const uint32_t q = pbase + __popc(bw & lt);
+          const uint32_t kidx = fbase + __popc(hb & le);
+          pbase += __popc(bw);
+          fbase += __popc(hb);
+          if (t >= ta && t < tb) {
+            const bool isins = (bw >> lane) & 1u;
+            uint32_t d, v;
+            if (isins && q - q_lo >= (uint32_t)MPINS) {  // beyond the stage (a long run of inserts)
+              d = A.ins_dst[q];
+              v = A.ins_val[q];
+            } else {
+              uint32_t idx;
+              if (isins) {
+                idx = insb + q;
+              } else if (TOMB) {
+                const uint32_t ki = t - q + S.D[kidx];  // leaf base + kept index
+                idx = sbase + (ki & ~leaf_mask) + S.kmap[ki];
+              } else {
+                idx = sbase + t - q + S.D[kidx];
+              }
+              d = W[idx];
+              v = W[idx + VOFF];
+            }
+            const uint32_t pos = S.pos[t];
+            S.out_d[pos] = d;
+            S.out_v[pos] = v;
+            // fix_sentinel (reference PCSR.cpp:168-183): a sentinel that lands here refreshes its vertex's back pointer
+            if (d == PPCSR_SENT) A.beg[v - 1u] = out_slot0 + pos;
+          }
+        }
+      }
+    }
+    r++;
+    if (!last_seg) {
+      seg += seg_leaves;
+      continue;
+    }
+    // every source leaf of the chunk has been read and placed: the chunk is stored after the next barrier
+    st_out_slot0 = P.out_slot0;
+    st_n_out = P.n_out;
+    st_multi = P.multi;
+    store_pending = true;
+    c += G;
+    k++;
+    seg = 0;
+  }
+  if (is_issuer) bulk_wait_read0();  // the staging buffers must outlive the last copy
+}
+
+// copy the chunks of multi-CTA windows back from the out-of-place target into the live array
+__global__ void __launch_bounds__(RT) k_copy_back_m(const ChunkPlanM *__restrict__ plan, uint32_t ls,
+                                                    const uint32_t *__restrict__ alt_dest,
+                                                    const uint32_t *__restrict__ alt_val, uint32_t *__restrict__ dest,
+                                                    uint32_t *__restrict__ val) {
+  const ChunkPlanM p = plan[blockIdx.x];
+  if (!p.multi) return;
+  const size_t base = (size_t)p.out_slot0;
+  const uint32_t slots = p.n_out << ls;
+  for (uint32_t x = threadIdx.x * 4; x < slots; x += RT * 4) {
+    *reinterpret_cast<uint4 *>(dest + base + x) = *reinterpret_cast<const uint4 *>(alt_dest + base + x);
+    *reinterpret_cast<uint4 *>(val + base + x) = *reinterpret_cast<const uint4 *>(alt_val + base + x);
+  }
+}
+
+}  // namespace reb
