@@ -27,6 +27,8 @@
 // 512 inserts -- are issued at the top of round r into the other half of a double buffer, a full round ahead.
 // Two block barriers per round (three with tombstones).
 #pragma once
+#include <type_traits>
+
 #include "rebalance.cuh"
 
 namespace reb {
@@ -240,26 +242,40 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
 
   uint32_t k = 0, seg = 0, r = 0;  // chunks done by this CTA, first leaf of the segment within the chunk, round
   bool store_pending = false;
-  uint32_t st_out_slot0 = 0, st_n_out = 0, st_multi = 0;  // the finished chunk waiting for its store
+  // the chunk in progress (registers, set by its first round)
+  uint32_t nl = 0, q_lo = 0, q_hi = 0, a = 0, span = 0, R0 = 0, gl0 = 0, out_slot0 = 0, n_out = 0, multi = 0;
+  uint32_t *const beg_m1 = A.beg - 1;  // a sentinel's value is its vertex + 1
+  const uint32_t lbit = 1u << lane;
 
   for (;;) {
     if (store_pending) fence_proxy_async_smem();  // my placements are visible to the bulk-copy engine
     __syncthreads();                              // B0: everybody has left round r-1
     if (store_pending) {
       if (is_issuer) {  // the finished chunk leaves: one bulk store per array
-        const uint32_t bytes = (st_n_out << ls_dst) * 4u;
-        bulk_s2g((st_multi ? A.out_dest_multi : A.out_dest_single) + st_out_slot0, S.out_d, bytes);
-        bulk_s2g((st_multi ? A.out_val_multi : A.out_val_single) + st_out_slot0, S.out_v, bytes);
+        const uint32_t bytes = (n_out << ls_dst) * 4u;
+        bulk_s2g((multi ? A.out_dest_multi : A.out_dest_single) + out_slot0, S.out_d, bytes);
+        bulk_s2g((multi ? A.out_val_multi : A.out_val_single) + out_slot0, S.out_v, bytes);
         bulk_commit();
       }
       store_pending = false;
       if (c >= n_chunks) break;
     }
     const uint32_t rpar = r & 1u, cpar = k & 1u;
-    const ChunkPlanM &P = *reinterpret_cast<const ChunkPlanM *>(&S.plan[cpar][0]);
-    const uint32_t nl = P.nl, q_lo = P.q_lo, q_hi = P.q_hi, a = P.a, span = P.span, R0 = P.R0;
-    const uint32_t gl0 = P.leaf0 + P.i_lo;
-    const bool first_seg = seg == 0, last_seg = seg + seg_leaves >= nl;
+    const bool first_seg = seg == 0;
+    if (first_seg) {
+      const uint4 p0 = S.plan[cpar][0], p1 = S.plan[cpar][1], p2 = S.plan[cpar][2];
+      multi = p0.y;
+      n_out = p0.w;
+      gl0 = p0.x + p1.x;
+      nl = p1.y;
+      q_lo = p1.z;
+      q_hi = p1.w;
+      R0 = p2.x;
+      a = p2.y;
+      span = p2.z;
+      out_slot0 = p2.w;
+    }
+    const bool last_seg = seg + seg_leaves >= nl;
     // ---- the next round's operands
     if (is_issuer) {
       if (!last_seg) {
@@ -281,21 +297,26 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
     const uint32_t seg_slots = snl << ls_src;
     const uint32_t *t_R = S.st_R[rpar] + ((gl0 + seg) & 3u), *t_ioff = S.st_ioff[rpar] + ((gl0 + seg) & 3u);
     const uint32_t ish = q_lo & 3u;
-    const uint32_t qa = snl ? max(q_lo, t_ioff[0]) : 0u, qb = snl ? min(q_hi, t_ioff[snl]) : 0u;
-    // chunk-relative rank range of the segment
-    uint32_t ta = 0, tb = 0;
-    if (snl) {
-      const uint32_t r_lo = t_R[0] - R0, r_hi = t_R[snl] - R0;
-      ta = r_lo > a ? r_lo - a : 0u;
-      tb = min(span, r_hi > a ? r_hi - a : 0u);
+    const uint32_t Ra = R0 + a;  // absolute rank of the chunk's first item
+    // the segment's inserts [qa, qb) and its chunk-relative rank range [ta, tb); a chunk of one segment needs no look-up
+    uint32_t qa = q_lo, qb = q_hi, ta = 0, tb = span;
+    if (!(first_seg && last_seg)) {
+      qa = max(q_lo, t_ioff[0]);
+      qb = min(q_hi, t_ioff[snl]);
+      const uint32_t r_lo = t_R[0], r_hi = t_R[snl];
+      ta = r_lo > Ra ? r_lo - Ra : 0u;
+      tb = min(span, r_hi > Ra ? r_hi - Ra : 0u);
       if (tb < ta) tb = ta;
     }
+    const bool staged_all = q_hi - q_lo <= (uint32_t)MPINS;  // every insert of the chunk sits in the stage
 
     if (TOMB) {
-      // ---- pre-pass: kept flags of the staged lines (tombstones have val 0), per leaf: kept index -> offset (kmap) and
-      // kept items up to each slot (kupto).  One 16-byte quad per thread and step, a leaf = 2, 4 or 8 lanes.
+      // ---- pre-pass: kept flags of the staged lines (tombstones have val 0), per leaf: kept index -> offset (kmap) and,
+      // when the chunk has inserts, kept items up to each slot (kupto).  One 16-byte quad per thread and step, a leaf =
+      // 2, 4 or 8 lanes.
       const uint32_t lpl = 1u << (ls_src - 2u);
       const uint32_t warp_rel0 = (threadIdx.x & ~31u) * 4u;
+      const bool want_kupto = q_hi != q_lo;
 #pragma unroll
       for (int u = 0; u < MSEG / 4 / MT; u++) {
         if (u * MT * 4u + warp_rel0 >= seg_slots) continue;  // warp-uniform
@@ -305,14 +326,16 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
         const uint32_t k0 = V.x != 0u, k1 = V.y != 0u, k2 = V.z != 0u, k3 = V.w != 0u;
         const uint32_t cc = k0 + k1 + k2 + k3;
         const uint32_t pre = leaf_incl_scan(cc, lane, lpl) - cc;  // kept items of my leaf in lower lanes
-        const uint32_t p0 = pre + k0, p1 = p0 + k1, p2 = p1 + k2, p3 = p2 + k3;
+        const uint32_t p0 = pre + k0, p1 = p0 + k1, p2 = p1 + k2;
         if (rel < seg_slots) {
-          *reinterpret_cast<uint32_t *>(&S.kupto[rel]) = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
-          const uint32_t lb = rel & ~leaf_mask, f0 = rel & leaf_mask;
-          if (k0) S.kmap[lb + pre] = (uint8_t)f0;
-          if (k1) S.kmap[lb + p0] = (uint8_t)(f0 + 1u);
-          if (k2) S.kmap[lb + p1] = (uint8_t)(f0 + 2u);
-          if (k3) S.kmap[lb + p2] = (uint8_t)(f0 + 3u);
+          if (want_kupto)
+            *reinterpret_cast<uint32_t *>(&S.kupto[rel]) = p0 | (p1 << 8) | (p2 << 16) | ((p2 + k3) << 24);
+          uint8_t *km = &S.kmap[rel & ~leaf_mask];
+          const uint32_t f0 = rel & leaf_mask;
+          if (k0) km[pre] = (uint8_t)f0;
+          if (k1) km[p0] = (uint8_t)(f0 + 1u);
+          if (k2) km[p1] = (uint8_t)(f0 + 2u);
+          if (k3) km[p2] = (uint8_t)(f0 + 3u);
         }
       }
       __syncthreads();  // the inserts below read kupto
@@ -331,11 +354,11 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
         bool ne = false;
         uint32_t p = 0, dv = 0;
         if (x < snl) {
-          const uint32_t Rx = t_R[x] - R0, Rx1 = t_R[x + 1u] - R0;
-          // the leaf's merged run [Rx, Rx1) meets the chunk's ranks [a, a + span)
-          ne = Rx1 > Rx && Rx1 > a && Rx < a + span;
-          p = Rx > a ? Rx - a : 0u;
-          dv = (x << ls_src) + a - Rx + t_ioff[x];
+          const uint32_t Rx = t_R[x], Rx1 = t_R[x + 1u];
+          // the leaf's merged run [Rx, Rx1) meets the chunk's ranks [Ra, Ra + span)
+          ne = Rx1 > Rx && Rx1 > Ra && Rx < Ra + span;
+          p = Rx > Ra ? Rx - Ra : 0u;
+          dv = (x << ls_src) + Ra - Rx + t_ioff[x];
         }
         const unsigned nm = __ballot_sync(0xFFFFFFFFu, ne);
         if (ne) {
@@ -346,13 +369,17 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
       }
     } else if (warp <= 2) {
       if (first_seg) {  // rank -> slot table and post-rebalance leaf counts of the chunk: one thread per output leaf
-        for (uint32_t kk = threadIdx.x - 32u; kk < P.n_out; kk += 64u) {
-          const uint32_t a_k = leaf_rank0(P.o_lo + kk, P.items, P.lg) - a;
-          const uint32_t c_k = leaf_rank0(P.o_lo + kk + 1u, P.items, P.lg) - a - a_k;
+        const uint4 p0 = S.plan[cpar][0], p3 = S.plan[cpar][3];
+        const uint32_t o_lo = p0.z, items = p3.x, lg = p3.y, dst_leaf = p3.z;
+        for (uint32_t kk = threadIdx.x - 32u; kk < n_out; kk += 64u) {
+          const uint32_t a_k = leaf_rank0(o_lo + kk, items, lg) - a;
+          const uint32_t c_k = leaf_rank0(o_lo + kk + 1u, items, lg) - a - a_k;
+          uint16_t *pk = &S.pos[a_k];
           const uint32_t b_k = kk << ls_dst;
-          for (uint32_t i = 0; i < c_k; i++) S.pos[a_k + i] = (uint16_t)(b_k + i);
-          A.tree_leaf_out[P.dst_leaf + kk] = c_k;
-          if (A.leaf_cnt_out) A.leaf_cnt_out[P.dst_leaf + kk] = c_k;
+#pragma unroll 4
+          for (uint32_t i = 0; i < c_k; i++) pk[i] = (uint16_t)(b_k + i);
+          A.tree_leaf_out[dst_leaf + kk] = c_k;
+          if (A.leaf_cnt_out) A.leaf_cnt_out[dst_leaf + kk] = c_k;
         }
       }
     } else if (warp == 3) {
@@ -367,15 +394,20 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
     } else {
       // the segment's inserts: rank = R[leaf] + index in the leaf's run + kept items up to the predecessor -> B
       uint32_t below = 0;
-      for (uint32_t q = qa + (threadIdx.x - 128u); q < qb; q += 128u) {
-        const uint32_t qi = q - q_lo;
-        const uint32_t pred = qi < (uint32_t)MPINS ? S.st_ip[cpar][qi + ish] : A.ins_pred[q];
+      const uint32_t *sip = S.st_ip[cpar] + ish - q_lo;  // + q = staged predecessor of insert q
+      auto one = [&](uint32_t q, uint32_t pred) {
         const uint32_t rel = pred - seg_slot0;
         const uint32_t x = rel >> ls_src;
         const uint32_t kup = TOMB ? (uint32_t)S.kupto[rel] : (rel & leaf_mask) + 1u;
-        const uint32_t tt = (t_R[x] - R0) + (q - t_ioff[x]) + kup - a;
+        const uint32_t tt = t_R[x] + (q - t_ioff[x]) + kup - Ra;
         if (tt < span) atomicOr(&S.B[rpar][tt >> 5], 1u << (tt & 31u));
         else if ((int32_t)tt < 0) below++;
+      };
+      if (staged_all) {
+        for (uint32_t q = qa + (threadIdx.x - 128u); q < qb; q += 128u) one(q, sip[q]);
+      } else {
+        for (uint32_t q = qa + (threadIdx.x - 128u); q < qb; q += 128u)
+          one(q, q - q_lo < (uint32_t)MPINS ? sip[q] : A.ins_pred[q]);
       }
       if (first_seg) {
         below = __reduce_add_sync(0xFFFFFFFFu, below);
@@ -384,55 +416,65 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
     }
     __syncthreads();  // B1: masks, tables and the nulled staging buffers are complete
 
-    // ---- phase 2: the segment's ranks [ta, tb), 32 per warp and step, each warp a contiguous run of units
+    // ---- phase 2: the segment's ranks [ta, tb), 32 per warp and step ("unit"), each warp a contiguous run of units
     {
-      const uint32_t wa = ta >> 5, wb = (tb + 31u) >> 5;
-      const uint32_t per = (wb - wa + 7u) >> 3;
-      const uint32_t w0 = min(wa + warp * per, wb), w1 = min(w0 + per, wb);
+      const uint32_t wa = ta >> 5, wb = (tb + 31u) >> 5, nu = wb - wa;
+      const uint32_t w0 = wa + ((nu * warp) >> 3), w1 = wa + ((nu * (warp + 1u)) >> 3);
       if (w0 < w1) {
         // inserts / leaf heads before my first unit
         uint32_t cnt = 0;
         if (lane < w0) cnt = __popc(S.B[rpar][lane]) | (__popc(S.HB[rpar][lane]) << 16);
-        if (MWORDS > 32 && lane + 32u < w0) cnt += __popc(S.B[rpar][lane + 32u]) | (__popc(S.HB[rpar][lane + 32u]) << 16);
+        if (lane + 32u < w0) cnt += __popc(S.B[rpar][lane + 32u]) | (__popc(S.HB[rpar][lane + 32u]) << 16);
         cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
         uint32_t pbase = (first_seg ? q_lo + S.n_below[cpar] : qa) + (cnt & 0xFFFFu);
         uint32_t fbase = (cnt >> 16) - 1u;
-        const uint32_t sbase = rpar * (uint32_t)MSEG;
-        const uint32_t insb = INS_W + cpar * (uint32_t)(MPINS + 8) + ish - q_lo;  // + q = word index of staged insert q
-        const uint32_t out_slot0 = P.out_slot0;
-        for (uint32_t w = w0; w < w1; w++) {
-          const uint32_t bw = S.B[rpar][w], hb = S.HB[rpar][w];
-          const uint32_t t = (w << 5) + lane;
+        const uint32_t sbt = rpar * (uint32_t)MSEG + lane;                        // + 32 w - q + D = word of a kept item
+        const uint32_t insb = INS_W + cpar * (uint32_t)(MPINS + 8) + ish - q_lo;  // + q = word of staged insert q
+        const uint32_t *Bm = S.B[rpar], *Hm = S.HB[rpar];
+        // one unit; CHECK: the unit is cut by the segment's rank range, STAGED: no insert lies beyond the stage
+        auto unit = [&](auto CHECK, auto STAGED, uint32_t w) {
+          const uint32_t bw = Bm[w], hb = Hm[w];
           const uint32_t q = pbase + __popc(bw & lt);
           const uint32_t kidx = fbase + __popc(hb & le);
           pbase += __popc(bw);
           fbase += __popc(hb);
-          if (t >= ta && t < tb) {
-            const bool isins = (bw >> lane) & 1u;
-            uint32_t d, v;
-            if (isins && q - q_lo >= (uint32_t)MPINS) {  // beyond the stage (a long run of inserts)
-              d = A.ins_dst[q];
-              v = A.ins_val[q];
-            } else {
-              uint32_t idx;
-              if (isins) {
-                idx = insb + q;
-              } else if (TOMB) {
-                const uint32_t ki = t - q + S.D[kidx];  // leaf base + kept index
-                idx = sbase + (ki & ~leaf_mask) + S.kmap[ki];
-              } else {
-                idx = sbase + t - q + S.D[kidx];
-              }
-              d = W[idx];
-              v = W[idx + VOFF];
-            }
-            const uint32_t pos = S.pos[t];
-            S.out_d[pos] = d;
-            S.out_v[pos] = v;
-            // fix_sentinel (reference PCSR.cpp:168-183): a sentinel that lands here refreshes its vertex's back pointer
-            if (d == PPCSR_SENT) A.beg[v - 1u] = out_slot0 + pos;
+          const uint32_t t = (w << 5) + lane;
+          if (decltype(CHECK)::value && !(t >= ta && t < tb)) return;
+          const uint32_t dk = S.D[kidx];
+          uint32_t idx;
+          if (TOMB) {
+            const uint32_t ki = t - q + dk;  // leaf base + kept index
+            idx = rpar * (uint32_t)MSEG + (ki & ~leaf_mask) + S.kmap[ki & (uint32_t)(MSEG - 1)];
+          } else {
+            idx = sbt + (w << 5) - q + dk;
           }
-        }
+          const bool isins = (bw & lbit) != 0u;
+          if (isins) idx = insb + q;
+          uint32_t d, v;
+          if (!decltype(STAGED)::value && isins && q - q_lo >= (uint32_t)MPINS) {  // a long run of inserts
+            d = A.ins_dst[q];
+            v = A.ins_val[q];
+          } else {
+            d = W[idx];
+            v = W[idx + VOFF];
+          }
+          const uint32_t pos = S.pos[t];
+          S.out_d[pos] = d;
+          S.out_v[pos] = v;
+          // fix_sentinel (reference PCSR.cpp:168-183): a sentinel that lands here refreshes its vertex's back pointer
+          if (d == PPCSR_SENT) beg_m1[v] = out_slot0 + pos;
+        };
+        auto run = [&](auto STAGED) {
+          uint32_t w = w0, wl = w1;
+          if (w == wa && (ta & 31u)) unit(std::true_type{}, STAGED, w++);
+          const bool cut_tail = w1 == wb && (tb & 31u) && w < w1;
+          if (cut_tail) wl--;
+#pragma unroll 2
+          for (; w < wl; w++) unit(std::false_type{}, STAGED, w);
+          if (cut_tail) unit(std::true_type{}, STAGED, w);
+        };
+        if (staged_all) run(std::true_type{});
+        else run(std::false_type{});
       }
     }
     r++;
@@ -441,9 +483,6 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
       continue;
     }
     // every source leaf of the chunk has been read and placed: the chunk is stored after the next barrier
-    st_out_slot0 = P.out_slot0;
-    st_n_out = P.n_out;
-    st_multi = P.multi;
     store_pending = true;
     c += G;
     k++;
