@@ -6,10 +6,10 @@ for rep in $(seq 1 ${REPS:-2}); do
 for v in "$@"; do   # each v: name:ENV=VAL,ENV=VAL
   name=${v%%:*}; envs=${v#*:}
   ( IFS=,; for e in $envs; do export "$e"; done
-    python bench.py --config C2 --no-cpu-baseline --steps 10 > gpurun_out/${tag}_${name}_c2_$rep.json 2>/dev/null
-    if [ "${C4:-0}" = "1" ]; then python bench.py --no-cpu-baseline --config C4 --steps 3 > gpurun_out/${tag}_${name}_c4_$rep.json 2>/dev/null; fi
-    if [ "${C5:-0}" = "1" ]; then python bench.py --no-cpu-baseline --config C5 --steps 10 > gpurun_out/${tag}_${name}_c5_$rep.json 2>/dev/null; fi
-    if [ "${C3:-0}" = "1" ]; then python bench.py --no-cpu-baseline --config C3 --steps 10 > gpurun_out/${tag}_${name}_c3_$rep.json 2>/dev/null; fi
+    python bench.py --config C2 --only-headline --no-cpu-baseline --steps 10 > gpurun_out/${tag}_${name}_c2_$rep.json 2>/dev/null
+    if [ "${C4:-0}" = "1" ]; then python bench.py --only-headline --no-cpu-baseline --config C4 --steps 3 > gpurun_out/${tag}_${name}_c4_$rep.json 2>/dev/null; fi
+    if [ "${C5:-0}" = "1" ]; then python bench.py --only-headline --no-cpu-baseline --config C5 --steps 10 > gpurun_out/${tag}_${name}_c5_$rep.json 2>/dev/null; fi
+    if [ "${C3:-0}" = "1" ]; then python bench.py --only-headline --no-cpu-baseline --config C3 --steps 10 > gpurun_out/${tag}_${name}_c3_$rep.json 2>/dev/null; fi
   )
   python - <<PY
 import json,glob

@@ -179,8 +179,19 @@ int launch_rebalance_m(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
     return e ? atol(e) : (long)PPCSR_M_CTAS;
   }();
   const unsigned grid = std::min<unsigned>(n_chunks, (unsigned)(sms[dv] * ctas));
-  reb::k_rebalance_m<TOMB><<<grid, reb::MT, sizeof(reb::MSmem<TOMB>), s->stream>>>(
+  reb::k_rebalance_m<TOMB><<<grid, reb::MTT, sizeof(reb::MSmem<TOMB>), s->stream>>>(
       A, reinterpret_cast<const reb::ChunkPlanM *>(s->plan.p), n_chunks);
+#ifdef PPCSR_M_TRACE
+  if (const char *path = getenv("PPCSR_TRACE_OUT")) {  // development build: clock stamps of the launch just made
+    static uint32_t host_trace[4 * 64 * 9 * 8];
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpyFromSymbol(host_trace, reb::g_m_trace, sizeof(host_trace)));
+    if (FILE *f = fopen(path, "wb")) {
+      fwrite(host_trace, 1, sizeof(host_trace), f);
+      fclose(f);
+    }
+  }
+#endif
   return PPCSR_OK;
 }
 // tomb: the batch wrote tombstones (it deleted edges); without, the leaves are still left-packed

@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(RT) k_plan_chunks_m(const WindowDesc *__restri
 #ifndef PPCSR_M_PINS
 #define PPCSR_M_PINS 512
 #endif
-constexpr int MT = 256;                        // threads of a k_rebalance_m CTA
+constexpr int MT = 256;                        // consumer threads of a k_rebalance_m CTA (warps 0..7)
+constexpr int MTT = MT + 32;                   // + the producer warp
 constexpr int MCHUNK = CHUNK_SLOTS;            // output slots per chunk
 constexpr int MSEG = SEG_LEAVES_SLOTS;         // source slots per round
 constexpr int MSEG_MAX_LEAVES = PSEG_MAX_LEAVES;
@@ -124,6 +125,19 @@ constexpr int MPINS = PPCSR_M_PINS;            // staged inserts per chunk
 constexpr int MWORDS = MCHUNK / 32;            // mask words
 static_assert(MT == 256, "k_rebalance_m deals its phases to eight warps");
 static_assert(MCHUNK <= 65536, "rank -> slot table entries are 16-bit");
+
+#ifdef PPCSR_M_TRACE
+// development: clock stamps of the first rounds of four CTAs (lane 0 of every warp), dumped by capi.cu after the launch
+__device__ uint32_t g_m_trace[4][64][9][8];
+#define MTRACE(ev)                                                                     \
+  do {                                                                                 \
+    if (blockIdx.x < 4 && r < 64 && lane == 0) g_m_trace[blockIdx.x][r][warp][ev] = (uint32_t)clock64(); \
+  } while (0)
+#else
+#define MTRACE(ev) \
+  do {             \
+  } while (0)
+#endif
 
 template <bool TOMB>
 struct MSmem {
@@ -147,11 +161,22 @@ struct MSmem {
   alignas(16) uint4 plan[2][4];               // [chunk parity]
   uint32_t n_below[2];                        // [chunk parity] staged inserts of the chunk's first leaf that rank below it
   alignas(8) uint64_t full[2];                // [round parity] the round's bulk loads have landed
+  alignas(8) uint64_t stready;                // the staging buffers are free again (previous chunk read out, nulled)
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(MT) : "memory"); }
+
+// Warps 0..7 are CONSUMERS (masks, tables, placement); warp 8 is the PRODUCER: after the round's opening barrier its
+// lane 0 stores the finished chunk (bulk store), issues the bulk loads of the NEXT round -- one cp.async.bulk costs the
+// issuing thread 70-170 cycles (benchmarks/micro/tma_issue.cu), a dozen of them was the longest path of a round when a
+// consumer issued them --, waits until the copy engine has read the staging buffers, re-nulls them where needed and
+// arrives on `stready`.  It takes no part in the consumers' mid-round barrier.
 template <bool TOMB>
-__global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const ChunkPlanM *__restrict__ gplan,
-                                                                 uint32_t n_chunks) {
+__global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const ChunkPlanM *__restrict__ gplan,
+                                                                  uint32_t n_chunks) {
   extern __shared__ __align__(128) uint8_t m_smem_raw[];
   using SM = MSmem<TOMB>;
   SM &S = *reinterpret_cast<SM *>(m_smem_raw);
@@ -162,17 +187,17 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
 
   const unsigned lane = lane_id(), lt = lanemask_lt(), le = lt | (1u << lane);
   const unsigned warp = threadIdx.x >> 5;
+  const bool producer = warp == 8;
   const uint32_t ls_src = A.ls_src, ls_dst = A.ls_dst;
   const uint32_t leaf_mask = (1u << ls_src) - 1u;
   const uint32_t seg_leaves = min((uint32_t)MSEG >> ls_src, (uint32_t)MSEG_MAX_LEAVES);
   const uint32_t G = gridDim.x;
   uint32_t c = blockIdx.x;
   if (c >= n_chunks) return;
-  const bool is_issuer = threadIdx.x == 3u * 32u;  // lane 0 of the IO warp
 
-  // ---- the bulk loads of one round (issuer only): source lines + table slices of the leaves [gl, gl + snl), and, when
-  // the round opens a chunk, the chunk's first MPINS inserts
-  auto issue_round = [&](uint32_t rpar, uint32_t gl, uint32_t snl, bool first_seg, uint32_t cpar, uint32_t q_lo,
+  // ---- the bulk loads of one round (producer, lane 0): source lines + table slices of the leaves [gl, gl + snl), and,
+  // when the round opens a chunk, the chunk's first MPINS inserts
+  auto issue_round = [&](uint32_t rpar, uint32_t gl, uint32_t snl, bool first, uint32_t cpar, uint32_t q_lo,
                          uint32_t q_hi) {
     uint64_t *bar = &S.full[rpar];
     if (snl == 0) {
@@ -183,45 +208,39 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
     const uint32_t sh = gl & 3u;
     // 16-byte granules: reads up to 3 entries past the logical end of the arrays (covered by DEV_PAD_ELEMS)
     const uint32_t tb = ((snl + 1u + sh + 3u) & ~3u) * 4u;
-    const uint32_t nq = first_seg ? min(q_hi - q_lo, (uint32_t)MPINS) : 0u;
+    const uint32_t nq = first ? min(q_hi - q_lo, (uint32_t)MPINS) : 0u;
     const uint32_t ish = q_lo & 3u;
     const uint32_t ib = nq ? ((nq + ish + 3u) & ~3u) * 4u : 0u;
     mbar_expect_tx(bar, 2u * qb + 2u * tb + 3u * ib);
-    bulk_g2s(S.st_d[rpar], A.src_dest + ((size_t)gl << ls_src), qb, bar);
-    bulk_g2s(S.st_v[rpar], A.src_val + ((size_t)gl << ls_src), qb, bar);
     bulk_g2s(S.st_R[rpar], A.rank_off + (gl - sh), tb, bar);
     bulk_g2s(S.st_ioff[rpar], A.ins_off + (gl - sh), tb, bar);
     if (ib) {
       bulk_g2s(S.st_ip[cpar], A.ins_pred + (q_lo - ish), ib, bar);
       bulk_g2s(S.st_id[cpar], A.ins_dst + (q_lo - ish), ib, bar);
       bulk_g2s(S.st_iv[cpar], A.ins_val + (q_lo - ish), ib, bar);
-      if (q_hi - q_lo > (uint32_t)MPINS) {  // a longer run is read straight from global memory: pull it into L2
-        const uint32_t q1 = (q_lo + MPINS) & ~3u;
-        const uint32_t pb = min(((q_hi - q1 + 3u) & ~3u) * 4u, 16384u);
-        bulk_prefetch_l2(A.ins_pred + q1, pb);
-        bulk_prefetch_l2(A.ins_dst + q1, pb);
-        bulk_prefetch_l2(A.ins_val + q1, pb);
-      }
     }
-  };
-  auto load_plan = [&](uint32_t chunk, uint4 (&p)[4]) {
-    const uint4 *g = reinterpret_cast<const uint4 *>(gplan + chunk);
-    p[0] = __ldg(g);
-    p[1] = __ldg(g + 1);
-    p[2] = __ldg(g + 2);
-    p[3] = __ldg(g + 3);
+    bulk_g2s(S.st_d[rpar], A.src_dest + ((size_t)gl << ls_src), qb, bar);
+    bulk_g2s(S.st_v[rpar], A.src_val + ((size_t)gl << ls_src), qb, bar);
+    if (ib && q_hi - q_lo > (uint32_t)MPINS) {  // a longer run is read straight from global memory: pull it into L2
+      const uint32_t q1 = (q_lo + MPINS) & ~3u;
+      const uint32_t pb = min(((q_hi - q1 + 3u) & ~3u) * 4u, 16384u);
+      bulk_prefetch_l2(A.ins_pred + q1, pb);
+      bulk_prefetch_l2(A.ins_dst + q1, pb);
+      bulk_prefetch_l2(A.ins_val + q1, pb);
+    }
   };
 
   // ---- prologue: the first chunk's plan entry, clear masks, arm the barriers, loads of round 0
-  uint4 pn[4];  // issuer: plan entry of this CTA's NEXT chunk
+  uint4 n0, n1, n2, n3;  // producer: plan entry of this CTA's NEXT chunk
+  n0 = n1 = n2 = n3 = make_uint4(0u, 0u, 0u, 0u);
   {
-    uint4 p0[4];
-    load_plan(c, p0);
+    const uint4 *g = reinterpret_cast<const uint4 *>(gplan + c);
+    const uint4 p0 = __ldg(g), p1 = __ldg(g + 1);
     if (threadIdx.x == 0) {
-      S.plan[0][0] = p0[0];
-      S.plan[0][1] = p0[1];
-      S.plan[0][2] = p0[2];
-      S.plan[0][3] = p0[3];
+      S.plan[0][0] = p0;
+      S.plan[0][1] = p1;
+      S.plan[0][2] = __ldg(g + 2);
+      S.plan[0][3] = __ldg(g + 3);
     }
     if (threadIdx.x < 2u * MWORDS) {
       (&S.B[0][0])[threadIdx.x] = 0u;
@@ -231,12 +250,18 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
       S.n_below[0] = S.n_below[1] = 0u;
       mbar_init(&S.full[0], 1u);
       mbar_init(&S.full[1], 1u);
+      mbar_init(&S.stready, 1u);
     }
     __syncthreads();
-    if (is_issuer) {
-      const ChunkPlanM &P = *reinterpret_cast<const ChunkPlanM *>(p0);
-      issue_round(0u, P.leaf0 + P.i_lo, min(seg_leaves, P.nl), true, 0u, P.q_lo, P.q_hi);
-      if (c + G < n_chunks) load_plan(c + G, pn);
+    if (producer && lane == 0) {
+      issue_round(0u, p0.x + p1.x, min(seg_leaves, p1.y), true, 0u, p1.z, p1.w);
+      if (c + G < n_chunks) {
+        const uint4 *gn = reinterpret_cast<const uint4 *>(gplan + c + G);
+        n0 = __ldg(gn);
+        n1 = __ldg(gn + 1);
+        n2 = __ldg(gn + 2);
+        n3 = __ldg(gn + 3);
+      }
     }
   }
 
@@ -248,10 +273,10 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
   const uint32_t lbit = 1u << lane;
 
   for (;;) {
-    if (store_pending) fence_proxy_async_smem();  // my placements are visible to the bulk-copy engine
-    __syncthreads();                              // B0: everybody has left round r-1
+    if (store_pending && !producer) fence_proxy_async_smem();  // my placements are visible to the bulk-copy engine
+    __syncthreads();                                           // B0: everybody has left round r-1
     if (store_pending) {
-      if (is_issuer) {  // the finished chunk leaves: one bulk store per array
+      if (producer && lane == 0) {  // the finished chunk leaves: one bulk store per array
         const uint32_t bytes = (n_out << ls_dst) * 4u;
         bulk_s2g((multi ? A.out_dest_multi : A.out_dest_single) + out_slot0, S.out_d, bytes);
         bulk_s2g((multi ? A.out_val_multi : A.out_val_single) + out_slot0, S.out_v, bytes);
@@ -260,6 +285,7 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
       store_pending = false;
       if (c >= n_chunks) break;
     }
+    MTRACE(0);
     const uint32_t rpar = r & 1u, cpar = k & 1u;
     const bool first_seg = seg == 0;
     if (first_seg) {
@@ -276,148 +302,173 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
       out_slot0 = p2.w;
     }
     const bool last_seg = seg + seg_leaves >= nl;
-    // ---- the next round's operands
-    if (is_issuer) {
-      if (!last_seg) {
-        issue_round(rpar ^ 1u, gl0 + seg + seg_leaves, min(seg_leaves, nl - seg - seg_leaves), false, cpar, 0u, 0u);
-      } else if (c + G < n_chunks) {
-        S.plan[cpar ^ 1u][0] = pn[0];
-        S.plan[cpar ^ 1u][1] = pn[1];
-        S.plan[cpar ^ 1u][2] = pn[2];
-        S.plan[cpar ^ 1u][3] = pn[3];
-        const ChunkPlanM &N = *reinterpret_cast<const ChunkPlanM *>(pn);
-        issue_round(rpar ^ 1u, N.leaf0 + N.i_lo, min(seg_leaves, N.nl), true, cpar ^ 1u, N.q_lo, N.q_hi);
-        if (c + 2u * G < n_chunks) load_plan(c + 2u * G, pn);
-      }
-    }
-    mbar_wait(&S.full[rpar], (r >> 1) & 1u);  // this round's operands have landed
+    // A whole-array rebuild gives every output leaf floor(j / m) or that + 1 items, chunk after chunk: the staging
+    // buffers need no re-nulling between chunks -- the only slot of a leaf that can hold a stale item is the one
+    // behind its last item (nulled by the leaf's thread, see zpos).  Chunks of <= 64 output leaves only.
+    const bool keep_nulls = A.m_dst_override != 0u && k > 0u && n_out <= 64u;
 
-    const uint32_t snl = min(seg_leaves, nl - seg);  // nl == 0: seg == 0, snl == 0
-    const uint32_t seg_slot0 = (gl0 + seg) << ls_src;
-    const uint32_t seg_slots = snl << ls_src;
-    const uint32_t *t_R = S.st_R[rpar] + ((gl0 + seg) & 3u), *t_ioff = S.st_ioff[rpar] + ((gl0 + seg) & 3u);
-    const uint32_t ish = q_lo & 3u;
-    const uint32_t Ra = R0 + a;  // absolute rank of the chunk's first item
-    // the segment's inserts [qa, qb) and its chunk-relative rank range [ta, tb); a chunk of one segment needs no look-up
-    uint32_t qa = q_lo, qb = q_hi, ta = 0, tb = span;
-    if (!(first_seg && last_seg)) {
-      qa = max(q_lo, t_ioff[0]);
-      qb = min(q_hi, t_ioff[snl]);
-      const uint32_t r_lo = t_R[0], r_hi = t_R[snl];
-      ta = r_lo > Ra ? r_lo - Ra : 0u;
-      tb = min(span, r_hi > Ra ? r_hi - Ra : 0u);
-      if (tb < ta) tb = ta;
-    }
-    const bool staged_all = q_hi - q_lo <= (uint32_t)MPINS;  // every insert of the chunk sits in the stage
-
-    if (TOMB) {
-      // ---- pre-pass: kept flags of the staged lines (tombstones have val 0), per leaf: kept index -> offset (kmap) and,
-      // when the chunk has inserts, kept items up to each slot (kupto).  One 16-byte quad per thread and step, a leaf =
-      // 2, 4 or 8 lanes.
-      const uint32_t lpl = 1u << (ls_src - 2u);
-      const uint32_t warp_rel0 = (threadIdx.x & ~31u) * 4u;
-      const bool want_kupto = q_hi != q_lo;
-#pragma unroll
-      for (int u = 0; u < MSEG / 4 / MT; u++) {
-        if (u * MT * 4u + warp_rel0 >= seg_slots) continue;  // warp-uniform
-        const uint32_t rel = (u * MT + threadIdx.x) * 4u;
-        uint4 V = make_uint4(0u, 0u, 0u, 0u);
-        if (rel < seg_slots) V = *reinterpret_cast<const uint4 *>(&S.st_v[rpar][rel]);
-        const uint32_t k0 = V.x != 0u, k1 = V.y != 0u, k2 = V.z != 0u, k3 = V.w != 0u;
-        const uint32_t cc = k0 + k1 + k2 + k3;
-        const uint32_t pre = leaf_incl_scan(cc, lane, lpl) - cc;  // kept items of my leaf in lower lanes
-        const uint32_t p0 = pre + k0, p1 = p0 + k1, p2 = p1 + k2;
-        if (rel < seg_slots) {
-          if (want_kupto)
-            *reinterpret_cast<uint32_t *>(&S.kupto[rel]) = p0 | (p1 << 8) | (p2 << 16) | ((p2 + k3) << 24);
-          uint8_t *km = &S.kmap[rel & ~leaf_mask];
-          const uint32_t f0 = rel & leaf_mask;
-          if (k0) km[pre] = (uint8_t)f0;
-          if (k1) km[p0] = (uint8_t)(f0 + 1u);
-          if (k2) km[p1] = (uint8_t)(f0 + 2u);
-          if (k3) km[p2] = (uint8_t)(f0 + 3u);
+    if (producer) {
+      if (lane == 0) {
+        // ---- the next round's operands
+        if (!last_seg) {
+          issue_round(rpar ^ 1u, gl0 + seg + seg_leaves, min(seg_leaves, nl - seg - seg_leaves), false, cpar, 0u, 0u);
+        } else if (c + G < n_chunks) {
+          S.plan[cpar ^ 1u][0] = n0;
+          S.plan[cpar ^ 1u][1] = n1;
+          S.plan[cpar ^ 1u][2] = n2;
+          S.plan[cpar ^ 1u][3] = n3;
+          issue_round(rpar ^ 1u, n0.x + n1.x, min(seg_leaves, n1.y), true, cpar ^ 1u, n1.z, n1.w);
+          if (c + 2u * G < n_chunks) {
+            const uint4 *gn = reinterpret_cast<const uint4 *>(gplan + c + 2u * G);
+            n0 = __ldg(gn);
+            n1 = __ldg(gn + 1);
+            n2 = __ldg(gn + 2);
+            n3 = __ldg(gn + 3);
+          }
         }
+        if (first_seg) bulk_wait_read0();  // the copy engine has read the previous chunk out of the staging buffers
       }
-      __syncthreads();  // the inserts below read kupto
-    }
-
-    // ---- phase 1, dealt by warp:
-    if (warp == 0) {
-      // leaf heads + per-leaf address offsets; the other parity's masks are cleared for the next round
-      static_assert(MWORDS == 64, "16 lanes x 16 bytes clear one mask");
-      if (lane < 16u) reinterpret_cast<uint4 *>(S.B[rpar ^ 1u])[lane] = make_uint4(0u, 0u, 0u, 0u);
-      else reinterpret_cast<uint4 *>(S.HB[rpar ^ 1u])[lane - 16u] = make_uint4(0u, 0u, 0u, 0u);
-      if (lane == 0) S.n_below[cpar ^ 1u] = 0u;
-      uint32_t base = 0;
-      for (uint32_t x0 = 0; x0 < snl; x0 += 32u) {
-        const uint32_t x = x0 + lane;
-        bool ne = false;
-        uint32_t p = 0, dv = 0;
-        if (x < snl) {
-          const uint32_t Rx = t_R[x], Rx1 = t_R[x + 1u];
-          // the leaf's merged run [Rx, Rx1) meets the chunk's ranks [Ra, Ra + span)
-          ne = Rx1 > Rx && Rx1 > Ra && Rx < Ra + span;
-          p = Rx > Ra ? Rx - Ra : 0u;
-          dv = (x << ls_src) + Ra - Rx + t_ioff[x];
-        }
-        const unsigned nm = __ballot_sync(0xFFFFFFFFu, ne);
-        if (ne) {
-          atomicOr(&S.HB[rpar][p >> 5], 1u << (p & 31u));
-          S.D[base + __popc(nm & lt)] = dv;
-        }
-        base += __popc(nm);
-      }
-    } else if (warp <= 2) {
-      if (first_seg) {  // rank -> slot table and post-rebalance leaf counts of the chunk: one thread per output leaf
-        const uint4 p0 = S.plan[cpar][0], p3 = S.plan[cpar][3];
-        const uint32_t o_lo = p0.z, items = p3.x, lg = p3.y, dst_leaf = p3.z;
-        for (uint32_t kk = threadIdx.x - 32u; kk < n_out; kk += 64u) {
-          const uint32_t a_k = leaf_rank0(o_lo + kk, items, lg) - a;
-          const uint32_t c_k = leaf_rank0(o_lo + kk + 1u, items, lg) - a - a_k;
-          uint16_t *pk = &S.pos[a_k];
-          const uint32_t b_k = kk << ls_dst;
-#pragma unroll 4
-          for (uint32_t i = 0; i < c_k; i++) pk[i] = (uint16_t)(b_k + i);
-          A.tree_leaf_out[dst_leaf + kk] = c_k;
-          if (A.leaf_cnt_out) A.leaf_cnt_out[dst_leaf + kk] = c_k;
-        }
-      }
-    } else if (warp == 3) {
-      if (first_seg) {  // null the staging buffers once the copy engine has read the previous chunk out of them
-        if (lane == 0) bulk_wait_read0();
+      if (first_seg && !keep_nulls) {
         __syncwarp();
         const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
         uint4 *z = reinterpret_cast<uint4 *>(S.out_d);  // out_d and out_v are adjacent
 #pragma unroll 8
         for (int x = 0; x < 2 * MCHUNK / 4 / 32; x++) z[x * 32 + lane] = zero;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.stready);
+      MTRACE(1);
     } else {
-      // the segment's inserts: rank = R[leaf] + index in the leaf's run + kept items up to the predecessor -> B
-      uint32_t below = 0;
-      const uint32_t *sip = S.st_ip[cpar] + ish - q_lo;  // + q = staged predecessor of insert q
-      auto one = [&](uint32_t q, uint32_t pred) {
-        const uint32_t rel = pred - seg_slot0;
-        const uint32_t x = rel >> ls_src;
-        const uint32_t kup = TOMB ? (uint32_t)S.kupto[rel] : (rel & leaf_mask) + 1u;
-        const uint32_t tt = t_R[x] + (q - t_ioff[x]) + kup - Ra;
-        if (tt < span) atomicOr(&S.B[rpar][tt >> 5], 1u << (tt & 31u));
-        else if ((int32_t)tt < 0) below++;
-      };
-      if (staged_all) {
-        for (uint32_t q = qa + (threadIdx.x - 128u); q < qb; q += 128u) one(q, sip[q]);
-      } else {
-        for (uint32_t q = qa + (threadIdx.x - 128u); q < qb; q += 128u)
-          one(q, q - q_lo < (uint32_t)MPINS ? sip[q] : A.ins_pred[q]);
-      }
-      if (first_seg) {
-        below = __reduce_add_sync(0xFFFFFFFFu, below);
-        if (lane == 0 && below) atomicAdd(&S.n_below[cpar], below);
-      }
-    }
-    __syncthreads();  // B1: masks, tables and the nulled staging buffers are complete
+      mbar_wait(&S.full[rpar], (r >> 1) & 1u);  // this round's operands have landed
+      MTRACE(2);
 
-    // ---- phase 2: the segment's ranks [ta, tb), 32 per warp and step ("unit"), each warp a contiguous run of units
-    {
+      const uint32_t snl = min(seg_leaves, nl - seg);  // nl == 0: seg == 0, snl == 0
+      const uint32_t seg_slot0 = (gl0 + seg) << ls_src;
+      const uint32_t seg_slots = snl << ls_src;
+      const uint32_t *t_R = S.st_R[rpar] + ((gl0 + seg) & 3u), *t_ioff = S.st_ioff[rpar] + ((gl0 + seg) & 3u);
+      const uint32_t ish = q_lo & 3u;
+      const uint32_t Ra = R0 + a;  // absolute rank of the chunk's first item
+      // the segment's inserts [qa, qb) and its chunk-relative rank range [ta, tb); a chunk of one segment needs no look-up
+      uint32_t qa = q_lo, qb = q_hi, ta = 0, tb = span;
+      if (!(first_seg && last_seg)) {
+        qa = max(q_lo, t_ioff[0]);
+        qb = min(q_hi, t_ioff[snl]);
+        const uint32_t r_lo = t_R[0], r_hi = t_R[snl];
+        ta = r_lo > Ra ? r_lo - Ra : 0u;
+        tb = min(span, r_hi > Ra ? r_hi - Ra : 0u);
+        if (tb < ta) tb = ta;
+      }
+      const bool staged_all = q_hi - q_lo <= (uint32_t)MPINS;  // every insert of the chunk sits in the stage
+
+      if (TOMB) {
+        // ---- pre-pass: kept flags of the staged lines (tombstones have val 0), per leaf: kept index -> offset (kmap)
+        // and, when the chunk has inserts, kept items up to each slot (kupto).  One 16-byte quad per thread and step, a
+        // leaf = 2, 4 or 8 lanes.
+        const uint32_t lpl = 1u << (ls_src - 2u);
+        const uint32_t warp_rel0 = (threadIdx.x & ~31u) * 4u;
+        const bool want_kupto = q_hi != q_lo;
+#pragma unroll
+        for (int u = 0; u < MSEG / 4 / MT; u++) {
+          if (u * MT * 4u + warp_rel0 >= seg_slots) continue;  // warp-uniform
+          const uint32_t rel = (u * MT + threadIdx.x) * 4u;
+          uint4 V = make_uint4(0u, 0u, 0u, 0u);
+          if (rel < seg_slots) V = *reinterpret_cast<const uint4 *>(&S.st_v[rpar][rel]);
+          const uint32_t k0 = V.x != 0u, k1 = V.y != 0u, k2 = V.z != 0u, k3 = V.w != 0u;
+          const uint32_t cc = k0 + k1 + k2 + k3;
+          const uint32_t pre = leaf_incl_scan(cc, lane, lpl) - cc;  // kept items of my leaf in lower lanes
+          const uint32_t p0 = pre + k0, p1 = p0 + k1, p2 = p1 + k2;
+          if (rel < seg_slots) {
+            if (want_kupto)
+              *reinterpret_cast<uint32_t *>(&S.kupto[rel]) = p0 | (p1 << 8) | (p2 << 16) | ((p2 + k3) << 24);
+            uint8_t *km = &S.kmap[rel & ~leaf_mask];
+            const uint32_t f0 = rel & leaf_mask;
+            if (k0) km[pre] = (uint8_t)f0;
+            if (k1) km[p0] = (uint8_t)(f0 + 1u);
+            if (k2) km[p1] = (uint8_t)(f0 + 2u);
+            if (k3) km[p2] = (uint8_t)(f0 + 3u);
+          }
+        }
+        bar_consumers();  // the inserts below read kupto
+      }
+
+      // ---- phase 1: a small task for the warps 0..2, then the segment's inserts dealt over the warps 3..7, 0..2
+      uint32_t zpos = 0xFFFFFFFFu;  // warps 1, 2: the slot of my output leaf that may hold a stale item (keep_nulls)
+      if (warp == 0) {
+        // leaf heads + per-leaf address offsets; the other parity's masks are cleared for the next round
+        static_assert(MWORDS == 64, "16 lanes x 16 bytes clear one mask");
+        if (lane < 16u) reinterpret_cast<uint4 *>(S.B[rpar ^ 1u])[lane] = make_uint4(0u, 0u, 0u, 0u);
+        else reinterpret_cast<uint4 *>(S.HB[rpar ^ 1u])[lane - 16u] = make_uint4(0u, 0u, 0u, 0u);
+        if (lane == 0) S.n_below[cpar ^ 1u] = 0u;
+        uint32_t base = 0;
+        for (uint32_t x0 = 0; x0 < snl; x0 += 32u) {
+          const uint32_t x = x0 + lane;
+          bool ne = false;
+          uint32_t p = 0, dv = 0;
+          if (x < snl) {
+            const uint32_t Rx = t_R[x], Rx1 = t_R[x + 1u];
+            // the leaf's merged run [Rx, Rx1) meets the chunk's ranks [Ra, Ra + span)
+            ne = Rx1 > Rx && Rx1 > Ra && Rx < Ra + span;
+            p = Rx > Ra ? Rx - Ra : 0u;
+            dv = (x << ls_src) + Ra - Rx + t_ioff[x];
+          }
+          const unsigned nm = __ballot_sync(0xFFFFFFFFu, ne);
+          if (ne) {
+            atomicOr(&S.HB[rpar][p >> 5], 1u << (p & 31u));
+            S.D[base + __popc(nm & lt)] = dv;
+          }
+          base += __popc(nm);
+        }
+      } else if (warp <= 2) {
+        if (first_seg) {  // rank -> slot table and post-rebalance leaf counts of the chunk: one thread per output leaf
+          const uint4 p0 = S.plan[cpar][0], p3 = S.plan[cpar][3];
+          const uint32_t o_lo = p0.z, items = p3.x, lg = p3.y, dst_leaf = p3.z;
+          for (uint32_t kk = threadIdx.x - 32u; kk < n_out; kk += 64u) {
+            const uint32_t a_k = leaf_rank0(o_lo + kk, items, lg) - a;
+            const uint32_t c_k = leaf_rank0(o_lo + kk + 1u, items, lg) - a - a_k;
+            uint16_t *pk = &S.pos[a_k];
+            const uint32_t b_k = kk << ls_dst;
+#pragma unroll 4
+            for (uint32_t i = 0; i < c_k; i++) pk[i] = (uint16_t)(b_k + i);
+            A.tree_leaf_out[dst_leaf + kk] = c_k;
+            if (A.leaf_cnt_out) A.leaf_cnt_out[dst_leaf + kk] = c_k;
+            if (keep_nulls && (c_k >> ls_dst) == 0u) zpos = b_k + c_k;
+          }
+        }
+      }
+      {
+        // the segment's inserts: rank = R[leaf] + index in the leaf's run + kept items up to the predecessor -> B
+        uint32_t below = 0;
+        const uint32_t itid = ((warp + 5u) & 7u) * 32u + lane;  // the warps without a task of their own come first
+        const uint32_t *sip = S.st_ip[cpar] + ish - q_lo;       // + q = staged predecessor of insert q
+        auto one = [&](uint32_t q, uint32_t pred) {
+          const uint32_t rel = pred - seg_slot0;
+          const uint32_t x = rel >> ls_src;
+          const uint32_t kup = TOMB ? (uint32_t)S.kupto[rel] : (rel & leaf_mask) + 1u;
+          const uint32_t tt = t_R[x] + (q - t_ioff[x]) + kup - Ra;
+          if (tt < span) atomicOr(&S.B[rpar][tt >> 5], 1u << (tt & 31u));
+          else if ((int32_t)tt < 0) below++;
+        };
+        if (staged_all) {
+          for (uint32_t q = qa + itid; q < qb; q += (uint32_t)MT) one(q, sip[q]);
+        } else {
+          for (uint32_t q = qa + itid; q < qb; q += (uint32_t)MT)
+            one(q, q - q_lo < (uint32_t)MPINS ? sip[q] : A.ins_pred[q]);
+        }
+        if (first_seg) {
+          below = __reduce_add_sync(0xFFFFFFFFu, below);
+          if (lane == 0 && below) atomicAdd(&S.n_below[cpar], below);
+        }
+      }
+      MTRACE(3);
+      bar_consumers();                   // B1: masks and tables are complete
+      mbar_wait(&S.stready, r & 1u);     // the staging buffers are free (and nulled)
+      MTRACE(4);
+      if (zpos != 0xFFFFFFFFu) {  // the slot behind my leaf's last item (see keep_nulls)
+        S.out_d[zpos] = 0u;
+        S.out_v[zpos] = 0u;
+      }
+
+      // ---- phase 2: the segment's ranks [ta, tb), 32 per warp and step ("unit"), each warp a contiguous run of units
       const uint32_t wa = ta >> 5, wb = (tb + 31u) >> 5, nu = wb - wa;
       const uint32_t w0 = wa + ((nu * warp) >> 3), w1 = wa + ((nu * (warp + 1u)) >> 3);
       if (w0 < w1) {
@@ -428,6 +479,7 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
         cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
         uint32_t pbase = (first_seg ? q_lo + S.n_below[cpar] : qa) + (cnt & 0xFFFFu);
         uint32_t fbase = (cnt >> 16) - 1u;
+        MTRACE(5);
         const uint32_t sbt = rpar * (uint32_t)MSEG + lane;                        // + 32 w - q + D = word of a kept item
         const uint32_t insb = INS_W + cpar * (uint32_t)(MPINS + 8) + ish - q_lo;  // + q = word of staged insert q
         const uint32_t *Bm = S.B[rpar], *Hm = S.HB[rpar];
@@ -469,13 +521,14 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
           if (w == wa && (ta & 31u)) unit(std::true_type{}, STAGED, w++);
           const bool cut_tail = w1 == wb && (tb & 31u) && w < w1;
           if (cut_tail) wl--;
-#pragma unroll 2
+#pragma unroll 4
           for (; w < wl; w++) unit(std::false_type{}, STAGED, w);
           if (cut_tail) unit(std::true_type{}, STAGED, w);
         };
         if (staged_all) run(std::true_type{});
         else run(std::false_type{});
       }
+      MTRACE(6);
     }
     r++;
     if (!last_seg) {
@@ -488,7 +541,7 @@ __global__ void __launch_bounds__(MT, PPCSR_M_CTAS) k_rebalance_m(Args A, const 
     k++;
     seg = 0;
   }
-  if (is_issuer) bulk_wait_read0();  // the staging buffers must outlive the last copy
+  if (producer && lane == 0) bulk_wait_read0();  // the staging buffers must outlive the last copy
 }
 
 // copy the chunks of multi-CTA windows back from the out-of-place target into the live array
