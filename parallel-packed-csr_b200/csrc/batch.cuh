@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
   __syncthreads();
   for (uint32_t x = tid; x < total; x += LT) {  // coalesced, into the tile's own region
     tile_dst[base + x] = S.o_dst[x];
-    tile_val[base + x] = S.o_val[x];
+    if (tile_val) tile_val[base + x] = S.o_val[x];  // nullptr: every insert carries the batch's one value
     tile_pred[base + x] = S.o_pred[x];
   }
 }
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(LT) k_gather_inserts(const uint32_t *__restric
   const size_t base = (size_t)blockIdx.x * LTILE;
   for (uint32_t x = threadIdx.x; x < cnt; x += LT) {
     ins_dst[off + x] = tile_dst[base + x];
-    ins_val[off + x] = tile_val[base + x];
+    if (tile_val) ins_val[off + x] = tile_val[base + x];
     ins_pred[off + x] = tile_pred[base + x];
   }
 }

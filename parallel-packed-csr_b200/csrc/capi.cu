@@ -161,7 +161,7 @@ void launch_plan(ppcsr_shard *s, const WindowDesc *windows, uint32_t n_windows, 
     reb::k_plan_chunks<<<div_up(n_chunks, reb::RT), reb::RT, 0, s->stream>>>(
         windows, n_windows, s->rank_off.p, s->ins_off.p, ls_src, ls_dst, m_dst_override, n_chunks, CL, s->plan.p);
 }
-template <bool TOMB>
+template <bool TOMB, bool UNIV>
 int launch_rebalance_m(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
   static std::once_flag once[64];
   static int sms[64] = {0};
@@ -170,8 +170,8 @@ int launch_rebalance_m(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
   std::call_once(once[dv], [&] {
     once_err[dv] = cudaDeviceGetAttribute(&sms[dv], cudaDevAttrMultiProcessorCount, s->device);
     if (once_err[dv] == cudaSuccess)
-      once_err[dv] = cudaFuncSetAttribute(reb::k_rebalance_m<TOMB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(reb::MSmem<TOMB>));
+      once_err[dv] = cudaFuncSetAttribute(reb::k_rebalance_m<TOMB, UNIV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(reb::MSmem<TOMB, UNIV>));
   });
   CUDA_TRY(once_err[dv]);
   static const long ctas = [] {  // development knob: resident CTAs per SM the grid is sized for
@@ -179,7 +179,7 @@ int launch_rebalance_m(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
     return e ? atol(e) : (long)PPCSR_M_CTAS;
   }();
   const unsigned grid = std::min<unsigned>(n_chunks, (unsigned)(sms[dv] * ctas));
-  reb::k_rebalance_m<TOMB><<<grid, reb::MTT, sizeof(reb::MSmem<TOMB>), s->stream>>>(
+  reb::k_rebalance_m<TOMB, UNIV><<<grid, reb::MTT, sizeof(reb::MSmem<TOMB, UNIV>), s->stream>>>(
       A, reinterpret_cast<const reb::ChunkPlanM *>(s->plan.p), n_chunks);
 #ifdef PPCSR_M_TRACE
   if (const char *path = getenv("PPCSR_TRACE_OUT")) {  // development build: clock stamps of the launch just made
@@ -196,7 +196,11 @@ int launch_rebalance_m(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A) {
 }
 // tomb: the batch wrote tombstones (it deleted edges); without, the leaves are still left-packed
 int launch_rebalance(ppcsr_shard *s, unsigned n_chunks, const reb::Args &A, bool tomb) {
-  if (reb_kernel_m()) return tomb ? launch_rebalance_m<true>(s, n_chunks, A) : launch_rebalance_m<false>(s, n_chunks, A);
+  if (reb_kernel_m()) {
+    if (A.ins_val == nullptr)
+      return tomb ? launch_rebalance_m<true, true>(s, n_chunks, A) : launch_rebalance_m<false, true>(s, n_chunks, A);
+    return tomb ? launch_rebalance_m<true, false>(s, n_chunks, A) : launch_rebalance_m<false, false>(s, n_chunks, A);
+  }
   if (reb_kernel() == 6) {
 #if PPCSR_HAVE_V6
     reb::k_rebalance<<<n_chunks, reb::KT, reb_pad_smem(), s->stream>>>(A);
@@ -352,7 +356,8 @@ int rebuild_whole_array(ppcsr_shard *s, uint64_t new_N, uint64_t items_new, cons
   A.rank_off = s->rank_off.p;
   A.ins_off = s->ins_off.p;
   A.ins_dst = s->ins_dst.p;
-  A.ins_val = s->ins_val.p;
+  A.ins_val = s->ins_uniform_val ? nullptr : s->ins_val.p;
+  A.ins_uniform = s->ins_uniform_val;
   A.ins_pred = s->ins_pred.p;
   A.out_dest_single = A.out_dest_multi = s->dest_alt.p;
   A.out_val_single = A.out_val_multi = s->val_alt.p;
@@ -534,7 +539,8 @@ int finish_batch_impl(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     A.rank_off = s->rank_off.p;
     A.ins_off = s->ins_off.p;
     A.ins_dst = s->ins_dst.p;
-    A.ins_val = s->ins_val.p;
+    A.ins_val = s->ins_uniform_val ? nullptr : s->ins_val.p;
+    A.ins_uniform = s->ins_uniform_val;
     A.ins_pred = s->ins_pred.p;
     A.out_dest_single = s->dest.p;
     A.out_val_single = s->val.p;
@@ -562,7 +568,8 @@ int finish_batch_impl(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
       S.rank_off = s->rank_off.p;
       S.ins_off = s->ins_off.p;
       S.ins_dst = s->ins_dst.p;
-      S.ins_val = s->ins_val.p;
+      S.ins_val = s->ins_uniform_val ? nullptr : s->ins_val.p;
+      S.ins_uniform = s->ins_uniform_val;
       S.ins_pred = s->ins_pred.p;
       S.tree_leaf_out = s->tree.p + L;
       S.beg = s->beg.p;
@@ -1031,7 +1038,13 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   PPCSR_TRY(dev_reserve(s->uloc, padded, s->stream));
   PPCSR_TRY(dev_reserve(s->tile_cnt, (size_t)lblocks + 1, s->stream));
   // a batch of ONE tile needs no scan and no gather: the tile's run is the insert list
-  uint32_t *t_dst = lblocks == 1 ? s->ins_dst.p : tile_dst, *t_val = lblocks == 1 ? s->ins_val.p : tile_val;
+  // With no payload every insert of the batch carries default_val: the general path then neither writes nor reads a
+  // value list (k_rebalance_m / k_rebalance_small take the one value; the small-batch path and the round-1 kernels
+  // keep the list)
+  s->ins_uniform_val = (!pay && !sparse && reb_kernel_m()) ? default_val : 0u;
+  if (s->ins_uniform_val) tile_val = nullptr;
+  uint32_t *t_dst = lblocks == 1 ? s->ins_dst.p : tile_dst;
+  uint32_t *t_val = s->ins_uniform_val ? nullptr : lblocks == 1 ? s->ins_val.p : tile_val;
   uint32_t *t_pred = lblocks == 1 ? s->ins_pred.p : s->uloc.p;
   const uint32_t dst_mask = lo_bits >= 32 ? 0xFFFFFFFFu : ((1u << lo_bits) - 1u);
   if (sparse) {
@@ -1363,6 +1376,7 @@ int ppcsr_add_nodes(ppcsr_shard *s, uint32_t count) {
   s->cnt_clean = false;
   s->last_sparse = false;
   s->ins_sentinels = true;
+  s->ins_uniform_val = 0;  // the new sentinels carry their vertex ids
   const int fb = finish_batch(s, count, &st);
   s->ins_sentinels = false;
   PPCSR_TRY(fb);

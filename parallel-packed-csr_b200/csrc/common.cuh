@@ -202,6 +202,7 @@ struct ppcsr_shard {
   DevBuf<uint32_t> win_chunk_off;      // [n_leaves+1]
   DevBuf<ChunkPlan> plan;              // [n_chunks]
   bool ins_sentinels = false;          // the pending insert list holds sentinels (ppcsr_add_nodes)
+  uint32_t ins_uniform_val = 0;        // != 0: the pending insert list has no value array, every insert carries this
   uint32_t all_touched = 0;            // invariant checker: bit 2 = the last batch rewrote every leaf (bit 0 inserts, bit 1 deletes)
   int whole_policy = 0;                // -1 never / 0 cost model / 1 always: one root window instead of a window list
   // small-batch path (sparse.cuh)

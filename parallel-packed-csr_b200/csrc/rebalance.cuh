@@ -59,6 +59,7 @@ struct Args {
   uint32_t prefetch_dist;   // L2 prefetch distance in chunks (0 = off)
   uint32_t chunk_leaves;    // output leaves per chunk (<= CHUNK_SLOTS >> ls_dst; not necessarily a power of two)
   uint32_t ins_sentinels;   // != 0: the insert list itself holds sentinels (add_nodes)
+  uint32_t ins_uniform;     // k_rebalance_m, ins_val == nullptr: the value every insert of the batch carries
 };
 
 
@@ -816,7 +817,8 @@ constexpr int SMALL_MAX_SLOTS = SMALL_MAX_LEAVES * 32;
 struct SmallArgs {
   uint32_t *dest, *val;          // rebalanced in place
   const uint32_t *leaf_cnt, *rank_off, *ins_off;
-  const uint32_t *ins_dst, *ins_val, *ins_pred;
+  const uint32_t *ins_dst, *ins_val, *ins_pred;  // ins_val == nullptr: every insert carries ins_uniform
+  uint32_t ins_uniform;
   uint32_t *tree_leaf_out, *beg;
   const WindowDesc *windows;
   uint32_t n_windows;            // one warp per window of the list; chunked (large) windows are skipped
@@ -877,7 +879,7 @@ __global__ void __launch_bounds__(RT) k_rebalance_small(SmallArgs A) {
     const uint32_t r = s_rank[warp][k] + t + (uint32_t)__popc(s_mask[warp][k] & ((2u << f) - 1u));
     atomicMax(&s_last[warp][k][f], t + 1u);
     sd[r] = A.ins_dst[q];
-    sv[r] = A.ins_val[q];
+    sv[r] = A.ins_val ? A.ins_val[q] : A.ins_uniform;
   }
   __syncwarp();
   // kept items

@@ -112,6 +112,9 @@ __global__ void __launch_bounds__(RT) k_plan_chunks_m(const WindowDesc *__restri
 #ifndef PPCSR_M_CTAS
 #define PPCSR_M_CTAS 3
 #endif
+#ifndef PPCSR_M_AGG
+#define PPCSR_M_AGG 0
+#endif
 #ifndef PPCSR_M_PINS
 #define PPCSR_M_PINS 512
 #endif
@@ -121,7 +124,12 @@ constexpr int MCHUNK = CHUNK_SLOTS;            // output slots per chunk
 constexpr int MSEG = SEG_LEAVES_SLOTS;         // source slots per round
 constexpr int MSEG_MAX_LEAVES = PSEG_MAX_LEAVES;
 constexpr int MTBL = MSEG_MAX_LEAVES + 1;
-constexpr int MPINS = PPCSR_M_PINS;            // staged inserts per chunk
+// staged inserts per chunk: what fits beside the other buffers at three CTAs per SM.  UNIV (every insert of the batch
+// carries the same value: no value array is read at all) leaves room for more of them
+template <bool TOMB, bool UNIV>
+struct MCfg {
+  static constexpr int PINS = UNIV ? (TOMB ? 768 : 1024) : PPCSR_M_PINS;
+};
 constexpr int MWORDS = MCHUNK / 32;            // mask words
 static_assert(MT == 256, "k_rebalance_m deals its phases to eight warps");
 static_assert(MCHUNK <= 65536, "rank -> slot table entries are 16-bit");
@@ -139,16 +147,18 @@ __device__ uint32_t g_m_trace[4][64][9][8];
   } while (0)
 #endif
 
-template <bool TOMB>
+template <bool TOMB, bool UNIV>
 struct MSmem {
+  static constexpr int MPINS = MCfg<TOMB, UNIV>::PINS;
   uint32_t out_d[MCHUNK];  // the chunk's output slots in their final layout (128-byte aligned: first member)
   uint32_t out_v[MCHUNK];
   // one word-indexed region W: the source lines and staged inserts.  st_v - st_d == st_iv - st_id (== VOFF words), so
-  // an item's value sits VOFF words behind its dest whichever it is
+  // an item's value sits VOFF words behind its dest whichever it is (UNIV: no st_iv; the insert lanes read a word of
+  // st_ip there and drop it)
   uint32_t st_d[2][MSEG];        // [round parity]
   uint32_t st_id[2][MPINS + 8];  // [chunk parity]
   uint32_t st_v[2][MSEG];
-  uint32_t st_iv[2][MPINS + 8];
+  uint32_t st_iv[UNIV ? 1 : 2][UNIV ? 4 : MPINS + 8];
   uint32_t st_ip[2][MPINS + 8];
   alignas(16) uint32_t st_R[2][MTBL + 7];     // R slice of the round's leaves; entry x sits at [x + (first leaf & 3)]
   alignas(16) uint32_t st_ioff[2][MTBL + 7];  // insert offsets of the same leaves
@@ -161,27 +171,32 @@ struct MSmem {
   alignas(16) uint4 plan[2][4];               // [chunk parity]
   uint32_t n_below[2];                        // [chunk parity] staged inserts of the chunk's first leaf that rank below it
   alignas(8) uint64_t full[2];                // [round parity] the round's bulk loads have landed
-  alignas(8) uint64_t stready;                // the staging buffers are free again (previous chunk read out, nulled)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(MT) : "memory"); }
+// mid-round barrier: the consumers wait, the producer only arrives (its part -- staging buffers free -- is done)
+__device__ __forceinline__ void bar_mid_sync() { asm volatile("bar.sync 2, %0;" ::"n"(MTT) : "memory"); }
+__device__ __forceinline__ void bar_mid_arrive() { asm volatile("bar.arrive 2, %0;" ::"n"(MTT) : "memory"); }
 
 // Warps 0..7 are CONSUMERS (masks, tables, placement); warp 8 is the PRODUCER: after the round's opening barrier its
 // lane 0 stores the finished chunk (bulk store), issues the bulk loads of the NEXT round -- one cp.async.bulk costs the
 // issuing thread 70-170 cycles (benchmarks/micro/tma_issue.cu), a dozen of them was the longest path of a round when a
 // consumer issued them --, waits until the copy engine has read the staging buffers, re-nulls them where needed and
 // arrives on `stready`.  It takes no part in the consumers' mid-round barrier.
-template <bool TOMB>
+template <bool TOMB, bool UNIV>
 __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const ChunkPlanM *__restrict__ gplan,
                                                                   uint32_t n_chunks) {
   extern __shared__ __align__(128) uint8_t m_smem_raw[];
-  using SM = MSmem<TOMB>;
+  using SM = MSmem<TOMB, UNIV>;
+  constexpr int MPINS = SM::MPINS;
   SM &S = *reinterpret_cast<SM *>(m_smem_raw);
   constexpr uint32_t VOFF = (uint32_t)(offsetof(SM, st_v) - offsetof(SM, st_d)) / 4u;
   static_assert(offsetof(SM, st_iv) - offsetof(SM, st_id) == offsetof(SM, st_v) - offsetof(SM, st_d), "VOFF");
+  static_assert(sizeof(SM) <= 75 * 1024, "three CTAs per SM");
+  const uint32_t uval = A.ins_uniform;
   constexpr uint32_t INS_W = (uint32_t)(offsetof(SM, st_id) - offsetof(SM, st_d)) / 4u;  // word index of st_id[0][0]
   const uint32_t *W = &S.st_d[0][0];
 
@@ -211,13 +226,13 @@ __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const
     const uint32_t nq = first ? min(q_hi - q_lo, (uint32_t)MPINS) : 0u;
     const uint32_t ish = q_lo & 3u;
     const uint32_t ib = nq ? ((nq + ish + 3u) & ~3u) * 4u : 0u;
-    mbar_expect_tx(bar, 2u * qb + 2u * tb + 3u * ib);
+    mbar_expect_tx(bar, 2u * qb + 2u * tb + (UNIV ? 2u : 3u) * ib);
     bulk_g2s(S.st_R[rpar], A.rank_off + (gl - sh), tb, bar);
     bulk_g2s(S.st_ioff[rpar], A.ins_off + (gl - sh), tb, bar);
     if (ib) {
       bulk_g2s(S.st_ip[cpar], A.ins_pred + (q_lo - ish), ib, bar);
       bulk_g2s(S.st_id[cpar], A.ins_dst + (q_lo - ish), ib, bar);
-      bulk_g2s(S.st_iv[cpar], A.ins_val + (q_lo - ish), ib, bar);
+      if (!UNIV) bulk_g2s(S.st_iv[cpar], A.ins_val + (q_lo - ish), ib, bar);
     }
     bulk_g2s(S.st_d[rpar], A.src_dest + ((size_t)gl << ls_src), qb, bar);
     bulk_g2s(S.st_v[rpar], A.src_val + ((size_t)gl << ls_src), qb, bar);
@@ -226,7 +241,7 @@ __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const
       const uint32_t pb = min(((q_hi - q1 + 3u) & ~3u) * 4u, 16384u);
       bulk_prefetch_l2(A.ins_pred + q1, pb);
       bulk_prefetch_l2(A.ins_dst + q1, pb);
-      bulk_prefetch_l2(A.ins_val + q1, pb);
+      if (!UNIV) bulk_prefetch_l2(A.ins_val + q1, pb);
     }
   };
 
@@ -250,7 +265,6 @@ __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const
       S.n_below[0] = S.n_below[1] = 0u;
       mbar_init(&S.full[0], 1u);
       mbar_init(&S.full[1], 1u);
-      mbar_init(&S.stready, 1u);
     }
     __syncthreads();
     if (producer && lane == 0) {
@@ -336,7 +350,7 @@ __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const
         for (int x = 0; x < 2 * MCHUNK / 4 / 32; x++) z[x * 32 + lane] = zero;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&S.stready);
+      bar_mid_arrive();  // the staging buffers are free (and nulled)
       MTRACE(1);
     } else {
       mbar_wait(&S.full[rpar], (r >> 1) & 1u);  // this round's operands have landed
@@ -388,7 +402,7 @@ __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const
             if (k3) km[p2] = (uint8_t)(f0 + 3u);
           }
         }
-        bar_consumers();  // the inserts below read kupto
+        if (want_kupto) bar_consumers();  // the inserts below read kupto (chunk-uniform)
       }
 
       // ---- phase 1: a small task for the warps 0..2, then the segment's inserts dealt over the warps 3..7, 0..2
@@ -438,21 +452,35 @@ __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const
       {
         // the segment's inserts: rank = R[leaf] + index in the leaf's run + kept items up to the predecessor -> B
         uint32_t below = 0;
-        const uint32_t itid = ((warp + 5u) & 7u) * 32u + lane;  // the warps without a task of their own come first
-        const uint32_t *sip = S.st_ip[cpar] + ish - q_lo;       // + q = staged predecessor of insert q
-        auto one = [&](uint32_t q, uint32_t pred) {
-          const uint32_t rel = pred - seg_slot0;
-          const uint32_t x = rel >> ls_src;
-          const uint32_t kup = TOMB ? (uint32_t)S.kupto[rel] : (rel & leaf_mask) + 1u;
-          const uint32_t tt = t_R[x] + (q - t_ioff[x]) + kup - Ra;
-          if (tt < span) atomicOr(&S.B[rpar][tt >> 5], 1u << (tt & 31u));
-          else if ((int32_t)tt < 0) below++;
-        };
-        if (staged_all) {
-          for (uint32_t q = qa + itid; q < qb; q += (uint32_t)MT) one(q, sip[q]);
-        } else {
-          for (uint32_t q = qa + itid; q < qb; q += (uint32_t)MT)
-            one(q, q - q_lo < (uint32_t)MPINS ? sip[q] : A.ins_pred[q]);
+        const uint32_t wbase = ((warp + 5u) & 7u) * 32u;   // the warps without a task of their own come first
+        const uint32_t *sip = S.st_ip[cpar] + ish - q_lo;  // + q = staged predecessor of insert q
+        for (uint32_t q0 = qa + wbase; q0 < qb; q0 += (uint32_t)MT) {  // warp-uniform trip count
+          const uint32_t q = q0 + lane;
+          uint32_t word = 0xFFFFFFFFu, bit = 0;
+          if (q < qb) {
+            const uint32_t pred = (staged_all || q - q_lo < (uint32_t)MPINS) ? sip[q] : A.ins_pred[q];
+            const uint32_t rel = pred - seg_slot0;
+            const uint32_t x = rel >> ls_src;
+            const uint32_t kup = TOMB ? (uint32_t)S.kupto[rel] : (rel & leaf_mask) + 1u;
+            const uint32_t tt = t_R[x] + (q - t_ioff[x]) + kup - Ra;
+            if (tt < span) {
+              word = tt >> 5;
+              bit = 1u << (tt & 31u);
+            } else if ((int32_t)tt < 0) {
+              below++;
+            }
+          }
+          // (PPCSR_M_AGG: the lanes that share a mask word OR their bits together and one of them updates the word --
+          // measured slower than the ~10-way same-word atomics it avoids: match.any costs more)
+#if PPCSR_M_AGG
+          const unsigned peers = __match_any_sync(0xFFFFFFFFu, word);
+          if (word != 0xFFFFFFFFu) {
+            const uint32_t bits = __reduce_or_sync(peers, bit);
+            if ((peers & lt) == 0u) atomicOr(&S.B[rpar][word], bits);
+          }
+#else
+          if (word != 0xFFFFFFFFu) atomicOr(&S.B[rpar][word], bit);
+#endif
         }
         if (first_seg) {
           below = __reduce_add_sync(0xFFFFFFFFu, below);
@@ -460,8 +488,7 @@ __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const
         }
       }
       MTRACE(3);
-      bar_consumers();                   // B1: masks and tables are complete
-      mbar_wait(&S.stready, r & 1u);     // the staging buffers are free (and nulled)
+      bar_mid_sync();  // B1: masks and tables are complete, the staging buffers are free (producer)
       MTRACE(4);
       if (zpos != 0xFFFFFFFFu) {  // the slot behind my leaf's last item (see keep_nulls)
         S.out_d[zpos] = 0u;
@@ -505,10 +532,11 @@ __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const
           uint32_t d, v;
           if (!decltype(STAGED)::value && isins && q - q_lo >= (uint32_t)MPINS) {  // a long run of inserts
             d = A.ins_dst[q];
-            v = A.ins_val[q];
+            v = UNIV ? uval : A.ins_val[q];
           } else {
             d = W[idx];
             v = W[idx + VOFF];
+            if (UNIV && isins) v = uval;
           }
           const uint32_t pos = S.pos[t];
           S.out_d[pos] = d;
