@@ -493,6 +493,10 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
     }
   }
   __syncthreads();
+  // (Measured and dropped: clipping a hub tile's window to the leaves between the positions of its first and last key
+  // -- two global searches by two threads, then the tile is staged after all -- made the stage SLOWER, C4 3.18 -> 3.88
+  // ms: the 512 parallel searches of such a tile share their upper probes through L1 and cost less than the serial
+  // pair plus a barrier.)
   const uint32_t wa = S.win[0], wb = S.win[1], mode = S.win[2];
   if (mode == 1u) {  // stage the window: coalesced 16-byte loads (wa is leaf aligned, leaves are >= 32 bytes)
     for (uint32_t x = tid * 4u; x < wb - wa; x += LT * 4u)

@@ -511,8 +511,9 @@ __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const
         const uint32_t insb = INS_W + cpar * (uint32_t)(MPINS + 8) + ish - q_lo;  // + q = word of staged insert q
         const uint32_t *Bm = S.B[rpar], *Hm = S.HB[rpar];
         // one unit; CHECK: the unit is cut by the segment's rank range, STAGED: no insert lies beyond the stage
-        auto unit = [&](auto CHECK, auto STAGED, uint32_t w) {
-          const uint32_t bw = Bm[w], hb = Hm[w];
+        // NOINS: the chunk has no inserts at all (a batch of deletes)
+        auto unit = [&](auto CHECK, auto STAGED, auto NOINS, uint32_t w) {
+          const uint32_t bw = decltype(NOINS)::value ? 0u : Bm[w], hb = Hm[w];
           const uint32_t q = pbase + __popc(bw & lt);
           const uint32_t kidx = fbase + __popc(hb & le);
           pbase += __popc(bw);
@@ -544,17 +545,18 @@ __global__ void __launch_bounds__(MTT, PPCSR_M_CTAS) k_rebalance_m(Args A, const
           // fix_sentinel (reference PCSR.cpp:168-183): a sentinel that lands here refreshes its vertex's back pointer
           if (d == PPCSR_SENT) beg_m1[v] = out_slot0 + pos;
         };
-        auto run = [&](auto STAGED) {
+        auto run = [&](auto STAGED, auto NOINS) {
           uint32_t w = w0, wl = w1;
-          if (w == wa && (ta & 31u)) unit(std::true_type{}, STAGED, w++);
+          if (w == wa && (ta & 31u)) unit(std::true_type{}, STAGED, NOINS, w++);
           const bool cut_tail = w1 == wb && (tb & 31u) && w < w1;
           if (cut_tail) wl--;
 #pragma unroll 4
-          for (; w < wl; w++) unit(std::false_type{}, STAGED, w);
-          if (cut_tail) unit(std::true_type{}, STAGED, w);
+          for (; w < wl; w++) unit(std::false_type{}, STAGED, NOINS, w);
+          if (cut_tail) unit(std::true_type{}, STAGED, NOINS, w);
         };
-        if (staged_all) run(std::true_type{});
-        else run(std::false_type{});
+        if (q_hi == q_lo) run(std::true_type{}, std::true_type{});
+        else if (staged_all) run(std::true_type{}, std::false_type{});
+        else run(std::false_type{}, std::false_type{});
       }
       MTRACE(6);
     }

@@ -206,11 +206,27 @@ __device__ __forceinline__ unsigned match_digit(uint32_t d) {
   return (m0 & m1 & m2) & (m3 & m4 & m5) & (m6 & m7);
 }
 
+// PPCSR_OS_MATCH_ATOMIC: the lanes holding the same digit find each other through ONE shared-memory atomicOr of their
+// lane bit into a per-warp, per-digit word (and one read back) instead of the eight ballots of match_digit: ~8
+// instead of ~36 instructions per key.  Keys-only passes (the extra 8 KB would cost a payload pass its fourth CTA).
+// Measured on B200 (C4, 100 M keys, six passes): 4.29 ms against 3.37 ms with the ballots -- three more shared-memory
+// operations per key cost more than the 28 ALU / vote instructions they replace.  Off.
+#ifndef PPCSR_OS_MATCH_ATOMIC
+#define PPCSR_OS_MATCH_ATOMIC 0
+#endif
+#ifndef PPCSR_OS_DPK  // keep the keys' digits in registers (four to a register) instead of extracting them three times
+#define PPCSR_OS_DPK 0
+#endif
+// PPCSR_OS_EARLY: the tile's digit histogram is taken by shared-memory atomics and published BEFORE the ranking phase
+// (the look-back of later tiles finds it sooner); 0: the counts fall out of the ranking and are published after it
+#ifndef PPCSR_OS_EARLY
+#define PPCSR_OS_EARLY 1
+#endif
 // dynamic shared memory of k_os_pass (bytes): keys[OS_TILE] u64 | pay[OS_TILE] u32 (HAS_PAY) |
-// cnt[OS_WARPS][OS_RADIX] u16 | goff[OS_RADIX] u32
+// cnt[OS_WARPS][OS_RADIX] u16 | goff[OS_RADIX] u32 | match[OS_WARPS][OS_RADIX] u32 (keys only)
 inline size_t os_pass_smem(bool has_pay) {
   return (size_t)OS_TILE * 8 + (has_pay ? (size_t)OS_TILE * 4 : 0) + (size_t)OS_WARPS * OS_RADIX * 2 +
-         (size_t)OS_RADIX * 4;
+         (size_t)OS_RADIX * 4 + ((PPCSR_OS_MATCH_ATOMIC && !has_pay) ? (size_t)OS_WARPS * OS_RADIX * 4 : 0);
 }
 
 template <bool HAS_PAY, class Src = KeyArray>
@@ -224,10 +240,14 @@ __global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(Src src, size_t n, Di
   uint32_t *s_pay = reinterpret_cast<uint32_t *>(s_dyn + (size_t)OS_TILE * 8);
   uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_dyn + (size_t)OS_TILE * 8 + (HAS_PAY ? (size_t)OS_TILE * 4 : 0));
   uint32_t *s_goff = reinterpret_cast<uint32_t *>(s_cnt + OS_WARPS * OS_RADIX);
+  constexpr bool MATCH_ATOMIC = PPCSR_OS_MATCH_ATOMIC && !HAS_PAY;
+  uint32_t *s_match = s_goff + OS_RADIX;  // [OS_WARPS][OS_RADIX], MATCH_ATOMIC only
   __shared__ uint32_t s_warp[33];
   __shared__ uint32_t s_tile;
   if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
   for (uint32_t d = threadIdx.x; d < OS_WARPS * OS_RADIX / 2; d += OS_THREADS) reinterpret_cast<uint32_t *>(s_cnt)[d] = 0;
+  if (MATCH_ATOMIC)
+    for (uint32_t d = threadIdx.x; d < OS_WARPS * OS_RADIX; d += OS_THREADS) s_match[d] = 0;
   s_goff[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
@@ -249,25 +269,63 @@ __global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(Src src, size_t n, Di
   // so that by the time this tile looks back most of its predecessors have already resolved their prefix
   static_assert(OS_THREADS == OS_RADIX, "one thread per digit");
   const uint32_t dg = threadIdx.x;
+#if PPCSR_OS_DPK
+  uint32_t dpk[OS_ITEMS / 4];  // the keys' digits, four to a register
+#endif
+#if PPCSR_OS_EARLY || PPCSR_OS_DPK
 #pragma unroll
-  for (int r = 0; r < OS_ITEMS; r++) atomicAdd(&s_goff[sel_digit(k[r], sel)], 1u);
+  for (int r = 0; r < OS_ITEMS; r++) {
+    const uint32_t d = sel_digit(k[r], sel);
+#if PPCSR_OS_DPK
+    if (r & 3) dpk[r >> 2] |= d << (8 * (r & 3));
+    else dpk[r >> 2] = d;
+#endif
+#if PPCSR_OS_EARLY
+    atomicAdd(&s_goff[d], 1u);
+#endif
+  }
+#endif
+#if PPCSR_OS_EARLY
   __syncthreads();
   // the padding keys of a partial last tile are counted in digit `mask`; nobody looks back through the last tile
   const uint32_t cnt = s_goff[dg];
   st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + dg, cnt | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG));
+#endif
+  uint32_t *my_match = s_match + (size_t)w * OS_RADIX;
+  const uint32_t lbit = 1u << l;
 #pragma unroll
   for (int r = 0; r < OS_ITEMS; r++) {
+#if PPCSR_OS_DPK
+    const uint32_t d = (dpk[r >> 2] >> (8 * (r & 3))) & 0xFFu;
+#else
     const uint32_t d = sel_digit(k[r], sel);
-    const unsigned peers = match_digit(d);
+#endif
+    unsigned peers;
+    if (MATCH_ATOMIC) {
+      atomicOr(&my_match[d], lbit);
+      __syncwarp();
+      peers = *reinterpret_cast<volatile uint32_t *>(&my_match[d]);
+    } else {
+      peers = match_digit(d);
+    }
     const uint32_t base = my_cnt[d];
     __syncwarp();
-    if ((peers & lt) == 0) my_cnt[d] = (uint16_t)(base + __popc(peers));
+    if ((peers & lt) == 0) {
+      my_cnt[d] = (uint16_t)(base + __popc(peers));
+      if (MATCH_ATOMIC) my_match[d] = 0u;  // left clear for the next round
+    }
     __syncwarp();
     const uint32_t rk = base + __popc(peers & lt);
     if (r & 1) rank[r >> 1] |= rk << 16;
     else rank[r >> 1] = rk;
   }
   __syncthreads();
+#if !PPCSR_OS_EARLY
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int ww = 0; ww < OS_WARPS; ww++) cnt += s_cnt[ww * OS_RADIX + dg];
+  st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + dg, cnt | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG));
+#endif
   uint32_t total;
   const uint32_t dbase = block_excl_scan(cnt, &total, s_warp);
   {  // s_cnt[w][d] := first tile-local position of warp w's keys of digit d
@@ -283,7 +341,11 @@ __global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(Src src, size_t n, Di
   // reorder the tile in shared memory: position = (digit base + warp offset) + rank inside the warp
 #pragma unroll
   for (int r = 0; r < OS_ITEMS; r++) {
+#if PPCSR_OS_DPK
+    const uint32_t d = (dpk[r >> 2] >> (8 * (r & 3))) & 0xFFu;
+#else
     const uint32_t d = sel_digit(k[r], sel);
+#endif
     const uint32_t rk = (r & 1) ? (rank[r >> 1] >> 16) : (rank[r >> 1] & 0xFFFFu);
     const uint32_t pos = my_cnt[d] + rk;
     s_keys[pos] = k[r];
