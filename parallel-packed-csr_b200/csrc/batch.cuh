@@ -379,6 +379,43 @@ __device__ __forceinline__ bool find_in(const uint32_t *D, uint32_t doff, const 
   return false;
 }
 
+// find_edge with the leaf-level half on a staged table (first item and live count of the leaves from leaf l0 on) and
+// the in-leaf half in global memory.  Same result as find_edge.
+__device__ __forceinline__ bool find_tab(const uint32_t *first, const uint8_t *cnt8, uint32_t l0,
+                                         const uint32_t *__restrict__ dest, uint32_t b, uint32_t e, uint32_t ls,
+                                         uint32_t d, uint32_t *slot) {
+  const uint32_t Lb = b >> ls, Le = (e - 1) >> ls;
+  uint32_t lo = Lb, hi = Le + 1;
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    uint32_t m2 = mid;
+    while (m2 < hi && cnt8[m2 - l0] == 0) m2++;
+    if (m2 == hi) {
+      hi = mid;
+      continue;
+    }
+    if (first[m2 - l0] <= d) lo = m2;
+    else hi = mid;
+  }
+  const uint32_t base = lo << ls;
+  const uint32_t f_lo = (lo == Lb) ? (b - base) + 1u : 0u;
+  uint32_t f_hi = cnt8[lo - l0];
+  if (lo == (e >> ls) && (e - base) < f_hi) f_hi = e - base;
+  const uint32_t *L = dest + base;
+  uint32_t x = f_lo, y = f_hi;  // lower_bound of d in the leaf's live prefix
+  while (x < y) {
+    const uint32_t mid = (x + y) >> 1;
+    if (L[mid] < d) x = mid + 1;
+    else y = mid;
+  }
+  if (x < f_hi && L[x] == d) {
+    *slot = base + x;
+    return true;
+  }
+  *slot = base + x - 1;
+  return false;
+}
+
 // ---- locate: one CTA per TILE of 512 consecutive sorted updates ------------------------------------------------
 // Fuses, over the sorted batch:
 //   * num_neighbors += (#add calls) - (#remove calls) per source, duplicates included (reference PCSR.cpp:1392,747);
@@ -413,14 +450,32 @@ constexpr int LTILE = LT * LI;  // updates per tile
 constexpr int LCAP = PPCSR_LOC_CAP;    // slots of dest[] a tile can stage
 constexpr int LCAP_LEAVES = LCAP / 8;  // leaves are >= 8 slots
 
+// A window too long to stage whole is staged as a TABLE -- the first item and the live count of each of its leaves
+// (one 32-byte sector per leaf instead of the whole line): the leaf-level half of every search then runs in shared
+// memory and only the in-leaf half (one 128-byte line per update, shared by neighbouring keys) goes to global memory.
+// At C4's update density (one update per ~5 slots) a tile of 512 sorted updates spans ~2.7 K slots: too long to stage,
+// ~90 table entries.
+#ifndef PPCSR_LOC_TAB
+#define PPCSR_LOC_TAB 1
+#endif
+constexpr int LTAB = PPCSR_LOC_TAB ? 1536 : 0;  // leaves a tile can stage as a table (in the place of dest[])
+struct LocTable {
+  uint32_t first[LTAB + 1];
+  uint8_t cnt8[LTAB + 1];
+};
+static_assert(sizeof(LocTable) <= sizeof(uint32_t) * LCAP, "the table lies in the staging area of dest[]");
+
 struct LocSmem {
-  uint32_t dest[LCAP];         // staged window of dest[]
+  union {
+    uint32_t dest[LCAP];       // staged window of dest[]
+    LocTable tab;              // or: first item + live count of each leaf of a longer window
+  };
   uint32_t cnt[LCAP_LEAVES];   // leaf counts of the window
   uint64_t key[LTILE + 2];     // the tile's keys; [0] and [LTILE + 1] are the neighbours' (or ~0: none)
   uint32_t o_dst[LTILE], o_val[LTILE], o_pred[LTILE];  // the tile's inserts, compacted in key order
   uint32_t warp[33];
   uint32_t stat[8];
-  uint32_t win[4];             // window [a, b), mode (0 nothing to search, 1 staged, 2 global), valid keys
+  uint32_t win[4];             // window [a, b), mode (0 nothing to search, 1 staged, 2 global, 3 leaf table), valid keys
 };
 static_assert(sizeof(LocSmem) <= 48 * 1024, "k_locate is launched without a shared-memory opt-in");
 
@@ -473,7 +528,7 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
       const uint32_t leaf = 1u << ls;
       a = (beg[s0] >> ls) << ls;
       b = (uint32_t)min((unsigned long long)n_slots, (((unsigned long long)beg[s1 + 1] + leaf - 1u) >> ls) << ls);
-      mode = (b - a <= (uint32_t)LCAP) ? 1u : 2u;
+      mode = (b - a <= (uint32_t)LCAP) ? 1u : (((b - a) >> ls) <= (uint32_t)LTAB) ? 3u : 2u;
     }
     S.win[0] = a;
     S.win[1] = b;
@@ -503,6 +558,13 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
       *reinterpret_cast<uint4 *>(&S.dest[x]) = *reinterpret_cast<const uint4 *>(&dest[wa + x]);
     const uint32_t nl = (wb - wa) >> ls, l0 = wa >> ls;
     for (uint32_t x = tid; x < nl; x += LT) S.cnt[x] = leaf_cnt[l0 + x];
+    __syncthreads();
+  } else if (mode == 3u) {  // the window's leaf table
+    const uint32_t nl = (wb - wa) >> ls, l0 = wa >> ls;
+    for (uint32_t x = tid; x < nl; x += LT) {
+      S.tab.first[x] = dest[(size_t)(l0 + x) << ls];
+      S.tab.cnt8[x] = (uint8_t)leaf_cnt[l0 + x];
+    }
     __syncthreads();
   }
   const uint32_t *D = mode == 1u ? S.dest : dest, *C = mode == 1u ? S.cnt : leaf_cnt;
@@ -541,7 +603,8 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
           }
           const uint32_t d = (uint32_t)k;
           uint32_t slot;
-          const bool hit = find_in(D, doff, C, coff, vb[r], ve[r], true, ls, d, &slot);
+          const bool hit = mode == 3u ? find_tab(S.tab.first, S.tab.cnt8, wa >> ls, dest, vb[r], ve[r], ls, d, &slot)
+                                      : find_in(D, doff, C, coff, vb[r], ve[r], true, ls, d, &slot);
           if (v != 0) {
             cls = hit ? CLS_OVERWRITE : CLS_INSERT;
             if (hit) val[slot] = v;  // duplicate insert overwrites the value (reference PCSR.cpp:529-532)
