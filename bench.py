@@ -572,7 +572,7 @@ def run_config(args, scale, B, workload, torch, dist, rank, world, local_rank, d
                        "compute of step k); the device-to-device state restore between steps is inside the timed "
                        "region; ms_per_step_unpipelined = one blocking ppcsr_apply_batch per step"},
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats_acc)),
-        "roofline": {"bound": "hbm", "kernel": "reb::k_rebalance_p", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "reb::k_rebalance_m", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": reb_bytes, "kernel_ms": reb_ms,
                      "note": "rank 0's shard" if world > 1 else "the whole array streamed once"},
