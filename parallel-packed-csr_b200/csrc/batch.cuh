@@ -479,6 +479,49 @@ struct LocSmem {
 };
 static_assert(sizeof(LocSmem) <= 48 * 1024, "k_locate is launched without a shared-memory opt-in");
 
+// The search of a staged tile without empty leaves, with UNIFORM trip counts: a warp's lanes search vertex ranges of
+// different lengths, so the data-dependent loops of find_in / find_tab run for the longest range in the warp at ~12
+// instructions per step, diverged (ncu: 47 % of k_locate's instructions, which is issue-bound).  Here the leaf level
+// takes `steps` = ceil(log2(leaves of the window)) branch-free halvings and the in-leaf lower_bound five (a leaf has
+// <= 32 slots).  TAB: the window is staged as a leaf table (the in-leaf half reads global memory), else whole.
+// Same result as find_in / find_tab when no leaf of the window is empty.
+template <bool TAB>
+__device__ __forceinline__ bool find_fast(const LocSmem &S, const uint32_t *__restrict__ dest, uint32_t wa,
+                                          uint32_t steps, uint32_t b, uint32_t e, uint32_t ls, uint32_t d,
+                                          uint32_t *slot) {
+  const uint32_t l0 = wa >> ls, fs = TAB ? 0u : ls;
+  const uint32_t Lb = b >> ls, Le = (e - 1) >> ls;
+  uint32_t lo = Lb - l0, n = Le - Lb + 1u;  // candidates: the window's leaves [lo, lo + n)
+  // as many halvings as the longest range among the lanes searching right now needs (most vertices span one or two
+  // leaves; the window's own ceil(log2(leaves)) bounds it)
+  steps = min(steps, 32u - (uint32_t)__clz(__reduce_max_sync(__activemask(), n)));
+  for (uint32_t st = 0; st < steps; st++) {
+    const uint32_t half = n >> 1;
+    if (half != 0u && S.dest[(lo + half) << fs] <= d) lo += half;  // S.tab.first aliases S.dest
+    n -= half;
+  }
+  const uint32_t leaf = lo + l0, base = leaf << ls;
+  const uint32_t cnt = TAB ? (uint32_t)S.tab.cnt8[lo] : S.cnt[lo];
+  const uint32_t f_lo = (leaf == Lb) ? (b - base) + 1u : 0u;
+  uint32_t f_hi = cnt;
+  if (leaf == (e >> ls) && (e - base) < f_hi) f_hi = e - base;
+  const uint32_t *L = TAB ? dest + base : S.dest + (base - wa);
+  uint32_t x = f_lo, m = f_hi > f_lo ? f_hi - f_lo : 0u;  // lower_bound of d in [f_lo, f_hi): the answer lies in [x, x + m]
+#pragma unroll
+  for (int st = 0; st < 5; st++) {
+    const uint32_t half = m >> 1;
+    if (half != 0u && L[x + half - 1u] < d) x += half;
+    m -= half;
+  }
+  if (m != 0u && L[x] < d) x++;
+  if (x < f_hi && L[x] == d) {
+    *slot = base + x;
+    return true;
+  }
+  *slot = base + x - 1;
+  return false;
+}
+
 // SPARSE: the small-batch variant (appends the touched leaves); a template so that the general instantiation keeps its
 // 32 registers -- 8 CTAs = all 64 warps of an SM (at 40 registers: 6 CTAs, locate stage 3.27 -> 4.02 ms on C4).
 template <bool SPARSE>
@@ -553,19 +596,29 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
   // ms: the 512 parallel searches of such a tile share their upper probes through L1 and cost less than the serial
   // pair plus a barrier.)
   const uint32_t wa = S.win[0], wb = S.win[1], mode = S.win[2];
-  if (mode == 1u) {  // stage the window: coalesced 16-byte loads (wa is leaf aligned, leaves are >= 32 bytes)
-    for (uint32_t x = tid * 4u; x < wb - wa; x += LT * 4u)
-      *reinterpret_cast<uint4 *>(&S.dest[x]) = *reinterpret_cast<const uint4 *>(&dest[wa + x]);
+  bool fast = false;           // a staged window without empty leaves: uniform-trip-count searches (find_fast)
+  uint32_t steps = 0;
+  if (mode == 1u || mode == 3u) {
     const uint32_t nl = (wb - wa) >> ls, l0 = wa >> ls;
-    for (uint32_t x = tid; x < nl; x += LT) S.cnt[x] = leaf_cnt[l0 + x];
-    __syncthreads();
-  } else if (mode == 3u) {  // the window's leaf table
-    const uint32_t nl = (wb - wa) >> ls, l0 = wa >> ls;
-    for (uint32_t x = tid; x < nl; x += LT) {
-      S.tab.first[x] = dest[(size_t)(l0 + x) << ls];
-      S.tab.cnt8[x] = (uint8_t)leaf_cnt[l0 + x];
+    steps = 32u - (uint32_t)__clz(nl);
+    int empty = 0;
+    if (mode == 1u) {  // stage the window: coalesced 16-byte loads (wa is leaf aligned, leaves are >= 32 bytes)
+      for (uint32_t x = tid * 4u; x < wb - wa; x += LT * 4u)
+        *reinterpret_cast<uint4 *>(&S.dest[x]) = *reinterpret_cast<const uint4 *>(&dest[wa + x]);
+      for (uint32_t x = tid; x < nl; x += LT) {
+        const uint32_t c = leaf_cnt[l0 + x];
+        S.cnt[x] = c;
+        empty |= c == 0u;
+      }
+    } else {  // the window's leaf table
+      for (uint32_t x = tid; x < nl; x += LT) {
+        const uint32_t c = leaf_cnt[l0 + x];
+        S.tab.first[x] = dest[(size_t)(l0 + x) << ls];
+        S.tab.cnt8[x] = (uint8_t)c;
+        empty |= c == 0u;
+      }
     }
-    __syncthreads();
+    fast = !__syncthreads_or(empty);
   }
   const uint32_t *D = mode == 1u ? S.dest : dest, *C = mode == 1u ? S.cnt : leaf_cnt;
   const uint32_t doff = mode == 1u ? wa : 0u, coff = mode == 1u ? wa >> ls : 0u;
@@ -603,8 +656,13 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
           }
           const uint32_t d = (uint32_t)k;
           uint32_t slot;
-          const bool hit = mode == 3u ? find_tab(S.tab.first, S.tab.cnt8, wa >> ls, dest, vb[r], ve[r], ls, d, &slot)
-                                      : find_in(D, doff, C, coff, vb[r], ve[r], true, ls, d, &slot);
+          bool hit;
+          if (fast && mode == 3u) {  // (whole-staged windows: measured 4 % slower than find_in's short loops, C2)
+            hit = find_fast<true>(S, dest, wa, steps, vb[r], ve[r], ls, d, &slot);
+          } else {
+            hit = mode == 3u ? find_tab(S.tab.first, S.tab.cnt8, wa >> ls, dest, vb[r], ve[r], ls, d, &slot)
+                             : find_in(D, doff, C, coff, vb[r], ve[r], true, ls, d, &slot);
+          }
           if (v != 0) {
             cls = hit ? CLS_OVERWRITE : CLS_INSERT;
             if (hit) val[slot] = v;  // duplicate insert overwrites the value (reference PCSR.cpp:529-532)
