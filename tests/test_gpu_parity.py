@@ -358,6 +358,40 @@ def test_hub_vertex_grow_and_shrink():
     assert g.neighbours(0).size == 0 and g.geometry.N < big
 
 
+@pytest.mark.parametrize("policy", POLICIES, ids=["windows", "auto"])
+def test_long_insert_runs_one_value(policy):
+    """Thousands of inserts hanging on a handful of slots, every one with the same value: the rebalance kernel's chunks
+    are fed almost only by the insert list -- runs far longer than the staged part of it, clipped per chunk -- and the
+    batch carries no value list at all (reb::k_rebalance_m, UNIV).  Then a batch that deletes every third edge and
+    inserts between the survivors (tombstones + inserts in one rebuild)."""
+    n = 64
+    g = pp.Shard(n)
+    g.set_whole_array_policy(policy)
+    o = O.OraclePCSR(n)
+    rng = np.random.default_rng(5)
+    for b in range(3):
+        d = np.arange(b, 30000, 3)  # interleaves with the earlier batches: every old edge gets neighbours
+        s = np.where(rng.integers(0, 8, d.size) == 0, rng.integers(1, n, d.size), 0)  # 7/8 on the hub vertex 0
+        one = np.full(d.size, 9)
+        g.apply(s, d, one)
+        o.apply(s, d, one)
+        assert_invariants(g, where=f"long runs, batch {b}")
+        assert_same_graph(g, *o.export(), where=f"long runs, batch {b}")
+    rp, c, _ = o.export()
+    hub = c[int(rp[0]):int(rp[1])]
+    dels = hub[::3]
+    ins = np.arange(30000, 36000)
+    s2 = np.zeros(dels.size + ins.size, dtype=np.int64)
+    d2 = np.concatenate([dels, ins])
+    v2 = np.concatenate([np.zeros(dels.size, dtype=np.int64), np.full(ins.size, 9)])
+    perm = rng.permutation(d2.size)
+    g.apply(s2[perm], d2[perm], v2[perm])
+    o.apply(s2[perm], d2[perm], v2[perm])
+    assert_invariants(g, check_lower=True, where="long runs, mixed")
+    assert_same_graph(g, *o.export(), where="long runs, mixed")
+    g.close()
+
+
 def test_reference_unit_tests_single_ops():
     """reference test/DataStructureTest.cpp:12-49 through single-op calls."""
     g = pp.Shard(10)
