@@ -891,13 +891,18 @@ struct PeerTable {
 inline size_t bin_peers_smem(bool has_val) {
   return (size_t)prim::SORT_TILE * 8 + (has_val ? (size_t)prim::SORT_TILE * 4 : 0) + (size_t)prim::SORT_TILE;
 }
-template <bool HAS_VAL>
+// ORDERED == false: the tiles take their places in the destinations' regions by one atomicAdd per tile and destination
+// on `cursor` (no count pass, no scan in front of this kernel); the records of a region then stand in tile-arrival
+// order, which is indistinguishable from submission order when every update of the batch is the same operation (no
+// per-update values: only then the caller may use it).  k_publish_peer_counts deposits the counts afterwards.
+template <bool HAS_VAL, bool ORDERED = true>
 __global__ void __launch_bounds__(BT, 4) k_bin_scatter_peers(const uint32_t *__restrict__ src,
                                                              const uint32_t *__restrict__ dst,
                                                              const uint32_t *__restrict__ val, size_t count,
                                                              const uint64_t *__restrict__ starts, uint32_t parts,
                                                              const uint32_t *__restrict__ offs, uint32_t nblocks,
-                                                             uint32_t me, uint64_t cap, PeerTable P) {
+                                                             uint32_t me, uint64_t cap, PeerTable P,
+                                                             uint32_t *__restrict__ cursor = nullptr) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   uint64_t *s_rec = reinterpret_cast<uint64_t *>(s_dyn);
   uint32_t *s_v = reinterpret_cast<uint32_t *>(s_dyn + (size_t)prim::SORT_TILE * 8);
@@ -971,7 +976,7 @@ __global__ void __launch_bounds__(BT, 4) k_bin_scatter_peers(const uint32_t *__r
     }
     if (l == 0) s_tbase[parts] = carry;
   }
-  if (threadIdx.x >= 32 && threadIdx.x - 32 < parts) {
+  if (ORDERED && threadIdx.x >= 32 && threadIdx.x - 32 < parts) {
     const uint32_t p = threadIdx.x - 32;
     const size_t row = (size_t)p * nblocks;
     s_gbase[p] = offs[row + blockIdx.x] - offs[row];
@@ -981,6 +986,10 @@ __global__ void __launch_bounds__(BT, 4) k_bin_scatter_peers(const uint32_t *__r
     }
   }
   __syncthreads();
+  if (!ORDERED && threadIdx.x < parts) {  // (ordered against the write-out by the barrier behind the reorder loop)
+    const uint32_t p = threadIdx.x;
+    s_gbase[p] = atomicAdd(&cursor[p], s_tbase[p + 1] - s_tbase[p]);
+  }
 #pragma unroll
   for (int r = 0; r < prim::SORT_ROUNDS; r++) {
     const size_t i = wbase + (size_t)r * 32 + l;
@@ -1000,6 +1009,10 @@ __global__ void __launch_bounds__(BT, 4) k_bin_scatter_peers(const uint32_t *__r
     P.rec[d][at] = s_rec[x];
     if (HAS_VAL) P.val[d][at] = s_v[x];
   }
+}
+// after an unordered scatter: this rank's count for every destination, deposited at the destination
+__global__ void k_publish_peer_counts(uint32_t parts, uint32_t me, const uint32_t *__restrict__ cursor, PeerTable P) {
+  if (threadIdx.x < parts) P.cnt[threadIdx.x][me] = cursor[threadIdx.x];
 }
 // an empty local batch still has to tell every peer "nothing from me"
 __global__ void k_zero_peer_counts(uint32_t parts, uint32_t me, PeerTable P) {

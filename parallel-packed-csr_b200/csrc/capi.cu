@@ -1497,10 +1497,19 @@ int ppcsr_bin_to_peers(int device, void *cuda_stream, const uint64_t *d_starts, 
   tmp.stream = st;
   const unsigned nblocks = div_up(count, prim::SORT_TILE);
   const size_t hn = (size_t)n_parts * nblocks;
-  PPCSR_TRY(dev_reserve(tmp.hist, hn + 1, st));
-  batch::k_bin_count<<<nblocks, batch::BT, 0, st>>>(d_src, count, d_starts, n_parts, tmp.hist.p, nblocks);
-  PPCSR_TRY(prim::device_scan(&tmp, prim::InArray{tmp.hist.p}, prim::OutPrefixWithTotal{tmp.hist.p, hn}, hn, nullptr,
-                              nullptr));
+  PPCSR_TRY(dev_reserve(tmp.hist, std::max<size_t>(hn + 1, batch::BIN_MAX_PARTS), st));
+  // Without per-update values every update of the batch is the same operation and their order inside a destination's
+  // region does not matter: the tiles then claim their places with one atomicAdd per destination (tmp.hist[0 .. parts) is
+  // the cursor) and the count pass + scan in front of the scatter go away (PPCSR_ROUTE_ORDERED=1 keeps them).
+  static const bool force_ordered = getenv("PPCSR_ROUTE_ORDERED") != nullptr;
+  const bool ordered = d_val != nullptr || force_ordered;
+  if (ordered) {
+    batch::k_bin_count<<<nblocks, batch::BT, 0, st>>>(d_src, count, d_starts, n_parts, tmp.hist.p, nblocks);
+    PPCSR_TRY(prim::device_scan(&tmp, prim::InArray{tmp.hist.p}, prim::OutPrefixWithTotal{tmp.hist.p, hn}, hn, nullptr,
+                                nullptr));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(tmp.hist.p, 0, (size_t)n_parts * sizeof(uint32_t), st));
+  }
   {  // per device, once, thread-safe
     static std::once_flag once[64];
     static cudaError_t once_err[64];
@@ -1512,15 +1521,23 @@ int ppcsr_bin_to_peers(int device, void *cuda_stream, const uint64_t *d_starts, 
         once_err[dv] = cudaFuncSetAttribute(batch::k_bin_scatter_peers<false>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)batch::bin_peers_smem(false));
+      if (once_err[dv] == cudaSuccess)
+        once_err[dv] = cudaFuncSetAttribute(batch::k_bin_scatter_peers<false, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)batch::bin_peers_smem(false));
     });
     CUDA_TRY(once_err[dv]);
   }
   if (d_val) {
     batch::k_bin_scatter_peers<true><<<nblocks, batch::BT, batch::bin_peers_smem(true), st>>>(
         d_src, d_dst, d_val, count, d_starts, n_parts, tmp.hist.p, nblocks, my_rank, region_cap, P);
-  } else {
+  } else if (ordered) {
     batch::k_bin_scatter_peers<false><<<nblocks, batch::BT, batch::bin_peers_smem(false), st>>>(
         d_src, d_dst, nullptr, count, d_starts, n_parts, tmp.hist.p, nblocks, my_rank, region_cap, P);
+  } else {
+    batch::k_bin_scatter_peers<false, false><<<nblocks, batch::BT, batch::bin_peers_smem(false), st>>>(
+        d_src, d_dst, nullptr, count, d_starts, n_parts, nullptr, nblocks, my_rank, region_cap, P, tmp.hist.p);
+    batch::k_publish_peer_counts<<<1, batch::BIN_MAX_PARTS, 0, st>>>(n_parts, my_rank, tmp.hist.p, P);
   }
   CUDA_TRY(cudaGetLastError());
   return PPCSR_OK;
