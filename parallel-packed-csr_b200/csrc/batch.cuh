@@ -524,7 +524,11 @@ __device__ __forceinline__ bool find_fast(const LocSmem &S, const uint32_t *__re
 
 // SPARSE: the small-batch variant (appends the touched leaves); a template so that the general instantiation keeps its
 // 32 registers -- 8 CTAs = all 64 warps of an SM (at 40 registers: 6 CTAs, locate stage 3.27 -> 4.02 ms on C4).
-template <bool SPARSE>
+// INSONLY: the batch has neither per-update values nor an op bit and its one value is non-zero -- every update is an
+// insert: the remove / `not found` bookkeeping (runs of equal keys walked back to their first op, delete counts, three
+// of the seven ballots) is compiled out.  k_locate is issue-bound (ncu: 77 % issue-active) and that part was a quarter
+// of its instructions on an insert batch.
+template <bool SPARSE, bool INSONLY = false>
 __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay,
                                                uint32_t default_val, size_t count, uint64_t invalid_key,
                                                const uint32_t *__restrict__ dest, uint32_t *__restrict__ val,
@@ -641,14 +645,14 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
       const uint64_t k = kw & km;
       if (k < invalid_key) {
         s = (uint32_t)(k >> 32);
-        const uint32_t v = pay ? pay[i] : (op_bit && (kw & KEY_OP_BIT)) ? 0u : default_val;
-        delta = v != 0 ? 1 : -1;
-        const bool same_prev = (S.key[e] & km) == k && i > 0;
+        const uint32_t v = INSONLY ? default_val : pay ? pay[i] : (op_bit && (kw & KEY_OP_BIT)) ? 0u : default_val;
+        delta = INSONLY ? 1 : v != 0 ? 1 : -1;
+        const bool same_prev = !INSONLY && (S.key[e] & km) == k && i > 0;
         winner = (S.key[e + 2] & km) != k || i + 1 == count;
         // a remove right after a remove of the same key: the sequential reference reports `not found`
-        if (v == 0 && same_prev && value_at(i - 1) == 0) miss_dup = true;
+        if (!INSONLY && v == 0 && same_prev && value_at(i - 1) == 0) miss_dup = true;
         if (winner) {
-          bool first_del = v == 0;  // is the FIRST op of this key's run a remove?
+          bool first_del = !INSONLY && v == 0;  // is the FIRST op of this key's run a remove?
           if (same_prev) {
             size_t h = i - 1;
             while (h > 0 && (keys[h - 1] & km) == k) h--;
@@ -663,7 +667,7 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
             hit = mode == 3u ? find_tab(S.tab.first, S.tab.cnt8, wa >> ls, dest, vb[r], ve[r], ls, d, &slot)
                              : find_in(D, doff, C, coff, vb[r], ve[r], true, ls, d, &slot);
           }
-          if (v != 0) {
+          if (INSONLY || v != 0) {
             cls = hit ? CLS_OVERWRITE : CLS_INSERT;
             if (hit) val[slot] = v;  // duplicate insert overwrites the value (reference PCSR.cpp:529-532)
           } else {
@@ -684,11 +688,15 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
     // call counts: one atomic per run of equal sources inside the warp
     {
       const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
-      const unsigned adds = __ballot_sync(0xFFFFFFFFu, delta > 0);
-      const unsigned dels = __ballot_sync(0xFFFFFFFFu, delta < 0);
-      if (s != 0xFFFFFFFFu && (peers & lt) == 0) {
-        const int sum = __popc(peers & adds) - __popc(peers & dels);
-        if (sum) atomicAdd(&nn[s], (uint32_t)sum);
+      if (INSONLY) {  // every valid update is one add call
+        if (s != 0xFFFFFFFFu && (peers & lt) == 0) atomicAdd(&nn[s], (uint32_t)__popc(peers));
+      } else {
+        const unsigned adds = __ballot_sync(0xFFFFFFFFu, delta > 0);
+        const unsigned dels = __ballot_sync(0xFFFFFFFFu, delta < 0);
+        if (s != 0xFFFFFFFFu && (peers & lt) == 0) {
+          const int sum = __popc(peers & adds) - __popc(peers & dels);
+          if (sum) atomicAdd(&nn[s], (uint32_t)sum);
+        }
       }
     }
     // per-leaf counts: the batch is key-sorted, so equal leaves are adjacent -> one atomic per warp run.  The first
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
       if (key != 0xFFFFFFFFu && (peers & lt) == 0)
         first_touch = atomicAdd(&ins_cnt[leaf], (uint32_t)__popc(peers)) == 0u;
     }
-    {
+    if (!INSONLY) {
       const uint32_t key = (cls == CLS_DELETE) ? leaf : 0xFFFFFFFFu;
       const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
       if (key != 0xFFFFFFFFu && (peers & lt) == 0)
@@ -710,9 +718,9 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
     {
       const unsigned m0 = __ballot_sync(0xFFFFFFFFu, cls == CLS_INSERT);
       const unsigned m1 = __ballot_sync(0xFFFFFFFFu, cls == CLS_OVERWRITE);
-      const unsigned m2 = __ballot_sync(0xFFFFFFFFu, cls == CLS_DELETE);
-      const unsigned m3 = __ballot_sync(0xFFFFFFFFu, miss_dup);
-      const unsigned m5 = __ballot_sync(0xFFFFFFFFu, miss_first);
+      const unsigned m2 = INSONLY ? 0u : __ballot_sync(0xFFFFFFFFu, cls == CLS_DELETE);
+      const unsigned m3 = INSONLY ? 0u : __ballot_sync(0xFFFFFFFFu, miss_dup);
+      const unsigned m5 = INSONLY ? 0u : __ballot_sync(0xFFFFFFFFu, miss_first);
       const unsigned m4 = __ballot_sync(0xFFFFFFFFu, winner);
       const unsigned m6 = __ballot_sync(0xFFFFFFFFu, first_touch);
       if (SPARSE) {  // one entry per leaf and batch, whatever touched it first; the warp takes its places in one go

@@ -1047,16 +1047,19 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   uint32_t *t_val = s->ins_uniform_val ? nullptr : lblocks == 1 ? s->ins_val.p : tile_val;
   uint32_t *t_pred = lblocks == 1 ? s->ins_pred.p : s->uloc.p;
   const uint32_t dst_mask = lo_bits >= 32 ? 0xFFFFFFFFu : ((1u << lo_bits) - 1u);
+  const bool ins_only = !pay && !op_bit && default_val != 0u;  // every update of the batch is an insert
+  auto locate = [&](auto kernel, uint32_t *touched, uint32_t *stamp, uint32_t epoch) {
+    kernel<<<lblocks, batch::LT, sizeof(batch::LocSmem), s->stream>>>(
+        keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
+        (uint32_t)g.N, s->nn.p, t_dst, t_val, t_pred, s->tile_cnt.p, s->ins_cnt.p, s->del_cnt.p, op_bit, sc, touched,
+        stamp, epoch, dst_mask);
+  };
   if (sparse) {
-    batch::k_locate<true><<<lblocks, batch::LT, sizeof(batch::LocSmem), s->stream>>>(
-        keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
-        (uint32_t)g.N, s->nn.p, t_dst, t_val, t_pred, s->tile_cnt.p, s->ins_cnt.p, s->del_cnt.p, op_bit, sc,
-        s->touched.p, s->touch_stamp.p, s->touch_epoch, dst_mask);
+    if (ins_only) locate(batch::k_locate<true, true>, s->touched.p, s->touch_stamp.p, s->touch_epoch);
+    else locate(batch::k_locate<true, false>, s->touched.p, s->touch_stamp.p, s->touch_epoch);
   } else {
-    batch::k_locate<false><<<lblocks, batch::LT, sizeof(batch::LocSmem), s->stream>>>(
-        keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
-        (uint32_t)g.N, s->nn.p, t_dst, t_val, t_pred, s->tile_cnt.p, s->ins_cnt.p, s->del_cnt.p, op_bit, sc, nullptr,
-        nullptr, 0u, dst_mask);
+    if (ins_only) locate(batch::k_locate<false, true>, nullptr, nullptr, 0u);
+    else locate(batch::k_locate<false, false>, nullptr, nullptr, 0u);
   }
   if (lblocks > 1) {
     PPCSR_TRY(prim::device_scan(s, prim::InArray{s->tile_cnt.p}, prim::OutPrefixWithTotal{s->tile_cnt.p, lblocks},
