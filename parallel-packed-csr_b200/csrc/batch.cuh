@@ -528,7 +528,9 @@ __device__ __forceinline__ bool find_fast(const LocSmem &S, const uint32_t *__re
 // insert: the remove / `not found` bookkeeping (runs of equal keys walked back to their first op, delete counts, three
 // of the seven ballots) is compiled out.  k_locate is issue-bound (ncu: 77 % issue-active) and that part was a quarter
 // of its instructions on an insert batch.
-template <bool SPARSE, bool INSONLY = false>
+// DELONLY: the mirror image -- no values, no op bit, value 0: every update is a remove (no insert counts, no insert
+// list; a remove misses iff the edge is absent or the previous update of the batch removed the same key).
+template <bool SPARSE, bool INSONLY = false, bool DELONLY = false>
 __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ pay,
                                                uint32_t default_val, size_t count, uint64_t invalid_key,
                                                const uint32_t *__restrict__ dest, uint32_t *__restrict__ val,
@@ -645,15 +647,16 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
       const uint64_t k = kw & km;
       if (k < invalid_key) {
         s = (uint32_t)(k >> 32);
-        const uint32_t v = INSONLY ? default_val : pay ? pay[i] : (op_bit && (kw & KEY_OP_BIT)) ? 0u : default_val;
-        delta = INSONLY ? 1 : v != 0 ? 1 : -1;
+        const uint32_t v = INSONLY ? default_val : DELONLY ? 0u : pay ? pay[i] : (op_bit && (kw & KEY_OP_BIT)) ? 0u : default_val;
+        delta = INSONLY ? 1 : DELONLY ? -1 : v != 0 ? 1 : -1;
         const bool same_prev = !INSONLY && (S.key[e] & km) == k && i > 0;
         winner = (S.key[e + 2] & km) != k || i + 1 == count;
         // a remove right after a remove of the same key: the sequential reference reports `not found`
-        if (!INSONLY && v == 0 && same_prev && value_at(i - 1) == 0) miss_dup = true;
+        if (DELONLY) miss_dup = same_prev;
+        else if (!INSONLY && v == 0 && same_prev && value_at(i - 1) == 0) miss_dup = true;
         if (winner) {
           bool first_del = !INSONLY && v == 0;  // is the FIRST op of this key's run a remove?
-          if (same_prev) {
+          if (same_prev && !DELONLY) {
             size_t h = i - 1;
             while (h > 0 && (keys[h - 1] & km) == k) h--;
             first_del = value_at(h) == 0;
@@ -667,7 +670,7 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
             hit = mode == 3u ? find_tab(S.tab.first, S.tab.cnt8, wa >> ls, dest, vb[r], ve[r], ls, d, &slot)
                              : find_in(D, doff, C, coff, vb[r], ve[r], true, ls, d, &slot);
           }
-          if (INSONLY || v != 0) {
+          if (INSONLY || (!DELONLY && v != 0)) {
             cls = hit ? CLS_OVERWRITE : CLS_INSERT;
             if (hit) val[slot] = v;  // duplicate insert overwrites the value (reference PCSR.cpp:529-532)
           } else {
@@ -688,8 +691,9 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
     // call counts: one atomic per run of equal sources inside the warp
     {
       const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
-      if (INSONLY) {  // every valid update is one add call
-        if (s != 0xFFFFFFFFu && (peers & lt) == 0) atomicAdd(&nn[s], (uint32_t)__popc(peers));
+      if (INSONLY || DELONLY) {  // every valid update is one add (remove) call
+        if (s != 0xFFFFFFFFu && (peers & lt) == 0)
+          atomicAdd(&nn[s], INSONLY ? (uint32_t)__popc(peers) : 0u - (uint32_t)__popc(peers));
       } else {
         const unsigned adds = __ballot_sync(0xFFFFFFFFu, delta > 0);
         const unsigned dels = __ballot_sync(0xFFFFFFFFu, delta < 0);
@@ -703,7 +707,7 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
     // update to reach a leaf also counts it as touched (a leaf hit by inserts AND deletes counts twice: the total
     // only steers the whole-array-versus-windows policy).
     bool first_touch = false;
-    {
+    if (!DELONLY) {
       const uint32_t key = (cls == CLS_INSERT) ? leaf : 0xFFFFFFFFu;
       const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
       if (key != 0xFFFFFFFFu && (peers & lt) == 0)
@@ -716,8 +720,8 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
         first_touch |= atomicAdd(&del_cnt[leaf], (uint32_t)__popc(peers)) == 0u;
     }
     {
-      const unsigned m0 = __ballot_sync(0xFFFFFFFFu, cls == CLS_INSERT);
-      const unsigned m1 = __ballot_sync(0xFFFFFFFFu, cls == CLS_OVERWRITE);
+      const unsigned m0 = DELONLY ? 0u : __ballot_sync(0xFFFFFFFFu, cls == CLS_INSERT);
+      const unsigned m1 = DELONLY ? 0u : __ballot_sync(0xFFFFFFFFu, cls == CLS_OVERWRITE);
       const unsigned m2 = INSONLY ? 0u : __ballot_sync(0xFFFFFFFFu, cls == CLS_DELETE);
       const unsigned m3 = INSONLY ? 0u : __ballot_sync(0xFFFFFFFFu, miss_dup);
       const unsigned m5 = INSONLY ? 0u : __ballot_sync(0xFFFFFFFFu, miss_first);

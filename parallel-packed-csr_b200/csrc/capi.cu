@@ -1048,6 +1048,7 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
   uint32_t *t_pred = lblocks == 1 ? s->ins_pred.p : s->uloc.p;
   const uint32_t dst_mask = lo_bits >= 32 ? 0xFFFFFFFFu : ((1u << lo_bits) - 1u);
   const bool ins_only = !pay && !op_bit && default_val != 0u;  // every update of the batch is an insert
+  const bool del_only = !pay && !op_bit && default_val == 0u;  // ... a remove
   auto locate = [&](auto kernel, uint32_t *touched, uint32_t *stamp, uint32_t epoch) {
     kernel<<<lblocks, batch::LT, sizeof(batch::LocSmem), s->stream>>>(
         keys, pay, default_val, count, invalid_key, s->dest.p, s->val.p, s->leaf_cnt.p, s->beg.p, g.leaf_shift,
@@ -1059,6 +1060,7 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
     else locate(batch::k_locate<true, false>, s->touched.p, s->touch_stamp.p, s->touch_epoch);
   } else {
     if (ins_only) locate(batch::k_locate<false, true>, nullptr, nullptr, 0u);
+    else if (del_only) locate(batch::k_locate<false, false, true>, nullptr, nullptr, 0u);
     else locate(batch::k_locate<false, false>, nullptr, nullptr, 0u);
   }
   if (lblocks > 1) {
