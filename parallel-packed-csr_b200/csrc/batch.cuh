@@ -497,7 +497,8 @@ __device__ __forceinline__ bool find_fast(const LocSmem &S, const uint32_t *__re
   steps = min(steps, 32u - (uint32_t)__clz(__reduce_max_sync(__activemask(), n)));
   for (uint32_t st = 0; st < steps; st++) {
     const uint32_t half = n >> 1;
-    if (half != 0u && S.dest[(lo + half) << fs] <= d) lo += half;  // S.tab.first aliases S.dest
+    // unconditional probe (branch-free): half == 0 re-reads [lo] and adds nothing.  S.tab.first aliases S.dest
+    lo += S.dest[(lo + half) << fs] <= d ? half : 0u;
     n -= half;
   }
   const uint32_t leaf = lo + l0, base = leaf << ls;
@@ -510,7 +511,7 @@ __device__ __forceinline__ bool find_fast(const LocSmem &S, const uint32_t *__re
 #pragma unroll
   for (int st = 0; st < 5; st++) {
     const uint32_t half = m >> 1;
-    if (half != 0u && L[x + half - 1u] < d) x += half;
+    x += L[x + half - (half != 0u ? 1u : 0u)] < d ? half : 0u;  // branch-free; half == 0 probes [x] (<= one slot past the leaf) and adds nothing
     m -= half;
   }
   if (m != 0u && L[x] < d) x++;
