@@ -458,6 +458,9 @@ constexpr int LCAP_LEAVES = LCAP / 8;  // leaves are >= 8 slots
 #ifndef PPCSR_LOC_TAB
 #define PPCSR_LOC_TAB 1
 #endif
+#ifndef PPCSR_LOC_FAST1  // find_fast for whole-staged windows too
+#define PPCSR_LOC_FAST1 0
+#endif
 constexpr int LTAB = PPCSR_LOC_TAB ? 1536 : 0;  // leaves a tile can stage as a table (in the place of dest[])
 struct LocTable {
   uint32_t first[LTAB + 1];
@@ -665,9 +668,16 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
           const uint32_t d = (uint32_t)k;
           uint32_t slot;
           bool hit;
+#if PPCSR_LOC_FAST1
+          if (fast) {
+            hit = mode == 3u ? find_fast<true>(S, dest, wa, steps, vb[r], ve[r], ls, d, &slot)
+                             : find_fast<false>(S, dest, wa, steps, vb[r], ve[r], ls, d, &slot);
+          } else {
+#else
           if (fast && mode == 3u) {  // (whole-staged windows: measured 4 % slower than find_in's short loops, C2)
             hit = find_fast<true>(S, dest, wa, steps, vb[r], ve[r], ls, d, &slot);
           } else {
+#endif
             hit = mode == 3u ? find_tab(S.tab.first, S.tab.cnt8, wa >> ls, dest, vb[r], ve[r], ls, d, &slot)
                              : find_in(D, doff, C, coff, vb[r], ve[r], true, ls, d, &slot);
           }
