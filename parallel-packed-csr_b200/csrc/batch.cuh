@@ -788,19 +788,25 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
 
 // the tiles' insert runs, moved to their place in the global key-ordered insert list (tile_off = exclusive scan of the
 // tile counts)
+constexpr int GATHER_TILES = 8;
 __global__ void __launch_bounds__(LT) k_gather_inserts(const uint32_t *__restrict__ tile_dst,
                                                        const uint32_t *__restrict__ tile_val,
                                                        const uint32_t *__restrict__ tile_pred,
                                                        const uint32_t *__restrict__ tile_off,
                                                        uint32_t *__restrict__ ins_dst, uint32_t *__restrict__ ins_val,
-                                                       uint32_t *__restrict__ ins_pred, const BatchScalars *sc) {
+                                                       uint32_t *__restrict__ ins_pred, const BatchScalars *sc,
+                                                       uint32_t n_tiles) {
   if (sc->sparse_abort) return;  // small-batch path: k_locate left without doing anything
-  const uint32_t off = tile_off[blockIdx.x], cnt = tile_off[blockIdx.x + 1] - off;
-  const size_t base = (size_t)blockIdx.x * LTILE;
-  for (uint32_t x = threadIdx.x; x < cnt; x += LT) {
-    ins_dst[off + x] = tile_dst[base + x];
-    if (tile_val) ins_val[off + x] = tile_val[base + x];
-    ins_pred[off + x] = tile_pred[base + x];
+  // GATHER_TILES tiles per CTA (a tile's run is ~500 elements: one tile per CTA left the kernel bound by CTA turnover)
+  const uint32_t t0 = blockIdx.x * GATHER_TILES, t1 = min(t0 + (uint32_t)GATHER_TILES, n_tiles);
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint32_t off = tile_off[t], cnt = tile_off[t + 1] - off;
+    const size_t base = (size_t)t * LTILE;
+    for (uint32_t x = threadIdx.x; x < cnt; x += LT) {
+      ins_dst[off + x] = tile_dst[base + x];
+      if (tile_val) ins_val[off + x] = tile_val[base + x];
+      ins_pred[off + x] = tile_pred[base + x];
+    }
   }
 }
 

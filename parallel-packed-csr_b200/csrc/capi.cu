@@ -422,6 +422,9 @@ int finish_batch_impl(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
   // The class counts decide on the host whether the ROOT leaves its density bounds (reference PCSR.cpp:578-591,
   // 616-628 reach the root => double_list / half_list): then the whole array is rebuilt and no window list is
   // needed at all.
+  // R[] and the insert offsets are needed whichever way the batch goes on: their scans are queued BEFORE the host waits
+  // for the class counts, so that the device has work while the round trip takes place
+  PPCSR_TRY(scan_rank_and_insert_offsets(s, L));
   PPCSR_TRY(read_scalars(s));
   BatchScalars h = *s->h_scalars;
   const uint64_t items_new = s->items + h.n_inserted - h.n_deleted;
@@ -472,7 +475,6 @@ int finish_batch_impl(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
     if (forced > 0 || (forced == 0 && windows_us > whole_us)) whole = true;
   }
   if (whole) {
-    PPCSR_TRY(scan_rank_and_insert_offsets(s, L));
     CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
     PPCSR_TRY(rebuild_whole_array(s, new_N, items_new, h, st));
     s->items = items_new;
@@ -509,7 +511,6 @@ int finish_batch_impl(ppcsr_shard *s, size_t list_cap, ppcsr_batch_stats *st) {
   PPCSR_TRY(prim::device_scan(s, prim::bounded_in(win::InWinChunks{s->windows.p}, &sc->n_windows),
                               prim::bounded_out(win::OutWinChunk0{s->windows.p}, &sc->n_windows), cap, nullptr,
                               &sc->n_chunks));
-  PPCSR_TRY(scan_rank_and_insert_offsets(s, L));
   CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
   PPCSR_TRY(read_scalars(s));
   h = *s->h_scalars;
@@ -1067,8 +1068,8 @@ static int apply_device_common(ppcsr_shard *s, const uint32_t *d_src, const uint
     PPCSR_TRY(prim::device_scan(s, prim::InArray{s->tile_cnt.p}, prim::OutPrefixWithTotal{s->tile_cnt.p, lblocks},
                                 lblocks, nullptr, nullptr));
     s->launches++;
-    batch::k_gather_inserts<<<lblocks, batch::LT, 0, s->stream>>>(tile_dst, tile_val, s->uloc.p, s->tile_cnt.p,
-                                                                 s->ins_dst.p, s->ins_val.p, s->ins_pred.p, sc);
+    batch::k_gather_inserts<<<div_up(lblocks, batch::GATHER_TILES), batch::LT, 0, s->stream>>>(
+        tile_dst, tile_val, s->uloc.p, s->tile_cnt.p, s->ins_dst.p, s->ins_val.p, s->ins_pred.p, sc, lblocks);
   }
   if (stage_ev) CUDA_TRY(cudaEventRecord(s->ev[2], s->stream));
   if (sparse) {
