@@ -569,6 +569,7 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
   // ---- the tile's slot window
   if (tid == 0) {
     uint32_t lo = 0, hi = tile_n;  // rejected updates carry invalid_key and sort last: count the valid ones
+    if (tile_n && (S.key[tile_n] & km) < invalid_key) lo = tile_n;  // (none in this tile: no search)
     while (lo < hi) {
       const uint32_t mid = (lo + hi) >> 1;
       if ((S.key[1 + mid] & km) < invalid_key) lo = mid + 1;
@@ -756,18 +757,24 @@ __global__ void __launch_bounds__(LT, 8) k_locate(const uint64_t *__restrict__ k
       }
     }
   }
-  // ---- the tile's inserts, compacted in element order (element = r * LT + tid)
-  uint32_t total = 0;
+  // ---- the tile's inserts, compacted in element order (element = r * LT + tid): ONE block scan over both rounds'
+  // flags, 16 bits each
+  static_assert(LI == 2 && LT <= 32768, "the two rounds' counts share one scan word");
+  uint32_t total;
+  {
+    uint32_t both;
+    const uint32_t ex = prim::block_excl_scan(is_ins[0] | (is_ins[1] << 16), &both, S.warp);  // ends with a block barrier
+    const uint32_t total0 = both & 0xFFFFu;
+    total = total0 + (both >> 16);
+    const uint32_t at[LI] = {ex & 0xFFFFu, total0 + (ex >> 16)};
 #pragma unroll
-  for (int r = 0; r < LI; r++) {
-    uint32_t t;
-    const uint32_t ex = total + prim::block_excl_scan(is_ins[r], &t, S.warp);  // ends with a block barrier
-    if (is_ins[r]) {
-      S.o_dst[ex] = o_d[r];
-      S.o_val[ex] = o_v[r];
-      S.o_pred[ex] = o_p[r];
+    for (int r = 0; r < LI; r++) {
+      if (is_ins[r]) {
+        S.o_dst[at[r]] = o_d[r];
+        S.o_val[at[r]] = o_v[r];
+        S.o_pred[at[r]] = o_p[r];
+      }
     }
-    total += t;
   }
   if (tid == 0) {
     tile_cnt[blockIdx.x] = total;
