@@ -37,6 +37,7 @@ constexpr uint32_t OS_FLAG_AGG = 1u << 30;  // tile-local count published
 constexpr uint32_t OS_FLAG_INC = 2u << 30;  // inclusive prefix over all tiles up to this one published
 constexpr uint32_t OS_VAL_MASK = (1u << 30) - 1u;
 constexpr int OS_LB_DEPTH = 8;               // predecessors examined per look-back step
+constexpr size_t OS_LATE_MIN_KEYS = (size_t)1 << 25;  // see k_os_pass<.., EARLY>
 constexpr uint64_t OS_MAX_COUNT = OS_VAL_MASK;  // look-back words carry 30-bit counts
 
 struct SortPasses {
@@ -229,7 +230,10 @@ inline size_t os_pass_smem(bool has_pay) {
          (size_t)OS_RADIX * 4 + ((PPCSR_OS_MATCH_ATOMIC && !has_pay) ? (size_t)OS_WARPS * OS_RADIX * 4 : 0);
 }
 
-template <bool HAS_PAY, class Src = KeyArray>
+// EARLY: the tile's digit counts are taken by shared-memory atomics and published before the ranking (see below);
+// !EARLY: they fall out of the ranking and are published after it -- measured faster for large batches (100 M keys:
+// 0.561 -> 0.545 ms per pass), slower for small ones (12.5 M: +3 %), so the host picks by batch size.
+template <bool HAS_PAY, class Src = KeyArray, bool EARLY = (PPCSR_OS_EARLY != 0)>
 __global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(Src src, size_t n, DigitSel sel,
                                                            const uint32_t *__restrict__ gbase,
                                                            uint32_t *__restrict__ lookback, uint32_t *tile_counter,
@@ -272,25 +276,24 @@ __global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(Src src, size_t n, Di
 #if PPCSR_OS_DPK
   uint32_t dpk[OS_ITEMS / 4];  // the keys' digits, four to a register
 #endif
-#if PPCSR_OS_EARLY || PPCSR_OS_DPK
+  uint32_t cnt = 0;
+  if (EARLY || PPCSR_OS_DPK) {
 #pragma unroll
-  for (int r = 0; r < OS_ITEMS; r++) {
-    const uint32_t d = sel_digit(k[r], sel);
+    for (int r = 0; r < OS_ITEMS; r++) {
+      const uint32_t d = sel_digit(k[r], sel);
 #if PPCSR_OS_DPK
-    if (r & 3) dpk[r >> 2] |= d << (8 * (r & 3));
-    else dpk[r >> 2] = d;
+      if (r & 3) dpk[r >> 2] |= d << (8 * (r & 3));
+      else dpk[r >> 2] = d;
 #endif
-#if PPCSR_OS_EARLY
-    atomicAdd(&s_goff[d], 1u);
-#endif
+      if (EARLY) atomicAdd(&s_goff[d], 1u);
+    }
   }
-#endif
-#if PPCSR_OS_EARLY
-  __syncthreads();
-  // the padding keys of a partial last tile are counted in digit `mask`; nobody looks back through the last tile
-  const uint32_t cnt = s_goff[dg];
-  st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + dg, cnt | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG));
-#endif
+  if (EARLY) {
+    __syncthreads();
+    // the padding keys of a partial last tile are counted in digit `mask`; nobody looks back through the last tile
+    cnt = s_goff[dg];
+    st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + dg, cnt | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG));
+  }
   uint32_t *my_match = s_match + (size_t)w * OS_RADIX;
   const uint32_t lbit = 1u << l;
 #pragma unroll
@@ -320,12 +323,11 @@ __global__ void __launch_bounds__(OS_THREADS, 4) k_os_pass(Src src, size_t n, Di
     else rank[r >> 1] = rk;
   }
   __syncthreads();
-#if !PPCSR_OS_EARLY
-  uint32_t cnt = 0;
+  if (!EARLY) {
 #pragma unroll
-  for (int ww = 0; ww < OS_WARPS; ww++) cnt += s_cnt[ww * OS_RADIX + dg];
-  st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + dg, cnt | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG));
-#endif
+    for (int ww = 0; ww < OS_WARPS; ww++) cnt += s_cnt[ww * OS_RADIX + dg];
+    st_relaxed_gpu(lookback + (size_t)tile * OS_RADIX + dg, cnt | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG));
+  }
   uint32_t total;
   const uint32_t dbase = block_excl_scan(cnt, &total, s_warp);
   {  // s_cnt[w][d] := first tile-local position of warp w's keys of digit d
@@ -569,6 +571,8 @@ inline int radix_sort_from(ppcsr_shard *s, const Src &src, bool has_pay, uint64_
         once_err[dv] = cudaFuncSetAttribute(k_os_pass<true, KeyArray>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(true));
       if (once_err[dv] == cudaSuccess)
         once_err[dv] = cudaFuncSetAttribute(k_os_pass<false, KeyArray>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(false));
+      if (once_err[dv] == cudaSuccess)
+        once_err[dv] = cudaFuncSetAttribute(k_os_pass<false, KeyArray, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)os_pass_smem(false));
     });
     CUDA_TRY(once_err[dv]);
   }
@@ -579,6 +583,7 @@ inline int radix_sort_from(ppcsr_shard *s, const Src &src, bool has_pay, uint64_
     k_os_hist<Src><<<hblocks, OSH_THREADS, 0, s->stream>>>(src, n, P, ghist);
   }
   k_os_scan<<<P.n_pass, OS_RADIX, 0, s->stream>>>(ghist, lookback, rows);
+  const bool late_counts = n >= OS_LATE_MIN_KEYS;  // keys-only passes of a large batch publish their counts after the ranking
   // pass 0 reads the source and writes (kb, pb); the later passes alternate between the two buffer pairs
   uint64_t *src_k = ka, *dst_k = kb;
   uint32_t *src_p = pa, *dst_p = pb;
@@ -591,6 +596,7 @@ inline int radix_sort_from(ppcsr_shard *s, const Src &src, bool has_pay, uint64_
     } else {
       const KeyArray a{src_k, src_p};
       if (has_pay) k_os_pass<true, KeyArray><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(true), s->stream>>>(a, n, sel, gb, lb, counters + p, dst_k, dst_p);
+      else if (late_counts) k_os_pass<false, KeyArray, false><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(false), s->stream>>>(a, n, sel, gb, lb, counters + p, dst_k, nullptr);
       else k_os_pass<false, KeyArray><<<(unsigned)ntiles, OS_THREADS, os_pass_smem(false), s->stream>>>(a, n, sel, gb, lb, counters + p, dst_k, nullptr);
     }
     std::swap(src_k, dst_k);
